@@ -1,0 +1,2 @@
+#pragma once
+#include <create_fundamentals/DiffDrive.h>

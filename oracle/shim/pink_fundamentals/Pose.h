@@ -1,0 +1,2 @@
+#pragma once
+#include <pink_fundamentals/PID_drive.h>
