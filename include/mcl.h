@@ -1,0 +1,181 @@
+/* mcl.h — C-ABI of the B200 Monte Carlo localisation engine (libmcl_b200.so).
+ *
+ * Drop-in boundary for the particle-filter hot path of Bright8787/MonteCarloLocalisation,
+ * pink_fundamentals/src/monte_carlo.cpp ("MC"). The reference has no FFI/plugin layer: the boundary is the
+ * set of call sites of its free functions in the ROS node shell. Each entry point below names
+ * the reference function / call site it replaces. INTEGRATION.md shows the few lines a maintainer changes in
+ * monte_carlo.cpp to bind them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the engine owns all device memory behind an opaque handle; the caller owns
+ *     every host pointer, which is read/written only during the call.
+ *   - particles cross the boundary as float[4*N], column-major 4xN = {x,y,theta,w} per particle: the exact
+ *     layout of the reference's Eigen::MatrixXf particles(4,N).data() (MC:82,417), so
+ *     Eigen::Map<Eigen::MatrixXf>(buf,4,N) works in the node.
+ *   - every function returns 0 on success, <0 on error (mcl_last_error gives the text); nothing throws across
+ *     the ABI; CUDA/NCCL errors are captured, not aborted on. There is no CPU fallback: without a usable
+ *     CUDA device mcl_create fails with MCL_ERR_CUDA.
+ *   - one handle = one GPU = one CUDA stream; calls on a handle must be sequential (the reference is a
+ *     single roscpp spinner thread, MC:1212).
+ *
+ * Two sensor/resampling modes share the interface:
+ *   MCL_MODE_REF  results identical to the reference given the same injected draws: step-scalar motion noise,
+ *                 ray-march sensor model, multinomial resampling with adaptive injection and jitter.
+ *   MCL_MODE_NS   the north-star formulation for scale: per-particle Philox motion noise, likelihood-field
+ *                 sensor model over a Euclidean distance transform, fixed-point systematic resampling that is
+ *                 bit-identical for 1/2/4/8 GPUs.
+ */
+#ifndef MCL_B200_H
+#define MCL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcl_handle mcl_handle;
+
+enum { MCL_MODE_REF = 0, MCL_MODE_NS = 1 };
+
+enum {
+    MCL_OK = 0,
+    MCL_ERR_ARG = -1,      /* bad argument / call order (e.g. update before set_map) */
+    MCL_ERR_CUDA = -2,     /* CUDA runtime error, or no CUDA device */
+    MCL_ERR_IO = -3,       /* map.txt could not be read or parsed */
+    MCL_ERR_COMM = -4,     /* NCCL / peer-memory error */
+    MCL_ERR_STATE = -5     /* feature not available in this mode */
+};
+
+/* Every literal the reference hard-codes on the path, as one POD. mcl_config_default() fills in the
+ * reference's values; the synthetic large-map configs override a few. */
+typedef struct mcl_config {
+    int32_t device;              /* CUDA device ordinal */
+    int32_t mode;                /* MCL_MODE_REF | MCL_MODE_NS */
+    int64_t max_particles;       /* capacity of the particle buffers on this GPU */
+    /* sensor model, MC:627-631, 180-181, 635, 650, 370, 333 */
+    double sigma_hit;            /* 0.1   Gaussian LUT sigma (MC:177) */
+    double max_laser_range;      /* 1.0   (MC:628) */
+    double laser_offset;         /* 0.1   (MC:631) */
+    double w_hit, w_rand;        /* 0.8, 0.2 (MC:180-181) */
+    double fov_lower_deg;        /* -120  (MC:635) */
+    double fov_upper_deg;        /*  120 */
+    int32_t beam_stride;         /* 20    (MC:650) */
+    int32_t _pad0;
+    double ray_step;             /* 0.1   (MC:370) */
+    double validity_offset;      /* 0.1   (MC:333) */
+    /* odometry noise, MC:1198, and robot geometry, PID_lib.hpp:19-20 */
+    double alpha[4];             /* 0.001, 0.001, 0.0001, 0.0001 */
+    double wheel_size;           /* 0.0620 */
+    double wheel_space;          /* 0.265 */
+    /* sampleParticles, MC:422, 396, 431, 442-443 */
+    int32_t cell_size_px;        /* 8 */
+    int32_t _pad1;
+    double cell_meters;          /* 0.8 */
+    double init_offset;          /* 0.2  uniform half-width inside a cell */
+    double init_shift;           /* 0.05 global offset */
+    /* resampleParticles, MC:473-482, 537-546 */
+    double inject_max_lost, inject_alpha_slow_lost, inject_alpha_fast_lost;   /* 200, 0.05, 0.5 */
+    double inject_max_conf, inject_alpha_slow_conf, inject_alpha_fast_conf;   /* 50, 0.02, 2 */
+    double jitter_xy_lost, jitter_theta_lost;                                 /* 0.05, pi/12 */
+    double jitter_xy_conf;                                                    /* 0.01 */
+    /* production draws (used when a call is given no injected draws) and NS mode */
+    uint64_t seed;               /* Philox4x32-10 key */
+    double ns_sigma_hit;         /* likelihood-field Gaussian sigma (m) */
+    double ns_z_hit, ns_z_rand;  /* mixture weights */
+    double ns_max_range;         /* beams at or beyond this range are skipped */
+    int32_t ns_beam_stride;      /* 1 = score every beam */
+    int32_t ns_use_fov;          /* 0 = full circle, 1 = apply fov_lower/upper like the reference */
+} mcl_config;
+
+/* Named draws for sampleParticles (MC:427-440): per particle yaw~U[0,1) canonical, row, col, dx, dy canonical. */
+typedef struct mcl_init_draws {
+    const double* u_yaw;
+    const int32_t* row;
+    const int32_t* col;
+    const double* u_dx;
+    const double* u_dy;
+} mcl_init_draws;
+
+/* Draws consumed by resampleParticles (MC:508-555), as sequential streams like the reference's engines:
+ *   u_r[N]      one canonical draw per output slot (MC:514)
+ *   u_jitter[]  consumed in slot order by non-injected slots: x, y, and theta when jitterState (MC:537-546)
+ *   inject      named sampleParticles(1) draws, consumed in order by injected slots (MC:520); n_inject entries */
+typedef struct mcl_resample_draws {
+    const double* u_r;
+    const double* u_jitter;
+    int64_t n_jitter;
+    mcl_init_draws inject;
+    int32_t n_inject;
+} mcl_resample_draws;
+
+typedef struct mcl_resample_stats {
+    int32_t injected;            /* value logged at MC:559 */
+    int32_t clamped;             /* slots whose lower_bound ran off the end (UB in the reference), clamped to N-1 */
+    double p_inject;             /* MC:492 */
+    double weight_slow;          /* MC:487 */
+    double weight_fast;          /* MC:488 */
+    double total_weight;         /* computeWeight's return, MC:681 */
+} mcl_resample_stats;
+
+/* ---- lifecycle --------------------------------------------------------------------------------------- */
+void mcl_config_default(mcl_config* cfg);
+int mcl_create(const mcl_config* cfg, mcl_handle** out);
+void mcl_destroy(mcl_handle* h);
+const char* mcl_last_error(mcl_handle* h);       /* h may be NULL: last mcl_create error */
+const char* mcl_version(void);
+
+/* ---- map: replaces mapCallback's stored grid (MC:291-295) and the map.txt pipeline
+ *      (publish_map.py:8-33 -> publish_map_rviz.cpp:306-437) ---------------------------------------------- */
+int mcl_rasterise_map_txt(const char* text, int8_t* out, int64_t cap, int32_t* width, int32_t* height);  /* host only */
+int mcl_set_map(mcl_handle* h, const int8_t* occ, int32_t width, int32_t height, float resolution,
+                double origin_x, double origin_y);
+int mcl_load_map_txt(mcl_handle* h, const char* path);    /* resolution 0.1f, origin (0,0) as RV:420-426 */
+int mcl_precompute_ray_directions(mcl_handle* h, double min_deg, double max_deg, double step_deg);  /* MC:1017-1023, 1199 */
+
+/* ---- particles --------------------------------------------------------------------------------------- */
+int mcl_init(mcl_handle* h, int64_t n, const mcl_init_draws* draws);   /* sampleParticles(N), MC:415-450, 1205 */
+int mcl_upload(mcl_handle* h, const float* particles4xn, int64_t n);   /* checkpoint/resume; tests */
+int mcl_download(mcl_handle* h, float* particles4xn);                  /* publishParticles' input, MC:563-579 */
+int64_t mcl_num_particles(mcl_handle* h);
+
+/* ---- predict: diffDriveModel + sampleMotionModelOdometry + updateParticlePos (MC:695-755, 1084-1086) -- */
+/* z3 = three standard-normal draws in call order (rot1, trans, rot2) or NULL to draw from Philox.
+ * motion_out3 (optional) receives the noised (rot_1, trans, rot_2) that was applied. */
+int mcl_predict_encoders(mcl_handle* h, double encoder_left, double encoder_right, const double* z3, double* motion_out3);
+int mcl_predict_motion(mcl_handle* h, double rot_1, double trans, double rot_2);   /* updateParticlePos with a given motionModel */
+
+/* ---- update: computeWeight(particles, latest_scan) (MC:623-682) --------------------------------------- */
+int mcl_update(mcl_handle* h, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
+               float range_min, float range_max, double* total_weight);
+
+/* ---- resample: the rest of resampleParticles(particles, jitterState) (MC:469-561). Must follow mcl_update. */
+int mcl_resample(mcl_handle* h, int32_t jitter_state, const mcl_resample_draws* draws, mcl_resample_stats* stats);
+int mcl_download_ancestors(mcl_handle* h, int32_t* idx);   /* ancestor index per output slot, -1 = injected */
+int mcl_download_cdf(mcl_handle* h, double* cdf);          /* REF: the f64 CDF of MC:496-505 */
+
+/* ---- estimate: estimateWeightedPose(particles) (MC:782-800) ------------------------------------------- */
+int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
+
+/* ---- state the reference keeps in globals (MC:189-192), for checkpoint/resume and tests ---------------- */
+int mcl_get_injection_state(mcl_handle* h, double* weight_slow, double* weight_fast);
+int mcl_set_injection_state(mcl_handle* h, double weight_slow, double weight_fast);
+int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------ */
+/* The u_r / u_jitter streams the last mcl_resample consumed (injected, or generated by the device Philox stream),
+ * so a checker can replay the same step. u_jitter holds N*(3 if jitter_state else 2) values. */
+int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter);
+/* Per-kernel CUDA-event timing on the handle's stream; off by default (it serialises launches). */
+int mcl_profile_enable(mcl_handle* h, int32_t on);
+int mcl_profile_kernel_count(void);
+const char* mcl_profile_kernel_name(int32_t id);
+int mcl_profile_read(mcl_handle* h, int32_t id, double* total_ms, int64_t* count);
+void* mcl_stream(mcl_handle* h);                  /* the cudaStream_t all kernels of this handle run on */
+int mcl_synchronize(mcl_handle* h);
+int64_t mcl_kernel_launches(mcl_handle* h);       /* kernels launched by this handle so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL_B200_H */

@@ -1,0 +1,7 @@
+"""montecarlolocalisation_b200 — B200-native particle-filter hot path of Bright8787/MonteCarloLocalisation.
+
+The product is libmcl_b200.so (hand-written sm_100a CUDA behind the C-ABI in include/mcl.h). This package is the thin
+Python host mirror used by the tests and bench.py; it never falls back to a CPU implementation.
+"""
+from ._lib import MODE_NS, MODE_REF, MclError, build, load  # noqa: F401
+from .particle_filter import ParticleFilter, default_config, rasterise_map_txt  # noqa: F401

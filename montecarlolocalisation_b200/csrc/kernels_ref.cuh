@@ -1,0 +1,434 @@
+// kernels_ref.cuh — MCL_MODE_REF kernels: results identical to the reference's CPU filter
+// (pink_fundamentals/src/monte_carlo.cpp, "MC") for the same particles, scan, motion and injected draws.
+//
+// All parity-critical f64 arithmetic goes through __dmul_rn/__dadd_rn/__ddiv_rn so it can never be contracted
+// into FMAs; the translation unit is additionally compiled with -fmad=false.
+#pragma once
+#include "mcl_device.cuh"
+
+namespace mcl {
+
+// One used beam (every beam_stride-th of the FOV-filtered list, MC:650-657), prepared on the host in f64.
+struct RefBeam {
+    double off_deg;    // -(angle) * 180.0 / M_PI                           (MC:653)
+    double obs;        // observed_distance                                   (MC:657)
+    double rand_term;  // w_rand * (|obs - max_range| < 0.01 ? 1.0 : 0.0)     (MC:669)
+};
+
+struct RefParams {
+    // occupancy: 1 byte per cell, 1 = value > 50 (MC:327,377)
+    const uint8_t* occ;
+    int width, height;
+    int map_in_smem;           // stage occ into shared memory (w*h small enough)
+    double res, inv_res;       // (double)float32 resolution (Q10) and its rounded reciprocal
+    double ox, oy;             // origin (MC:300-301)
+    double max_x, max_y;       // isInsideMap upper bounds (MC:688-689)
+    double laser_offset;       // MC:631
+    double validity_offset;    // MC:333
+    double max_range;          // MC:628
+    double w_hit;              // MC:180
+    // ray radii r = 0, step, 2*step ... accumulated in f64 exactly like `r += step` (MC:372)
+    const double* radii;
+    int n_radii;
+    // Gaussian LUT (MC:139-177)
+    const double* gauss;
+    int gauss_size;
+    double gauss_res, gauss_min, gauss_max;
+    // ray direction LUT (MC:192, 355-366): entry k holds (cos,sin) for angle_key = key_min + k
+    const double2* lut;
+    const uint8_t* lut_filled;
+    int key_min, n_keys;
+    // beams
+    const RefBeam* beams;
+    int n_beams;
+};
+
+// ---- map probes ---------------------------------------------------------------------------------------
+struct MapView {
+    const uint8_t* occ;
+    int width, height;
+    double res, inv_res, ox, oy;
+    // worldToMap + getCell > 50 (MC:298-319). Returns 0 free, 1 occupied, -1 outside the grid.
+    __device__ __forceinline__ int probe(double wx, double wy) const {
+        int mx = cell_of(dsub(wx, ox), res, inv_res);
+        int my = cell_of(dsub(wy, oy), res, inv_res);
+        if (mx < 0 || my < 0 || mx >= width || my >= height) return -1;
+        return occ[my * width + mx];
+    }
+};
+
+// isValidPos (MC:331-349): inside the map and none of the 9 stencil points occupied.
+__device__ __forceinline__ bool ref_is_valid(const MapView& m, const RefParams& P, double x, double y) {
+    if (!((x >= P.ox && x < P.max_x) && (y >= P.oy && y < P.max_y))) return false;
+    const double o = P.validity_offset;
+    const double offx[9] = {0, o, 0, -o, 0, o, o, -o, -o};
+    const double offy[9] = {0, 0, o, 0, -o, o, -o, o, -o};
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+        if (m.probe(dadd(x, offx[k]), dadd(y, offy[k])) == 1) return false;
+    return true;
+}
+
+// tf::getYaw(tf::createQuaternionMsgFromYaw(theta)) in the library's operation order (Q8), then degrees.
+__device__ __forceinline__ double ref_yaw(float theta) {
+    double h = dmul((double)theta, 0.5);
+    double sy, cy;
+    sincos(h, &sy, &cy);
+    double d = dadd(dmul(sy, sy), dmul(cy, cy));
+    double s = ddiv(2.0, d);
+    double zs = dmul(sy, s);
+    double wz = dmul(cy, zs);
+    double zz = dmul(sy, zs);
+    double m00 = dsub(1.0, zz);
+    return atan2(wz, m00);
+}
+
+// GaussianLookup::get (MC:154-168)
+__device__ __forceinline__ double ref_gauss(const RefParams& P, double diff) {
+    if (diff < P.gauss_min || diff > P.gauss_max) return 0.0;
+    double index_f = ddiv(dsub(diff, P.gauss_min), P.gauss_res);
+    int index = trunc_x86(index_f);
+    if (index + 1 < P.gauss_size) {
+        double w = dsub(index_f, (double)index);
+        return dadd(dmul(dsub(1.0, w), __ldg(P.gauss + index)), dmul(w, __ldg(P.gauss + index + 1)));
+    }
+    return __ldg(P.gauss + index);
+}
+
+struct RefSmem {
+    double2* lut;
+    RefBeam* beams;
+    double* radii;
+    uint8_t* occ;
+};
+
+__device__ __forceinline__ RefSmem ref_stage_smem(const RefParams& P, unsigned char* raw, bool stage_map) {
+    RefSmem s;
+    s.lut = reinterpret_cast<double2*>(raw);
+    s.beams = reinterpret_cast<RefBeam*>(s.lut + P.n_keys);
+    s.radii = reinterpret_cast<double*>(s.beams + P.n_beams);
+    s.occ = reinterpret_cast<uint8_t*>(s.radii + P.n_radii);
+    for (int i = threadIdx.x; i < P.n_keys; i += blockDim.x) s.lut[i] = P.lut[i];
+    for (int i = threadIdx.x; i < P.n_beams; i += blockDim.x) s.beams[i] = P.beams[i];
+    for (int i = threadIdx.x; i < P.n_radii; i += blockDim.x) s.radii[i] = P.radii[i];
+    if (stage_map) {
+        int cells = P.width * P.height;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) s.occ[i] = P.occ[i];
+    }
+    __syncthreads();
+    return s;
+}
+
+// angle_key = (int)round(yaw_deg + off_deg) (MC:352-355) as an index into the LUT arrays.
+__device__ __forceinline__ int ref_key_index(const RefParams& P, double yaw_deg, double off_deg) {
+    int key = trunc_x86(round(dadd(yaw_deg, off_deg)));
+    int k = key - P.key_min;
+    return (k < 0 || k >= P.n_keys) ? -1 : k;
+}
+
+// ---- first-touch pre-pass (Q9) ---------------------------------------------------------------------------
+// The reference memoises the direction of a missing key from whichever (particle j ascending, beam i ascending)
+// touches it first. For every still-unfilled key find that first toucher: touch[k] = min over (j<<32 | beam).
+__global__ void __launch_bounds__(256) k_ref_first_touch(const float4* __restrict__ part, int64_t n, RefParams P,
+                                                         unsigned long long* __restrict__ touch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RefSmem S = ref_stage_smem(P, smem_raw, P.map_in_smem != 0);
+    MapView m{P.map_in_smem ? S.occ : P.occ, P.width, P.height, P.res, P.inv_res, P.ox, P.oy};
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float4 p = part[j];
+    if (!ref_is_valid(m, P, (double)p.x, (double)p.y)) return;
+    double yaw_deg = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);
+    for (int b = 0; b < P.n_beams; b++) {
+        int k = ref_key_index(P, yaw_deg, S.beams[b].off_deg);
+        if (k >= 0 && !P.lut_filled[k])
+            atomicMin(&touch[k], ((unsigned long long)j << 32) | (unsigned)b);
+    }
+}
+
+// theta of each first toucher, so the host can evaluate the direction with the same libm as the CPU filter.
+__global__ void k_ref_touch_theta(const float4* __restrict__ part, const unsigned long long* __restrict__ touch, int n_keys,
+                                  float* __restrict__ theta_out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    unsigned long long t = touch[k];
+    theta_out[k] = (t == ~0ull) ? 0.f : part[t >> 32].z;
+}
+
+// ---- computeWeight (MC:623-682): one thread per particle ---------------------------------------------------
+__global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, int64_t n, RefParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RefSmem S = ref_stage_smem(P, smem_raw, P.map_in_smem != 0);
+    MapView m{P.map_in_smem ? S.occ : P.occ, P.width, P.height, P.res, P.inv_res, P.ox, P.oy};
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float4 p = part[j];
+    double prob = 0.0;
+    if (ref_is_valid(m, P, (double)p.x, (double)p.y)) {                                   // MC:648
+        double posx = dadd((double)p.x, dmul(P.laser_offset, (double)cr_cosf(p.z)));      // MC:644
+        double posy = dadd((double)p.y, dmul(P.laser_offset, (double)cr_sinf(p.z)));      // MC:645
+        double yaw_deg = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);         // MC:351-352
+        for (int b = 0; b < P.n_beams; b++) {
+            RefBeam bm = S.beams[b];
+            int k = ref_key_index(P, yaw_deg, bm.off_deg);
+            double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
+            double expected = P.max_range;                                                // MC:389
+            for (int s = 0; s < P.n_radii; s++) {                                         // MC:372
+                double r = S.radii[s];
+                int c = m.probe(dadd(posx, dmul(r, dir.x)), dadd(posy, dmul(r, dir.y)));
+                if (c < 0) break;                                                         // MC:376
+                if (c == 1) { expected = r; break; }                                      // MC:377-381
+            }
+            double diff = fabs(dsub(bm.obs, expected));                                   // MC:662
+            prob = dadd(prob, dmul(P.w_hit, ref_gauss(P, diff)));                         // MC:665
+            prob = dadd(prob, bm.rand_term);                                              // MC:669
+        }
+    }
+    part[j].w = __double2float_rn(prob);                                                  // MC:673
+}
+
+// ---- sequential f64 accumulations (MC:675 and MC:496-505) --------------------------------------------------
+// The reference sums fp32 weights into an f64 total one by one, and builds the CDF the same way. fp addition is
+// not associative, so bit-identical results need the same order: one thread walks the chain while the rest of
+// the block stages tiles through shared memory. (Round-1 baseline; the parallel exact scan replaces it.)
+constexpr int SEQ_TILE = 1024;
+
+__global__ void __launch_bounds__(256) k_ref_seq_total(const float4* __restrict__ part, int64_t n, double* __restrict__ total_out) {
+    __shared__ float tile[2][SEQ_TILE];
+    double acc = 0.0;
+    int64_t n_tiles = (n + SEQ_TILE - 1) / SEQ_TILE;
+    // prologue: stage tile 0
+    for (int i = threadIdx.x; i < SEQ_TILE; i += blockDim.x) { int64_t g = i; tile[0][i] = g < n ? part[g].w : 0.f; }
+    __syncthreads();
+    for (int64_t t = 0; t < n_tiles; t++) {
+        int cur = t & 1;
+        if (threadIdx.x == 0) {
+            int64_t cnt = min((int64_t)SEQ_TILE, n - t * SEQ_TILE);
+            for (int i = 0; i < cnt; i++) acc = dadd(acc, (double)tile[cur][i]);
+        } else if (t + 1 < n_tiles) {
+            int64_t base = (t + 1) * SEQ_TILE;
+            for (int i = threadIdx.x - 1; i < SEQ_TILE; i += blockDim.x - 1) { int64_t g = base + i; tile[cur ^ 1][i] = g < n ? part[g].w : 0.f; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = acc;
+}
+
+// w_i <- (float)((double)w_i / total) (MC:497,503), cdf[i] = cdf[i-1] + (double)w_i (MC:498,504).
+__global__ void __launch_bounds__(256) k_ref_seq_cdf(float4* __restrict__ part, int64_t n, const double* __restrict__ total_in,
+                                                     double* __restrict__ cdf) {
+    __shared__ float wn[2][SEQ_TILE];
+    __shared__ double out[2][SEQ_TILE];
+    const double total = *total_in;
+    double acc = 0.0;
+    int64_t n_tiles = (n + SEQ_TILE - 1) / SEQ_TILE;
+    auto stage = [&](int buf, int64_t t, int first, int stride) {
+        int64_t base = t * SEQ_TILE;
+        for (int i = first; i < SEQ_TILE; i += stride) {
+            int64_t g = base + i;
+            if (g < n) { float w = __double2float_rn(ddiv((double)part[g].w, total)); part[g].w = w; wn[buf][i] = w; }
+        }
+    };
+    auto flush = [&](int buf, int64_t t, int first, int stride) {
+        int64_t base = t * SEQ_TILE;
+        for (int i = first; i < SEQ_TILE; i += stride) { int64_t g = base + i; if (g < n) cdf[g] = out[buf][i]; }
+    };
+    stage(0, 0, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (int64_t t = 0; t < n_tiles; t++) {
+        int cur = t & 1;
+        if (threadIdx.x == 0) {
+            int64_t cnt = min((int64_t)SEQ_TILE, n - t * SEQ_TILE);
+            for (int i = 0; i < cnt; i++) { acc = dadd(acc, (double)wn[cur][i]); out[cur][i] = acc; }
+        } else {
+            if (t > 0) flush(cur ^ 1, t - 1, threadIdx.x - 1, blockDim.x - 1);
+            if (t + 1 < n_tiles) stage(cur ^ 1, t + 1, threadIdx.x - 1, blockDim.x - 1);
+        }
+        __syncthreads();
+    }
+    flush((n_tiles - 1) & 1, n_tiles - 1, threadIdx.x, blockDim.x);
+}
+
+// ---- resample (MC:508-555) ---------------------------------------------------------------------------------
+struct RefResampleParams {
+    double p_inject;       // MC:492
+    int max_inject;        // MC:474/479
+    int jitter_state;      // 1 = lost (x,y,theta jitter), 0 = confident (x,y only)
+    double jit_xy_a, jit_xy_w;     // uniform(a,b): u*(b-a)+a with w=b-a  (libstdc++ formula)
+    double jit_th_a, jit_th_w;
+    float new_weight;      // (float)(1.0/N) (MC:524,551)
+    // sampleParticles constants (MC:396-403, 431-432, 442-443)
+    double cell_meters, half_cell, init_a, init_w, yaw_a, yaw_w, init_shift;
+};
+
+// flags[i] = (u_r[i] < p_inject); block_counts[b] = number of flags in block b.
+__global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
+                                                          int* __restrict__ block_counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int f = (i < n && u_r[i] < p_inject) ? 1 : 0;
+    int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+// exclusive scan of block counts in place (single block, sequential chunks; n_blocks is small).
+__global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < n_blocks; b++) { int c = block_counts[b]; block_counts[b] = acc; acc += c; }
+        *total = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n,
+                                                      const double* __restrict__ cdf, const double* __restrict__ u_r,
+                                                      const double* __restrict__ u_jit,
+                                                      const double* __restrict__ inj_u_yaw, const int* __restrict__ inj_row,
+                                                      const int* __restrict__ inj_col, const double* __restrict__ inj_u_dx,
+                                                      const double* __restrict__ inj_u_dy,
+                                                      const int* __restrict__ block_flag_offsets,   // null when p_inject == 0
+                                                      RefResampleParams R, int* __restrict__ ancestors,
+                                                      int* __restrict__ counters /* [0]=injected, [1]=clamped */) {
+    __shared__ int warp_counts[8];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < n;
+    double r = live ? u_r[i] : 2.0;
+    // rank of this slot among the slots whose draw fell below p_inject (sequential injection counter, MC:518,525)
+    int flag = (block_flag_offsets != nullptr && r < R.p_inject) ? 1 : 0;
+    int rank = 0;
+    if (block_flag_offsets != nullptr) {
+        unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) warp_counts[warp] = __popc(ballot);
+        __syncthreads();
+        int before = block_flag_offsets[blockIdx.x];
+        for (int w = 0; w < warp; w++) before += warp_counts[w];
+        rank = before + __popc(ballot & ((1u << lane) - 1u));
+    }
+    if (!live) return;
+    float4 o;
+    if (flag && rank < R.max_inject) {
+        // sampleParticles(1) with named draws (MC:434-446)
+        double orientation = dadd(dmul(inj_u_yaw[rank], R.yaw_w), R.yaw_a);
+        double x_move = dadd(dmul(inj_u_dx[rank], R.init_w), R.init_a);
+        double y_move = dadd(dmul(inj_u_dy[rank], R.init_w), R.init_a);
+        double base_x = dadd(dmul((double)inj_col[rank], R.cell_meters), R.half_cell);
+        double base_y = dadd(dmul((double)inj_row[rank], R.cell_meters), R.half_cell);
+        o.x = __double2float_rn(dadd(dadd(base_x, x_move), R.init_shift));
+        o.y = __double2float_rn(dadd(dadd(base_y, y_move), R.init_shift));
+        o.z = __double2float_rn(orientation);
+        o.w = R.new_weight;
+        ancestors[i] = -1;
+        atomicAdd(&counters[0], 1);
+    } else {
+        // std::lower_bound(cdf, r): first idx with !(cdf[idx] < r) (MC:530); NaN entries compare false.
+        int64_t lo = 0, len = n;
+        while (len > 0) {
+            int64_t half = len >> 1;
+            if (cdf[lo + half] < r) { lo += half + 1; len -= half + 1; } else { len = half; }
+        }
+        if (lo >= n) { lo = n - 1; atomicAdd(&counters[1], 1); }
+        float4 a = src[lo];
+        int64_t inj_before = rank < R.max_inject ? rank : R.max_inject;
+        int64_t jpos = (i - inj_before) * (R.jitter_state ? 3 : 2);
+        double jx = dadd(dmul(u_jit[jpos], R.jit_xy_w), R.jit_xy_a);
+        double jy = dadd(dmul(u_jit[jpos + 1], R.jit_xy_w), R.jit_xy_a);
+        double jt = (double)a.z;
+        if (R.jitter_state) jt = dadd(jt, dadd(dmul(u_jit[jpos + 2], R.jit_th_w), R.jit_th_a));
+        o.x = __double2float_rn(dadd((double)a.x, jx));          // MC:548
+        o.y = __double2float_rn(dadd((double)a.y, jy));          // MC:549
+        double sn, cs;
+        sincos(jt, &sn, &cs);
+        o.z = __double2float_rn(atan2(sn, cs));                  // MC:550
+        o.w = R.new_weight;                                      // MC:551
+        ancestors[i] = (int)lo;
+    }
+    dst[i] = o;
+}
+
+// ---- production draws: the u_r / u_jitter streams from Philox4x32-10, counter = (2i | 2i+1, stream 0x30, step) -------
+__global__ void __launch_bounds__(256) k_fill_resample_draws(double* __restrict__ u_r, double* __restrict__ u_jit, int64_t n, int per,
+                                                             uint32_t step, uint32_t k0, uint32_t k1) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a[4], b[4];
+    uint64_t c = 2 * (uint64_t)i;
+    Philox::gen((uint32_t)c, (uint32_t)(c >> 32), 0x30u, step, k0, k1, a);
+    Philox::gen((uint32_t)(c + 1), (uint32_t)((c + 1) >> 32), 0x30u, step, k0, k1, b);
+    u_r[i] = canonical53(a[0], a[1]);
+    u_jit[i * per] = canonical53(a[2], a[3]);
+    u_jit[i * per + 1] = canonical53(b[0], b[1]);
+    if (per == 3) u_jit[i * per + 2] = canonical53(b[2], b[3]);
+}
+
+// ---- sampleParticles(N) (MC:415-450) with named draws ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ref_init(float4* __restrict__ part, int64_t n, const double* __restrict__ u_yaw,
+                                                  const int* __restrict__ row, const int* __restrict__ col,
+                                                  const double* __restrict__ u_dx, const double* __restrict__ u_dy,
+                                                  RefResampleParams R) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double orientation = dadd(dmul(u_yaw[i], R.yaw_w), R.yaw_a);
+    double x_move = dadd(dmul(u_dx[i], R.init_w), R.init_a);
+    double y_move = dadd(dmul(u_dy[i], R.init_w), R.init_a);
+    double base_x = dadd(dmul((double)col[i], R.cell_meters), R.half_cell);
+    double base_y = dadd(dmul((double)row[i], R.cell_meters), R.half_cell);
+    float4 o;
+    o.x = __double2float_rn(dadd(dadd(base_x, x_move), R.init_shift));
+    o.y = __double2float_rn(dadd(dadd(base_y, y_move), R.init_shift));
+    o.z = __double2float_rn(orientation);
+    o.w = 1.0f;
+    part[i] = o;
+}
+
+// ---- updateParticlePos (MC:740-755): fp32 element math -----------------------------------------------------
+__global__ void __launch_bounds__(256) k_ref_predict(float4* __restrict__ part, int64_t n, float rot1, float trans, float dtheta) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = part[i];
+    float h = __fadd_rn(p.z, rot1);
+    p.x = __fadd_rn(p.x, __fmul_rn(trans, cr_cosf(h)));
+    p.y = __fadd_rn(p.y, __fmul_rn(trans, cr_sinf(h)));
+    p.z = __fadd_rn(p.z, dtheta);
+    part[i] = p;
+}
+
+// ---- estimateWeightedPose (MC:782-800) ---------------------------------------------------------------------
+// pass 1: sum of weights (f64). pass 2: sums of (w/ws)*{x, y, sin, cos} with fp32 element math, f64 accumulation.
+// Partials are written per block and reduced in a fixed order, so the result is deterministic.
+__global__ void __launch_bounds__(256) k_pose_wsum(const float4* __restrict__ part, int64_t n, double* __restrict__ partials) {
+    __shared__ double ws[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += (double)part[i].w;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w]; partials[blockIdx.x] = s; }
+}
+__global__ void k_reduce_partials(const double* __restrict__ partials, int n_partials, int stride, int n_out, double* __restrict__ out) {
+    int o = threadIdx.x;
+    if (o >= n_out) return;
+    double s = 0;
+    for (int b = 0; b < n_partials; b++) s += partials[(size_t)b * stride + o];
+    out[o] = s;
+}
+__global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum,
+                                                   double* __restrict__ partials /* [grid][4] */) {
+    __shared__ double ws[8][4];
+    const float weight_sum = __double2float_rn(*wsum);
+    double a[4] = {0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = part[i];
+        float w = __fdiv_rn(p.w, weight_sum);
+        a[0] += (double)__fmul_rn(w, p.x);
+        a[1] += (double)__fmul_rn(w, p.y);
+        a[2] += (double)__fmul_rn(w, cr_sinf(p.z));
+        a[3] += (double)__fmul_rn(w, cr_cosf(p.z));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) a[k] = warp_sum(a[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 4; k++) ws[threadIdx.x >> 5][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < 4) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w][threadIdx.x]; partials[(size_t)blockIdx.x * 4 + threadIdx.x] = s; }
+}
+
+}  // namespace mcl

@@ -1,0 +1,101 @@
+// mcl_capi.cu — the extern "C" boundary declared in include/mcl.h. Nothing throws across it.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "mcl_engine.hpp"
+
+struct mcl_handle {
+    mcl::Engine engine;
+    explicit mcl_handle(const mcl_config& c) : engine(c) {}
+};
+
+static thread_local std::string g_create_error;
+
+#define GUARD(h) do { if (!(h)) return MCL_ERR_ARG; } while (0)
+#define TRY(expr)                                                                       \
+    try { return (expr); }                                                              \
+    catch (const std::exception& ex) { h->engine.err = std::string("exception: ") + ex.what(); return MCL_ERR_ARG; } \
+    catch (...) { h->engine.err = "unknown exception"; return MCL_ERR_ARG; }
+
+extern "C" {
+
+const char* mcl_version(void) { return "mcl_b200 0.1 (sm_100a)"; }
+
+void mcl_config_default(mcl_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->device = 0; c->mode = MCL_MODE_REF; c->max_particles = 0;
+    c->sigma_hit = 0.1; c->max_laser_range = 1.0; c->laser_offset = 0.1;            // MC:627-631
+    c->w_hit = 0.8; c->w_rand = 0.2;                                                 // MC:180-181
+    c->fov_lower_deg = -120.00; c->fov_upper_deg = 120.00; c->beam_stride = 20;      // MC:635,650
+    c->ray_step = 0.1; c->validity_offset = 0.1;                                     // MC:370,333
+    c->alpha[0] = 0.001; c->alpha[1] = 0.001; c->alpha[2] = 0.0001; c->alpha[3] = 0.0001;   // MC:1198
+    c->wheel_size = 0.0620; c->wheel_space = 0.265;                                  // PID_lib.hpp:19-20
+    c->cell_size_px = 8; c->cell_meters = 0.8; c->init_offset = 0.2; c->init_shift = 0.05;  // MC:422,396,431,442
+    c->inject_max_lost = 200; c->inject_alpha_slow_lost = 0.05; c->inject_alpha_fast_lost = 0.5;   // MC:474-476
+    c->inject_max_conf = 50; c->inject_alpha_slow_conf = 0.02; c->inject_alpha_fast_conf = 2;      // MC:479-481
+    c->jitter_xy_lost = 0.05; c->jitter_theta_lost = M_PI / 12; c->jitter_xy_conf = 0.01;          // MC:537-545
+    c->seed = 0x9E3779B97F4A7C15ull;
+    c->ns_sigma_hit = 0.1; c->ns_z_hit = 0.8; c->ns_z_rand = 0.2; c->ns_max_range = 5.6;
+    c->ns_beam_stride = 1; c->ns_use_fov = 0;
+}
+
+int mcl_create(const mcl_config* cfg, mcl_handle** out) {
+    if (!cfg || !out) { g_create_error = "mcl_create: null argument"; return MCL_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->mode != MCL_MODE_REF && cfg->mode != MCL_MODE_NS) { g_create_error = "mcl_create: unknown mode"; return MCL_ERR_ARG; }
+    mcl_handle* h = new (std::nothrow) mcl_handle(*cfg);
+    if (!h) { g_create_error = "mcl_create: out of host memory"; return MCL_ERR_ARG; }
+    int rc;
+    try { rc = h->engine.open(); } catch (...) { rc = MCL_ERR_CUDA; h->engine.err = "exception during open"; }
+    if (rc) { g_create_error = h->engine.err; delete h; return rc; }
+    *out = h;
+    return MCL_OK;
+}
+void mcl_destroy(mcl_handle* h) { delete h; }
+const char* mcl_last_error(mcl_handle* h) { return h ? h->engine.err.c_str() : g_create_error.c_str(); }
+
+int mcl_rasterise_map_txt(const char* text, int8_t* out, int64_t cap, int32_t* width, int32_t* height) {
+    if (!text || !width || !height) return MCL_ERR_ARG;
+    mcl::WallGrid g; std::string perr;
+    if (!mcl::parse_map_txt(text, g, perr)) { g_create_error = "map.txt: " + perr; return MCL_ERR_IO; }
+    std::vector<int8_t> occ; int w, hh;
+    mcl::rasterise_walls(g, 8, occ, w, hh);
+    *width = w; *height = hh;
+    if (!out) return MCL_OK;
+    if ((int64_t)occ.size() > cap) return MCL_ERR_ARG;
+    memcpy(out, occ.data(), occ.size());
+    return MCL_OK;
+}
+
+int mcl_set_map(mcl_handle* h, const int8_t* occ, int32_t w, int32_t hh, float res, double ox, double oy) { GUARD(h); TRY(h->engine.set_map(occ, w, hh, res, ox, oy)) }
+int mcl_load_map_txt(mcl_handle* h, const char* path) { GUARD(h); TRY(h->engine.load_map_txt(path)) }
+int mcl_precompute_ray_directions(mcl_handle* h, double a, double b, double s) { GUARD(h); TRY(h->engine.precompute_ray_directions(a, b, s)) }
+int mcl_init(mcl_handle* h, int64_t n, const mcl_init_draws* d) { GUARD(h); TRY(h->engine.init(n, d)) }
+int mcl_upload(mcl_handle* h, const float* p, int64_t n) { GUARD(h); TRY(h->engine.upload(p, n)) }
+int mcl_download(mcl_handle* h, float* p) { GUARD(h); TRY(h->engine.download(p)) }
+int64_t mcl_num_particles(mcl_handle* h) { return h ? h->engine.n : 0; }
+int mcl_predict_encoders(mcl_handle* h, double l, double r, const double* z3, double* m) { GUARD(h); TRY(h->engine.predict_encoders(l, r, z3, m)) }
+int mcl_predict_motion(mcl_handle* h, double r1, double t, double r2) { GUARD(h); TRY(h->engine.predict_motion(r1, t, r2)) }
+int mcl_update(mcl_handle* h, const float* ranges, int32_t nb, float amin, float ainc, float rmin, float rmax, double* total) {
+    GUARD(h); TRY(h->engine.update(ranges, nb, amin, ainc, rmin, rmax, total))
+}
+int mcl_resample(mcl_handle* h, int32_t js, const mcl_resample_draws* d, mcl_resample_stats* st) { GUARD(h); TRY(h->engine.resample(js, d, st)) }
+int mcl_download_ancestors(mcl_handle* h, int32_t* idx) { GUARD(h); TRY(h->engine.download_ancestors(idx)) }
+int mcl_download_cdf(mcl_handle* h, double* cdf) { GUARD(h); TRY(h->engine.download_cdf(cdf)) }
+int mcl_estimate(mcl_handle* h, double* x, double* y, double* th) { GUARD(h); TRY(h->engine.estimate(x, y, th)) }
+int mcl_get_injection_state(mcl_handle* h, double* s, double* f) { GUARD(h); if (s) *s = h->engine.inj_slow; if (f) *f = h->engine.inj_fast; return MCL_OK; }
+int mcl_set_injection_state(mcl_handle* h, double s, double f) { GUARD(h); h->engine.inj_slow = s; h->engine.inj_fast = f; return MCL_OK; }
+int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count) { GUARD(h); TRY(h->engine.get_ray_lut(keys, dx, dy, cap, count)) }
+int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter) { GUARD(h); TRY(h->engine.download_resample_draws(u_r, u_jitter)) }
+int mcl_profile_enable(mcl_handle* h, int32_t on) { GUARD(h); h->engine.profile_enable(on != 0); return MCL_OK; }
+int mcl_profile_kernel_count(void) { return mcl::Engine::K_COUNT; }
+const char* mcl_profile_kernel_name(int32_t id) { return mcl::Engine::kernel_name(id); }
+int mcl_profile_read(mcl_handle* h, int32_t id, double* total_ms, int64_t* count) { GUARD(h); TRY(h->engine.profile_read(id, total_ms, count)) }
+void* mcl_stream(mcl_handle* h) { return h ? (void*)h->engine.stream : nullptr; }
+int mcl_synchronize(mcl_handle* h) { GUARD(h); TRY(h->engine.synchronize()) }
+int64_t mcl_kernel_launches(mcl_handle* h) { return h ? h->engine.launches : 0; }
+
+}  // extern "C"

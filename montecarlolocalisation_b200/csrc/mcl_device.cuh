@@ -1,0 +1,75 @@
+// mcl_device.cuh — device-side helpers shared by the REF and NS kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcl {
+
+// ---- float trig -------------------------------------------------------------------------------------
+// The reference calls cosf/sinf (MC:644-645) and Eigen's fp32 cos/sin (MC:747-748). Neither libm's nor
+// Eigen's rounding is portable, so the engine is held to the portable definition "correctly rounded fp32":
+// evaluate in f64 (error ~1e-16) and round once. Differs from a correctly rounded result only when the f64
+// value falls within ~1e-16 of an fp32 rounding boundary (probability ~1e-9 per call). See DESIGN.md.
+__device__ __forceinline__ float cr_cosf(float t) { return __double2float_rn(cos((double)t)); }
+__device__ __forceinline__ float cr_sinf(float t) { return __double2float_rn(sin((double)t)); }
+
+// ---- exact f64 building blocks (never contracted into FMA) -----------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// static_cast<int>(double) as x86-64 does it (cvttsd2si): truncate toward zero; NaN and out-of-range give
+// INT_MIN, which then fails the reference's bounds test (MC:307-309).
+__device__ __forceinline__ int trunc_x86(double v) {
+    return (fabs(v) < 2147483648.0) ? __double2int_rz(v) : INT32_MIN;
+}
+
+// (int)((a) / res) with the quotient correctly rounded first, as the CPU computes it (MC:304-305).
+// Fast path: multiply by the rounded reciprocal (|error| <= 3.4e-16*|q|) and accept its truncation unless
+// the product lies within 4.5e-16*|q| of an integer; only then pay for the IEEE division.
+__device__ __forceinline__ int cell_of(double a, double res, double inv_res) {
+    double q = dmul(a, inv_res);
+    double t = trunc(q);
+    double f = fabs(q - t);
+    double tol = fabs(q) * 4.5e-16;
+    if (f > tol && f < 1.0 - tol && fabs(q) < 2147483000.0) return __double2int_rz(t);
+    return trunc_x86(ddiv(a, res));
+}
+
+// ---- Philox4x32-10 (counter-based; Salmon et al. 2011) ---------------------------------------------------
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
+#else
+        uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c[2]) >> 32);
+#endif
+        uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    // counter = (c0,c1,c2,c3), key = (k0,k1); out = 4 x 32 random bits
+    __host__ __device__ static inline void gen(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                               uint32_t (&out)[4]) {
+        uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+        for (int i = 0; i < 10; i++) { round(c, k0, k1); k0 += W0; k1 += W1; }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+};
+// 53-bit canonical double in [0,1) from two 32-bit words.
+__host__ __device__ inline double canonical53(uint32_t hi, uint32_t lo) {
+    uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+    return (double)v * (1.0 / 9007199254740992.0);
+}
+
+// ---- block reductions ------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace mcl

@@ -1,0 +1,576 @@
+// mcl_engine.cu — host orchestration of the B200 particle filter (one handle = one GPU = one stream).
+#include "mcl_engine.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "kernels_ref.cuh"
+
+namespace mcl {
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+// every kernel launch goes through LAUNCH: counts it and, when profiling, brackets it with CUDA events on the stream
+#define LAUNCH(id, kernel, grid, block, smem, ...)                      \
+    do {                                                                \
+        prof_begin(id);                                                 \
+        kernel<<<(grid), (block), (smem), stream>>>(__VA_ARGS__);       \
+        prof_end();                                                     \
+        ++launches;                                                     \
+    } while (0)
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+Engine::Engine(const mcl_config& c) : cfg(c) {}
+
+Engine::~Engine() {
+    if (!opened) return;
+    cudaSetDevice(cfg.device);
+    part[0].release(); part[1].release(); cdf.release(); ancestors.release(); d_occ.release(); d_gauss.release();
+    d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
+    d_beams.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
+    d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+const char* Engine::kernel_name(int id) {
+    static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update",
+                                         "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
+                                         "k_ref_seq_cdf", "k_ref_resample", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+    return (id >= 0 && id < K_COUNT) ? names[id] : "?";
+}
+void Engine::profile_enable(bool on) {
+    prof_collect();
+    profiling = on;
+    if (on) for (int i = 0; i < K_COUNT; i++) { prof_ms[i] = 0; prof_count[i] = 0; }
+}
+void Engine::prof_begin(int id) {
+    if (!profiling) return;
+    ProfEvent e; e.id = id;
+    cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, stream);
+    prof_events.push_back(e);
+}
+void Engine::prof_end() {
+    if (!profiling) return;
+    cudaEventRecord(prof_events.back().b, stream);
+}
+void Engine::prof_collect() {
+    if (prof_events.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& e : prof_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { prof_ms[e.id] += ms; prof_count[e.id]++; }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    prof_events.clear();
+}
+int Engine::profile_read(int id, double* total_ms, int64_t* count) {
+    if (id < 0 || id >= K_COUNT) return fail(MCL_ERR_ARG, "profile_read: bad kernel id");
+    CK(cudaSetDevice(cfg.device));
+    prof_collect();
+    if (total_ms) *total_ms = prof_ms[id];
+    if (count) *count = prof_count[id];
+    return MCL_OK;
+}
+
+int Engine::fail(int code, const std::string& what) { err = what; return code; }
+int Engine::cuda_fail(cudaError_t e, const char* where) {
+    err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + where;
+    return MCL_ERR_CUDA;
+}
+
+int Engine::ensure_pinned(size_t bytes) {
+    if (bytes <= h_pinned_bytes) return MCL_OK;
+    if (h_pinned) cudaFreeHost(h_pinned);
+    h_pinned = nullptr; h_pinned_bytes = 0;
+    CK(cudaMallocHost(&h_pinned, bytes));
+    h_pinned_bytes = bytes;
+    return MCL_OK;
+}
+
+int Engine::open() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MCL_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                      " (this engine has no CPU fallback)");
+    if (cfg.device < 0 || cfg.device >= count) return fail(MCL_ERR_ARG, "device ordinal out of range");
+    CK(cudaSetDevice(cfg.device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    opened = true;
+    // static tables
+    gauss.build(cfg.sigma_hit);
+    CK(d_gauss.ensure(gauss.v.size()));
+    CK(cudaMemcpyAsync(d_gauss.p, gauss.v.data(), gauss.v.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    h_radii.clear();
+    for (double r = 0.0; r < cfg.max_laser_range; r += cfg.ray_step) h_radii.push_back(r);       // MC:372
+    CK(d_radii.ensure(h_radii.size()));
+    CK(cudaMemcpyAsync(d_radii.p, h_radii.data(), h_radii.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    // ray-direction LUT: keys reachable by round(yaw_deg + off_deg), yaw in [-180,180], off in (-fov_hi, -fov_lo)
+    const int span = 181 + (int)std::ceil(std::max(std::fabs(cfg.fov_lower_deg), std::fabs(cfg.fov_upper_deg)));
+    key_min = -span;
+    n_keys = 2 * span + 1;
+    h_lut.assign(n_keys, make_double2(0.0, 0.0));
+    h_lut_filled.assign(n_keys, 0);
+    n_unfilled = n_keys;
+    CK(d_lut.ensure(n_keys)); CK(d_lut_filled.ensure(n_keys)); CK(d_touch.ensure(n_keys)); CK(d_touch_theta.ensure(n_keys));
+    CK(cudaMemcpyAsync(d_lut.p, h_lut.data(), n_keys * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
+    CK(d_counters.ensure(4)); CK(d_scalars.ensure(8));
+    CK(d_partials.ensure(4 * 1024));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::synchronize() { CK(cudaSetDevice(cfg.device)); CK(cudaStreamSynchronize(stream)); return MCL_OK; }
+
+// ---- map ----------------------------------------------------------------------------------------------------
+int Engine::set_map(const int8_t* occ, int w, int h, float res, double ox, double oy) {
+    if (!occ || w <= 0 || h <= 0 || !(res > 0.f)) return fail(MCL_ERR_ARG, "set_map: bad grid");
+    CK(cudaSetDevice(cfg.device));
+    map_w = w; map_h = h; res_f = res; origin_x = ox; origin_y = oy;
+    max_x = ox + w * res;      // int * float -> float, then + double (MC:688)
+    max_y = oy + h * res;      // MC:689
+    h_occ.assign(occ, occ + (size_t)w * h);
+    std::vector<uint8_t> flags((size_t)w * h);
+    for (size_t i = 0; i < flags.size(); ++i) flags[i] = occ[i] > 50 ? 1 : 0;    // MC:327,377
+    CK(d_occ.ensure(flags.size()));
+    CK(cudaMemcpyAsync(d_occ.p, flags.data(), flags.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    map_ready = true;
+    return MCL_OK;
+}
+
+int Engine::load_map_txt(const char* path) {
+    std::ifstream f(path ? path : "");
+    if (!f) return fail(MCL_ERR_IO, std::string("cannot open ") + (path ? path : "(null)"));
+    std::stringstream ss; ss << f.rdbuf();
+    WallGrid g; std::string perr;
+    if (!parse_map_txt(ss.str(), g, perr)) return fail(MCL_ERR_IO, "map.txt: " + perr);
+    std::vector<int8_t> occ; int w, h;
+    rasterise_walls(g, cfg.cell_size_px, occ, w, h);
+    return set_map(occ.data(), w, h, (float)(cfg.cell_meters / cfg.cell_size_px), 0.0, 0.0);   // RV:274,420-426
+}
+
+// precomputeRayDirections (MC:1017-1023): keys are (int)(a*100) although lookups use whole degrees (Q9).
+int Engine::precompute_ray_directions(double lo, double hi, double step) {
+    CK(cudaSetDevice(cfg.device));
+    if (!(step > 0)) return fail(MCL_ERR_ARG, "precompute_ray_directions: step must be > 0");
+    for (double a = lo; a <= hi; a += step) {
+        const int key = static_cast<int>(a * 100);
+        const double rad = a * M_PI / 180.0;
+        const int k = key - key_min;
+        if (k < 0 || k >= n_keys) continue;          // never looked up
+        h_lut[k] = make_double2(std::cos(rad), std::sin(rad));
+        if (!h_lut_filled[k]) { h_lut_filled[k] = 1; --n_unfilled; }
+    }
+    CK(cudaMemcpyAsync(d_lut.p, h_lut.data(), n_keys * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count) {
+    int c = 0;
+    for (int k = 0; k < n_keys; ++k) {
+        if (!h_lut_filled[k]) continue;
+        if (c < cap && keys && dx && dy) { keys[c] = key_min + k; dx[c] = h_lut[k].x; dy[c] = h_lut[k].y; }
+        ++c;
+    }
+    if (count) *count = c;
+    return MCL_OK;
+}
+
+// ---- particles ----------------------------------------------------------------------------------------------
+int Engine::ensure_particles(int64_t count) {
+    if (count <= 0) return fail(MCL_ERR_ARG, "particle count must be > 0");
+    if (cfg.max_particles > 0 && count > cfg.max_particles) return fail(MCL_ERR_ARG, "particle count exceeds max_particles");
+    if (count > (int64_t)INT32_MAX) return fail(MCL_ERR_ARG, "particle count exceeds 2^31-1 per GPU");
+    CK(part[0].ensure(count)); CK(part[1].ensure(count));
+    CK(cdf.ensure(count)); CK(ancestors.ensure(count));
+    return MCL_OK;
+}
+
+void Engine::philox_host(uint32_t stream_id, uint64_t index, uint32_t out[4]) const {
+    uint32_t o[4];
+    Philox::gen((uint32_t)index, (uint32_t)(index >> 32), stream_id, (uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), o);
+    for (int i = 0; i < 4; i++) out[i] = o[i];
+}
+
+static RefResampleParams make_resample_params(const mcl_config& c, int64_t n, int jitter_state, double p_inject) {
+    RefResampleParams R;
+    R.p_inject = p_inject;
+    R.max_inject = (int)(jitter_state ? c.inject_max_lost : c.inject_max_conf);
+    R.jitter_state = jitter_state;
+    const double jxy = jitter_state ? c.jitter_xy_lost : c.jitter_xy_conf;
+    R.jit_xy_a = -jxy; R.jit_xy_w = jxy - (-jxy);
+    R.jit_th_a = -c.jitter_theta_lost; R.jit_th_w = c.jitter_theta_lost - (-c.jitter_theta_lost);
+    R.new_weight = (float)(1.0 / (double)n);
+    R.cell_meters = c.cell_meters;
+    R.half_cell = 0.5 * c.cell_meters;
+    R.init_a = -c.init_offset; R.init_w = c.init_offset - (-c.init_offset);
+    R.yaw_a = -M_PI; R.yaw_w = M_PI - (-M_PI);
+    R.init_shift = c.init_shift;
+    return R;
+}
+
+int Engine::init(int64_t count, const mcl_init_draws* d) {
+    CK(cudaSetDevice(cfg.device));
+    if (!map_ready) return fail(MCL_ERR_ARG, "init: set a map first (sampleParticles reads the grid size, MC:423-424)");
+    int rc = ensure_particles(count);
+    if (rc) return rc;
+    const int n_cols = (int)((unsigned)map_w / (unsigned)cfg.cell_size_px);    // MC:423
+    const int n_rows = (int)((unsigned)map_h / (unsigned)cfg.cell_size_px);    // MC:424
+    if (n_cols <= 0 || n_rows <= 0) return fail(MCL_ERR_ARG, "init: map smaller than one cell");
+    // stage the five named draws: [u_yaw | u_dx | u_dy] f64 and [row | col] i32
+    const size_t f64_bytes = 3 * (size_t)count * sizeof(double), i32_bytes = 2 * (size_t)count * sizeof(int);
+    rc = ensure_pinned(f64_bytes + i32_bytes);
+    if (rc) return rc;
+    double* hf = (double*)h_pinned;
+    int* hi = (int*)((char*)h_pinned + f64_bytes);
+    if (d) {
+        if (!d->u_yaw || !d->row || !d->col || !d->u_dx || !d->u_dy) return fail(MCL_ERR_ARG, "init: null draw array");
+        memcpy(hf, d->u_yaw, count * sizeof(double));
+        memcpy(hf + count, d->u_dx, count * sizeof(double));
+        memcpy(hf + 2 * count, d->u_dy, count * sizeof(double));
+        memcpy(hi, d->row, count * sizeof(int));
+        memcpy(hi + count, d->col, count * sizeof(int));
+    } else {
+        for (int64_t i = 0; i < count; ++i) {
+            uint32_t a[4], b[4];
+            philox_host(0x10, 2 * (uint64_t)i, a);
+            philox_host(0x10, 2 * (uint64_t)i + 1, b);
+            hf[i] = canonical53(a[0], a[1]);
+            hf[count + i] = canonical53(a[2], a[3]);
+            hf[2 * count + i] = canonical53(b[0], b[1]);
+            hi[i] = (int)(b[2] % (uint32_t)n_rows);
+            hi[count + i] = (int)(b[3] % (uint32_t)n_cols);
+        }
+    }
+    CK(d_u_jit.ensure(3 * (size_t)count));
+    CK(d_u_r.ensure((size_t)count));
+    // reuse d_u_jit as the f64 staging area and ancestors/cdf space for the ints
+    CK(cudaMemcpyAsync(d_u_jit.p, hf, f64_bytes, cudaMemcpyHostToDevice, stream));
+    int* d_rc = (int*)cdf.p;      // cdf holds count doubles = 2*count ints
+    CK(cudaMemcpyAsync(d_rc, hi, i32_bytes, cudaMemcpyHostToDevice, stream));
+    RefResampleParams R = make_resample_params(cfg, count, 1, 0.0);
+    LAUNCH(K_INIT, k_ref_init, grid_for(count, 256), 256, 0, part[cur].p, count, d_u_jit.p, d_rc, d_rc + count, d_u_jit.p + count,
+           d_u_jit.p + 2 * count, R);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+    n = count;
+    have_weights = false;
+    return MCL_OK;
+}
+
+int Engine::upload(const float* p, int64_t count) {
+    CK(cudaSetDevice(cfg.device));
+    if (!p) return fail(MCL_ERR_ARG, "upload: null pointer");
+    int rc = ensure_particles(count);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(part[cur].p, p, (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    n = count;
+    have_weights = false;
+    return MCL_OK;
+}
+
+int Engine::download(float* p) {
+    CK(cudaSetDevice(cfg.device));
+    if (!p) return fail(MCL_ERR_ARG, "download: null pointer");
+    if (n == 0) return fail(MCL_ERR_ARG, "download: no particles");
+    CK(cudaMemcpyAsync(p, part[cur].p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::download_ancestors(int32_t* idx) {
+    CK(cudaSetDevice(cfg.device));
+    if (!idx || n == 0) return fail(MCL_ERR_ARG, "download_ancestors: nothing to download");
+    CK(cudaMemcpyAsync(idx, ancestors.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::download_resample_draws(double* u_r, double* u_jit) {
+    CK(cudaSetDevice(cfg.device));
+    if (!u_r || !u_jit || n == 0) return fail(MCL_ERR_ARG, "download_resample_draws: nothing to download");
+    CK(cudaMemcpyAsync(u_r, d_u_r.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(u_jit, d_u_jit.p, (size_t)n * last_per * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::download_cdf(double* out) {
+    CK(cudaSetDevice(cfg.device));
+    if (!out || n == 0) return fail(MCL_ERR_ARG, "download_cdf: nothing to download");
+    CK(cudaMemcpyAsync(out, cdf.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+// ---- predict --------------------------------------------------------------------------------------------------
+int Engine::predict_motion(double r1, double t, double r2) {
+    CK(cudaSetDevice(cfg.device));
+    if (n == 0) return fail(MCL_ERR_ARG, "predict: no particles");
+    // Eigen narrows the f64 scalars to the array's fp32 first (MC:746-753)
+    LAUNCH(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2));
+    CK(cudaGetLastError());
+    have_weights = false;
+    return MCL_OK;
+}
+
+int Engine::predict_encoders(double enc_l, double enc_r, const double* z3, double* motion_out) {
+    double z[3];
+    if (z3) { z[0] = z3[0]; z[1] = z3[1]; z[2] = z3[2]; }
+    else {
+        // Box-Muller on host Philox draws (production path; parity runs inject z3)
+        uint32_t a[4], b[4];
+        philox_host(0x20, 0, a); philox_host(0x20, 1, b);
+        const double u1 = 1.0 - canonical53(a[0], a[1]), u2 = canonical53(a[2], a[3]);
+        const double u3 = 1.0 - canonical53(b[0], b[1]), u4 = canonical53(b[2], b[3]);
+        z[0] = std::sqrt(-2.0 * std::log(u1)) * std::cos(2 * M_PI * u2);
+        z[1] = std::sqrt(-2.0 * std::log(u1)) * std::sin(2 * M_PI * u2);
+        z[2] = std::sqrt(-2.0 * std::log(u3)) * std::cos(2 * M_PI * u4);
+    }
+    Motion m = odometry_step(odo, cfg, enc_l, enc_r, z);
+    if (motion_out) { motion_out[0] = m.rot_1; motion_out[1] = m.trans; motion_out[2] = m.rot_2; }
+    ++step_counter;
+    return predict_motion(m.rot_1, m.trans, m.rot_2);
+}
+
+// ---- update -----------------------------------------------------------------------------------------------------
+int Engine::update(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, double* total) {
+    CK(cudaSetDevice(cfg.device));
+    if (!map_ready) return fail(MCL_ERR_ARG, "update: no map (the reference warns 'NO MAP RECEVIED', MC:311)");
+    if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
+    if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "update: bad scan");
+    if (cfg.mode == MCL_MODE_REF) return ref_update(ranges, n_beams, angle_min, angle_inc, range_min, range_max, total);
+    return fail(MCL_ERR_STATE, "update: NS mode not built in this library");
+}
+
+static size_t ref_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes) {
+    return (size_t)n_keys * sizeof(double2) + (size_t)n_beams * sizeof(RefBeam) + (size_t)n_radii * sizeof(double) + map_bytes;
+}
+
+int Engine::ref_update(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, double* total) {
+    filter_scan(ranges, n_beams, angle_min, angle_inc, range_min, range_max, true, cfg.fov_lower_deg, cfg.fov_upper_deg, beams_all);
+    const int stride = std::max(1, cfg.beam_stride);
+    std::vector<RefBeam> used;
+    for (size_t i = 0; i < beams_all.size(); i += stride) {                       // MC:650
+        RefBeam b;
+        b.off_deg = -(beams_all[i].angle) * 180.0 / M_PI;                         // MC:653
+        b.obs = beams_all[i].radius;                                              // MC:657
+        b.rand_term = cfg.w_rand * ((std::abs(b.obs - cfg.max_laser_range) < 0.01) ? 1.0 : 0.0);   // MC:669
+        used.push_back(b);
+    }
+    n_used_beams = (int)used.size();
+    CK(d_beams.ensure(std::max<size_t>(1, used.size())));
+    if (!used.empty()) {
+        int rc = ensure_pinned(used.size() * sizeof(RefBeam));
+        if (rc) return rc;
+        memcpy(h_pinned, used.data(), used.size() * sizeof(RefBeam));
+        CK(cudaMemcpyAsync(d_beams.p, h_pinned, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+    }
+    RefParams P;
+    P.occ = d_occ.p; P.width = map_w; P.height = map_h;
+    const size_t map_bytes = (size_t)map_w * map_h;
+    P.map_in_smem = map_bytes <= 64 * 1024 ? 1 : 0;
+    P.res = (double)res_f; P.inv_res = 1.0 / (double)res_f;
+    P.ox = origin_x; P.oy = origin_y; P.max_x = max_x; P.max_y = max_y;
+    P.laser_offset = cfg.laser_offset; P.validity_offset = cfg.validity_offset; P.max_range = cfg.max_laser_range;
+    P.w_hit = cfg.w_hit;
+    P.radii = d_radii.p; P.n_radii = (int)h_radii.size();
+    P.gauss = d_gauss.p; P.gauss_size = (int)gauss.v.size(); P.gauss_res = gauss.step; P.gauss_min = gauss.lo; P.gauss_max = gauss.hi;
+    P.lut = d_lut.p; P.lut_filled = d_lut_filled.p; P.key_min = key_min; P.n_keys = n_keys;
+    P.beams = d_beams.p; P.n_beams = n_used_beams;
+    const size_t smem = ref_smem_bytes(n_keys, n_used_beams, P.n_radii, P.map_in_smem ? map_bytes : 0);
+    if (smem > 200 * 1024) return fail(MCL_ERR_ARG, "update: too many beams for the shared-memory staging area");
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_ref_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ref_first_touch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    // First-touch memoisation of still-missing ray directions (Q9); stops once every key is filled.
+    if (n_unfilled > 0 && n_used_beams > 0) {
+        CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream));
+        LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
+        CK(cudaGetLastError());
+        LAUNCH(K_TOUCH_THETA, k_ref_touch_theta, grid_for(n_keys, 256), 256, 0, part[cur].p, d_touch.p, n_keys, d_touch_theta.p);
+        CK(cudaGetLastError());
+        int rc = ref_fill_ray_lut();
+        if (rc) return rc;
+    }
+    LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, n, P);
+    CK(cudaGetLastError());
+    LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, part[cur].p, n, d_scalars.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&last_total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    have_weights = true;
+    if (total) *total = last_total;
+    return MCL_OK;
+}
+
+// Evaluate the direction of each newly touched key from its first toucher's theta, with host libm (MC:361-362).
+int Engine::ref_fill_ray_lut() {
+    std::vector<unsigned long long> touch(n_keys);
+    std::vector<float> theta(n_keys);
+    CK(cudaMemcpyAsync(touch.data(), d_touch.p, n_keys * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(theta.data(), d_touch_theta.p, n_keys * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    bool changed = false;
+    const int stride = std::max(1, cfg.beam_stride);
+    for (int k = 0; k < n_keys; ++k) {
+        if (h_lut_filled[k] || touch[k] == ~0ull) continue;
+        const unsigned beam = (unsigned)(touch[k] & 0xffffffffu);
+        const double off_deg = -(beams_all[(size_t)beam * stride].angle) * 180.0 / M_PI;
+        const double yaw = tf_yaw_roundtrip((double)theta[k]);
+        const double angle_rad = yaw + off_deg * M_PI / 180.0;
+        h_lut[k] = make_double2(std::cos(angle_rad), std::sin(angle_rad));
+        h_lut_filled[k] = 1;
+        --n_unfilled;
+        changed = true;
+    }
+    if (changed) {
+        CK(cudaMemcpyAsync(d_lut.p, h_lut.data(), n_keys * sizeof(double2), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));     // h_lut must not change under an in-flight copy
+    }
+    return MCL_OK;
+}
+
+// ---- resample ---------------------------------------------------------------------------------------------------
+int Engine::resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st) {
+    CK(cudaSetDevice(cfg.device));
+    if (n == 0) return fail(MCL_ERR_ARG, "resample: no particles");
+    if (!have_weights) return fail(MCL_ERR_ARG, "resample: call mcl_update first (resampleParticles weighs before it resamples, MC:468)");
+    if (cfg.mode == MCL_MODE_REF) return ref_resample(jitter_state, d, st);
+    return fail(MCL_ERR_STATE, "resample: NS mode not built in this library");
+}
+
+int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st) {
+    jitter_state = jitter_state ? 1 : 0;
+    // adaptive injection EMA (MC:469-492)
+    const double weight_avg = last_total / (double)n;
+    const double a_slow = jitter_state ? cfg.inject_alpha_slow_lost : cfg.inject_alpha_slow_conf;
+    const double a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
+    inj_slow = inj_slow + a_slow * (weight_avg - inj_slow);
+    inj_fast = inj_fast + a_fast * (weight_avg - inj_fast);
+    const double p_inject = std::max(0.0, 1.0 - (inj_fast / inj_slow));
+    RefResampleParams R = make_resample_params(cfg, n, jitter_state, p_inject);
+    const int per = jitter_state ? 3 : 2;
+    const int max_inj = R.max_inject;
+    // stage draws
+    CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3));
+    CK(d_inj_f64.ensure(3 * (size_t)std::max(1, max_inj))); CK(d_inj_i32.ensure(2 * (size_t)std::max(1, max_inj)));
+    const size_t inj_f64 = 3 * (size_t)max_inj, inj_i32 = 2 * (size_t)max_inj;
+    int rc = ensure_pinned(((size_t)(d ? n : 0) * (1 + per) + inj_f64) * sizeof(double) + inj_i32 * sizeof(int));
+    if (rc) return rc;
+    double* hr = (double*)h_pinned;
+    double* hj = hr + (d ? n : 0);
+    double* hif = hj + (size_t)(d ? n : 0) * per;
+    int* hii = (int*)(hif + inj_f64);
+    const int n_cols = (int)((unsigned)map_w / (unsigned)cfg.cell_size_px), n_rows = (int)((unsigned)map_h / (unsigned)cfg.cell_size_px);
+    if (d) {
+        if (!d->u_r || !d->u_jitter) return fail(MCL_ERR_ARG, "resample: null draw array");
+        if (d->n_jitter < (int64_t)n * per) return fail(MCL_ERR_ARG, "resample: u_jitter shorter than N*(2|3)");
+        memcpy(hr, d->u_r, (size_t)n * sizeof(double));
+        memcpy(hj, d->u_jitter, (size_t)n * per * sizeof(double));
+        const int have = std::min(d->n_inject, max_inj);
+        if (p_inject > 0.0 && have < max_inj)
+            if (!d->inject.u_yaw || d->n_inject < max_inj) return fail(MCL_ERR_ARG, "resample: p_inject > 0 needs max_injection named draws");
+        for (int i = 0; i < max_inj; ++i) {
+            const bool ok = i < have && d->inject.u_yaw;
+            hif[i] = ok ? d->inject.u_yaw[i] : 0.0;
+            hif[max_inj + i] = ok ? d->inject.u_dx[i] : 0.0;
+            hif[2 * max_inj + i] = ok ? d->inject.u_dy[i] : 0.0;
+            hii[i] = ok ? d->inject.row[i] : 0;
+            hii[max_inj + i] = ok ? d->inject.col[i] : 0;
+        }
+    } else {
+        // u_r / u_jitter come from the device Philox stream (k_fill_resample_draws); only the <= max_inj named
+        // injection draws are made on the host
+        for (int i = 0; i < max_inj; ++i) {
+            uint32_t a[4], b[4];
+            philox_host(0x31, 2 * (uint64_t)i, a); philox_host(0x31, 2 * (uint64_t)i + 1, b);
+            hif[i] = canonical53(a[0], a[1]);
+            hif[max_inj + i] = canonical53(a[2], a[3]);
+            hif[2 * max_inj + i] = canonical53(b[0], b[1]);
+            hii[i] = (int)(b[2] % (uint32_t)std::max(1, n_rows));
+            hii[max_inj + i] = (int)(b[3] % (uint32_t)std::max(1, n_cols));
+        }
+    }
+    last_per = per;
+    if (d) {
+        CK(cudaMemcpyAsync(d_u_r.p, hr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_u_jit.p, hj, (size_t)n * per * sizeof(double), cudaMemcpyHostToDevice, stream));
+    } else {
+        LAUNCH(K_FILL_DRAWS, k_fill_resample_draws, grid_for(n, 256), 256, 0, d_u_r.p, d_u_jit.p, n, per, (uint32_t)step_counter,
+               (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+        CK(cudaGetLastError());
+    }
+    if (max_inj > 0) {
+        CK(cudaMemcpyAsync(d_inj_f64.p, hif, inj_f64 * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_inj_i32.p, hii, inj_i32 * sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
+    CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(int), stream));
+    const unsigned blocks = grid_for(n, 256);
+    const bool inject_possible = p_inject > 0.0 && max_inj > 0;      // NaN p_inject compares false (MC:492, std::max(0.0, NaN) = 0.0)
+    if (inject_possible) {
+        CK(d_block_counts.ensure(blocks));
+        LAUNCH(K_INJECT_COUNT, k_ref_inject_count, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p);
+        LAUNCH(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2);
+        CK(cudaGetLastError());
+    }
+    // normalise + sequential CDF (MC:496-505)
+    LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, part[cur].p, n, d_scalars.p, cdf.p);
+    CK(cudaGetLastError());
+    LAUNCH(K_RESAMPLE, k_ref_resample, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
+           d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
+           inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p);
+    CK(cudaGetLastError());
+    int counters[4];
+    CK(cudaMemcpyAsync(counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    cur ^= 1;
+    have_weights = false;
+    ++step_counter;
+    if (st) {
+        st->injected = counters[0]; st->clamped = counters[1]; st->p_inject = p_inject;
+        st->weight_slow = inj_slow; st->weight_fast = inj_fast; st->total_weight = last_total;
+    }
+    return MCL_OK;
+}
+
+// ---- estimate -----------------------------------------------------------------------------------------------------
+int Engine::estimate(double* x, double* y, double* th) {
+    CK(cudaSetDevice(cfg.device));
+    if (n == 0) return fail(MCL_ERR_ARG, "estimate: no particles");
+    const int blocks = (int)std::min<int64_t>(1024, grid_for(n, 256));
+    LAUNCH(K_POSE_WSUM, k_pose_wsum, blocks, 256, 0, part[cur].p, n, d_partials.p);
+    LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
+    LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, d_scalars.p + 1, d_partials.p);
+    LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 4, 4, d_scalars.p + 2);
+    CK(cudaGetLastError());
+    double s[4];
+    CK(cudaMemcpyAsync(s, d_scalars.p + 2, sizeof(s), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const float xm = (float)s[0], ym = (float)s[1];
+    const float tm = std::atan2((float)s[2], (float)s[3]);      // MC:796 (fp32 atan2)
+    if (x) *x = xm;
+    if (y) *y = ym;
+    if (th) *th = tm;
+    return MCL_OK;
+}
+
+}  // namespace mcl

@@ -1,0 +1,134 @@
+// mcl_engine.hpp — host side of the engine: owns the device state of one GPU shard and sequences the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mcl.h"
+#include "host_models.hpp"
+
+namespace mcl {
+
+struct RefBeam;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+class Engine {
+public:
+    explicit Engine(const mcl_config& cfg);
+    ~Engine();
+    int open();                       // device, stream, static tables
+    std::string err;
+
+    // boundary (see include/mcl.h)
+    int set_map(const int8_t* occ, int w, int h, float res, double ox, double oy);
+    int load_map_txt(const char* path);
+    int precompute_ray_directions(double lo, double hi, double step);
+    int init(int64_t n, const mcl_init_draws* d);
+    int upload(const float* p, int64_t n);
+    int download(float* p);
+    int predict_encoders(double enc_l, double enc_r, const double* z3, double* motion_out);
+    int predict_motion(double r1, double t, double r2);
+    int update(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, double* total);
+    int resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st);
+    int download_ancestors(int32_t* idx);
+    int download_cdf(double* cdf);
+    int estimate(double* x, double* y, double* th);
+    int get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
+    int synchronize();
+    int download_resample_draws(double* u_r, double* u_jit);
+    // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
+    enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
+                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+    static const char* kernel_name(int id);
+    void profile_enable(bool on);
+    int profile_read(int id, double* total_ms, int64_t* count);
+
+    mcl_config cfg;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0;
+    int64_t launches = 0;
+    double inj_slow = 0, inj_fast = 0;      // adaptiveInjection (MC:191)
+
+private:
+    int fail(int code, const std::string& what);
+    int cuda_fail(cudaError_t e, const char* where);
+    int ensure_particles(int64_t count);
+    int ref_update(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, double* total);
+    int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st);
+    int ref_fill_ray_lut();
+    void philox_host(uint32_t stream_id, uint64_t index, uint32_t out[4]) const;
+
+    bool opened = false;
+    bool attr_set = false;
+    bool profiling = false;
+    struct ProfEvent { int id; cudaEvent_t a, b; };
+    std::vector<ProfEvent> prof_events;
+    double prof_ms[K_COUNT] = {0};
+    int64_t prof_count[K_COUNT] = {0};
+    void prof_begin(int id);
+    void prof_end();
+    void prof_collect();
+    int last_per = 3;
+    // particles: ping-pong float4 {x,y,theta,w} (= column-major 4xN of the reference)
+    DevBuf<float4> part[2];
+    int cur = 0;
+    DevBuf<double> cdf;
+    DevBuf<int> ancestors;
+    // map
+    bool map_ready = false;
+    int map_w = 0, map_h = 0;
+    float res_f = 0.f;
+    double origin_x = 0, origin_y = 0, max_x = 0, max_y = 0;
+    std::vector<int8_t> h_occ;
+    DevBuf<uint8_t> d_occ;            // 1 = occupied (value > 50)
+    // tables
+    GaussTable gauss;
+    DevBuf<double> d_gauss;
+    std::vector<double> h_radii;
+    DevBuf<double> d_radii;
+    int key_min = 0, n_keys = 0, n_unfilled = 0;
+    std::vector<double2> h_lut;
+    std::vector<uint8_t> h_lut_filled;
+    DevBuf<double2> d_lut;
+    DevBuf<uint8_t> d_lut_filled;
+    DevBuf<unsigned long long> d_touch;
+    DevBuf<float> d_touch_theta;
+    // per-step scan
+    std::vector<HostBeam> beams_all;
+    DevBuf<RefBeam> d_beams;
+    int n_used_beams = 0;
+    // motion / odometry
+    OdometryState odo;
+    uint64_t step_counter = 0;
+    // resample
+    DevBuf<double> d_u_r, d_u_jit, d_inj_f64;   // inj_f64: [u_yaw | u_dx | u_dy] x max_inject
+    DevBuf<int> d_inj_i32;                      // [row | col] x max_inject
+    DevBuf<int> d_block_counts;
+    DevBuf<int> d_counters;                     // [0] injected, [1] clamped, [2] flagged total
+    DevBuf<double> d_scalars;                   // [0] total weight, [1] wsum, [2..5] pose sums
+    DevBuf<double> d_partials;
+    double last_total = 0;
+    bool have_weights = false;
+    // pinned staging
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    int ensure_pinned(size_t bytes);
+};
+
+}  // namespace mcl

@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's particle-filter functions over the C-ABI (include/mcl.h).
+
+The reference (pink_fundamentals/src/monte_carlo.cpp, "MC") has no class: the filter is the free functions
+sampleParticles / diffDriveModel + updateParticlePos / computeWeight / resampleParticles / estimateWeightedPose over
+globals. ParticleFilter keeps those names and argument meanings so tests read like calls into the reference.
+The C++ twin for the ROS node is include/mcl_particle_filter.hpp.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_NS, MODE_REF, Config, InitDraws, MclError, ResampleDraws, ResampleStats
+
+_dp, _fp, _ip, _bp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int8)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def default_config(**overrides):
+    cfg = Config()
+    _lib.load().mcl_config_default(C.byref(cfg))
+    for k, v in overrides.items():
+        if k == "alpha":
+            for i in range(4):
+                cfg.alpha[i] = v[i]
+        else:
+            if not hasattr(cfg, k):
+                raise AttributeError("mcl_config has no field %r" % k)
+            setattr(cfg, k, v)
+    return cfg
+
+
+def rasterise_map_txt(text):
+    """map.txt text -> int8 occupancy grid (publish_map.py + publish_map_rviz.cpp:306-437). Host only."""
+    L = _lib.load()
+    w, h = C.c_int32(), C.c_int32()
+    rc = L.mcl_rasterise_map_txt(text.encode(), None, 0, C.byref(w), C.byref(h))
+    if rc:
+        raise MclError(rc, L.mcl_last_error(None).decode())
+    out = np.zeros((h.value, w.value), np.int8)
+    rc = L.mcl_rasterise_map_txt(text.encode(), out.ctypes.data_as(_bp), out.size, C.byref(w), C.byref(h))
+    if rc:
+        raise MclError(rc, L.mcl_last_error(None).decode())
+    return out
+
+
+class ParticleFilter:
+    def __init__(self, cfg=None, prefill_ray_directions=True, **overrides):
+        self.L = _lib.load()
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        h = C.c_void_p()
+        rc = self.L.mcl_create(C.byref(self.cfg), C.byref(h))
+        if rc:
+            raise MclError(rc, self.L.mcl_last_error(None).decode())
+        self.h = h
+        if prefill_ray_directions and self.cfg.mode == MODE_REF:
+            self.precomputeRayDirections(-120.0, 120.0, 0.1)       # MC:1199
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mcl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise MclError(rc, self.L.mcl_last_error(self.h).decode())
+
+    # -- map ------------------------------------------------------------------------------------------
+    def setMap(self, occ, resolution=np.float32(0.1), origin_x=0.0, origin_y=0.0):
+        occ = np.ascontiguousarray(occ, dtype=np.int8)
+        h, w = occ.shape
+        self._ck(self.L.mcl_set_map(self.h, occ.ctypes.data_as(_bp), w, h, C.c_float(resolution), origin_x, origin_y))
+
+    def loadMapTxt(self, path):
+        self._ck(self.L.mcl_load_map_txt(self.h, path.encode()))
+
+    def precomputeRayDirections(self, lo, hi, step):
+        self._ck(self.L.mcl_precompute_ray_directions(self.h, lo, hi, step))
+
+    # -- particles ----------------------------------------------------------------------------------------
+    def sampleParticles(self, n, draws=None):
+        """draws: dict(u_yaw,row,col,u_dx,u_dy) named draws, or None for the engine's Philox stream."""
+        if draws is None:
+            self._ck(self.L.mcl_init(self.h, n, None))
+            return
+        keep = [_f64(draws["u_yaw"]), _i32(draws["row"]), _i32(draws["col"]), _f64(draws["u_dx"]), _f64(draws["u_dy"])]
+        d = InitDraws(keep[0].ctypes.data_as(_dp), keep[1].ctypes.data_as(_ip), keep[2].ctypes.data_as(_ip),
+                      keep[3].ctypes.data_as(_dp), keep[4].ctypes.data_as(_dp))
+        self._ck(self.L.mcl_init(self.h, n, C.byref(d)))
+
+    def uploadParticles(self, P):
+        P = np.ascontiguousarray(P, dtype=np.float32)
+        assert P.ndim == 2 and P.shape[1] == 4
+        self._ck(self.L.mcl_upload(self.h, P.ctypes.data_as(_fp), len(P)))
+
+    def downloadParticles(self):
+        n = self.L.mcl_num_particles(self.h)
+        P = np.empty((n, 4), np.float32)
+        self._ck(self.L.mcl_download(self.h, P.ctypes.data_as(_fp)))
+        return P
+
+    @property
+    def num_particles(self):
+        return self.L.mcl_num_particles(self.h)
+
+    # -- predict --------------------------------------------------------------------------------------------
+    def diffDriveModel(self, encoder_left, encoder_right, z3=None):
+        """diffDriveModel + updateParticlePos (MC:1084-1086). Returns the noised (rot_1, trans, rot_2)."""
+        out = np.zeros(3)
+        z = _f64(z3) if z3 is not None else None
+        self._ck(self.L.mcl_predict_encoders(self.h, encoder_left, encoder_right,
+                                             z.ctypes.data_as(_dp) if z is not None else None, out.ctypes.data_as(_dp)))
+        return out
+
+    def updateParticlePos(self, rot_1, trans, rot_2):
+        self._ck(self.L.mcl_predict_motion(self.h, rot_1, trans, rot_2))
+
+    # -- update ---------------------------------------------------------------------------------------------
+    def computeWeight(self, ranges, angle_min, angle_inc, range_min, range_max):
+        r = np.ascontiguousarray(ranges, dtype=np.float32)
+        total = C.c_double()
+        self._ck(self.L.mcl_update(self.h, r.ctypes.data_as(_fp), len(r), C.c_float(angle_min), C.c_float(angle_inc),
+                                   C.c_float(range_min), C.c_float(range_max), C.byref(total)))
+        return total.value
+
+    # -- resample ---------------------------------------------------------------------------------------------
+    def resampleParticles(self, jitter_state, u_r=None, u_jitter=None, inject=None):
+        """The part of resampleParticles after computeWeight (MC:469-561). Returns the stats dict."""
+        st = ResampleStats()
+        if u_r is None:
+            self._ck(self.L.mcl_resample(self.h, int(bool(jitter_state)), None, C.byref(st)))
+        else:
+            keep = [_f64(u_r), _f64(u_jitter)]
+            d = ResampleDraws()
+            d.u_r = keep[0].ctypes.data_as(_dp)
+            d.u_jitter = keep[1].ctypes.data_as(_dp)
+            d.n_jitter = len(keep[1])
+            d.n_inject = 0
+            if inject is not None:
+                ik = [_f64(inject["u_yaw"]), _i32(inject["row"]), _i32(inject["col"]), _f64(inject["u_dx"]), _f64(inject["u_dy"])]
+                keep += ik
+                d.inject = InitDraws(ik[0].ctypes.data_as(_dp), ik[1].ctypes.data_as(_ip), ik[2].ctypes.data_as(_ip),
+                                     ik[3].ctypes.data_as(_dp), ik[4].ctypes.data_as(_dp))
+                d.n_inject = len(ik[0])
+            self._ck(self.L.mcl_resample(self.h, int(bool(jitter_state)), C.byref(d), C.byref(st)))
+        return dict(injected=st.injected, clamped=st.clamped, p_inject=st.p_inject, weight_slow=st.weight_slow,
+                    weight_fast=st.weight_fast, total_weight=st.total_weight)
+
+    def ancestors(self):
+        idx = np.empty(self.num_particles, np.int32)
+        self._ck(self.L.mcl_download_ancestors(self.h, idx.ctypes.data_as(_ip)))
+        return idx
+
+    def cdf(self):
+        out = np.empty(self.num_particles, np.float64)
+        self._ck(self.L.mcl_download_cdf(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    # -- estimate ---------------------------------------------------------------------------------------------
+    def estimateWeightedPose(self):
+        x, y, t = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.mcl_estimate(self.h, C.byref(x), C.byref(y), C.byref(t)))
+        return np.array([x.value, y.value, t.value])
+
+    # -- state ------------------------------------------------------------------------------------------------
+    def injectionState(self):
+        s, f = C.c_double(), C.c_double()
+        self._ck(self.L.mcl_get_injection_state(self.h, C.byref(s), C.byref(f)))
+        return np.array([s.value, f.value])
+
+    def setInjectionState(self, slow, fast):
+        self._ck(self.L.mcl_set_injection_state(self.h, slow, fast))
+
+    def rayLut(self):
+        cnt = C.c_int32()
+        self._ck(self.L.mcl_get_ray_lut(self.h, None, None, None, 0, C.byref(cnt)))
+        k = np.zeros(cnt.value, np.int32); dx = np.zeros(cnt.value); dy = np.zeros(cnt.value)
+        self._ck(self.L.mcl_get_ray_lut(self.h, k.ctypes.data_as(_ip), dx.ctypes.data_as(_dp), dy.ctypes.data_as(_dp), cnt.value, C.byref(cnt)))
+        return k, dx, dy
+
+    # -- instrumentation ----------------------------------------------------------------------------------------
+    def lastResampleDraws(self, jitter_state):
+        n = self.num_particles
+        u_r = np.empty(n); u_j = np.empty(n * (3 if jitter_state else 2))
+        self._ck(self.L.mcl_debug_download_resample_draws(self.h, u_r.ctypes.data_as(_dp), u_j.ctypes.data_as(_dp)))
+        return u_r, u_j
+
+    def profileEnable(self, on):
+        self._ck(self.L.mcl_profile_enable(self.h, int(bool(on))))
+
+    def profileRead(self):
+        """{kernel name: (total ms, launches)} accumulated since profileEnable(True)."""
+        out = {}
+        for i in range(self.L.mcl_profile_kernel_count()):
+            ms, cnt = C.c_double(), C.c_int64()
+            self._ck(self.L.mcl_profile_read(self.h, i, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[self.L.mcl_profile_kernel_name(i).decode()] = (ms.value, cnt.value)
+        return out
+
+    def stream(self):
+        return self.L.mcl_stream(self.h)
+
+    def synchronize(self):
+        self._ck(self.L.mcl_synchronize(self.h))
+
+    def kernelLaunches(self):
+        return self.L.mcl_kernel_launches(self.h)

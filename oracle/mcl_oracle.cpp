@@ -122,7 +122,7 @@ inline double yaw_from_quat(const Quat& q) {
     // Matrix3x3::setRotation + getEulerYPR, first solution.
     double d = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
     double s = 2.0 / d;
-    double xs = q.x * s, ys = q.y * s, zs = q.z * s;
+    double ys = q.y * s, zs = q.z * s;
     double wy = q.w * ys, wz = q.w * zs;
     double xy = q.x * ys, xz = q.x * zs;
     double yy = q.y * ys, zz = q.z * zs;

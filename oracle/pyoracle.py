@@ -290,6 +290,9 @@ class Ref:
     def injection_state(self):
         out = np.zeros(2); self.L.ref_get_injection_state(_p(out, c_dp)); return out
 
+    def set_injection_state(self, slow, fast):
+        self.L.ref_set_injection_state(C.c_double(slow), C.c_double(fast))
+
     def set_motion(self, r1, t, r2):
         self.L.ref_set_motion(C.c_double(r1), C.c_double(t), C.c_double(r2))
 

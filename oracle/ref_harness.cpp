@@ -91,6 +91,7 @@ int ref_ray_lut_dump(int lo, int hi, int* keys, double* dx, double* dy, int cap)
     return n;
 }
 void ref_get_injection_state(double* out) { out[0] = adaptiveInjection.weight_slow; out[1] = adaptiveInjection.weight_fast; }
+void ref_set_injection_state(double slow, double fast) { adaptiveInjection.weight_slow = slow; adaptiveInjection.weight_fast = fast; }
 void ref_set_motion(double r1, double t, double r2) { motionModel = OdometryModel{r1, t, r2}; }
 
 static void load(Eigen::MatrixXf& m, const float* P, int N) { m = Eigen::MatrixXf(4, N); memcpy(m.data(), P, sizeof(float) * 4 * (size_t)N); }

@@ -1,0 +1,58 @@
+"""The C-ABI library loads and exports every symbol include/mcl.h declares; host-only entry points work;
+without a GPU the engine refuses to start instead of falling back."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import montecarlolocalisation_b200 as m
+from montecarlolocalisation_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mcl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    L = C.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(s[0] for s in _lib.SYMBOLS) == names       # the Python binding covers the whole header
+
+
+def test_config_struct_matches_header_defaults():
+    cfg = m.default_config()
+    assert C.sizeof(cfg) % 8 == 0
+    assert (cfg.sigma_hit, cfg.max_laser_range, cfg.laser_offset, cfg.w_hit, cfg.w_rand) == (0.1, 1.0, 0.1, 0.8, 0.2)
+    assert (cfg.fov_lower_deg, cfg.fov_upper_deg, cfg.beam_stride) == (-120.0, 120.0, 20)
+    assert list(cfg.alpha) == [0.001, 0.001, 0.0001, 0.0001]
+    assert (cfg.wheel_size, cfg.wheel_space, cfg.cell_size_px, cfg.cell_meters) == (0.062, 0.265, 8, 0.8)
+    assert (cfg.inject_max_lost, cfg.inject_max_conf, cfg.jitter_xy_lost, cfg.jitter_xy_conf) == (200, 50, 0.05, 0.01)
+    assert cfg.ns_beam_stride == 1           # last fields land where the C struct puts them
+    assert b"sm_100a" in _lib.load().mcl_version()
+
+
+def test_host_rasteriser_matches_kat_and_oracle(map_txt):
+    from oracle.pyoracle import Oracle
+    occ = m.rasterise_map_txt(map_txt)
+    assert hashlib.sha256(occ.tobytes()).hexdigest() == "9d700e0d21c8b669621222f4c2514d9d80a7e502fc476f77120c348c4849c275"
+    for txt in ("[[[T,L],[T,R]],[[L,B]]]", "[[[T,L,B,R]]]", "[[[],[B]],[[R],[L,T]],[[B],[B,R]]]"):
+        assert np.array_equal(m.rasterise_map_txt(txt), Oracle.rasterise_map_txt(txt))
+    with pytest.raises(m.MclError):
+        m.rasterise_map_txt("[[[Q]]]")
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
+def test_no_gpu_means_loud_failure_not_fallback():
+    with pytest.raises(m.MclError) as e:
+        m.ParticleFilter()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
