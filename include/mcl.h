@@ -149,6 +149,12 @@ int mcl_predict_motion(mcl_handle* h, double rot_1, double trans, double rot_2);
 int mcl_update(mcl_handle* h, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
                float range_min, float range_max, double* total_weight);
 
+/* The same with the scan pre-processed and parked in device memory (slot in [0,4096)): replaying recorded scans,
+ * and benchmarks that want the inputs resident in HBM before the timed region. */
+int mcl_scan_stage(mcl_handle* h, int32_t slot, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
+                   float range_min, float range_max);
+int mcl_update_staged(mcl_handle* h, int32_t slot, double* total_weight);
+
 /* ---- resample: the rest of resampleParticles(particles, jitterState) (MC:469-561). Must follow mcl_update. */
 int mcl_resample(mcl_handle* h, int32_t jitter_state, const mcl_resample_draws* draws, mcl_resample_stats* stats);
 int mcl_download_ancestors(mcl_handle* h, int32_t* idx);   /* ancestor index per output slot, -1 = injected */

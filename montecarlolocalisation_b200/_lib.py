@@ -70,6 +70,8 @@ SYMBOLS = [
     ("mcl_predict_encoders", _i32, [_vp, _d, _d, _dp, _dp]),
     ("mcl_predict_motion", _i32, [_vp, _d, _d, _d]),
     ("mcl_update", _i32, [_vp, _fp, _i32, _f, _f, _f, _f, _dp]),
+    ("mcl_scan_stage", _i32, [_vp, _i32, _fp, _i32, _f, _f, _f, _f]),
+    ("mcl_update_staged", _i32, [_vp, _i32, _dp]),
     ("mcl_resample", _i32, [_vp, _i32, C.POINTER(ResampleDraws), C.POINTER(ResampleStats)]),
     ("mcl_download_ancestors", _i32, [_vp, _ip]),
     ("mcl_download_cdf", _i32, [_vp, _dp]),

@@ -82,6 +82,10 @@ int mcl_predict_motion(mcl_handle* h, double r1, double t, double r2) { GUARD(h)
 int mcl_update(mcl_handle* h, const float* ranges, int32_t nb, float amin, float ainc, float rmin, float rmax, double* total) {
     GUARD(h); TRY(h->engine.update(ranges, nb, amin, ainc, rmin, rmax, total))
 }
+int mcl_scan_stage(mcl_handle* h, int32_t slot, const float* ranges, int32_t nb, float amin, float ainc, float rmin, float rmax) {
+    GUARD(h); TRY(h->engine.stage_scan(slot, ranges, nb, amin, ainc, rmin, rmax))
+}
+int mcl_update_staged(mcl_handle* h, int32_t slot, double* total) { GUARD(h); TRY(h->engine.update_staged(slot, total)) }
 int mcl_resample(mcl_handle* h, int32_t js, const mcl_resample_draws* d, mcl_resample_stats* st) { GUARD(h); TRY(h->engine.resample(js, d, st)) }
 int mcl_download_ancestors(mcl_handle* h, int32_t* idx) { GUARD(h); TRY(h->engine.download_ancestors(idx)) }
 int mcl_download_cdf(mcl_handle* h, double* cdf) { GUARD(h); TRY(h->engine.download_cdf(cdf)) }

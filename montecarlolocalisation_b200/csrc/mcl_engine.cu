@@ -35,7 +35,7 @@ Engine::~Engine() {
     cudaSetDevice(cfg.device);
     part[0].release(); part[1].release(); cdf.release(); ancestors.release(); d_occ.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
-    d_beams.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
+    d_beams.release(); for (auto& sc : staged) sc.d_used.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
     d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();
     if (h_pinned) cudaFreeHost(h_pinned);
     if (stream) cudaStreamDestroy(stream);
@@ -354,33 +354,66 @@ int Engine::update(const float* ranges, int n_beams, float angle_min, float angl
     if (!map_ready) return fail(MCL_ERR_ARG, "update: no map (the reference warns 'NO MAP RECEVIED', MC:311)");
     if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
     if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "update: bad scan");
-    if (cfg.mode == MCL_MODE_REF) return ref_update(ranges, n_beams, angle_min, angle_inc, range_min, range_max, total);
-    return fail(MCL_ERR_STATE, "update: NS mode not built in this library");
+    if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "update: NS mode not built in this library");
+    std::vector<RefBeam> used;
+    int rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, beams_all, used);
+    if (rc) return rc;
+    CK(d_beams.ensure(std::max<size_t>(1, used.size())));
+    if (!used.empty()) {
+        rc = ensure_pinned(used.size() * sizeof(RefBeam));
+        if (rc) return rc;
+        memcpy(h_pinned, used.data(), used.size() * sizeof(RefBeam));
+        CK(cudaMemcpyAsync(d_beams.p, h_pinned, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+    }
+    return ref_run_update(d_beams.p, (int)used.size(), beams_all, total);
+}
+
+int Engine::stage_scan(int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max) {
+    CK(cudaSetDevice(cfg.device));
+    if (slot < 0 || slot >= 4096) return fail(MCL_ERR_ARG, "stage_scan: slot out of range [0,4096)");
+    if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "stage_scan: bad scan");
+    if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "stage_scan: NS mode not built in this library");
+    if ((size_t)slot >= staged.size()) staged.resize(slot + 1);
+    StagedScan& s = staged[slot];
+    std::vector<RefBeam> used;
+    int rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, s.all, used);
+    if (rc) return rc;
+    CK(s.d_used.ensure(std::max<size_t>(1, used.size())));
+    if (!used.empty()) CK(cudaMemcpy(s.d_used.p, used.data(), used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice));
+    s.n_used = (int)used.size();
+    s.valid = true;
+    return MCL_OK;
+}
+
+int Engine::update_staged(int slot, double* total) {
+    CK(cudaSetDevice(cfg.device));
+    if (!map_ready) return fail(MCL_ERR_ARG, "update: no map");
+    if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
+    if (slot < 0 || (size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "update_staged: empty slot");
+    return ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, total);
 }
 
 static size_t ref_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes) {
     return (size_t)n_keys * sizeof(double2) + (size_t)n_beams * sizeof(RefBeam) + (size_t)n_radii * sizeof(double) + map_bytes;
 }
 
-int Engine::ref_update(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, double* total) {
-    filter_scan(ranges, n_beams, angle_min, angle_inc, range_min, range_max, true, cfg.fov_lower_deg, cfg.fov_upper_deg, beams_all);
+// filterLaserReadings + filterAngles (MC:635), then the stride-picked beams in f64 (MC:650-669).
+int Engine::ref_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
+                              std::vector<HostBeam>& all, std::vector<RefBeam>& used) {
+    filter_scan(ranges, n_beams, angle_min, angle_inc, range_min, range_max, true, cfg.fov_lower_deg, cfg.fov_upper_deg, all);
     const int stride = std::max(1, cfg.beam_stride);
-    std::vector<RefBeam> used;
-    for (size_t i = 0; i < beams_all.size(); i += stride) {                       // MC:650
+    used.clear();
+    for (size_t i = 0; i < all.size(); i += stride) {                             // MC:650
         RefBeam b;
-        b.off_deg = -(beams_all[i].angle) * 180.0 / M_PI;                         // MC:653
-        b.obs = beams_all[i].radius;                                              // MC:657
+        b.off_deg = -(all[i].angle) * 180.0 / M_PI;                               // MC:653
+        b.obs = all[i].radius;                                                    // MC:657
         b.rand_term = cfg.w_rand * ((std::abs(b.obs - cfg.max_laser_range) < 0.01) ? 1.0 : 0.0);   // MC:669
         used.push_back(b);
     }
-    n_used_beams = (int)used.size();
-    CK(d_beams.ensure(std::max<size_t>(1, used.size())));
-    if (!used.empty()) {
-        int rc = ensure_pinned(used.size() * sizeof(RefBeam));
-        if (rc) return rc;
-        memcpy(h_pinned, used.data(), used.size() * sizeof(RefBeam));
-        CK(cudaMemcpyAsync(d_beams.p, h_pinned, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
-    }
+    return MCL_OK;
+}
+
+int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total) {
     RefParams P;
     P.occ = d_occ.p; P.width = map_w; P.height = map_h;
     const size_t map_bytes = (size_t)map_w * map_h;
@@ -392,8 +425,8 @@ int Engine::ref_update(const float* ranges, int n_beams, float angle_min, float 
     P.radii = d_radii.p; P.n_radii = (int)h_radii.size();
     P.gauss = d_gauss.p; P.gauss_size = (int)gauss.v.size(); P.gauss_res = gauss.step; P.gauss_min = gauss.lo; P.gauss_max = gauss.hi;
     P.lut = d_lut.p; P.lut_filled = d_lut_filled.p; P.key_min = key_min; P.n_keys = n_keys;
-    P.beams = d_beams.p; P.n_beams = n_used_beams;
-    const size_t smem = ref_smem_bytes(n_keys, n_used_beams, P.n_radii, P.map_in_smem ? map_bytes : 0);
+    P.beams = d_used; P.n_beams = n_used;
+    const size_t smem = ref_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0);
     if (smem > 200 * 1024) return fail(MCL_ERR_ARG, "update: too many beams for the shared-memory staging area");
     if (!attr_set) {
         CK(cudaFuncSetAttribute(k_ref_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -401,13 +434,13 @@ int Engine::ref_update(const float* ranges, int n_beams, float angle_min, float 
         attr_set = true;
     }
     // First-touch memoisation of still-missing ray directions (Q9); stops once every key is filled.
-    if (n_unfilled > 0 && n_used_beams > 0) {
+    if (n_unfilled > 0 && n_used > 0) {
         CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream));
         LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
         CK(cudaGetLastError());
         LAUNCH(K_TOUCH_THETA, k_ref_touch_theta, grid_for(n_keys, 256), 256, 0, part[cur].p, d_touch.p, n_keys, d_touch_theta.p);
         CK(cudaGetLastError());
-        int rc = ref_fill_ray_lut();
+        int rc = ref_fill_ray_lut(all);
         if (rc) return rc;
     }
     LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, n, P);
@@ -422,7 +455,7 @@ int Engine::ref_update(const float* ranges, int n_beams, float angle_min, float 
 }
 
 // Evaluate the direction of each newly touched key from its first toucher's theta, with host libm (MC:361-362).
-int Engine::ref_fill_ray_lut() {
+int Engine::ref_fill_ray_lut(const std::vector<HostBeam>& all) {
     std::vector<unsigned long long> touch(n_keys);
     std::vector<float> theta(n_keys);
     CK(cudaMemcpyAsync(touch.data(), d_touch.p, n_keys * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -433,7 +466,7 @@ int Engine::ref_fill_ray_lut() {
     for (int k = 0; k < n_keys; ++k) {
         if (h_lut_filled[k] || touch[k] == ~0ull) continue;
         const unsigned beam = (unsigned)(touch[k] & 0xffffffffu);
-        const double off_deg = -(beams_all[(size_t)beam * stride].angle) * 180.0 / M_PI;
+        const double off_deg = -(all[(size_t)beam * stride].angle) * 180.0 / M_PI;
         const double yaw = tf_yaw_roundtrip((double)theta[k]);
         const double angle_rad = yaw + off_deg * M_PI / 180.0;
         h_lut[k] = make_double2(std::cos(angle_rad), std::sin(angle_rad));

@@ -136,6 +136,16 @@ class ParticleFilter:
                                    C.c_float(range_min), C.c_float(range_max), C.byref(total)))
         return total.value
 
+    def stageScan(self, slot, ranges, angle_min, angle_inc, range_min, range_max):
+        r = np.ascontiguousarray(ranges, dtype=np.float32)
+        self._ck(self.L.mcl_scan_stage(self.h, slot, r.ctypes.data_as(_fp), len(r), C.c_float(angle_min), C.c_float(angle_inc),
+                                       C.c_float(range_min), C.c_float(range_max)))
+
+    def computeWeightStaged(self, slot):
+        total = C.c_double()
+        self._ck(self.L.mcl_update_staged(self.h, slot, C.byref(total)))
+        return total.value
+
     # -- resample ---------------------------------------------------------------------------------------------
     def resampleParticles(self, jitter_state, u_r=None, u_jitter=None, inject=None):
         """The part of resampleParticles after computeWeight (MC:469-561). Returns the stats dict."""

