@@ -172,6 +172,11 @@ int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_
 /* The u_r / u_jitter streams the last mcl_resample consumed (injected, or generated by the device Philox stream),
  * so a checker can replay the same step. u_jitter holds N*(3 if jitter_state else 2) values. */
 int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter);
+/* The engine's bit-exact sequential f64 accumulation s_i = s_{i-1} + (double)w[i] on an arbitrary fp32 vector:
+ * cdf[n] and/or total; *fell_back != 0 when the parallel path handed over to the single-chain kernel. */
+int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back);
+/* Use the single-chain sequential accumulation kernels instead of the parallel exact scan (cross-check; slow). */
+int mcl_debug_force_sequential(mcl_handle* h, int32_t on);
 /* Per-kernel CUDA-event timing on the handle's stream; off by default (it serialises launches). */
 int mcl_profile_enable(mcl_handle* h, int32_t on);
 int mcl_profile_kernel_count(void);

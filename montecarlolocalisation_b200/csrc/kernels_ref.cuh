@@ -156,7 +156,7 @@ __global__ void k_ref_touch_theta(const float4* __restrict__ part, const unsigne
 }
 
 // ---- computeWeight (MC:623-682): one thread per particle ---------------------------------------------------
-__global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, int64_t n, RefParams P) {
+__global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RefSmem S = ref_stage_smem(P, smem_raw, P.map_in_smem != 0);
     MapView m{P.map_in_smem ? S.occ : P.occ, P.width, P.height, P.res, P.inv_res, P.ox, P.oy};
@@ -184,21 +184,25 @@ __global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, i
             prob = dadd(prob, bm.rand_term);                                              // MC:669
         }
     }
-    part[j].w = __double2float_rn(prob);                                                  // MC:673
+    const float wf = __double2float_rn(prob);                                             // MC:673
+    part[j].w = wf;
+    w_dense[j] = wf;
 }
 
 // ---- sequential f64 accumulations (MC:675 and MC:496-505) --------------------------------------------------
 // The reference sums fp32 weights into an f64 total one by one, and builds the CDF the same way. fp addition is
-// not associative, so bit-identical results need the same order: one thread walks the chain while the rest of
-// the block stages tiles through shared memory. (Round-1 baseline; the parallel exact scan replaces it.)
+// not associative, so bit-identical results need the same roundings. The fast path is the parallel exact scan
+// (exact_scan.cuh); these single-chain kernels are its always-correct fallback (they run only when *run_if != 0, or
+// when run_if is null) and the cross-check the tests compare it with.
 constexpr int SEQ_TILE = 1024;
 
-__global__ void __launch_bounds__(256) k_ref_seq_total(const float4* __restrict__ part, int64_t n, double* __restrict__ total_out) {
+__global__ void __launch_bounds__(256) k_ref_seq_total(const float* __restrict__ w, int64_t n, double* __restrict__ total_out,
+                                                       const int* __restrict__ run_if) {
+    if (run_if && *run_if == 0) return;
     __shared__ float tile[2][SEQ_TILE];
     double acc = 0.0;
     int64_t n_tiles = (n + SEQ_TILE - 1) / SEQ_TILE;
-    // prologue: stage tile 0
-    for (int i = threadIdx.x; i < SEQ_TILE; i += blockDim.x) { int64_t g = i; tile[0][i] = g < n ? part[g].w : 0.f; }
+    for (int i = threadIdx.x; i < SEQ_TILE; i += blockDim.x) { int64_t g = i; tile[0][i] = g < n ? w[g] : 0.f; }
     __syncthreads();
     for (int64_t t = 0; t < n_tiles; t++) {
         int cur = t & 1;
@@ -207,27 +211,24 @@ __global__ void __launch_bounds__(256) k_ref_seq_total(const float4* __restrict_
             for (int i = 0; i < cnt; i++) acc = dadd(acc, (double)tile[cur][i]);
         } else if (t + 1 < n_tiles) {
             int64_t base = (t + 1) * SEQ_TILE;
-            for (int i = threadIdx.x - 1; i < SEQ_TILE; i += blockDim.x - 1) { int64_t g = base + i; tile[cur ^ 1][i] = g < n ? part[g].w : 0.f; }
+            for (int i = threadIdx.x - 1; i < SEQ_TILE; i += blockDim.x - 1) { int64_t g = base + i; tile[cur ^ 1][i] = g < n ? w[g] : 0.f; }
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) *total_out = acc;
 }
 
-// w_i <- (float)((double)w_i / total) (MC:497,503), cdf[i] = cdf[i-1] + (double)w_i (MC:498,504).
-__global__ void __launch_bounds__(256) k_ref_seq_cdf(float4* __restrict__ part, int64_t n, const double* __restrict__ total_in,
-                                                     double* __restrict__ cdf) {
+// cdf[i] = cdf[i-1] + (double)w_i over already-normalised weights (MC:498,504).
+__global__ void __launch_bounds__(256) k_ref_seq_cdf(const float* __restrict__ wn_in, int64_t n, double* __restrict__ cdf,
+                                                     const int* __restrict__ run_if) {
+    if (run_if && *run_if == 0) return;
     __shared__ float wn[2][SEQ_TILE];
     __shared__ double out[2][SEQ_TILE];
-    const double total = *total_in;
     double acc = 0.0;
     int64_t n_tiles = (n + SEQ_TILE - 1) / SEQ_TILE;
     auto stage = [&](int buf, int64_t t, int first, int stride) {
         int64_t base = t * SEQ_TILE;
-        for (int i = first; i < SEQ_TILE; i += stride) {
-            int64_t g = base + i;
-            if (g < n) { float w = __double2float_rn(ddiv((double)part[g].w, total)); part[g].w = w; wn[buf][i] = w; }
-        }
+        for (int i = first; i < SEQ_TILE; i += stride) { int64_t g = base + i; if (g < n) wn[buf][i] = wn_in[g]; }
     };
     auto flush = [&](int buf, int64_t t, int first, int stride) {
         int64_t base = t * SEQ_TILE;

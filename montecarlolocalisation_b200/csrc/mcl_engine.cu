@@ -7,6 +7,7 @@
 #include <fstream>
 #include <sstream>
 
+#include "exact_scan.cuh"
 #include "kernels_ref.cuh"
 
 namespace mcl {
@@ -33,7 +34,7 @@ Engine::Engine(const mcl_config& c) : cfg(c) {}
 Engine::~Engine() {
     if (!opened) return;
     cudaSetDevice(cfg.device);
-    part[0].release(); part[1].release(); cdf.release(); ancestors.release(); d_occ.release(); d_gauss.release();
+    part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); ancestors.release(); d_occ.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
     d_beams.release(); for (auto& sc : staged) sc.d_used.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
     d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();
@@ -44,7 +45,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
-                                         "k_ref_seq_cdf", "k_ref_resample", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+                                         "k_ref_seq_cdf", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
@@ -197,6 +198,74 @@ int Engine::ensure_particles(int64_t count) {
     if (count > (int64_t)INT32_MAX) return fail(MCL_ERR_ARG, "particle count exceeds 2^31-1 per GPU");
     CK(part[0].ensure(count)); CK(part[1].ensure(count));
     CK(cdf.ensure(count)); CK(ancestors.ensure(count));
+    CK(d_wraw.ensure(count)); CK(d_wn.ensure(count));
+    return ensure_xs(count);
+}
+
+int Engine::ensure_xs(int64_t count) {
+    const int nt = (int)((count + xs::XS_TILE - 1) / xs::XS_TILE);
+    CK(xs_flag.ensure(1));
+    if (nt <= xs_tiles_cap) return MCL_OK;
+    CK(xs_tsum.ensure(nt)); CK(xs_toff.ensure(nt + 1)); CK(xs_seq_s.ensure((size_t)nt * xs::XS_SEQ_CAP));
+    CK(xs_tiles.ensure((size_t)nt * sizeof(xs::TileSummary))); CK(xs_entries.ensure((size_t)nt * xs::XS_SEQ_CAP * sizeof(xs::SeqEntry)));
+    CK(xs_carry.ensure((size_t)(nt + 1) * sizeof(xs::Par))); CK(xs_seq_base.ensure(nt + 1));
+    xs_tiles_cap = nt;
+    return MCL_OK;
+}
+
+// The reference's sequential f64 accumulations, reproduced bit-exactly in parallel (exact_scan.cuh):
+//   normalise == false: *d_total_out = w_0 + w_1 + ... left to right over d_wraw            (MC:675)
+//   normalise == true : w_i <- (float)((double)w_i / total) into d_wn and part.w, then cdf[i]  (MC:496-505)
+int Engine::exact_accumulate(bool normalise, double* d_total_out) {
+    return exact_accumulate_on(normalise ? d_wn.p : d_wraw.p, normalise, normalise, d_total_out);
+}
+
+// w: the dense fp32 terms to accumulate (d_wraw, or d_wn which normalise==true fills from d_wraw first).
+int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out) {
+    const int nt = (int)((n + xs::XS_TILE - 1) / xs::XS_TILE);
+    xs::Workspace ws;
+    ws.tsum = xs_tsum.p; ws.toff = xs_toff.p; ws.tiles = (xs::TileSummary*)xs_tiles.p; ws.entries = (xs::SeqEntry*)xs_entries.p;
+    ws.carry = (xs::Par*)xs_carry.p; ws.seq_base = xs_seq_base.p; ws.seq_s = xs_seq_s.p; ws.flag = xs_flag.p;
+    if (normalise)
+        LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p);
+    else if (!force_sequential)
+        LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<false>, nt, xs::XS_THREADS, 0, w, (float*)nullptr, (float4*)nullptr, n,
+               (const double*)nullptr, xs_tsum.p);
+    CK(cudaGetLastError());
+    if (!force_sequential) {
+        LAUNCH(K_XS_OFFSETS, xs::k_xs_offsets, 1, 32, 0, xs_tsum.p, nt, xs_toff.p, xs_flag.p);
+        LAUNCH(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
+        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, 32, 0, nt, ws, d_total_out);
+        if (want_cdf) LAUNCH(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
+        CK(cudaGetLastError());
+    }
+    const int* run_if = force_sequential ? nullptr : xs_flag.p;
+    if (want_cdf) LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, run_if);
+    if (d_total_out) LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, w, n, d_total_out, run_if);
+    CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+// Debug/test entry: the exact accumulation of an arbitrary fp32 vector (no normalisation).
+int Engine::debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back) {
+    CK(cudaSetDevice(cfg.device));
+    if (!w || count <= 0) return fail(MCL_ERR_ARG, "debug_exact_scan: bad input");
+    int rc = ensure_particles(count);
+    if (rc) return rc;
+    const int64_t saved_n = n;
+    n = count;
+    CK(cudaMemcpyAsync(d_wn.p, w, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(xs_flag.p, 0, sizeof(int), stream));
+    rc = exact_accumulate_on(d_wn.p, false, true, d_scalars.p + 6);
+    if (rc) { n = saved_n; return rc; }
+    int flag = 0;
+    if (cdf_out) CK(cudaMemcpyAsync(cdf_out, cdf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (total_out) CK(cudaMemcpyAsync(total_out, d_scalars.p + 6, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&flag, xs_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (fell_back) *fell_back = force_sequential ? 1 : flag;
+    n = saved_n;
+    have_weights = false;
     return MCL_OK;
 }
 
@@ -443,10 +512,12 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         int rc = ref_fill_ray_lut(all);
         if (rc) return rc;
     }
-    LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, n, P);
+    LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
     CK(cudaGetLastError());
-    LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, part[cur].p, n, d_scalars.p);
-    CK(cudaGetLastError());
+    {
+        int rc = exact_accumulate(false, d_scalars.p);
+        if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(&last_total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     have_weights = true;
@@ -566,8 +637,8 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
         CK(cudaGetLastError());
     }
     // normalise + sequential CDF (MC:496-505)
-    LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, part[cur].p, n, d_scalars.p, cdf.p);
-    CK(cudaGetLastError());
+    rc = exact_accumulate(true, nullptr);
+    if (rc) return rc;
     LAUNCH(K_RESAMPLE, k_ref_resample, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
            d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
            inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p);

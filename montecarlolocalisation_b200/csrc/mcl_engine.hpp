@@ -55,14 +55,16 @@ public:
     int get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
     int synchronize();
     int download_resample_draws(double* u_r, double* u_jit);
+    int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
 
     mcl_config cfg;
+    bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
     cudaStream_t stream = nullptr;
     int64_t n = 0;
     int64_t launches = 0;
@@ -94,6 +96,15 @@ private:
     DevBuf<float4> part[2];
     int cur = 0;
     DevBuf<double> cdf;
+    DevBuf<float> d_wraw, d_wn;       // dense raw / normalised weights (4 B/particle streams for the scans)
+    // exact-scan workspace
+    DevBuf<double> xs_tsum, xs_toff, xs_seq_s;
+    DevBuf<unsigned char> xs_tiles, xs_entries, xs_carry;
+    DevBuf<int> xs_seq_base, xs_flag;
+    int xs_tiles_cap = 0;
+    int ensure_xs(int64_t count);
+    int exact_accumulate(bool normalise, double* d_total_out);   // total of d_wraw, or normalise + CDF
+    int exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out);
     DevBuf<int> ancestors;
     // map
     bool map_ready = false;

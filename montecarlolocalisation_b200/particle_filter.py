@@ -208,6 +208,16 @@ class ParticleFilter:
         self._ck(self.L.mcl_debug_download_resample_draws(self.h, u_r.ctypes.data_as(_dp), u_j.ctypes.data_as(_dp)))
         return u_r, u_j
 
+    def exactScan(self, w):
+        """(cdf, total, fell_back) of the engine's bit-exact sequential f64 accumulation over fp32 w."""
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        cdf = np.empty(len(w)); total = C.c_double(); fb = C.c_int32()
+        self._ck(self.L.mcl_debug_exact_scan(self.h, w.ctypes.data_as(_fp), len(w), cdf.ctypes.data_as(_dp), C.byref(total), C.byref(fb)))
+        return cdf, total.value, fb.value
+
+    def forceSequential(self, on):
+        self._ck(self.L.mcl_debug_force_sequential(self.h, int(bool(on))))
+
     def profileEnable(self, on):
         self._ck(self.L.mcl_profile_enable(self.h, int(bool(on))))
 
