@@ -259,35 +259,49 @@ __global__ void __launch_bounds__(XS_THREADS) k_xs_scan(const float* __restrict_
     if (bad || !okflag) atomicOr(ws.flag, 1);
 }
 
-// ---- pass 4: the sequential part, one thread ------------------------------------------------------------------------------
-__global__ void k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (*ws.flag) return;
+// ---- pass 4: the sequential part ----------------------------------------------------------------------------------------
+// One thread walks the tiles in order (carry composites, SEQ elements through the hardware adder, grand total); the rest
+// of the block only stages tile summaries through shared memory so that walk never waits on HBM.
+constexpr int XS_CHAIN_CHUNK = 1024;
+__global__ void __launch_bounds__(256) k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out) {
+    __shared__ TileSummary sm_ts[XS_CHAIN_CHUNK];
+    __shared__ Par sm_carry[XS_CHAIN_CHUNK];
+    __shared__ int sm_base[XS_CHAIN_CHUNK];
+    if (*ws.flag) return;                      // uniform: every thread reads the same word
     Par carry = par_identity();
     int base = 0;
     double s = 0.0;
     bool ok = true;
-    for (int t = 0; t < nt; t++) {
-        ws.carry[t] = carry;
-        ws.seq_base[t] = base;
-        const TileSummary ts = ws.tiles[t];
-        if (ts.seq_count > XS_SEQ_CAP) { ok = false; break; }
-        for (int k = 0; k < ts.seq_count; k++) {
-            const SeqEntry e = ws.entries[(size_t)t * XS_SEQ_CAP + k];
-            const Par comp = e.first_in_tile ? par_compose(carry, e.pre) : e.pre;
-            s = par_apply(s, comp, e.E_prev, ok);
-            s = dadd(s, (double)e.w);                    // the hardware adder: exactly the reference's rounding
-            ws.seq_s[base + k] = s;
+    for (int c0 = 0; c0 < nt; c0 += XS_CHAIN_CHUNK) {
+        const int cnt = min(XS_CHAIN_CHUNK, nt - c0);
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) sm_ts[i] = ws.tiles[c0 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < cnt; i++) {
+                sm_carry[i] = carry;
+                sm_base[i] = base;
+                const TileSummary ts = sm_ts[i];
+                if (ts.seq_count > XS_SEQ_CAP) { ok = false; continue; }
+                for (int k = 0; k < ts.seq_count; k++) {
+                    const SeqEntry e = ws.entries[(size_t)(c0 + i) * XS_SEQ_CAP + k];
+                    const Par comp = e.first_in_tile ? par_compose(carry, e.pre) : e.pre;
+                    s = par_apply(s, comp, e.E_prev, ok);
+                    s = dadd(s, (double)e.w);            // the hardware adder: exactly the reference's rounding
+                    ws.seq_s[base + k] = s;
+                }
+                carry = ts.seq_count ? ts.vlast : par_compose(carry, ts.vlast);
+                base += ts.seq_count;
+            }
         }
-        carry = ts.seq_count ? ts.vlast : par_compose(carry, ts.vlast);
-        base += ts.seq_count;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) { ws.carry[c0 + i] = sm_carry[i]; ws.seq_base[c0 + i] = sm_base[i]; }
+        __syncthreads();
     }
+    if (threadIdx.x != 0) return;
     ws.carry[nt] = carry;
     ws.seq_base[nt] = base;
-    if (ok) {
-        // the run after the last SEQ element: its binade is that of P~_{n-1} = toff[nt]
-        s = par_apply(s, carry, f64_exponent(ws.toff[nt]), ok);
-    }
+    // the run after the last SEQ element: its binade is that of P~_{n-1} = toff[nt]
+    if (ok) s = par_apply(s, carry, f64_exponent(ws.toff[nt]), ok);
     if (!ok) { atomicOr(ws.flag, 1); return; }
     if (total_out) *total_out = s;
 }

@@ -404,12 +404,14 @@ __global__ void __launch_bounds__(256) k_pose_wsum(const float4* __restrict__ pa
     __syncthreads();
     if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w]; partials[blockIdx.x] = s; }
 }
+// out[o] = sum over b of partials[b*stride + o]; one warp per output, fixed lane striding => deterministic.
 __global__ void k_reduce_partials(const double* __restrict__ partials, int n_partials, int stride, int n_out, double* __restrict__ out) {
-    int o = threadIdx.x;
+    const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (o >= n_out) return;
     double s = 0;
-    for (int b = 0; b < n_partials; b++) s += partials[(size_t)b * stride + o];
-    out[o] = s;
+    for (int b = lane; b < n_partials; b += 32) s += partials[(size_t)b * stride + o];
+    s = warp_sum(s);
+    if (lane == 0) out[o] = s;
 }
 __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum,
                                                    double* __restrict__ partials /* [grid][4] */) {

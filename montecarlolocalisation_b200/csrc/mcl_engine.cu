@@ -235,7 +235,7 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
     if (!force_sequential) {
         LAUNCH(K_XS_OFFSETS, xs::k_xs_offsets, 1, 32, 0, xs_tsum.p, nt, xs_toff.p, xs_flag.p);
         LAUNCH(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
-        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, 32, 0, nt, ws, d_total_out);
+        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, 256, 0, nt, ws, d_total_out);
         if (want_cdf) LAUNCH(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
         CK(cudaGetLastError());
     }
@@ -502,8 +502,21 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         CK(cudaFuncSetAttribute(k_ref_first_touch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    // First-touch memoisation of still-missing ray directions (Q9); stops once every key is filled.
+    // First-touch memoisation of still-missing ray directions (Q9). Only keys round(yaw_deg + off_deg) with yaw in
+    // [-180,180] and off among this scan's used beams can be touched; once those are all filled the pre-pass is skipped.
+    bool need_prepass = false;
     if (n_unfilled > 0 && n_used > 0) {
+        const int stride = std::max(1, cfg.beam_stride);
+        double off_lo = 1e300, off_hi = -1e300;
+        for (size_t i = 0; i < all.size(); i += stride) {
+            const double off = -(all[i].angle) * 180.0 / M_PI;
+            off_lo = std::min(off_lo, off); off_hi = std::max(off_hi, off);
+        }
+        const int k_lo = std::max(0, (int)std::floor(-180.0 + off_lo) - 1 - key_min);
+        const int k_hi = std::min(n_keys - 1, (int)std::ceil(180.0 + off_hi) + 1 - key_min);
+        for (int k = k_lo; k <= k_hi && !need_prepass; ++k) need_prepass = !h_lut_filled[k];
+    }
+    if (need_prepass) {
         CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream));
         LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
         CK(cudaGetLastError());
@@ -664,7 +677,7 @@ int Engine::estimate(double* x, double* y, double* th) {
     LAUNCH(K_POSE_WSUM, k_pose_wsum, blocks, 256, 0, part[cur].p, n, d_partials.p);
     LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
     LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, d_scalars.p + 1, d_partials.p);
-    LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 4, 4, d_scalars.p + 2);
+    LAUNCH(K_REDUCE, k_reduce_partials, 1, 128, 0, d_partials.p, blocks, 4, 4, d_scalars.p + 2);
     CK(cudaGetLastError());
     double s[4];
     CK(cudaMemcpyAsync(s, d_scalars.p + 2, sizeof(s), cudaMemcpyDeviceToHost, stream));
