@@ -86,6 +86,7 @@ typedef struct mcl_config {
     double ns_max_range;         /* beams at or beyond this range are skipped */
     int32_t ns_beam_stride;      /* 1 = score every beam */
     int32_t ns_use_fov;          /* 0 = full circle, 1 = apply fov_lower/upper like the reference */
+    double ns_temper;            /* weight = exp(ns_temper * (loglik - max loglik)); 1 = plain product of beam likelihoods */
 } mcl_config;
 
 /* Named draws for sampleParticles (MC:427-440): per particle yaw~U[0,1) canonical, row, col, dx, dy canonical. */
@@ -162,6 +163,33 @@ int mcl_download_cdf(mcl_handle* h, double* cdf);          /* REF: the f64 CDF o
 
 /* ---- estimate: estimateWeightedPose(particles) (MC:782-800) ------------------------------------------- */
 int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
+
+/* ---- NS mode across GPUs: particles shard by contiguous global index; one handle per GPU. A driver sequences the
+ *      *_local phases around three tiny collectives (max of the local maxima; all-gather of the local totals; a barrier),
+ *      which keeps systematic resampling globally exact and bit-identical for any GPU count. Each shard stores its
+ *      resampled particles straight into the shard that owns the output slot (peer memory over NVLink), so the
+ *      rebalance is fused into the resampling kernel. With world == 1, mcl_update / mcl_resample do all of this. ---- */
+int mcl_ns_set_shard(mcl_handle* h, int32_t rank, int32_t world, int64_t n_global);   /* allocates this shard */
+int mcl_ns_update_local(mcl_handle* h, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
+                        float range_min, float range_max, float* local_max_loglik);
+int mcl_ns_weights_local(mcl_handle* h, float global_max_loglik, uint64_t* local_total_q32);
+int mcl_ns_resample_local(mcl_handle* h, uint64_t offset_q32, uint64_t total_q32, uint32_t u0, int64_t* k_lo, int64_t* k_hi);
+int mcl_ns_end_step(mcl_handle* h);                   /* after every shard finished resampling: swap buffers */
+uint32_t mcl_ns_u0(mcl_handle* h);                    /* this step's systematic offset (same on every shard) */
+int mcl_ns_pose_partials(mcl_handle* h, double* out5);/* {sum w, sum w x, sum w y, sum w sin, sum w cos} of this shard */
+/* host-only planning helpers (no GPU touched) */
+int mcl_ns_first_slot(uint64_t offset_q32, uint64_t total_q32, uint64_t n_global, uint32_t u0, int64_t* slot);
+int mcl_ns_shard_range(int64_t n_global, int32_t world, int32_t rank, int64_t* begin, int64_t* count, int64_t* per_rank);
+/* peer memory. which: 0/1 = the two particle buffers, 2 = ancestors. export/import move a 64-byte CUDA IPC handle
+ * between processes; mcl_peer_set wires two handles of one process (tests, single-process multi-GPU). */
+int mcl_peer_export(mcl_handle* h, int32_t which, void* out64);
+int mcl_peer_import(mcl_handle* h, int32_t rank, int32_t which, const void* in64);
+int mcl_peer_set(mcl_handle* h, int32_t rank, int32_t which, void* device_ptr);
+void* mcl_device_buffer(mcl_handle* h, int32_t which);
+/* inspection */
+int mcl_ns_download_field(mcl_handle* h, float* loglik_field, uint16_t* d2);
+int mcl_ns_download_loglik(mcl_handle* h, float* loglik);
+int mcl_ns_download_prefix(mcl_handle* h, uint64_t* prefix_q32);
 
 /* ---- state the reference keeps in globals (MC:189-192), for checkpoint/resume and tests ---------------- */
 int mcl_get_injection_state(mcl_handle* h, double* weight_slow, double* weight_fast);

@@ -4,4 +4,5 @@ The product is libmcl_b200.so (hand-written sm_100a CUDA behind the C-ABI in inc
 Python host mirror used by the tests and bench.py; it never falls back to a CPU implementation.
 """
 from ._lib import MODE_NS, MODE_REF, MclError, build, load  # noqa: F401
-from .particle_filter import ParticleFilter, default_config, rasterise_map_txt  # noqa: F401
+from .particle_filter import (NsShard, ParticleFilter, default_config, ns_first_slot, ns_shard_range,  # noqa: F401
+                              ns_step_in_process, rasterise_map_txt)

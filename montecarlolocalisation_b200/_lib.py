@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("inject_max_conf", C.c_double), ("inject_alpha_slow_conf", C.c_double), ("inject_alpha_fast_conf", C.c_double),
         ("jitter_xy_lost", C.c_double), ("jitter_theta_lost", C.c_double), ("jitter_xy_conf", C.c_double),
         ("seed", C.c_uint64), ("ns_sigma_hit", C.c_double), ("ns_z_hit", C.c_double), ("ns_z_rand", C.c_double),
-        ("ns_max_range", C.c_double), ("ns_beam_stride", C.c_int32), ("ns_use_fov", C.c_int32),
+        ("ns_max_range", C.c_double), ("ns_beam_stride", C.c_int32), ("ns_use_fov", C.c_int32), ("ns_temper", C.c_double),
     ]
 
 
@@ -86,6 +86,22 @@ SYMBOLS = [
     ("mcl_profile_kernel_count", _i32, []),
     ("mcl_profile_kernel_name", C.c_char_p, [_i32]),
     ("mcl_profile_read", _i32, [_vp, _i32, _dp, C.POINTER(C.c_int64)]),
+    ("mcl_ns_set_shard", _i32, [_vp, _i32, _i32, _i64]),
+    ("mcl_ns_update_local", _i32, [_vp, _fp, _i32, _f, _f, _f, _f, _fp]),
+    ("mcl_ns_weights_local", _i32, [_vp, _f, C.POINTER(C.c_uint64)]),
+    ("mcl_ns_resample_local", _i32, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_i64), C.POINTER(_i64)]),
+    ("mcl_ns_end_step", _i32, [_vp]),
+    ("mcl_ns_u0", C.c_uint32, [_vp]),
+    ("mcl_ns_pose_partials", _i32, [_vp, _dp]),
+    ("mcl_ns_first_slot", _i32, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_i64)]),
+    ("mcl_ns_shard_range", _i32, [_i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    ("mcl_peer_export", _i32, [_vp, _i32, _vp]),
+    ("mcl_peer_import", _i32, [_vp, _i32, _i32, _vp]),
+    ("mcl_peer_set", _i32, [_vp, _i32, _i32, _vp]),
+    ("mcl_device_buffer", _vp, [_vp, _i32]),
+    ("mcl_ns_download_field", _i32, [_vp, _fp, C.POINTER(C.c_uint16)]),
+    ("mcl_ns_download_loglik", _i32, [_vp, _fp]),
+    ("mcl_ns_download_prefix", _i32, [_vp, C.POINTER(C.c_uint64)]),
     ("mcl_stream", _vp, [_vp]),
     ("mcl_synchronize", _i32, [_vp]),
     ("mcl_kernel_launches", _i64, [_vp]),

@@ -1,0 +1,336 @@
+// kernels_ns.cuh — MCL_MODE_NS kernels (the north-star formulation; definitions in ns_core.cuh and DESIGN.md "NS").
+//
+//   k_ns_edt_cols / k_ns_edt_rows   exact capped squared Euclidean distance transform (integers) -> likelihood field
+//   k_ns_init                       uniform particles from Philox (global index keyed)
+//   k_ns_predict                    odometry motion model with per-particle Philox noise, float4 in/out
+//   k_ns_update                     likelihood-field sensor model: warp per particle, beams across lanes, field staged in
+//                                   shared memory by TMA (cp.async.bulk) when it fits, else read through L2
+//   k_ns_weights_sum / k_ns_weights_scan   Q32 fixed-point weights + block-scan prefix sum (integers: order-independent)
+//   k_ns_resample                   systematic resampling by 128-bit integer search; each output is stored straight into
+//                                   the shard that owns its slot (own memory or a peer GPU's over NVLink)
+#pragma once
+#include "mcl_device.cuh"
+#include "ns_core.cuh"
+
+namespace mcl {
+
+// ---- distance transform -------------------------------------------------------------------------------------------------
+// pass 1, one thread per column: g[y][x] = rows to the nearest occupied cell of the same column, capped at R+1.
+__global__ void k_ns_edt_cols(const uint8_t* __restrict__ occ, int W, int H, int R, uint16_t* __restrict__ g) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    int d = R + 1;
+    for (int y = 0; y < H; y++) {
+        d = occ[(size_t)y * W + x] ? 0 : min(d + 1, R + 1);
+        g[(size_t)y * W + x] = (uint16_t)d;
+    }
+    d = R + 1;
+    for (int y = H - 1; y >= 0; y--) {
+        d = occ[(size_t)y * W + x] ? 0 : min(d + 1, R + 1);
+        size_t i = (size_t)y * W + x;
+        if (d < g[i]) g[i] = (uint16_t)d;
+    }
+}
+// pass 2, one thread per cell: d2 = min over |dx| <= R of dx^2 + g^2, capped at R^2; field = table[d2].
+__global__ void k_ns_edt_rows(const uint16_t* __restrict__ g, int W, int H, int R, const float* __restrict__ lf_of_d2,
+                              uint16_t* __restrict__ d2_out, float* __restrict__ lf_out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int cap = R * R;
+    int best = cap;
+    const uint16_t* row = g + (size_t)y * W;
+    int lo = max(0, x - R), hi = min(W - 1, x + R);
+    for (int xx = lo; xx <= hi; xx++) {
+        int gy = row[xx];
+        if (gy > R) continue;
+        int dx = xx - x;
+        int v = dx * dx + gy * gy;
+        best = min(best, v);
+    }
+    size_t i = (size_t)y * W + x;
+    if (d2_out) d2_out[i] = (uint16_t)best;
+    lf_out[i] = lf_of_d2[best];
+}
+
+// ---- init / predict -------------------------------------------------------------------------------------------------------
+struct NsMotion {
+    float rot1, trans, rot2;          // odometry increment (MC:699-702)
+    float sd_rot1, sd_trans, sd_rot2; // sqrt of the reference's noise variances (MC:706-710)
+};
+
+// particle i (global index g0 + i): x,y uniform over the map extent, theta uniform in [-pi,pi), weight 1.
+__global__ void __launch_bounds__(256) k_ns_init(float4* __restrict__ part, int64_t n, int64_t g0, double ox, double oy,
+                                                 double ext_x, double ext_y, uint32_t k0, uint32_t k1) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t g = (uint64_t)(g0 + i);
+    uint32_t r[4];
+    Philox::gen((uint32_t)g, (uint32_t)(g >> 32), 0x60u, 0u, k0, k1, r);
+    const double s = 2.3283064365386963e-10;
+    double u1 = ns::mul(ns::add((double)r[0], 0.5), s), u2 = ns::mul(ns::add((double)r[1], 0.5), s), u3 = ns::mul(ns::add((double)r[2], 0.5), s);
+    float4 p;
+    p.x = (float)ns::add(ox, ns::mul(u1, ext_x));
+    p.y = (float)ns::add(oy, ns::mul(u2, ext_y));
+    p.z = (float)ns::add(-3.14159265358979323846, ns::mul(u3, 6.28318530717958647692));
+    p.w = 1.0f;
+    part[i] = p;
+}
+
+__global__ void __launch_bounds__(256) k_ns_predict(float4* __restrict__ part, int64_t n, int64_t g0, NsMotion m, uint32_t step,
+                                                    uint32_t k0, uint32_t k1) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t g = (uint64_t)(g0 + i);
+    uint32_t r[4];
+    Philox::gen((uint32_t)g, (uint32_t)(g >> 32), 0x50u, step, k0, k1, r);
+    float z0, z1, z2, z3;
+    ns::det_normal_pair(r[0], r[1], z0, z1);
+    ns::det_normal_pair(r[2], r[3], z2, z3);
+    (void)z3;
+    float4 p = part[i];
+    const float r1 = ns::fmaf_(z0, m.sd_rot1, m.rot1);
+    const float tr = ns::fmaf_(z1, m.sd_trans, m.trans);
+    const float r2 = ns::fmaf_(z2, m.sd_rot2, m.rot2);
+    float s, c;
+    ns::det_sincosf(ns::addf(p.z, r1), s, c);
+    p.x = ns::fmaf_(tr, c, p.x);
+    p.y = ns::fmaf_(tr, s, p.y);
+    p.z = ns::wrap_pi(ns::addf(p.z, ns::addf(r1, r2)));
+    part[i] = p;
+}
+
+// ---- update: likelihood field -----------------------------------------------------------------------------------------------
+struct NsField {
+    const float* lf;        // [H*W] log-likelihood per cell
+    int W, H;
+    float ox, oy, inv_res;
+    float lf_out;           // value for endpoints outside the grid
+    int bytes_padded;       // field bytes rounded up to 16 (TMA bulk copy granularity)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (PTX cp.async.bulk; SASS UBLKCP).
+__device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        const uint32_t CH = 32768;
+        for (uint32_t off = 0; off < bytes; off += CH) {
+            uint32_t sz = min(CH, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32((char*)smem_dst + off)),
+                         "l"((const char*)gsrc + off), "r"(sz), "r"(b)
+                         : "memory");
+        }
+    }
+    // every thread waits for phase 0 of the barrier
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(b)
+                     : "memory");
+    }
+}
+
+// One warp scores 32 particles at a time: lane l owns particle l's pose and trig; for each particle in turn the pose is
+// broadcast with shuffles and the 32 lanes take beams l, l+32, ...; per-lane partial sums are combined by a fixed
+// xor-butterfly, so the fp32 result is order-defined.
+template <bool SMEM_FIELD>
+__global__ void __launch_bounds__(512) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
+                                                   const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
+                                                   int* __restrict__ max_bits /* ordered-int max of ll */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ float warp_max[16];
+    float* s_lf = reinterpret_cast<float*>(smem_raw);
+    float2* s_beams = reinterpret_cast<float2*>(smem_raw + (SMEM_FIELD ? F.bytes_padded : 0));
+    if (SMEM_FIELD) tma_stage(s_lf, F.lf, (uint32_t)F.bytes_padded, &bar);
+    for (int b = threadIdx.x; b < n_beams; b += blockDim.x) s_beams[b] = beams[b];
+    __syncthreads();
+    const float* lf = SMEM_FIELD ? s_lf : F.lf;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    const int64_t n_batches = (n + 31) / 32;
+    float best = -3.0e38f;
+    for (int64_t batch = (int64_t)blockIdx.x * warps_per_block + warp; batch < n_batches; batch += (int64_t)gridDim.x * warps_per_block) {
+        const int64_t i = batch * 32 + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) p = part[i];
+        float s, c;
+        ns::det_sincosf(p.z, s, c);
+        float mine = 0.f;
+        const int count = (int)min((int64_t)32, n - batch * 32);
+        for (int k = 0; k < count; k++) {
+            const float x = __shfl_sync(0xffffffffu, p.x, k), y = __shfl_sync(0xffffffffu, p.y, k);
+            const float ck = __shfl_sync(0xffffffffu, c, k), sk = __shfl_sync(0xffffffffu, s, k);
+            float acc = 0.f;
+            for (int b = lane; b < n_beams; b += 32) {
+                const float2 bm = s_beams[b];
+                const float ex = ns::fmaf_(ck, bm.x, ns::fmaf_(-sk, bm.y, x));
+                const float ey = ns::fmaf_(sk, bm.x, ns::fmaf_(ck, bm.y, y));
+                const int ix = __float2int_rd(ns::mulf(ns::addf(ex, -F.ox), F.inv_res));
+                const int iy = __float2int_rd(ns::mulf(ns::addf(ey, -F.oy), F.inv_res));
+                const bool in = (unsigned)ix < (unsigned)F.W && (unsigned)iy < (unsigned)F.H;
+                const int idx = in ? iy * F.W + ix : 0;
+                const float v = SMEM_FIELD ? lf[idx] : __ldg(lf + idx);
+                acc = ns::addf(acc, in ? v : F.lf_out);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = ns::addf(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if (lane == k) mine = acc;
+        }
+        if (i < n) { ll_out[i] = mine; best = fmaxf(best, mine); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) warp_max[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = warp_max[0];
+        for (int w = 1; w < warps_per_block; w++) m = fmaxf(m, warp_max[w]);
+        // order-preserving float -> int so atomicMax works for negative values too
+        int bits = __float_as_int(m);
+        bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
+        atomicMax(max_bits, bits);
+    }
+}
+
+// ---- weights + prefix sum -------------------------------------------------------------------------------------------------
+constexpr int NS_SCAN_THREADS = 256;
+constexpr int NS_SCAN_ITEMS = 8;
+constexpr int NS_SCAN_TILE = NS_SCAN_THREADS * NS_SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t ns_weight(float ll, float max_ll, float temper) {
+    return ns::det_exp_q32(ns::mulf(temper, ns::addf(ll, -max_ll)));
+}
+__device__ __forceinline__ uint64_t block_scan_u64(uint64_t v, uint64_t* sm8, uint64_t& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) sm8[warp] = v;
+    __syncthreads();
+    uint64_t pre = 0, tot = 0;
+    for (int k = 0; k < NS_SCAN_THREADS / 32; k++) { if (k < warp) pre += sm8[k]; tot += sm8[k]; }
+    __syncthreads();
+    block_total = tot;
+    return pre + v;      // inclusive
+}
+// pass 1: per-tile sums of W
+__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float* __restrict__ ll, int64_t n, float max_ll, float temper,
+                                                                   uint64_t* __restrict__ tile_sums) {
+    __shared__ uint64_t sm[8];
+    const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)threadIdx.x * NS_SCAN_ITEMS;
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < NS_SCAN_ITEMS; j++)
+        if (base + j < n) s += ns_weight(ll[base + j], max_ll, temper);
+    uint64_t tot;
+    block_scan_u64(s, sm, tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+// pass 2: exclusive scan of tile sums (one block), grand total
+__global__ void __launch_bounds__(1024) k_ns_tile_offsets(uint64_t* __restrict__ tile_sums, int nt, uint64_t* __restrict__ total) {
+    __shared__ uint64_t sm[1024];
+    uint64_t carry = 0;
+    for (int c0 = 0; c0 < nt; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        uint64_t v = i < nt ? tile_sums[i] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint64_t t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nt) tile_sums[i] = carry + sm[threadIdx.x] - v;      // exclusive
+        carry += sm[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+// pass 3: inclusive prefix per particle (local to this shard), and the unnormalised weight into the particle record
+__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float* __restrict__ ll, int64_t n, float max_ll, float temper,
+                                                                    const uint64_t* __restrict__ tile_offsets, uint64_t* __restrict__ prefix,
+                                                                    float4* __restrict__ part) {
+    __shared__ uint64_t sm[8];
+    const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)threadIdx.x * NS_SCAN_ITEMS;
+    uint64_t w[NS_SCAN_ITEMS];
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < NS_SCAN_ITEMS; j++) {
+        w[j] = (base + j < n) ? ns_weight(ll[base + j], max_ll, temper) : 0;
+        s += w[j];
+    }
+    uint64_t tot;
+    uint64_t incl = block_scan_u64(s, sm, tot);
+    uint64_t run = tile_offsets[blockIdx.x] + incl - s;
+#pragma unroll
+    for (int j = 0; j < NS_SCAN_ITEMS; j++) {
+        run += w[j];
+        if (base + j < n) {
+            prefix[base + j] = run;
+            part[base + j].w = (float)((double)w[j] * 2.3283064365386963e-10);      // W * 2^-32, max particle = 1
+        }
+    }
+}
+
+// ---- systematic resampling ------------------------------------------------------------------------------------------------
+struct NsDest {
+    float4* part[8];        // next-step particle buffer of every shard (own memory or mapped peer memory)
+    int* anc[8];            // ancestor (global index) per output slot, same sharding
+    int64_t per_rank;       // slots [r*per_rank, (r+1)*per_rank) live on shard r
+    int world;
+};
+// Output slot k (global) takes the first particle i of this shard with (offset + prefix[i]) selecting k. Slots
+// [k_lo, k_hi) are exactly those whose ancestor lives here (host plan, ns_plan.hpp).
+__global__ void __launch_bounds__(256) k_ns_resample(const float4* __restrict__ src, const uint64_t* __restrict__ prefix, int64_t n_local,
+                                                     int64_t g0, uint64_t offset, uint64_t total, uint64_t n_global, uint32_t u0,
+                                                     int64_t k_lo, int64_t k_hi, NsDest D, float new_weight) {
+    const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_hi) return;
+    const ns::U128 rhs = ns::rhs_of((uint64_t)k, u0, total);
+    int64_t lo = 0, len = n_local;
+    while (len > 0) {                       // first i with selects(offset + prefix[i])
+        const int64_t half = len >> 1;
+        if (!ns::selects(offset + prefix[lo + half], n_global, rhs)) { lo += half + 1; len -= half + 1; } else len = half;
+    }
+    if (lo >= n_local) lo = n_local - 1;    // cannot happen when the plan is right; keeps the access in range
+    float4 p = src[lo];
+    p.w = new_weight;
+    int r = (int)(k / D.per_rank);
+    if (r >= D.world) r = D.world - 1;
+    const int64_t slot = k - (int64_t)r * D.per_rank;
+    D.part[r][slot] = p;
+    D.anc[r][slot] = (int)(g0 + lo);
+}
+
+// Weighted pose sums with the particle weights as they stand: {sum w, sum w x, sum w y, sum w sin, sum w cos} per block.
+__global__ void __launch_bounds__(256) k_ns_pose_partials(const float4* __restrict__ part, int64_t n, double* __restrict__ partials) {
+    __shared__ double ws[8][5];
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = part[i];
+        float s, c;
+        ns::det_sincosf(p.z, s, c);
+        const double w = (double)p.w;
+        a[0] += w; a[1] += w * (double)p.x; a[2] += w * (double)p.y; a[3] += w * (double)s; a[4] += w * (double)c;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) a[k] = warp_sum(a[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 5; k++) ws[threadIdx.x >> 5][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < 5) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w][threadIdx.x]; partials[(size_t)blockIdx.x * 5 + threadIdx.x] = s; }
+}
+
+}  // namespace mcl

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "mcl_engine.hpp"
+#include "ns_plan.hpp"
 
 struct mcl_handle {
     mcl::Engine engine;
@@ -39,7 +40,7 @@ void mcl_config_default(mcl_config* c) {
     c->jitter_xy_lost = 0.05; c->jitter_theta_lost = M_PI / 12; c->jitter_xy_conf = 0.01;          // MC:537-545
     c->seed = 0x9E3779B97F4A7C15ull;
     c->ns_sigma_hit = 0.1; c->ns_z_hit = 0.8; c->ns_z_rand = 0.2; c->ns_max_range = 5.6;
-    c->ns_beam_stride = 1; c->ns_use_fov = 0;
+    c->ns_beam_stride = 1; c->ns_use_fov = 0; c->ns_temper = 0.05;
 }
 
 int mcl_create(const mcl_config* cfg, mcl_handle** out) {
@@ -100,6 +101,32 @@ int mcl_profile_enable(mcl_handle* h, int32_t on) { GUARD(h); h->engine.profile_
 int mcl_profile_kernel_count(void) { return mcl::Engine::K_COUNT; }
 const char* mcl_profile_kernel_name(int32_t id) { return mcl::Engine::kernel_name(id); }
 int mcl_profile_read(mcl_handle* h, int32_t id, double* total_ms, int64_t* count) { GUARD(h); TRY(h->engine.profile_read(id, total_ms, count)) }
+int mcl_ns_set_shard(mcl_handle* h, int32_t rank, int32_t world, int64_t ng) { GUARD(h); TRY(h->engine.ns_set_shard(rank, world, ng)) }
+int mcl_ns_update_local(mcl_handle* h, const float* ranges, int32_t nb, float amin, float ainc, float rmin, float rmax, float* lm) {
+    GUARD(h); TRY(h->engine.ns_update_local(ranges, nb, amin, ainc, rmin, rmax, lm))
+}
+int mcl_ns_weights_local(mcl_handle* h, float gm, uint64_t* lt) { GUARD(h); TRY(h->engine.ns_weights_local(gm, lt)) }
+int mcl_ns_resample_local(mcl_handle* h, uint64_t off, uint64_t tot, uint32_t u0, int64_t* klo, int64_t* khi) { GUARD(h); TRY(h->engine.ns_resample_local(off, tot, u0, klo, khi)) }
+int mcl_ns_end_step(mcl_handle* h) { GUARD(h); TRY(h->engine.ns_end_step()) }
+uint32_t mcl_ns_u0(mcl_handle* h) { return h ? h->engine.ns_u0() : 0; }
+int mcl_ns_pose_partials(mcl_handle* h, double* out5) { GUARD(h); TRY(h->engine.ns_pose_partials(out5)) }
+int mcl_ns_first_slot(uint64_t off, uint64_t tot, uint64_t n, uint32_t u0, int64_t* slot) {
+    if (!slot || tot == 0) return MCL_ERR_ARG;
+    *slot = mcl::ns::first_slot(off, tot, n, u0);
+    return MCL_OK;
+}
+int mcl_ns_shard_range(int64_t ng, int32_t world, int32_t rank, int64_t* b, int64_t* c, int64_t* per) {
+    if (!b || !c || !per || world < 1 || rank < 0 || rank >= world) return MCL_ERR_ARG;
+    mcl::ns::shard_range(ng, world, rank, b, c, per);
+    return MCL_OK;
+}
+int mcl_peer_export(mcl_handle* h, int32_t which, void* out64) { GUARD(h); TRY(h->engine.peer_export(which, out64)) }
+int mcl_peer_import(mcl_handle* h, int32_t rank, int32_t which, const void* in64) { GUARD(h); TRY(h->engine.peer_import(rank, which, in64)) }
+int mcl_peer_set(mcl_handle* h, int32_t rank, int32_t which, void* p) { GUARD(h); TRY(h->engine.peer_set(rank, which, p)) }
+void* mcl_device_buffer(mcl_handle* h, int32_t which) { return h ? h->engine.device_buffer(which) : nullptr; }
+int mcl_ns_download_field(mcl_handle* h, float* lf, uint16_t* d2) { GUARD(h); TRY(h->engine.ns_download_field(lf, d2)) }
+int mcl_ns_download_loglik(mcl_handle* h, float* ll) { GUARD(h); TRY(h->engine.ns_download_loglik(ll)) }
+int mcl_ns_download_prefix(mcl_handle* h, uint64_t* p) { GUARD(h); TRY(h->engine.ns_download_prefix(p)) }
 void* mcl_stream(mcl_handle* h) { return h ? (void*)h->engine.stream : nullptr; }
 int mcl_synchronize(mcl_handle* h) { GUARD(h); TRY(h->engine.synchronize()) }
 int64_t mcl_kernel_launches(mcl_handle* h) { return h ? h->engine.launches : 0; }

@@ -7,34 +7,19 @@
 #include <fstream>
 #include <sstream>
 
+#include "engine_internal.hpp"
 #include "exact_scan.cuh"
 #include "kernels_ref.cuh"
 
 namespace mcl {
-
-#define CK(call)                                                   \
-    do {                                                           \
-        cudaError_t e__ = (call);                                  \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
-    } while (0)
-
-// every kernel launch goes through LAUNCH: counts it and, when profiling, brackets it with CUDA events on the stream
-#define LAUNCH(id, kernel, grid, block, smem, ...)                      \
-    do {                                                                \
-        prof_begin(id);                                                 \
-        kernel<<<(grid), (block), (smem), stream>>>(__VA_ARGS__);       \
-        prof_end();                                                     \
-        ++launches;                                                     \
-    } while (0)
-
-static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 Engine::Engine(const mcl_config& c) : cfg(c) {}
 
 Engine::~Engine() {
     if (!opened) return;
     cudaSetDevice(cfg.device);
-    part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); ancestors.release(); d_occ.release(); d_gauss.release();
+    part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); d_lf.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
+    for (int w = 0; w < 3; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]); ancestors.release(); d_occ.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
     d_beams.release(); for (auto& sc : staged) sc.d_used.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
     d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();
@@ -45,7 +30,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
-                                         "k_ref_seq_cdf", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+                                         "k_ref_seq_cdf", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_tile_offsets", "k_ns_weights_scan", "k_ns_resample", "k_ns_pose_partials", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
@@ -148,6 +133,7 @@ int Engine::set_map(const int8_t* occ, int w, int h, float res, double ox, doubl
     CK(cudaMemcpyAsync(d_occ.p, flags.data(), flags.size(), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
     map_ready = true;
+    if (cfg.mode == MCL_MODE_NS) return ns_build_field();
     return MCL_OK;
 }
 
@@ -197,7 +183,14 @@ int Engine::ensure_particles(int64_t count) {
     if (cfg.max_particles > 0 && count > cfg.max_particles) return fail(MCL_ERR_ARG, "particle count exceeds max_particles");
     if (count > (int64_t)INT32_MAX) return fail(MCL_ERR_ARG, "particle count exceeds 2^31-1 per GPU");
     CK(part[0].ensure(count)); CK(part[1].ensure(count));
-    CK(cdf.ensure(count)); CK(ancestors.ensure(count));
+    CK(ancestors.ensure(count));
+    if (cfg.mode == MCL_MODE_NS) {
+        CK(d_ll.ensure(count)); CK(d_prefix.ensure(count));
+        CK(d_tile_sums.ensure((size_t)(count + 2047) / 2048 + 1)); CK(d_u64.ensure(4)); CK(d_maxbits.ensure(1));
+        if (shard_world == 1) { n_global = count; shard_begin = 0; per_rank = count; }
+        return MCL_OK;
+    }
+    CK(cdf.ensure(count));
     CK(d_wraw.ensure(count)); CK(d_wn.ensure(count));
     return ensure_xs(count);
 }
@@ -295,6 +288,7 @@ static RefResampleParams make_resample_params(const mcl_config& c, int64_t n, in
 int Engine::init(int64_t count, const mcl_init_draws* d) {
     CK(cudaSetDevice(cfg.device));
     if (!map_ready) return fail(MCL_ERR_ARG, "init: set a map first (sampleParticles reads the grid size, MC:423-424)");
+    if (cfg.mode == MCL_MODE_NS) return ns_init(count);
     int rc = ensure_particles(count);
     if (rc) return rc;
     const int n_cols = (int)((unsigned)map_w / (unsigned)cfg.cell_size_px);    // MC:423
@@ -391,6 +385,7 @@ int Engine::download_cdf(double* out) {
 int Engine::predict_motion(double r1, double t, double r2) {
     CK(cudaSetDevice(cfg.device));
     if (n == 0) return fail(MCL_ERR_ARG, "predict: no particles");
+    if (cfg.mode == MCL_MODE_NS) { Motion m; m.rot_1 = r1; m.trans = t; m.rot_2 = r2; return ns_predict(m); }
     // Eigen narrows the f64 scalars to the array's fp32 first (MC:746-753)
     LAUNCH(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2));
     CK(cudaGetLastError());
@@ -411,6 +406,13 @@ int Engine::predict_encoders(double enc_l, double enc_r, const double* z3, doubl
         z[1] = std::sqrt(-2.0 * std::log(u1)) * std::sin(2 * M_PI * u2);
         z[2] = std::sqrt(-2.0 * std::log(u3)) * std::cos(2 * M_PI * u4);
     }
+    if (cfg.mode == MCL_MODE_NS) {
+        // per-particle noise: the odometry increment itself stays clean (zero draws), the kernel adds Philox noise
+        const double zero[3] = {0.0, 0.0, 0.0};
+        Motion m = odometry_step(odo, cfg, enc_l, enc_r, zero);
+        if (motion_out) { motion_out[0] = m.rot_1; motion_out[1] = m.trans; motion_out[2] = m.rot_2; }
+        return ns_predict(m);
+    }
     Motion m = odometry_step(odo, cfg, enc_l, enc_r, z);
     if (motion_out) { motion_out[0] = m.rot_1; motion_out[1] = m.trans; motion_out[2] = m.rot_2; }
     ++step_counter;
@@ -423,7 +425,17 @@ int Engine::update(const float* ranges, int n_beams, float angle_min, float angl
     if (!map_ready) return fail(MCL_ERR_ARG, "update: no map (the reference warns 'NO MAP RECEVIED', MC:311)");
     if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
     if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "update: bad scan");
-    if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "update: NS mode not built in this library");
+    if (cfg.mode == MCL_MODE_NS) {
+        if (shard_world != 1) return fail(MCL_ERR_STATE, "update: sharded NS filters are driven through the mcl_ns_*_local phases");
+        float local_max = 0.f;
+        int rc = ns_update_local(ranges, n_beams, angle_min, angle_inc, range_min, range_max, &local_max);
+        if (rc) return rc;
+        uint64_t tot = 0;
+        rc = ns_weights_local(local_max, &tot);
+        if (rc) return rc;
+        if (total) *total = (double)tot * 2.3283064365386963e-10;
+        return MCL_OK;
+    }
     std::vector<RefBeam> used;
     int rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, beams_all, used);
     if (rc) return rc;
@@ -572,7 +584,17 @@ int Engine::resample(int jitter_state, const mcl_resample_draws* d, mcl_resample
     if (n == 0) return fail(MCL_ERR_ARG, "resample: no particles");
     if (!have_weights) return fail(MCL_ERR_ARG, "resample: call mcl_update first (resampleParticles weighs before it resamples, MC:468)");
     if (cfg.mode == MCL_MODE_REF) return ref_resample(jitter_state, d, st);
-    return fail(MCL_ERR_STATE, "resample: NS mode not built in this library");
+    if (shard_world != 1) return fail(MCL_ERR_STATE, "resample: sharded NS filters are driven through the mcl_ns_*_local phases");
+    uint64_t tot = 0;
+    CK(cudaMemcpyAsync(&tot, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    int64_t k_lo = 0, k_hi = 0;
+    int rc = ns_resample_local(0, tot, ns_u0(), &k_lo, &k_hi);
+    if (rc) return rc;
+    rc = ns_end_step();
+    if (rc) return rc;
+    if (st) { st->injected = 0; st->clamped = 0; st->p_inject = 0; st->weight_slow = 0; st->weight_fast = 0; st->total_weight = (double)tot * 2.3283064365386963e-10; }
+    return MCL_OK;
 }
 
 int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st) {

@@ -54,11 +54,28 @@ public:
     int estimate(double* x, double* y, double* th);
     int get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
     int synchronize();
+    // NS mode (north-star formulation); the *_local phases are what a multi-GPU driver sequences around its collectives
+    int ns_set_shard(int rank, int world, int64_t n_global);
+    int ns_update_local(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, float* local_max);
+    int ns_weights_local(float global_max, uint64_t* local_total);
+    int ns_resample_local(uint64_t offset, uint64_t total, uint32_t u0, int64_t* k_lo, int64_t* k_hi);
+    int ns_end_step();
+    uint32_t ns_u0() const;
+    int ns_pose_partials(double* out5);
+    int ns_download_field(float* lf, uint16_t* d2);
+    int ns_download_loglik(float* ll);
+    int ns_download_prefix(uint64_t* prefix);
+    int peer_export(int which, void* out64);
+    int peer_import(int rank, int which, const void* in64);
+    int peer_set(int rank, int which, void* devptr);
+    void* device_buffer(int which);
+    int shard_rank = 0, shard_world = 1;
+    int64_t n_global = 0, shard_begin = 0, per_rank = 0;
     int download_resample_draws(double* u_r, double* u_jit);
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_TILEOFF, K_NS_WSCAN, K_NS_RESAMPLE, K_NS_POSE, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
@@ -142,6 +159,22 @@ private:
     DevBuf<double> d_partials;
     double last_total = 0;
     bool have_weights = false;
+    // NS state
+    int ns_build_field();
+    int ns_init(int64_t count);
+    int ns_predict(const Motion& clean);
+    DevBuf<float> d_lf, d_lf_table, d_ll;
+    DevBuf<uint16_t> d_d2, d_g;
+    DevBuf<float2> d_ns_beams;
+    DevBuf<uint64_t> d_prefix, d_tile_sums, d_u64;      // d_u64[0] = local total
+    DevBuf<int> d_maxbits;
+    int ns_R = 0, ns_beams_n = 0;
+    size_t lf_bytes_padded = 0;
+    float lf_out = 0.f, ns_last_max = 0.f;
+    bool ns_attr_set = false;
+    bool ns_have_ll = false;
+    void* peer_ptr[3][8] = {{nullptr}};    // [0],[1]: particle ping-pong buffers of shard r; [2]: ancestors
+    bool peer_ipc[3][8] = {{false}};
     // pinned staging
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;

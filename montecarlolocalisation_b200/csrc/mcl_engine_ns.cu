@@ -1,0 +1,291 @@
+// mcl_engine_ns.cu — host orchestration of MCL_MODE_NS (likelihood field, Philox motion noise, fixed-point systematic
+// resampling, sharding across GPUs). Definitions: ns_core.cuh / DESIGN.md "NS".
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "mcl_engine.hpp"
+#include "engine_internal.hpp"
+#include "kernels_ns.cuh"
+#include "ns_plan.hpp"
+
+namespace mcl {
+
+int Engine::ns_set_shard(int rank, int world, int64_t ng) {
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "set_shard: NS mode only (REF resampling needs the global f64 CDF on one GPU)");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || ng <= 0) return fail(MCL_ERR_ARG, "set_shard: bad rank/world/count");
+    shard_rank = rank; shard_world = world; n_global = ng;
+    int64_t cnt;
+    ns::shard_range(ng, world, rank, &shard_begin, &cnt, &per_rank);
+    if (cnt <= 0) return fail(MCL_ERR_ARG, "set_shard: empty shard");
+    int rc = ensure_particles(cnt);
+    if (rc) return rc;
+    n = cnt;
+    return MCL_OK;
+}
+
+// Exact capped squared distance transform -> log-likelihood field.
+int Engine::ns_build_field() {
+    const double max_dist = 2.0;                                   // metres beyond which the field is flat
+    ns_R = std::min(255, std::max(1, (int)std::ceil(max_dist / (double)res_f)));
+    const int cap = ns_R * ns_R;
+    std::vector<float> table(cap + 1);
+    const double sigma = cfg.ns_sigma_hit;
+    for (int d2 = 0; d2 <= cap; ++d2) {
+        const double d = (double)res_f * std::sqrt((double)d2);
+        const double p = cfg.ns_z_hit * std::exp(-(d * d) / (2.0 * sigma * sigma)) / (sigma * std::sqrt(2.0 * M_PI)) + cfg.ns_z_rand / cfg.ns_max_range;
+        table[d2] = (float)std::log(p);
+    }
+    lf_out = table[cap];
+    const size_t cells = (size_t)map_w * map_h;
+    lf_bytes_padded = (cells * sizeof(float) + 15) & ~(size_t)15;
+    CK(d_lf_table.ensure(table.size())); CK(d_lf.ensure(lf_bytes_padded / sizeof(float))); CK(d_d2.ensure(cells)); CK(d_g.ensure(cells));
+    CK(cudaMemcpyAsync(d_lf_table.p, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(d_lf.p, 0, lf_bytes_padded, stream));
+    LAUNCH(K_NS_EDT_COLS, k_ns_edt_cols, grid_for(map_w, 128), 128, 0, d_occ.p, map_w, map_h, ns_R, d_g.p);
+    LAUNCH(K_NS_EDT_ROWS, k_ns_edt_rows, dim3(grid_for(map_w, 128), map_h), 128, 0, d_g.p, map_w, map_h, ns_R, d_lf_table.p, d_d2.p, d_lf.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::ns_download_field(float* lf, uint16_t* d2) {
+    CK(cudaSetDevice(cfg.device));
+    if (!map_ready || cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "download_field: NS mode with a map only");
+    const size_t cells = (size_t)map_w * map_h;
+    if (lf) CK(cudaMemcpyAsync(lf, d_lf.p, cells * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (d2) CK(cudaMemcpyAsync(d2, d_d2.p, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+int Engine::ns_init(int64_t count) {
+    if (shard_world == 1) {
+        int rc = ensure_particles(count);
+        if (rc) return rc;
+        n = count; n_global = count; shard_begin = 0; per_rank = count;
+    } else if (count != n_global) {
+        return fail(MCL_ERR_ARG, "init: pass the GLOBAL particle count given to mcl_ns_set_shard");
+    }
+    const double ext_x = (double)map_w * (double)res_f, ext_y = (double)map_h * (double)res_f;
+    LAUNCH(K_NS_INIT, k_ns_init, grid_for(n, 256), 256, 0, part[cur].p, n, shard_begin, origin_x, origin_y, ext_x, ext_y,
+           (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+    have_weights = false; ns_have_ll = false;
+    return MCL_OK;
+}
+
+// The clean odometry increment plus, per particle, N(0, variance) noise with the reference's variances (MC:706-710).
+int Engine::ns_predict(const Motion& m) {
+    NsMotion k;
+    k.rot1 = (float)m.rot_1; k.trans = (float)m.trans; k.rot2 = (float)m.rot_2;
+    k.sd_rot1 = (float)std::sqrt(cfg.alpha[0] * std::fabs(m.rot_1) + cfg.alpha[1] * std::fabs(m.trans));
+    k.sd_trans = (float)std::sqrt(cfg.alpha[2] * std::fabs(m.trans) + cfg.alpha[3] * (std::fabs(m.rot_1) + std::fabs(m.rot_2)));
+    k.sd_rot2 = (float)std::sqrt(cfg.alpha[0] * std::fabs(m.rot_2) + cfg.alpha[1] * std::fabs(m.trans));
+    LAUNCH(K_NS_PREDICT, k_ns_predict, grid_for(n, 256), 256, 0, part[cur].p, n, shard_begin, k, (uint32_t)step_counter,
+           (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+    CK(cudaGetLastError());
+    have_weights = false; ns_have_ll = false;
+    return MCL_OK;
+}
+
+// Scan -> beam endpoints in the robot frame, then the likelihood-field kernel. Returns this shard's max.
+int Engine::ns_update_local(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
+                            float* local_max) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_update_local: NS mode only");
+    if (!map_ready) return fail(MCL_ERR_ARG, "update: no map");
+    if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
+    if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "update: bad scan");
+    std::vector<float2> pts;
+    const int stride = std::max(1, cfg.ns_beam_stride);
+    int kept = 0;
+    for (int i = 0; i < n_beams; ++i) {
+        const double r = ranges[i];
+        if (std::isnan(r) || std::isinf(r)) continue;
+        if (!(r >= range_min && r <= range_max) || r >= cfg.ns_max_range) continue;
+        const double ang = (double)angle_min + ((size_t)i * (double)angle_inc);
+        if (cfg.ns_use_fov) {
+            const double deg = ang * 180.0 / M_PI;
+            if (!(deg > cfg.fov_lower_deg && deg < cfg.fov_upper_deg)) continue;
+        }
+        if ((kept++ % stride) != 0) continue;
+        const double phi = -ang;                                        // the reference mirrors beam angles (MC:653)
+        pts.push_back(make_float2((float)(cfg.laser_offset + r * std::cos(phi)), (float)(r * std::sin(phi))));
+    }
+    ns_beams_n = (int)pts.size();
+    CK(d_ns_beams.ensure(std::max<size_t>(1, pts.size())));
+    if (!pts.empty()) {
+        int rc = ensure_pinned(pts.size() * sizeof(float2));
+        if (rc) return rc;
+        memcpy(h_pinned, pts.data(), pts.size() * sizeof(float2));
+        CK(cudaMemcpyAsync(d_ns_beams.p, h_pinned, pts.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+    }
+    NsField F;
+    F.lf = d_lf.p; F.W = map_w; F.H = map_h; F.ox = (float)origin_x; F.oy = (float)origin_y;
+    F.inv_res = 1.0f / res_f; F.lf_out = lf_out; F.bytes_padded = (int)lf_bytes_padded;
+    const int init_bits = INT32_MIN;
+    CK(cudaMemcpyAsync(d_maxbits.p, &init_bits, sizeof(int), cudaMemcpyHostToDevice, stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    const size_t beam_bytes = (size_t)ns_beams_n * sizeof(float2);
+    const bool in_smem = lf_bytes_padded + beam_bytes <= 200 * 1024;
+    if (!ns_attr_set) {
+        CK(cudaFuncSetAttribute(k_ns_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ns_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        ns_attr_set = true;
+    }
+    const int threads = 512;
+    const int64_t batches = (n + 31) / 32;
+    if (in_smem) {
+        const size_t smem = lf_bytes_padded + beam_bytes;
+        const int ctas_per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
+        const int grid = (int)std::min<int64_t>((int64_t)sms * ctas_per_sm, (batches + threads / 32 - 1) / (threads / 32));
+        LAUNCH(K_NS_UPDATE, k_ns_update<true>, std::max(1, grid), threads, smem, part[cur].p, n, F, d_ns_beams.p, ns_beams_n, d_ll.p, d_maxbits.p);
+    } else {
+        if (beam_bytes > 64 * 1024) return fail(MCL_ERR_ARG, "update: too many beams");
+        const int grid = (int)std::min<int64_t>((int64_t)sms * 4, (batches + threads / 32 - 1) / (threads / 32));
+        LAUNCH(K_NS_UPDATE, k_ns_update<false>, std::max(1, grid), threads, beam_bytes, part[cur].p, n, F, d_ns_beams.p, ns_beams_n, d_ll.p, d_maxbits.p);
+    }
+    CK(cudaGetLastError());
+    int bits = 0;
+    CK(cudaMemcpyAsync(&bits, d_maxbits.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
+    float mx;
+    memcpy(&mx, &bits, 4);
+    ns_last_max = mx;
+    ns_have_ll = true;
+    have_weights = false;
+    if (local_max) *local_max = mx;
+    return MCL_OK;
+}
+
+int Engine::ns_weights_local(float global_max, uint64_t* local_total) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_weights_local: NS mode only");
+    if (!ns_have_ll) return fail(MCL_ERR_ARG, "weights: run the update first");
+    const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
+    const float temper = (float)cfg.ns_temper;
+    LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, global_max, temper, d_tile_sums.p);
+    LAUNCH(K_NS_TILEOFF, k_ns_tile_offsets, 1, 1024, 0, d_tile_sums.p, nt, d_u64.p);
+    LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, global_max, temper, d_tile_sums.p, d_prefix.p, part[cur].p);
+    CK(cudaGetLastError());
+    uint64_t tot = 0;
+    CK(cudaMemcpyAsync(&tot, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    have_weights = true;
+    last_total = (double)tot * 2.3283064365386963e-10;
+    if (local_total) *local_total = tot;
+    return MCL_OK;
+}
+
+uint32_t Engine::ns_u0() const {
+    uint32_t o[4];
+    Philox::gen(0u, 0u, 0x40u, (uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), o);
+    return o[0];
+}
+
+int Engine::ns_resample_local(uint64_t offset, uint64_t total, uint32_t u0, int64_t* k_lo_out, int64_t* k_hi_out) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_resample_local: NS mode only");
+    if (!have_weights) return fail(MCL_ERR_ARG, "resample: run the update first");
+    if (total == 0) return fail(MCL_ERR_ARG, "resample: total weight is zero");
+    uint64_t mine = 0;
+    CK(cudaMemcpyAsync(&mine, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const int64_t k_lo = ns::first_slot(offset, total, (uint64_t)n_global, u0);
+    const int64_t k_hi = ns::first_slot(offset + mine, total, (uint64_t)n_global, u0);
+    NsDest D;
+    D.per_rank = per_rank; D.world = shard_world;
+    const int next = cur ^ 1;
+    for (int r = 0; r < 8; ++r) { D.part[r] = nullptr; D.anc[r] = nullptr; }
+    for (int r = 0; r < shard_world; ++r) {
+        if (r == shard_rank) { D.part[r] = part[next].p; D.anc[r] = ancestors.p; }
+        else {
+            if (!peer_ptr[next][r] || !peer_ptr[2][r]) return fail(MCL_ERR_COMM, "resample: peer buffers of a shard are not mapped (mcl_peer_import / mcl_peer_set)");
+            D.part[r] = (float4*)peer_ptr[next][r]; D.anc[r] = (int*)peer_ptr[2][r];
+        }
+    }
+    if (k_hi > k_lo) {
+        LAUNCH(K_NS_RESAMPLE, k_ns_resample, grid_for(k_hi - k_lo, 256), 256, 0, part[cur].p, d_prefix.p, n, shard_begin, offset, total,
+               (uint64_t)n_global, u0, k_lo, k_hi, D, (float)(1.0 / (double)n_global));
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(stream));       // peers may only swap once every shard's stores have landed
+    if (k_lo_out) *k_lo_out = k_lo;
+    if (k_hi_out) *k_hi_out = k_hi;
+    return MCL_OK;
+}
+
+int Engine::ns_end_step() {
+    cur ^= 1;
+    have_weights = false; ns_have_ll = false;
+    ++step_counter;
+    return MCL_OK;
+}
+
+int Engine::ns_pose_partials(double* out5) {
+    CK(cudaSetDevice(cfg.device));
+    if (n == 0 || !out5) return fail(MCL_ERR_ARG, "pose_partials: no particles");
+    const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
+    CK(d_partials.ensure(5 * 512));
+    LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, d_partials.p);
+    CK(cudaGetLastError());
+    std::vector<double> h((size_t)blocks * 5);
+    CK(cudaMemcpyAsync(h.data(), d_partials.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int k = 0; k < 5; ++k) { double s = 0; for (int b = 0; b < blocks; ++b) s += h[(size_t)b * 5 + k]; out5[k] = s; }
+    return MCL_OK;
+}
+
+int Engine::ns_download_loglik(float* ll) {
+    CK(cudaSetDevice(cfg.device));
+    if (!ll || !ns_have_ll) return fail(MCL_ERR_ARG, "download_loglik: run the update first");
+    CK(cudaMemcpyAsync(ll, d_ll.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+int Engine::ns_download_prefix(uint64_t* prefix) {
+    CK(cudaSetDevice(cfg.device));
+    if (!prefix || !have_weights) return fail(MCL_ERR_ARG, "download_prefix: run the update first");
+    CK(cudaMemcpyAsync(prefix, d_prefix.p, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+// ---- peer memory: every shard's two particle buffers and its ancestor buffer are visible to the others -------------------
+void* Engine::device_buffer(int which) {
+    if (which == 0 || which == 1) return part[which].p;
+    if (which == 2) return ancestors.p;
+    return nullptr;
+}
+int Engine::peer_export(int which, void* out64) {
+    CK(cudaSetDevice(cfg.device));
+    void* p = device_buffer(which);
+    if (!p || !out64) return fail(MCL_ERR_ARG, "peer_export: allocate the shard first (mcl_ns_set_shard)");
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, p));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out64, &hnd, 64);
+    return MCL_OK;
+}
+int Engine::peer_import(int rank, int which, const void* in64) {
+    CK(cudaSetDevice(cfg.device));
+    if (rank < 0 || rank >= 8 || which < 0 || which > 2 || !in64) return fail(MCL_ERR_ARG, "peer_import: bad argument");
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, in64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); return MCL_ERR_COMM; }
+    peer_ptr[which][rank] = p; peer_ipc[which][rank] = true;
+    return MCL_OK;
+}
+int Engine::peer_set(int rank, int which, void* devptr) {
+    if (rank < 0 || rank >= 8 || which < 0 || which > 2) return fail(MCL_ERR_ARG, "peer_set: bad argument");
+    peer_ptr[which][rank] = devptr; peer_ipc[which][rank] = false;
+    return MCL_OK;
+}
+
+}  // namespace mcl

@@ -239,3 +239,108 @@ class ParticleFilter:
 
     def kernelLaunches(self):
         return self.L.mcl_kernel_launches(self.h)
+
+
+class NsShard:
+    """One shard (= one GPU handle) of an MCL_MODE_NS filter, phase by phase (include/mcl.h "NS mode across GPUs")."""
+
+    def __init__(self, rank=0, world=1, n_global=None, device=0, **overrides):
+        self.pf = ParticleFilter(prefill_ray_directions=False, mode=MODE_NS, device=device, **overrides)
+        self.L, self.h = self.pf.L, self.pf.h
+        self.rank, self.world = rank, world
+        if n_global is not None:
+            self.pf._ck(self.L.mcl_ns_set_shard(self.h, rank, world, n_global))
+            self.n_global = n_global
+
+    def update_local(self, ranges, angle_min, angle_inc, range_min, range_max):
+        r = np.ascontiguousarray(ranges, dtype=np.float32)
+        mx = C.c_float()
+        self.pf._ck(self.L.mcl_ns_update_local(self.h, r.ctypes.data_as(_fp), len(r), C.c_float(angle_min), C.c_float(angle_inc),
+                                               C.c_float(range_min), C.c_float(range_max), C.byref(mx)))
+        return mx.value
+
+    def weights_local(self, global_max):
+        t = C.c_uint64()
+        self.pf._ck(self.L.mcl_ns_weights_local(self.h, C.c_float(global_max), C.byref(t)))
+        return t.value
+
+    def resample_local(self, offset, total, u0):
+        lo, hi = C.c_int64(), C.c_int64()
+        self.pf._ck(self.L.mcl_ns_resample_local(self.h, C.c_uint64(offset), C.c_uint64(total), C.c_uint32(u0), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def end_step(self):
+        self.pf._ck(self.L.mcl_ns_end_step(self.h))
+
+    def u0(self):
+        return self.L.mcl_ns_u0(self.h)
+
+    def pose_partials(self):
+        out = np.zeros(5)
+        self.pf._ck(self.L.mcl_ns_pose_partials(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    def field(self, shape):
+        lf = np.zeros(shape, np.float32); d2 = np.zeros(shape, np.uint16)
+        self.pf._ck(self.L.mcl_ns_download_field(self.h, lf.ctypes.data_as(_fp), d2.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return lf, d2
+
+    def loglik(self):
+        ll = np.zeros(self.pf.num_particles, np.float32)
+        self.pf._ck(self.L.mcl_ns_download_loglik(self.h, ll.ctypes.data_as(_fp)))
+        return ll
+
+    def prefix(self):
+        p = np.zeros(self.pf.num_particles, np.uint64)
+        self.pf._ck(self.L.mcl_ns_download_prefix(self.h, p.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return p
+
+    def device_buffer(self, which):
+        return self.L.mcl_device_buffer(self.h, which)
+
+    def peer_set(self, rank, which, ptr):
+        self.pf._ck(self.L.mcl_peer_set(self.h, rank, which, C.c_void_p(ptr)))
+
+    def peer_export(self, which):
+        buf = C.create_string_buffer(64)
+        self.pf._ck(self.L.mcl_peer_export(self.h, which, buf))
+        return buf.raw
+
+    def peer_import(self, rank, which, raw64):
+        self.pf._ck(self.L.mcl_peer_import(self.h, rank, which, C.create_string_buffer(raw64, 64)))
+
+
+def ns_first_slot(offset, total, n_global, u0):
+    out = C.c_int64()
+    rc = _lib.load().mcl_ns_first_slot(C.c_uint64(offset), C.c_uint64(total), C.c_uint64(n_global), C.c_uint32(u0), C.byref(out))
+    if rc:
+        raise MclError(rc, "mcl_ns_first_slot")
+    return out.value
+
+
+def ns_shard_range(n_global, world, rank):
+    b, c, p = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = _lib.load().mcl_ns_shard_range(n_global, world, rank, C.byref(b), C.byref(c), C.byref(p))
+    if rc:
+        raise MclError(rc, "mcl_ns_shard_range")
+    return b.value, c.value, p.value
+
+
+def ns_step_in_process(shards, scan, motion):
+    """Drive G shards living in ONE process through a filter step; the three collectives are plain Python here.
+    (bench.py and multi-process users do the same with torch.distributed over NCCL.)"""
+    for s in shards:
+        s.pf.updateParticlePos(*motion)
+    maxes = [s.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"]) for s in shards]
+    gmax = max(maxes)                                        # all-reduce(max)
+    totals = [s.weights_local(gmax) for s in shards]         # all-gather of the local totals
+    total = sum(totals)
+    u0 = shards[0].u0()
+    off = 0
+    ranges = []
+    for s, t in zip(shards, totals):
+        ranges.append(s.resample_local(off, total, u0))
+        off += t
+    for s in shards:                                         # barrier, then everyone swaps
+        s.end_step()
+    return dict(max=gmax, totals=totals, total=total, u0=u0, slots=ranges)

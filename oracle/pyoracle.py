@@ -339,3 +339,94 @@ class Ref:
         out = np.zeros(3)
         self.L.ref_estimate_weighted_pose(_p(np.ascontiguousarray(P, np.float32), c_fp), len(P), _p(out, c_dp))
         return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# NS-mode oracle (oracle/mcl_oracle_ns.cpp): the engine's own north-star formulation; parity unpinned by the reference.
+# ------------------------------------------------------------------------------------------------------
+c_u64p = C.POINTER(C.c_uint64)
+c_i64p = C.POINTER(C.c_int64)
+
+
+class NsOracle:
+    def __init__(self, sigma=0.1, z_hit=0.8, z_rand=0.2, max_range=5.6, laser_offset=0.1, temper=0.05, seed=0x9E3779B97F4A7C15, beam_stride=1):
+        L = self.L = oracle_lib()
+        L.ons_create.restype = C.c_void_p
+        L.ons_weights.restype = C.c_uint64
+        L.ons_u0.restype = C.c_uint32
+        L.ons_det_log.restype = C.c_double
+        L.ons_det_exp_q32.restype = C.c_uint64
+        self.h = C.c_void_p(L.ons_create())
+        L.ons_config(self.h, C.c_double(sigma), C.c_double(z_hit), C.c_double(z_rand), C.c_double(max_range), C.c_double(laser_offset),
+                     C.c_double(temper), C.c_uint64(seed), beam_stride)
+
+    def __del__(self):
+        try:
+            self.L.ons_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_map(self, occ, res=np.float32(0.1), ox=0.0, oy=0.0):
+        occ = np.ascontiguousarray(occ, dtype=np.int8)
+        self.H, self.W = occ.shape
+        self.L.ons_set_map(self.h, _p(occ, c_bp), self.W, self.H, C.c_float(res), C.c_double(ox), C.c_double(oy))
+
+    def field(self):
+        lf = np.zeros((self.H, self.W), np.float32); d2 = np.zeros((self.H, self.W), np.uint16)
+        self.L.ons_get_field(self.h, _p(lf, c_fp), d2.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return lf, d2
+
+    def init(self, g0, n):
+        P = np.zeros((n, 4), np.float32)
+        self.L.ons_init(self.h, C.c_int64(g0), C.c_int64(n), _p(P, c_fp))
+        return P
+
+    def predict(self, P, g0, rot1, trans, rot2, step):
+        assert P.dtype == np.float32 and P.flags.c_contiguous
+        self.L.ons_predict(self.h, _p(P, c_fp), C.c_int64(g0), C.c_int64(len(P)), C.c_double(rot1), C.c_double(trans), C.c_double(rot2), C.c_uint32(step))
+
+    def beams(self, scan):
+        cap = len(scan.ranges)
+        pts = np.zeros((max(cap, 1), 2), np.float32)
+        n = self.L.ons_beams(self.h, *scan.args(), _p(pts, c_fp), cap)
+        return pts[:n].copy()
+
+    def loglik(self, P, pts):
+        ll = np.zeros(len(P), np.float32)
+        pts = np.ascontiguousarray(pts, np.float32)
+        self.L.ons_loglik(self.h, _p(np.ascontiguousarray(P, np.float32), c_fp), C.c_int64(len(P)), _p(pts, c_fp), len(pts), _p(ll, c_fp))
+        return ll
+
+    def weights(self, ll, max_ll):
+        n = len(ll)
+        W = np.zeros(n, np.uint64); pre = np.zeros(n, np.uint64); wf = np.zeros(n, np.float32)
+        ll = np.ascontiguousarray(ll, np.float32)
+        tot = self.L.ons_weights(self.h, _p(ll, c_fp), C.c_int64(n), C.c_float(max_ll), W.ctypes.data_as(c_u64p), pre.ctypes.data_as(c_u64p), _p(wf, c_fp))
+        return W, pre, wf, int(tot)
+
+    def u0(self, step):
+        return int(self.L.ons_u0(self.h, C.c_uint32(step)))
+
+    def resample(self, prefix_global, u0, k_begin=0, k_end=None):
+        Cg = np.ascontiguousarray(prefix_global, np.uint64)
+        n = len(Cg)
+        k_end = n if k_end is None else k_end
+        anc = np.zeros(k_end - k_begin, np.int64)
+        self.L.ons_resample(Cg.ctypes.data_as(c_u64p), C.c_int64(n), C.c_uint32(u0), C.c_int64(k_begin), C.c_int64(k_end), anc.ctypes.data_as(c_i64p))
+        return anc
+
+    def pose_partials(self, P):
+        out = np.zeros(5)
+        self.L.ons_pose_partials(_p(np.ascontiguousarray(P, np.float32), c_fp), C.c_int64(len(P)), _p(out, c_dp))
+        return out
+
+    def step(self, P, g0, scan, motion, step):
+        """One full NS filter step on a single span holding ALL particles: returns (new particles, ancestors, ll, prefix)."""
+        self.predict(P, g0, motion[0], motion[1], motion[2], step)
+        pts = self.beams(scan)
+        ll = self.loglik(P, pts)
+        W, pre, wf, tot = self.weights(ll, ll.max())
+        anc = self.resample(pre, self.u0(step))
+        newP = P[anc].copy()
+        newP[:, 3] = np.float32(1.0 / len(P))
+        return newP, anc, ll, pre

@@ -1,0 +1,152 @@
+"""GPU parity, MCL_MODE_NS: the CUDA engine against the NS oracle (its own CPU restatement; parity unpinned by the
+reference, see oracle/mcl_oracle_ns.cpp). NS is defined with IEEE-only arithmetic, so EVERYTHING is required to be
+bit-exact: distance transform, field, predicted poses, log-likelihoods, Q32 prefix sums, ancestors, resampled particles,
+for one shard and for 2..8 shards."""
+import numpy as np
+import pytest
+
+import montecarlolocalisation_b200 as m
+from montecarlolocalisation_b200 import NsShard, ns_step_in_process, synth
+from oracle.pyoracle import NsOracle, Scan
+from scenario import RES, Scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def make_shards(world, n, occ, **cfg):
+    shards = [NsShard(r, world, n, **cfg) for r in range(world)]
+    for s in shards:
+        s.pf.setMap(occ, RES)
+    for a in shards:
+        for b in shards:
+            if a is not b:
+                for which in (0, 1, 2):
+                    a.peer_set(b.rank, which, b.device_buffer(which))
+    for s in shards:
+        s.pf.sampleParticles(n)
+    return shards
+
+
+def gather(shards):
+    return np.concatenate([s.pf.downloadParticles() for s in shards])
+
+
+def gather_anc(shards):
+    return np.concatenate([s.pf.ancestors() for s in shards]).astype(np.int64)
+
+
+def run(world, n, steps, occ=None, n_beams=360, scenario=None, **cfg):
+    sc = scenario or Scenario(steps, n_beams=n_beams)
+    occ = sc.occ if occ is None else occ
+    o = NsOracle(**{k.replace("ns_", ""): v for k, v in cfg.items() if k in ("ns_temper",)})
+    o.set_map(occ, RES)
+    shards = make_shards(world, n, occ, **cfg)
+    P = o.init(0, n)
+    assert np.array_equal(gather(shards), P), "init"
+    for step in range(steps):
+        motion = (0.01 * (step + 1), 0.02 + 0.005 * step, -0.015)
+        scan = sc.scans[step]
+        Pp = P.copy()
+        o.predict(Pp, 0, *motion, step)
+        pts = o.beams(Scan(**scan))
+        ll = o.loglik(Pp, pts)
+        W, pre, wf, tot = o.weights(ll, float(ll.max()))
+        anc = o.resample(pre, o.u0(step))
+        # engine, phase by phase so intermediate products can be compared
+        for s in shards:
+            s.pf.updateParticlePos(*motion)
+        assert np.array_equal(gather(shards)[:, :3], Pp[:, :3]), "predict step %d" % step
+        maxes = [s.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"]) for s in shards]
+        assert np.array_equal(np.concatenate([s.loglik() for s in shards]), ll), "loglik step %d" % step
+        gmax = max(maxes)
+        assert gmax == float(ll.max())
+        totals = [s.weights_local(gmax) for s in shards]
+        assert sum(totals) == tot
+        off = 0
+        for s, t in zip(shards, totals):
+            b, c, per = m.ns_shard_range(n, world, s.rank)
+            assert np.array_equal(s.prefix() + np.uint64(off), pre[b:b + c]), "prefix step %d" % step
+            off += t
+        assert np.array_equal(gather(shards)[:, 3], wf), "unnormalised weights step %d" % step
+        u0 = shards[0].u0()
+        assert u0 == o.u0(step)
+        off = 0
+        slots = []
+        for s, t in zip(shards, totals):
+            slots.append(s.resample_local(off, tot, u0))
+            off += t
+        assert slots[0][0] == 0 and slots[-1][1] == n and all(a[1] == b[0] for a, b in zip(slots, slots[1:]))
+        for s in shards:
+            s.end_step()
+        assert np.array_equal(gather_anc(shards), anc), "ancestors step %d" % step
+        P = Pp[anc].copy()
+        P[:, 3] = np.float32(1.0 / n)
+        assert np.array_equal(gather(shards), P), "resampled particles step %d" % step
+    return shards, P
+
+
+def test_field_matches_oracle():
+    for occ in (Scenario(1).occ, synth.maze_occupancy(32, 3)):
+        o = NsOracle()
+        o.set_map(occ, RES)
+        s = NsShard()
+        s.pf.setMap(occ, RES)
+        lf_g, d2_g = s.field(occ.shape)
+        lf_o, d2_o = o.field()
+        assert np.array_equal(d2_g, d2_o) and np.array_equal(lf_g, lf_o)
+
+
+def test_single_shard_loop_config1_shape():
+    run(1, 5000, 6)
+
+
+@pytest.mark.parametrize("n_beams", [720, 1080])
+def test_single_shard_more_beams(n_beams):
+    run(1, 3000, 2, n_beams=n_beams)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_sharded_equals_oracle(world):
+    run(world, 4001, 4)
+
+
+def test_ragged_sizes():
+    for n in (1, 33, 2049):
+        run(1, n, 2)
+    run(2, 7, 2)
+
+
+def test_field_through_l2_1024_map():
+    """1024^2-cell map (4 MiB field: not shared-memory resident, gathered through L2)."""
+    occ = synth.maze_occupancy(128, 3)
+    assert occ.shape == (1025, 1025)
+    pose = (30.45, 40.45, 0.3)
+    sc = Scenario(2)
+    sc.scans = [synth.make_scan(occ, float(RES), pose, 720, 50 + i) for i in range(2)]
+    run(1, 20000, 2, occ=occ, scenario=sc)
+
+
+def test_one_shard_api_matches_phases():
+    """mcl_update + mcl_resample (world == 1 convenience path) give the same particles as the explicit phases."""
+    sc = Scenario(3)
+    n = 10000
+    a = NsShard()
+    a.pf.setMap(sc.occ, RES)
+    a.pf.sampleParticles(n)
+    (b,) = make_shards(1, n, sc.occ)
+    for step in range(3):
+        scan = sc.scans[step]
+        a.pf.updateParticlePos(0.01, 0.02, 0.0)
+        a.pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        a.pf.resampleParticles(1)
+        ns_step_in_process([b], scan, (0.01, 0.02, 0.0))
+        assert np.array_equal(a.pf.downloadParticles(), b.pf.downloadParticles())
+        assert np.array_equal(a.pf.ancestors(), b.pf.ancestors())
+    pose = a.pf.estimateWeightedPose()
+    assert np.isfinite(pose).all()
+
+
+def test_200k_particles_bit_exact_and_systematic_properties():
+    shards, P = run(1, 200_000, 1)
+    anc = gather_anc(shards)
+    assert (np.diff(anc) >= 0).all()
