@@ -327,6 +327,14 @@ def ours(args):
             "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None, "traffic": None, "peak_source": peak_src,
             "share_of_step": kernels[top]["share"]}
 
+    ns = None
+    if not args.no_ns:
+        del flush
+        torch.cuda.empty_cache()
+        ns = {}
+        ns["map_txt_1M"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 6, 1_000_000, 360, "configs[1] shape", K, W)
+        ns["grid4096"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, args.ns_cells, args.ns_particles, 720,
+                                "configs[3] per-GPU shape", K, W)
     if rank == 0:
         scan_bytes = int(sc.scans[0]["ranges"].nbytes) + 16 + 16         # ranges + 4 float32 scan fields + 2 encoder doubles
         line = {
@@ -342,6 +350,8 @@ def ours(args):
             "kernels": kernels,
             "wall_ms_per_step": 1e3 * wall_res / K,
         }
+        if ns is not None:
+            line["ns"] = ns
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = min(n, 200_000)
             csc = workload(3)
@@ -355,6 +365,158 @@ def ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# NS leg: the north-star formulation (likelihood field, Philox motion noise, fixed-point systematic resampling), sharded
+# across the GPUs of the job. Three collectives per step go through torch.distributed/NCCL (max of local maxima,
+# all-gather of local Q32 totals, barrier); resampled particles are stored by the resampling kernel straight into the
+# owning shard's memory (CUDA IPC peer mappings over NVLink), so no separate rebalance pass exists.
+# ------------------------------------------------------------------------------------------------------------------
+def ns_workload(cells, n_beams, n_scans, seed):
+    from montecarlolocalisation_b200 import synth
+    occ = synth.maze_occupancy(cells, seed)
+    res = 0.1
+    # a pose in the middle of a cell near the map centre
+    cx = (cells // 2) * 8 * res + 0.45
+    pose = (cx, cx, 0.3)
+    scans = [synth.make_scan(occ, res, pose, n_beams, 1000 * seed + i) for i in range(n_scans)]
+    return occ, scans
+
+
+def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label, K, W):
+    import montecarlolocalisation_b200 as m
+    from montecarlolocalisation_b200 import NsShard
+    n_global = per_gpu * world
+    n_scans = 4
+    if cells == 6:
+        from scenario import Scenario
+        sc = Scenario(n_scans, n_beams=n_beams)
+        occ, scans = sc.occ, sc.scans
+    else:
+        occ, scans = ns_workload(cells, n_beams, n_scans, seed=4)
+    shard = NsShard(rank, world, n_global, device=local, max_particles=0, seed=0xABCDEF)
+    shard.pf.setMap(occ, np.float32(0.1))
+    if world > 1:
+        handles = [shard.peer_export(w) for w in (0, 1, 2)]
+        allh = [None] * world
+        dist.all_gather_object(allh, handles)
+        for r in range(world):
+            if r != rank:
+                for w in (0, 1, 2):
+                    shard.peer_import(r, w, allh[r][w])
+    shard.pf.sampleParticles(n_global)
+    for i, sca in enumerate(scans):
+        shard.pf.stageScan(i, sca["ranges"], sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
+    stream = torch.cuda.ExternalStream(shard.pf.stream(), device=local)
+    pinned = [torch.from_numpy(np.ascontiguousarray(sca["ranges"])).pin_memory() for sca in scans]
+    valid_beams = [int((np.isfinite(sca["ranges"]) & (sca["ranges"] >= sca["range_min"]) & (sca["ranges"] <= sca["range_max"]) &
+                        (sca["ranges"] < 5.6)).sum()) for sca in scans]
+    motion = (0.01, 0.02, -0.005)
+    red = torch.zeros(1, dtype=torch.float32, device="cuda")
+    tot_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+    all_t = torch.zeros(world, dtype=torch.int64, device="cuda")
+    pose_t = torch.zeros(5, dtype=torch.float64, device="cuda")
+
+    def step(i, e2e):
+        slot = i % n_scans
+        shard.pf.updateParticlePos(*motion)
+        if e2e:
+            sca = scans[slot]
+            mx = shard.update_local(pinned[slot].numpy(), sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
+        else:
+            mx = shard.update_local_staged(slot)
+        if world > 1:
+            red[0] = mx
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            mx = float(red.item())
+        t = shard.weights_local(mx)
+        if world > 1:
+            tot_t[0] = t
+            dist.all_gather_into_tensor(all_t, tot_t)
+            totals = all_t.tolist()
+        else:
+            totals = [t]
+        pose = None
+        if e2e:
+            pp = shard.pose_partials()
+            if world > 1:
+                pose_t.copy_(torch.from_numpy(pp))
+                dist.all_reduce(pose_t)
+                pp = pose_t.cpu().numpy()
+            pose = (pp[1] / pp[0], pp[2] / pp[0], float(np.arctan2(pp[3], pp[4])))
+        shard.resample_local(sum(totals[:rank]), sum(totals), shard.u0())
+        if world > 1:
+            dist.barrier()
+        shard.end_step()
+        return pose
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, first):
+        for i in range(first, first + W):
+            step(i, e2e)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        w0 = time.perf_counter()
+        for k in range(K):
+            ev[k][0].record(stream)
+            step(first + W + k, e2e)
+            ev[k][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - w0
+        return [a.elapsed_time(b) for a, b in ev], wall
+
+    l0 = shard.pf.kernelLaunches()
+    ms_res, wall_res = timed(False, 0)
+    launches = shard.pf.kernelLaunches() - l0
+    ms_e2e, wall_e2e = timed(True, W + K)
+    shard.pf.profileEnable(True)
+    for k in range(K):
+        step(2 * (W + K) + k, False)
+    prof = shard.pf.profileRead()
+    shard.pf.profileEnable(False)
+    t_res, t_e2e = sum(ms_res) * 1e-3, sum(ms_e2e) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = tt.tolist()
+    evals_res = sum(n_global * valid_beams[i % n_scans] for i in range(W, W + K))
+    evals_e2e = sum(n_global * valid_beams[i % n_scans] for i in range(2 * W + K, 2 * (W + K)))
+    peak, peak_src = peaks()
+    kernels = {}
+    tot_ms = sum(v[0] for v in prof.values())
+    nb = valid_beams[0]
+    algo = {"k_ns_update": per_gpu * (20 + 4 * nb), "k_ns_predict": per_gpu * 32, "k_ns_weights_sum": per_gpu * 4,
+            "k_ns_weights_scan": per_gpu * 16, "k_ns_resample": per_gpu * 44}
+    for name, (msv, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        a = algo.get(name)
+        kernels[name] = {"ms_per_launch": msv / cnt, "launches": cnt, "share": msv / tot_ms, "algo_bytes": a,
+                         "gbs": (a / (msv / cnt * 1e-3) / 1e9) if a else None}
+    top = next(iter(kernels))
+    field_bytes = occ.size * 4
+    out = {
+        "label": label, "value": evals_res / t_res, "unit": UNIT, "ms_per_step": 1e3 * t_res / K, "steps_per_s": K / t_res,
+        "e2e": {"value": evals_e2e / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K, "h2d_bytes_per_step": int(scans[0]["ranges"].nbytes) + 28,
+                "d2h_bytes_per_step": 40 + 4 + 8, "wall_ms_per_step": 1e3 * wall_e2e / K},
+        "config": {"workload": "%s: %dx%d occupancy grid, %d particles per GPU x %d GPU(s) = %d, %d-beam scan (%d valid beams scored per particle), "
+                               "NS mode: Philox motion noise -> likelihood field -> Q32 systematic resampling" % (
+                                   label, occ.shape[1], occ.shape[0], per_gpu, world, n_global, n_beams, nb),
+                   "field": "%d KiB log-likelihood field, %s" % (field_bytes // 1024, "TMA-staged into shared memory" if field_bytes <= 190 * 1024 else "gathered through L2"),
+                   "collectives": "none (1 GPU)" if world == 1 else "NCCL all-reduce(max), all-gather(Q32 totals), barrier; resampled particles stored into peer shards over NVLink (CUDA IPC)",
+                   "l2": "per-GPU working set %.0f MB exceeds or displaces L2 between steps" % (per_gpu * 48 / 1e6)},
+        "gpu_launches": launches, "scaling": "weak",
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                     "share_of_step": kernels[top]["share"],
+                     "note": "algorithmic bytes = 20 B/particle + 4 B per scored beam (table gather); the gathers are served by shared memory or L2, not HBM"},
+        "kernels": kernels,
+    }
+    del shard
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -363,6 +525,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ns", action="store_true", help="skip the NS (north-star) leg")
+    ap.add_argument("--ns-cells", type=int, default=512, help="NS leg: maze cells per side (512 -> 4097x4097 grid)")
+    ap.add_argument("--ns-particles", type=int, default=12_500_000, help="NS leg: particles per GPU")
     args = ap.parse_args()
     if args.warmup < 1:
         args.warmup = 1

@@ -172,6 +172,7 @@ int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
 int mcl_ns_set_shard(mcl_handle* h, int32_t rank, int32_t world, int64_t n_global);   /* allocates this shard */
 int mcl_ns_update_local(mcl_handle* h, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
                         float range_min, float range_max, float* local_max_loglik);
+int mcl_ns_update_local_staged(mcl_handle* h, int32_t slot, float* local_max_loglik);   /* scan parked by mcl_scan_stage */
 int mcl_ns_weights_local(mcl_handle* h, float global_max_loglik, uint64_t* local_total_q32);
 int mcl_ns_resample_local(mcl_handle* h, uint64_t offset_q32, uint64_t total_q32, uint32_t u0, int64_t* k_lo, int64_t* k_hi);
 int mcl_ns_end_step(mcl_handle* h);                   /* after every shard finished resampling: swap buffers */

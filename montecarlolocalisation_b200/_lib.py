@@ -88,6 +88,7 @@ SYMBOLS = [
     ("mcl_profile_read", _i32, [_vp, _i32, _dp, C.POINTER(C.c_int64)]),
     ("mcl_ns_set_shard", _i32, [_vp, _i32, _i32, _i64]),
     ("mcl_ns_update_local", _i32, [_vp, _fp, _i32, _f, _f, _f, _f, _fp]),
+    ("mcl_ns_update_local_staged", _i32, [_vp, _i32, _fp]),
     ("mcl_ns_weights_local", _i32, [_vp, _f, C.POINTER(C.c_uint64)]),
     ("mcl_ns_resample_local", _i32, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_i64), C.POINTER(_i64)]),
     ("mcl_ns_end_step", _i32, [_vp]),

@@ -105,6 +105,7 @@ int mcl_ns_set_shard(mcl_handle* h, int32_t rank, int32_t world, int64_t ng) { G
 int mcl_ns_update_local(mcl_handle* h, const float* ranges, int32_t nb, float amin, float ainc, float rmin, float rmax, float* lm) {
     GUARD(h); TRY(h->engine.ns_update_local(ranges, nb, amin, ainc, rmin, rmax, lm))
 }
+int mcl_ns_update_local_staged(mcl_handle* h, int32_t slot, float* lm) { GUARD(h); TRY(h->engine.ns_update_local_staged(slot, lm)) }
 int mcl_ns_weights_local(mcl_handle* h, float gm, uint64_t* lt) { GUARD(h); TRY(h->engine.ns_weights_local(gm, lt)) }
 int mcl_ns_resample_local(mcl_handle* h, uint64_t off, uint64_t tot, uint32_t u0, int64_t* klo, int64_t* khi) { GUARD(h); TRY(h->engine.ns_resample_local(off, tot, u0, klo, khi)) }
 int mcl_ns_end_step(mcl_handle* h) { GUARD(h); TRY(h->engine.ns_end_step()) }

@@ -21,7 +21,7 @@ Engine::~Engine() {
     part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); d_lf.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
     for (int w = 0; w < 3; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]); ancestors.release(); d_occ.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
-    d_beams.release(); for (auto& sc : staged) sc.d_used.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
+    d_beams.release(); for (auto& sc : staged) sc.d_used.release(); for (auto& sc : ns_staged) sc.d_pts.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
     d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();
     if (h_pinned) cudaFreeHost(h_pinned);
     if (stream) cudaStreamDestroy(stream);
@@ -453,7 +453,7 @@ int Engine::stage_scan(int slot, const float* ranges, int n_beams, float angle_m
     CK(cudaSetDevice(cfg.device));
     if (slot < 0 || slot >= 4096) return fail(MCL_ERR_ARG, "stage_scan: slot out of range [0,4096)");
     if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "stage_scan: bad scan");
-    if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "stage_scan: NS mode not built in this library");
+    if (cfg.mode == MCL_MODE_NS) return ns_stage_scan(slot, ranges, n_beams, angle_min, angle_inc, range_min, range_max);
     if ((size_t)slot >= staged.size()) staged.resize(slot + 1);
     StagedScan& s = staged[slot];
     std::vector<RefBeam> used;
@@ -470,6 +470,17 @@ int Engine::update_staged(int slot, double* total) {
     CK(cudaSetDevice(cfg.device));
     if (!map_ready) return fail(MCL_ERR_ARG, "update: no map");
     if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
+    if (cfg.mode == MCL_MODE_NS) {
+        if (shard_world != 1) return fail(MCL_ERR_STATE, "update_staged: sharded NS filters use mcl_ns_update_local_staged");
+        float local_max = 0.f;
+        int rc = ns_update_local_staged(slot, &local_max);
+        if (rc) return rc;
+        uint64_t tot = 0;
+        rc = ns_weights_local(local_max, &tot);
+        if (rc) return rc;
+        if (total) *total = (double)tot * 2.3283064365386963e-10;
+        return MCL_OK;
+    }
     if (slot < 0 || (size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "update_staged: empty slot");
     return ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, total);
 }

@@ -57,6 +57,8 @@ public:
     // NS mode (north-star formulation); the *_local phases are what a multi-GPU driver sequences around its collectives
     int ns_set_shard(int rank, int world, int64_t n_global);
     int ns_update_local(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, float* local_max);
+    int ns_stage_scan(int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max);
+    int ns_update_local_staged(int slot, float* local_max);
     int ns_weights_local(float global_max, uint64_t* local_total);
     int ns_resample_local(uint64_t offset, uint64_t total, uint32_t u0, int64_t* k_lo, int64_t* k_hi);
     int ns_end_step();
@@ -163,6 +165,11 @@ private:
     int ns_build_field();
     int ns_init(int64_t count);
     int ns_predict(const Motion& clean);
+    void ns_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
+                          std::vector<float2>& pts) const;
+    int ns_run_update(const float2* d_pts, int n_pts, float* local_max);
+    struct NsStagedScan { DevBuf<float2> d_pts; int n = 0; bool valid = false; };
+    std::vector<NsStagedScan> ns_staged;
     DevBuf<float> d_lf, d_lf_table, d_ll;
     DevBuf<uint16_t> d_d2, d_g;
     DevBuf<float2> d_ns_beams;

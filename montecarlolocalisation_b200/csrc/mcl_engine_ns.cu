@@ -90,15 +90,10 @@ int Engine::ns_predict(const Motion& m) {
     return MCL_OK;
 }
 
-// Scan -> beam endpoints in the robot frame, then the likelihood-field kernel. Returns this shard's max.
-int Engine::ns_update_local(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
-                            float* local_max) {
-    CK(cudaSetDevice(cfg.device));
-    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_update_local: NS mode only");
-    if (!map_ready) return fail(MCL_ERR_ARG, "update: no map");
-    if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
-    if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "update: bad scan");
-    std::vector<float2> pts;
+// Scan -> beam endpoints in the robot frame.
+void Engine::ns_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
+                              std::vector<float2>& pts) const {
+    pts.clear();
     const int stride = std::max(1, cfg.ns_beam_stride);
     int kept = 0;
     for (int i = 0; i < n_beams; ++i) {
@@ -114,7 +109,15 @@ int Engine::ns_update_local(const float* ranges, int n_beams, float angle_min, f
         const double phi = -ang;                                        // the reference mirrors beam angles (MC:653)
         pts.push_back(make_float2((float)(cfg.laser_offset + r * std::cos(phi)), (float)(r * std::sin(phi))));
     }
-    ns_beams_n = (int)pts.size();
+}
+
+int Engine::ns_update_local(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
+                            float* local_max) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_update_local: NS mode only");
+    if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "update: bad scan");
+    std::vector<float2> pts;
+    ns_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, pts);
     CK(d_ns_beams.ensure(std::max<size_t>(1, pts.size())));
     if (!pts.empty()) {
         int rc = ensure_pinned(pts.size() * sizeof(float2));
@@ -122,6 +125,33 @@ int Engine::ns_update_local(const float* ranges, int n_beams, float angle_min, f
         memcpy(h_pinned, pts.data(), pts.size() * sizeof(float2));
         CK(cudaMemcpyAsync(d_ns_beams.p, h_pinned, pts.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
     }
+    return ns_run_update(d_ns_beams.p, (int)pts.size(), local_max);
+}
+
+int Engine::ns_stage_scan(int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max) {
+    if ((size_t)slot >= ns_staged.size()) ns_staged.resize(slot + 1);
+    std::vector<float2> pts;
+    ns_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, pts);
+    NsStagedScan& s = ns_staged[slot];
+    CK(s.d_pts.ensure(std::max<size_t>(1, pts.size())));
+    if (!pts.empty()) CK(cudaMemcpy(s.d_pts.p, pts.data(), pts.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    s.n = (int)pts.size();
+    s.valid = true;
+    return MCL_OK;
+}
+
+int Engine::ns_update_local_staged(int slot, float* local_max) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_update_local_staged: NS mode only");
+    if (slot < 0 || (size_t)slot >= ns_staged.size() || !ns_staged[slot].valid) return fail(MCL_ERR_ARG, "update_staged: empty slot");
+    return ns_run_update(ns_staged[slot].d_pts.p, ns_staged[slot].n, local_max);
+}
+
+// The likelihood-field kernel over this shard. Returns the shard's maximum log-likelihood.
+int Engine::ns_run_update(const float2* d_pts, int n_pts, float* local_max) {
+    if (!map_ready) return fail(MCL_ERR_ARG, "update: no map");
+    if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
+    ns_beams_n = n_pts;
     NsField F;
     F.lf = d_lf.p; F.W = map_w; F.H = map_h; F.ox = (float)origin_x; F.oy = (float)origin_y;
     F.inv_res = 1.0f / res_f; F.lf_out = lf_out; F.bytes_padded = (int)lf_bytes_padded;
@@ -142,11 +172,11 @@ int Engine::ns_update_local(const float* ranges, int n_beams, float angle_min, f
         const size_t smem = lf_bytes_padded + beam_bytes;
         const int ctas_per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
         const int grid = (int)std::min<int64_t>((int64_t)sms * ctas_per_sm, (batches + threads / 32 - 1) / (threads / 32));
-        LAUNCH(K_NS_UPDATE, k_ns_update<true>, std::max(1, grid), threads, smem, part[cur].p, n, F, d_ns_beams.p, ns_beams_n, d_ll.p, d_maxbits.p);
+        LAUNCH(K_NS_UPDATE, k_ns_update<true>, std::max(1, grid), threads, smem, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
     } else {
         if (beam_bytes > 64 * 1024) return fail(MCL_ERR_ARG, "update: too many beams");
         const int grid = (int)std::min<int64_t>((int64_t)sms * 4, (batches + threads / 32 - 1) / (threads / 32));
-        LAUNCH(K_NS_UPDATE, k_ns_update<false>, std::max(1, grid), threads, beam_bytes, part[cur].p, n, F, d_ns_beams.p, ns_beams_n, d_ll.p, d_maxbits.p);
+        LAUNCH(K_NS_UPDATE, k_ns_update<false>, std::max(1, grid), threads, beam_bytes, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
     }
     CK(cudaGetLastError());
     int bits = 0;

@@ -259,6 +259,11 @@ class NsShard:
                                                C.c_float(range_min), C.c_float(range_max), C.byref(mx)))
         return mx.value
 
+    def update_local_staged(self, slot):
+        mx = C.c_float()
+        self.pf._ck(self.L.mcl_ns_update_local_staged(self.h, slot, C.byref(mx)))
+        return mx.value
+
     def weights_local(self, global_max):
         t = C.c_uint64()
         self.pf._ck(self.L.mcl_ns_weights_local(self.h, C.c_float(global_max), C.byref(t)))
