@@ -220,6 +220,7 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU filter)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

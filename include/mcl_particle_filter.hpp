@@ -1,0 +1,121 @@
+// mcl_particle_filter.hpp — C++ host class over the C-ABI (include/mcl.h) for the ROS node in
+// pink_fundamentals/src/monte_carlo.cpp ("MC").
+//
+// The reference has no particle-filter class: the filter is a set of free functions over globals. This header gives
+// those functions one home, with the SAME names, argument meaning and call order, so that the swap inside
+// executeParticleFilter (MC:1084-1092) and main (MC:1198-1206) is line for line:
+//
+//     reference global / function                     ->  mcl::ParticleFilter member
+//     map_msg (mapCallback, MC:291-295)               ->  setMap(*msg)  / loadMapTxt(path)
+//     precomputeRayDirections(-120,120,0.1) MC:1199   ->  precomputeRayDirections(-120,120,0.1)
+//     particles = sampleParticles(N)        MC:1205   ->  sampleParticles(N)
+//     diffDriveModel(...) + updateParticlePos(...)    ->  diffDriveModel(encoderLeft, encoderRight)
+//     particles = resampleParticles(particles, lost)  ->  resampleParticles(latest_scan..., lost)   (computeWeight inside)
+//     estimateWeightedPose(particles)       MC:782    ->  estimateWeightedPose()
+//     particles (Eigen::MatrixXf 4xN)                 ->  downloadParticles(float*)  (same column-major 4xN layout)
+//
+// Header-only, no ROS or Eigen dependency; link with -lmcl_b200. Errors throw std::runtime_error on this side of the ABI.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mcl.h"
+
+namespace mcl {
+
+struct RobotPosition { double x, y, theta; };          // MC:106-110
+struct OdometryModel { double rot_1, trans, rot_2; };  // MC:112-116
+
+class ParticleFilter {
+public:
+    explicit ParticleFilter(int device = 0, int mode = MCL_MODE_REF) {
+        mcl_config_default(&cfg_);
+        cfg_.device = device;
+        cfg_.mode = mode;
+        open();
+    }
+    explicit ParticleFilter(const mcl_config& cfg) : cfg_(cfg) { open(); }
+    ~ParticleFilter() { mcl_destroy(h_); }
+    ParticleFilter(const ParticleFilter&) = delete;
+    ParticleFilter& operator=(const ParticleFilter&) = delete;
+
+    // ---- map ----
+    // occupancy: int8 row-major data[my*width+mx], occupied iff > 50 (MC:316-327); resolution is the float32 on the wire.
+    void setMap(const int8_t* data, int width, int height, float resolution, double origin_x = 0.0, double origin_y = 0.0) {
+        check(mcl_set_map(h_, data, width, height, resolution, origin_x, origin_y));
+    }
+    // Works with nav_msgs::OccupancyGrid without including ROS headers here.
+    template <class OccupancyGridMsg>
+    void setMap(const OccupancyGridMsg& msg) {
+        setMap(msg.data.data(), (int)msg.info.width, (int)msg.info.height, msg.info.resolution, msg.info.origin.position.x,
+               msg.info.origin.position.y);
+    }
+    void loadMapTxt(const std::string& path) { check(mcl_load_map_txt(h_, path.c_str())); }
+    void precomputeRayDirections(double min_angle_deg, double max_angle_deg, double step_deg) {
+        check(mcl_precompute_ray_directions(h_, min_angle_deg, max_angle_deg, step_deg));
+    }
+
+    // ---- particles ----
+    void sampleParticles(int num_particles) { check(mcl_init(h_, num_particles, nullptr)); }
+    int64_t cols() const { return mcl_num_particles(h_); }
+    // dst: 4*cols() floats, column-major 4xN {x,y,theta,w} = Eigen::Map<Eigen::MatrixXf>(dst, 4, cols())
+    void downloadParticles(float* dst) { check(mcl_download(h_, dst)); }
+    void uploadParticles(const float* src, int64_t n) { check(mcl_upload(h_, src, n)); }
+
+    // ---- predict: diffDriveModel + sampleMotionModelOdometry + updateParticlePos (MC:1084-1086) ----
+    OdometryModel diffDriveModel(double current_encoderLeft, double current_encoderRight) {
+        double m[3];
+        check(mcl_predict_encoders(h_, current_encoderLeft, current_encoderRight, nullptr, m));
+        return OdometryModel{m[0], m[1], m[2]};
+    }
+    void updateParticlePos(const OdometryModel& motionModel) { check(mcl_predict_motion(h_, motionModel.rot_1, motionModel.trans, motionModel.rot_2)); }
+
+    // ---- update + resample ----
+    // computeWeight(particles, real_scan) (MC:623-682): returns totalWeight
+    double computeWeight(const float* ranges, int n_beams, float angle_min, float angle_increment, float range_min, float range_max) {
+        double total = 0;
+        check(mcl_update(h_, ranges, n_beams, angle_min, angle_increment, range_min, range_max, &total));
+        return total;
+    }
+    template <class LaserScanMsg>
+    double computeWeight(const LaserScanMsg& s) {
+        return computeWeight(s.ranges.data(), (int)s.ranges.size(), s.angle_min, s.angle_increment, s.range_min, s.range_max);
+    }
+    // resampleParticles(particles, jitterState) (MC:457-561), computeWeight included like the reference; returns the
+    // injected-particle count the reference logs at MC:559.
+    template <class LaserScanMsg>
+    int resampleParticles(const LaserScanMsg& latest_scan, bool jitterState) {
+        computeWeight(latest_scan);
+        mcl_resample_stats st;
+        check(mcl_resample(h_, jitterState ? 1 : 0, nullptr, &st));
+        last_stats_ = st;
+        return st.injected;
+    }
+    const mcl_resample_stats& lastResampleStats() const { return last_stats_; }
+
+    // ---- estimate ----
+    RobotPosition estimateWeightedPose() {
+        RobotPosition p;
+        check(mcl_estimate(h_, &p.x, &p.y, &p.theta));
+        return p;
+    }
+
+    mcl_handle* handle() { return h_; }
+    const mcl_config& config() const { return cfg_; }
+
+private:
+    void open() {
+        int rc = mcl_create(&cfg_, &h_);
+        if (rc) throw std::runtime_error(std::string("mcl_create: ") + mcl_last_error(nullptr));
+    }
+    void check(int rc) {
+        if (rc) throw std::runtime_error(std::string("mcl: ") + mcl_last_error(h_));
+    }
+    mcl_config cfg_;
+    mcl_handle* h_ = nullptr;
+    mcl_resample_stats last_stats_{};
+};
+
+}  // namespace mcl

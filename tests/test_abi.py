@@ -56,3 +56,18 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(m.MclError) as e:
         m.ParticleFilter()
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_cxx_host_class_compiles_and_links(tmp_path):
+    """include/mcl_particle_filter.hpp (the class the ROS node would use) builds against the library; without a GPU its
+    constructor throws instead of silently computing on the CPU."""
+    import subprocess
+    exe = str(tmp_path / "cxx_binding_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "native", "cxx_binding_check.cpp"),
+                    "-L" + libdir, "-lmcl_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if os.path.exists("/dev/nvidia0"):
+        assert r.returncode == 0 and "gpu ok" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
