@@ -206,6 +206,9 @@ int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitt
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back);
 /* Use the single-chain sequential accumulation kernels instead of the parallel exact scan (cross-check; slow). */
 int mcl_debug_force_sequential(mcl_handle* h, int32_t on);
+/* Random 4-byte gather micro-benchmark: the roofline denominator of the sensor-model kernel.
+ * tier 0 = table in shared memory (<= 200 KiB), tier 1 = table in global memory (L2- or HBM-resident by its size). */
+int mcl_bench_gather(mcl_handle* h, int32_t tier, int64_t table_bytes, int32_t iters, double* reads_per_s);
 /* Per-kernel CUDA-event timing on the handle's stream; off by default (it serialises launches). */
 int mcl_profile_enable(mcl_handle* h, int32_t on);
 int mcl_profile_kernel_count(void);

@@ -314,6 +314,29 @@ __global__ void __launch_bounds__(256) k_ns_resample(const float4* __restrict__ 
     D.anc[r][slot] = (int)(g0 + lo);
 }
 
+// ---- gather micro-benchmark: the denominator for the sensor-model kernel ------------------------------------------------
+// Independent random 4-byte reads from a table held in shared memory (SMEM) or in global memory (L2- or HBM-resident,
+// depending on its size), issued with the thread/block shape of k_ns_update. Reports nothing itself: the host times it.
+template <bool SMEM>
+__global__ void __launch_bounds__(512) k_gather_bench(const float* __restrict__ table, uint32_t n_words, int iters, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_t = reinterpret_cast<float*>(smem_raw);
+    if (SMEM) {
+        for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) s_t[i] = table[i];
+        __syncthreads();
+    }
+    const float* t = SMEM ? s_t : table;
+    uint32_t state = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int it = 0; it < iters; it++) {
+        state = state * 1664525u + 1013904223u;
+        const uint32_t idx = __umulhi(state, n_words);
+        acc += SMEM ? t[idx] : __ldg(t + idx);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 // Weighted pose sums with the particle weights as they stand: {sum w, sum w x, sum w y, sum w sin, sum w cos} per block.
 __global__ void __launch_bounds__(256) k_ns_pose_partials(const float4* __restrict__ part, int64_t n, double* __restrict__ partials) {
     __shared__ double ws[8][5];

@@ -67,6 +67,7 @@ public:
     int ns_download_field(float* lf, uint16_t* d2);
     int ns_download_loglik(float* ll);
     int ns_download_prefix(uint64_t* prefix);
+    int gather_bench(int tier, size_t table_bytes, int iters, double* reads_per_s);
     int peer_export(int which, void* out64);
     int peer_import(int rank, int which, const void* in64);
     int peer_set(int rank, int which, void* devptr);

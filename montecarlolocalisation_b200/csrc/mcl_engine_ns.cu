@@ -285,6 +285,46 @@ int Engine::ns_download_prefix(uint64_t* prefix) {
     return MCL_OK;
 }
 
+// Random-gather micro-benchmark: reads/s for a table of `table_bytes` in shared memory (tier 0) or global
+// memory (tier 1: whatever level of the hierarchy a table of that size lives in).
+int Engine::gather_bench(int tier, size_t table_bytes, int iters, double* reads_per_s) {
+    CK(cudaSetDevice(cfg.device));
+    if (!reads_per_s || table_bytes < 64 || iters < 1) return fail(MCL_ERR_ARG, "gather_bench: bad argument");
+    if (tier == 0 && table_bytes > 200 * 1024) return fail(MCL_ERR_ARG, "gather_bench: shared-memory tier is limited to 200 KiB");
+    const uint32_t n_words = (uint32_t)(table_bytes / 4);
+    DevBuf<float> table, out;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    const int threads = 512;
+    const int ctas_per_sm = tier == 0 ? std::max(1, std::min(4, (int)((220 * 1024) / (table_bytes + 1024)))) : 4;
+    const int grid = sms * ctas_per_sm;
+    CK(table.ensure(n_words)); CK(out.ensure((size_t)grid * threads));
+    CK(cudaMemsetAsync(table.p, 0, (size_t)n_words * 4, stream));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(a, stream));
+        if (tier == 0) {
+            CK(cudaFuncSetAttribute(k_gather_bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_gather_bench<true><<<grid, threads, table_bytes, stream>>>(table.p, n_words, iters, out.p);
+        } else {
+            k_gather_bench<false><<<grid, threads, 0, stream>>>(table.p, n_words, iters, out.p);
+        }
+        ++launches;
+        CK(cudaEventRecord(b, stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    CK(cudaGetLastError());
+    *reads_per_s = (double)grid * threads * iters / (best * 1e-3);
+    table.release(); out.release();
+    return MCL_OK;
+}
+
 // ---- peer memory: every shard's two particle buffers and its ancestor buffer are visible to the others -------------------
 void* Engine::device_buffer(int which) {
     if (which == 0 || which == 1) return part[which].p;

@@ -218,6 +218,12 @@ class ParticleFilter:
     def forceSequential(self, on):
         self._ck(self.L.mcl_debug_force_sequential(self.h, int(bool(on))))
 
+    def benchGather(self, tier, table_bytes, iters=256):
+        """Random 4-byte gathers per second from a table in shared memory (tier 0) or global memory (tier 1)."""
+        out = C.c_double()
+        self._ck(self.L.mcl_bench_gather(self.h, tier, table_bytes, iters, C.byref(out)))
+        return out.value
+
     def profileEnable(self, on):
         self._ck(self.L.mcl_profile_enable(self.h, int(bool(on))))
 
