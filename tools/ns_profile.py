@@ -1,7 +1,8 @@
 """Run one NS case for a few steps (for ncu / quick timing): python tools/ns_profile.py <cells> <particles> <beams> <uniform 0|1> [steps]"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from bench import ns_workload
 from montecarlolocalisation_b200 import NsShard
