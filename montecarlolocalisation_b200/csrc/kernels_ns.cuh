@@ -139,11 +139,30 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, uint
     }
 }
 
-// One warp scores 32 particles at a time: lane l owns particle l's pose and trig; for each particle in turn the pose is
-// broadcast with shuffles and the 32 lanes take beams l, l+32, ...; per-lane partial sums are combined by a fixed
-// xor-butterfly, so the fp32 result is order-defined.
+// One warp scores 32 particles at a time. Lane l owns particle l's pose: it computes sin/cos and the particle position
+// in CELL units (origin and resolution folded in once per particle, and -0.5 so that round-to-nearest gives the cell).
+// Particles are then taken four at a time: their poses are broadcast by shuffle and the 32 lanes take beams l, l+32, ...
+// (beam points are pre-scaled to cell units on the host), so one shared-memory beam load feeds four evaluations.
+// Cell index = round-to-nearest-even via the 1.5*2^23 magic add (FMA pipe) instead of F2I (XU pipe).
+// Per-lane partial sums of the 32 particles are combined by a transpose-reduction: 31 shuffles per 32 particles, and
+// for every particle exactly the xor-butterfly (16,8,4,2,1) summation tree that DESIGN.md NS-3 specifies.
+constexpr float NS_MAGIC = 12582912.0f;          // 1.5 * 2^23
+constexpr int NS_MAGIC_BITS = 0x4B400000;
+
+__device__ __forceinline__ float ns_eval(const float* __restrict__ lf, float gx0, float gy0, float c, float s, float2 bm, unsigned W, unsigned H,
+                                         float lf_out, bool smem) {
+    const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
+    const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
+    const unsigned ix = (unsigned)(__float_as_int(tx) - NS_MAGIC_BITS);
+    const unsigned iy = (unsigned)(__float_as_int(ty) - NS_MAGIC_BITS);
+    const bool in = ix < W && iy < H;
+    const unsigned idx = in ? iy * W + ix : 0u;
+    const float v = smem ? lf[idx] : __ldg(lf + idx);
+    return in ? v : lf_out;
+}
+
 template <bool SMEM_FIELD>
-__global__ void __launch_bounds__(512) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
+__global__ void __launch_bounds__(512, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
                                                    const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
                                                    int* __restrict__ max_bits /* ordered-int max of ll */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -155,6 +174,8 @@ __global__ void __launch_bounds__(512) k_ns_update(const float4* __restrict__ pa
     for (int b = threadIdx.x; b < n_beams; b += blockDim.x) s_beams[b] = beams[b];
     __syncthreads();
     const float* lf = SMEM_FIELD ? s_lf : F.lf;
+    const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
+    const float lf_out = F.lf_out, ox = F.ox, oy = F.oy, inv_res = F.inv_res;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const int64_t n_batches = (n + 31) / 32;
     float best = -3.0e38f;
@@ -164,28 +185,39 @@ __global__ void __launch_bounds__(512) k_ns_update(const float4* __restrict__ pa
         if (i < n) p = part[i];
         float s, c;
         ns::det_sincosf(p.z, s, c);
-        float mine = 0.f;
-        const int count = (int)min((int64_t)32, n - batch * 32);
-        for (int k = 0; k < count; k++) {
-            const float x = __shfl_sync(0xffffffffu, p.x, k), y = __shfl_sync(0xffffffffu, p.y, k);
-            const float ck = __shfl_sync(0xffffffffu, c, k), sk = __shfl_sync(0xffffffffu, s, k);
-            float acc = 0.f;
+        const float gx0 = ns::fmaf_(ns::addf(p.x, -ox), inv_res, -0.5f);
+        const float gy0 = ns::fmaf_(ns::addf(p.y, -oy), inv_res, -0.5f);
+        float acc[32];
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            float X[4], Y[4], C[4], S[4], a[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                X[q] = __shfl_sync(0xffffffffu, gx0, k0 + q); Y[q] = __shfl_sync(0xffffffffu, gy0, k0 + q);
+                C[q] = __shfl_sync(0xffffffffu, c, k0 + q); S[q] = __shfl_sync(0xffffffffu, s, k0 + q);
+                a[q] = 0.f;
+            }
+#pragma unroll 2
             for (int b = lane; b < n_beams; b += 32) {
                 const float2 bm = s_beams[b];
-                const float ex = ns::fmaf_(ck, bm.x, ns::fmaf_(-sk, bm.y, x));
-                const float ey = ns::fmaf_(sk, bm.x, ns::fmaf_(ck, bm.y, y));
-                const int ix = __float2int_rd(ns::mulf(ns::addf(ex, -F.ox), F.inv_res));
-                const int iy = __float2int_rd(ns::mulf(ns::addf(ey, -F.oy), F.inv_res));
-                const bool in = (unsigned)ix < (unsigned)F.W && (unsigned)iy < (unsigned)F.H;
-                const int idx = in ? iy * F.W + ix : 0;
-                const float v = SMEM_FIELD ? lf[idx] : __ldg(lf + idx);
-                acc = ns::addf(acc, in ? v : F.lf_out);
+#pragma unroll
+                for (int q = 0; q < 4; q++) a[q] = ns::addf(a[q], ns_eval(lf, X[q], Y[q], C[q], S[q], bm, W, H, lf_out, SMEM_FIELD));
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc = ns::addf(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if (lane == k) mine = acc;
+            for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
         }
-        if (i < n) { ll_out[i] = mine; best = fmaxf(best, mine); }
+        // transpose-reduction: after the stage with offset o, lanes with bit o set hold the upper half of the particles
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; j++) {
+                const float keep = up ? acc[j + o] : acc[j];
+                const float send = up ? acc[j] : acc[j + o];
+                acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            }
+        }
+        if (i < n) { ll_out[i] = acc[0]; best = fmaxf(best, acc[0]); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));

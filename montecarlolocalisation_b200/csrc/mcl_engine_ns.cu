@@ -107,7 +107,8 @@ void Engine::ns_prepare_beams(const float* ranges, int n_beams, float angle_min,
         }
         if ((kept++ % stride) != 0) continue;
         const double phi = -ang;                                        // the reference mirrors beam angles (MC:653)
-        pts.push_back(make_float2((float)(cfg.laser_offset + r * std::cos(phi)), (float)(r * std::sin(phi))));
+        const double inv_res = 1.0 / (double)res_f;                     // beam points in CELL units
+        pts.push_back(make_float2((float)((cfg.laser_offset + r * std::cos(phi)) * inv_res), (float)((r * std::sin(phi)) * inv_res)));
     }
 }
 
@@ -168,14 +169,18 @@ int Engine::ns_run_update(const float2* d_pts, int n_pts, float* local_max) {
     }
     const int threads = 512;
     const int64_t batches = (n + 31) / 32;
+    const int64_t ctas_needed = (batches + threads / 32 - 1) / (threads / 32);
     if (in_smem) {
         const size_t smem = lf_bytes_padded + beam_bytes;
-        const int ctas_per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
-        const int grid = (int)std::min<int64_t>((int64_t)sms * ctas_per_sm, (batches + threads / 32 - 1) / (threads / 32));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_update<true>, threads, smem));
+        const int grid = (int)std::min<int64_t>((int64_t)sms * std::max(1, occ), ctas_needed);     // persistent: resident CTAs only
         LAUNCH(K_NS_UPDATE, k_ns_update<true>, std::max(1, grid), threads, smem, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
     } else {
         if (beam_bytes > 64 * 1024) return fail(MCL_ERR_ARG, "update: too many beams");
-        const int grid = (int)std::min<int64_t>((int64_t)sms * 4, (batches + threads / 32 - 1) / (threads / 32));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_update<false>, threads, beam_bytes));
+        const int grid = (int)std::min<int64_t>((int64_t)sms * std::max(1, occ), ctas_needed);
         LAUNCH(K_NS_UPDATE, k_ns_update<false>, std::max(1, grid), threads, beam_bytes, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
     }
     CK(cudaGetLastError());

@@ -213,13 +213,16 @@ int ons_beams(void* h, const float* ranges, int B, float angle_min, float angle_
         double ang = (double)angle_min + ((size_t)i * (double)angle_inc);
         if ((kept++ % std::max(1, c.beam_stride)) != 0) continue;
         double phi = -ang;
-        if (out < cap) { pts[2 * out] = (float)(c.laser_offset + r * std::cos(phi)); pts[2 * out + 1] = (float)(r * std::sin(phi)); }
+        double inv_res = 1.0 / (double)c.res;           // beam points in CELL units
+        if (out < cap) { pts[2 * out] = (float)((c.laser_offset + r * std::cos(phi)) * inv_res); pts[2 * out + 1] = (float)((r * std::sin(phi)) * inv_res); }
         out++;
     }
     return out;
 }
 
-// NS-3: per-particle log-likelihood = 32 lane-strided fp32 partial sums combined by an xor butterfly (16,8,4,2,1)
+// NS-3: particle position in cell units, g0 = fma(x - ox, 1/res, -0.5); endpoint g = fma(c,bx, fma(-s,by, g0)); cell =
+// round-to-nearest-even(g) (so the -0.5 makes it the containing cell); per-particle log-likelihood = 32 lane-strided
+// fp32 partial sums combined by an xor butterfly (16,8,4,2,1)
 void ons_loglik(void* h, const float* P, int64_t n, const float* pts, int nb, float* ll) {
     NsCtx& c = *(NsCtx*)h;
     float oxf = (float)c.ox, oyf = (float)c.oy, inv_res = 1.0f / c.res;
@@ -228,17 +231,19 @@ void ons_loglik(void* h, const float* P, int64_t n, const float* pts, int nb, fl
         double sd, cd;
         det_sincos((double)p[2], sd, cd);
         float s = (float)sd, cs = (float)cd;
+        float gx0 = fmaf(p[0] + -oxf, inv_res, -0.5f), gy0 = fmaf(p[1] + -oyf, inv_res, -0.5f);
         float lane[32];
         for (int l = 0; l < 32; l++) {
             float acc = 0.f;
             for (int b = l; b < nb; b += 32) {
                 float bx = pts[2 * b], by = pts[2 * b + 1];
-                float ex = fmaf(cs, bx, fmaf(-s, by, p[0]));
-                float ey = fmaf(s, bx, fmaf(cs, by, p[1]));
-                float gx = (ex + -oxf) * inv_res, gy = (ey + -oyf) * inv_res;
-                float fx = floorf(gx), fy = floorf(gy);
+                float gx = fmaf(cs, bx, fmaf(-s, by, gx0));
+                float gy = fmaf(s, bx, fmaf(cs, by, gy0));
                 float v = c.lf_out;
-                if (fx >= 0.f && fy >= 0.f && fx < (float)c.W && fy < (float)c.H) v = c.lf[(size_t)(int)fy * c.W + (int)fx];
+                if (fabsf(gx) < 4194304.f && fabsf(gy) < 4194304.f) {         // |g| < 2^22: lrintf is the magic-add result
+                    long ix = lrintf(gx), iy = lrintf(gy);                     // ties to even (default rounding mode)
+                    if (ix >= 0 && iy >= 0 && ix < c.W && iy < c.H) v = c.lf[(size_t)iy * c.W + ix];
+                }
                 acc = acc + v;
             }
             lane[l] = acc;
