@@ -34,7 +34,7 @@ UNIT = "evals/s"
 
 # algorithmic bytes per particle per launch (SURVEY.md §8d / DESIGN.md "kernels"); update adds 1 B per map probe
 ALGO_BYTES = {
-    "k_ref_predict": 32, "k_ref_update": 20, "k_ref_first_touch": 16, "k_ref_seq_total": 4, "k_ref_seq_cdf": 16,
+    "k_ref_predict": 32, "k_ref_update": 20, "k_ref_update_v2": 20, "k_ref_first_touch": 16, "k_ref_seq_total": 4, "k_ref_seq_cdf": 16,
     "k_ref_resample": 44 + 32, "k_fill_resample_draws": 32, "k_pose_wsum": 16, "k_pose_sums": 16,
     "k_ref_exact_scan": 12, "k_ref_normalise": 8,
 }
@@ -319,7 +319,7 @@ def ours(args):
         algo = None
         if b is not None:
             algo = n * b
-            if name == "k_ref_update":
+            if name in ("k_ref_update", "k_ref_update_v2"):
                 algo += n * 12 * 11        # <= 11 one-byte map probes per scored beam
         kernels[name] = {"ms_per_launch": per_launch_ms, "launches": cnt, "share": ms / total_kernel_ms,
                          "algo_bytes": algo, "gbs": (algo / (per_launch_ms * 1e-3) / 1e9) if algo else None}

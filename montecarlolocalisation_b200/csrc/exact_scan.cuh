@@ -259,49 +259,87 @@ __global__ void __launch_bounds__(XS_THREADS) k_xs_scan(const float* __restrict_
     if (bad || !okflag) atomicOr(ws.flag, 1);
 }
 
-// ---- pass 4: the sequential part ----------------------------------------------------------------------------------------
-// One thread walks the tiles in order (carry composites, SEQ elements through the hardware adder, grand total); the rest
-// of the block only stages tile summaries through shared memory so that walk never waits on HBM.
-constexpr int XS_CHAIN_CHUNK = 1024;
-__global__ void __launch_bounds__(256) k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out) {
-    __shared__ TileSummary sm_ts[XS_CHAIN_CHUNK];
-    __shared__ Par sm_carry[XS_CHAIN_CHUNK];
-    __shared__ int sm_base[XS_CHAIN_CHUNK];
+// ---- pass 4: carries across tiles (parallel), then the SEQ elements one by one (sequential) ---------------------------------
+// The composite carried into tile t is a segmented scan of the tile summaries under the parity monoid (a tile with SEQ
+// elements restarts the composite), done by one block with warp shuffles. Only the few SEQ elements and the binade runs
+// between them need the hardware adder in order; one thread walks those.
+constexpr int XS_CHAIN_THREADS = 512;
+constexpr int XS_CHAIN_LIST = 2048;
+__global__ void __launch_bounds__(XS_CHAIN_THREADS) k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out) {
+    __shared__ ScanState sm_warp[XS_CHAIN_THREADS / 32];
+    __shared__ ScanState sm_carry_in;          // running state entering the current chunk of tiles
+    __shared__ int sm_fail;
+    __shared__ int sm_list[XS_CHAIN_LIST];     // tiles that contain SEQ elements, in order
+    __shared__ int sm_list_n;
+    __shared__ int sm_wcount[XS_CHAIN_THREADS / 32];
     if (*ws.flag) return;                      // uniform: every thread reads the same word
-    Par carry = par_identity();
-    int base = 0;
-    double s = 0.0;
-    bool ok = true;
-    for (int c0 = 0; c0 < nt; c0 += XS_CHAIN_CHUNK) {
-        const int cnt = min(XS_CHAIN_CHUNK, nt - c0);
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) sm_ts[i] = ws.tiles[c0 + i];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0; sm_fail = 0; sm_list_n = 0; }
+    __syncthreads();
+    for (int c0 = 0; c0 < nt; c0 += XS_CHAIN_THREADS) {
+        const int t = c0 + tid;
+        ScanState mine;
+        mine.v = par_identity(); mine.reset = 0; mine.cnt = 0;
+        if (t < nt) {
+            const TileSummary ts = ws.tiles[t];
+            mine.v = ts.vlast; mine.reset = ts.seq_count ? 1 : 0; mine.cnt = ts.seq_count;
+            if (ts.seq_count > XS_SEQ_CAP) sm_fail = 1;
+        }
+        ScanState inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            ScanState up = st_shfl_up(inc, o);
+            if (lane >= o) inc = st_combine(up, inc);
+        }
+        // ordered compaction of the tiles that hold SEQ elements
+        const unsigned has = __ballot_sync(0xffffffffu, mine.cnt > 0);
+        if (lane == 31) sm_warp[warp] = inc;
+        if (lane == 0) sm_wcount[warp] = __popc(has);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < cnt; i++) {
-                sm_carry[i] = carry;
-                sm_base[i] = base;
-                const TileSummary ts = sm_ts[i];
-                if (ts.seq_count > XS_SEQ_CAP) { ok = false; continue; }
-                for (int k = 0; k < ts.seq_count; k++) {
-                    const SeqEntry e = ws.entries[(size_t)(c0 + i) * XS_SEQ_CAP + k];
-                    const Par comp = e.first_in_tile ? par_compose(carry, e.pre) : e.pre;
-                    s = par_apply(s, comp, e.E_prev, ok);
-                    s = dadd(s, (double)e.w);            // the hardware adder: exactly the reference's rounding
-                    ws.seq_s[base + k] = s;
-                }
-                carry = ts.seq_count ? ts.vlast : par_compose(carry, ts.vlast);
-                base += ts.seq_count;
-            }
+        {
+            int pos = sm_list_n;
+            for (int k = 0; k < warp; k++) pos += sm_wcount[k];
+            pos += __popc(has & ((1u << lane) - 1u));
+            if (mine.cnt > 0) { if (pos < XS_CHAIN_LIST) sm_list[pos] = t; else sm_fail = 1; }
+        }
+        ScanState pre = sm_carry_in;
+        for (int k = 0; k < warp; k++) pre = st_combine(pre, sm_warp[k]);
+        ScanState lane_excl = st_shfl_up(inc, 1);
+        if (lane > 0) pre = st_combine(pre, lane_excl);          // state entering tile t
+        if (t < nt) { ws.carry[t] = pre.v; ws.seq_base[t] = pre.cnt; }
+        __syncthreads();
+        if (tid == XS_CHAIN_THREADS - 1) {
+            sm_carry_in = st_combine(pre, mine);      // state leaving the chunk
+            int add = 0;
+            for (int k = 0; k < XS_CHAIN_THREADS / 32; k++) add += sm_wcount[k];
+            sm_list_n += add;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) { ws.carry[c0 + i] = sm_carry[i]; ws.seq_base[c0 + i] = sm_base[i]; }
-        __syncthreads();
     }
-    if (threadIdx.x != 0) return;
-    ws.carry[nt] = carry;
-    ws.seq_base[nt] = base;
-    // the run after the last SEQ element: its binade is that of P~_{n-1} = toff[nt]
-    if (ok) s = par_apply(s, carry, f64_exponent(ws.toff[nt]), ok);
+    if (tid != 0) return;
+    const ScanState fin = sm_carry_in;
+    ws.carry[nt] = fin.v;
+    ws.seq_base[nt] = fin.cnt;
+    bool ok = sm_fail == 0;
+    double s = 0.0;
+    if (ok) {
+        const int n_list = min(sm_list_n, XS_CHAIN_LIST);
+        for (int li = 0; li < n_list; li++) {
+            const int t = sm_list[li];
+            const int cnt = ws.tiles[t].seq_count;
+            const Par carry = ws.carry[t];
+            const int base = ws.seq_base[t];
+            for (int k = 0; k < cnt; k++) {
+                const SeqEntry e = ws.entries[(size_t)t * XS_SEQ_CAP + k];
+                const Par comp = e.first_in_tile ? par_compose(carry, e.pre) : e.pre;
+                s = par_apply(s, comp, e.E_prev, ok);
+                s = dadd(s, (double)e.w);            // the hardware adder: exactly the reference's rounding
+                ws.seq_s[base + k] = s;
+            }
+        }
+        // the run after the last SEQ element: its binade is that of P~_{n-1} = toff[nt]
+        if (ok) s = par_apply(s, fin.v, f64_exponent(ws.toff[nt]), ok);
+    }
     if (!ok) { atomicOr(ws.flag, 1); return; }
     if (total_out) *total_out = s;
 }

@@ -189,6 +189,166 @@ __global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, f
     w_dense[j] = wf;
 }
 
+// ---- computeWeight, restructured: a block takes 256 particles; rays, not particles, are the unit of parallel work -----------
+// The one-thread-per-particle kernel above is issue-bound with only ~70 % of lanes active: invalid particles idle for the
+// whole ray march and ray lengths vary between lanes. Here:
+//   phase A (thread = particle)   validity stencil (3+3 cell lookups instead of 18), laser origin, yaw; valid particles are
+//                                 compacted into shared memory
+//   phase B (thread = ray)        the (valid particle, beam) pairs are spread evenly over the block; each marches its ray
+//                                 and leaves w_hit*gauss in shared memory
+//   phase C (thread = particle)   the per-beam terms are added in the reference's order (f64, left to right) -> weight
+// Cell lookups avoid both the IEEE division and the XU-pipe conversions: q = a*(1/res) is rounded with the 2^52+2^51 magic
+// add, accepted when it is farther than 1e-6 from an integer (|q - a/res| <= 3.4e-16*q), and resolved by the exact
+// division only otherwise. Results are bit-identical to the kernel above (and to the CPU).
+constexpr int RU_TILE = 256;
+constexpr double RU_MAGIC = 6755399441055744.0;       // 2^52 + 2^51
+
+// Cell along one axis: 0 = inside (cell set), 1 = outside the grid.
+__device__ __forceinline__ int cell_axis(double w, double o, double res, double inv_res, double hi_lim, int W, int& cell) {
+    const double a = dsub(w, o);
+    const double q = dmul(a, inv_res);
+    if (q > 1e-6 && q < hi_lim) {
+        const double t = dadd(q, RU_MAGIC);
+        const double d = dsub(q, dsub(t, RU_MAGIC));
+        if (fabs(d) > 1e-6) {
+            const int nn = __double2loint(t) - (d < 0.0 ? 1 : 0);
+            cell = nn;
+            return nn < W ? 0 : 1;
+        }
+    } else if (q >= hi_lim) {
+        return 1;
+    }
+    const int nn = trunc_x86(ddiv(a, res));            // rare: near a cell edge, at or below the low edge, NaN
+    cell = nn;
+    return (nn >= 0 && nn < W) ? 0 : 1;
+}
+
+struct RuSmem {
+    double2* lut;
+    RefBeam* beams;
+    double* radii;
+    double* posx;
+    double* posy;
+    double* yawd;
+    double* terms;
+    int* vlist;
+    uint8_t* occ;
+};
+__host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes) {
+    return (size_t)n_keys * 16 + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
+           RU_TILE * 4 + ((map_bytes + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
+                                                           uint32_t div_magic /* ceil(2^32 / n_beams) */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int warp_cnt[RU_TILE / 32];
+    RuSmem S;
+    S.lut = reinterpret_cast<double2*>(smem_raw);
+    S.beams = reinterpret_cast<RefBeam*>(S.lut + P.n_keys);
+    S.radii = reinterpret_cast<double*>(S.beams + P.n_beams);
+    S.posx = S.radii + P.n_radii;
+    S.posy = S.posx + RU_TILE;
+    S.yawd = S.posy + RU_TILE;
+    S.terms = S.yawd + RU_TILE;
+    S.vlist = reinterpret_cast<int*>(S.terms + (size_t)RU_TILE * (P.n_beams + 1));
+    S.occ = reinterpret_cast<uint8_t*>(S.vlist + RU_TILE);
+    for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) S.lut[i] = P.lut[i];
+    for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = P.beams[i];
+    for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii[i] = P.radii[i];
+    if (P.map_in_smem) {
+        const int cells = P.width * P.height;
+        for (int i = threadIdx.x; i < cells; i += RU_TILE) S.occ[i] = P.occ[i];
+    }
+    __syncthreads();
+    const uint8_t* occ = P.map_in_smem ? S.occ : P.occ;
+    // constants in registers
+    const double res = P.res, inv_res = P.inv_res, ox = P.ox, oy = P.oy;
+    const int W = P.width, H = P.height;
+    const double hx = (double)W + 0.5, hy = (double)H + 0.5;
+    const int nb = P.n_beams, nr = P.n_radii, stride = nb + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (n + RU_TILE - 1) / RU_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- phase A -------------------------------------------------------------------------------------------------
+        const int64_t j = tile * RU_TILE + threadIdx.x;
+        bool valid = false;
+        double posx = 0, posy = 0, yawd = 0;
+        if (j < n) {
+            const float4 p = part[j];
+            const double x = (double)p.x, y = (double)p.y;
+            if ((x >= ox && x < P.max_x) && (y >= oy && y < P.max_y)) {                  // isInsideMap, MC:685-692
+                const double o = P.validity_offset;
+                int cx[3], cy[3], sx[3], sy[3];
+                sx[0] = cell_axis(dadd(x, -o), ox, res, inv_res, hx, W, cx[0]);
+                sx[1] = cell_axis(x, ox, res, inv_res, hx, W, cx[1]);
+                sx[2] = cell_axis(dadd(x, o), ox, res, inv_res, hx, W, cx[2]);
+                sy[0] = cell_axis(dadd(y, -o), oy, res, inv_res, hy, H, cy[0]);
+                sy[1] = cell_axis(y, oy, res, inv_res, hy, H, cy[1]);
+                sy[2] = cell_axis(dadd(y, o), oy, res, inv_res, hy, H, cy[2]);
+                bool hit = false;                                                        // any of the 9 stencil points occupied
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int b = 0; b < 3; b++)
+                        if (sx[a] == 0 && sy[b] == 0 && occ[cy[b] * W + cx[a]]) hit = true;
+                valid = !hit;
+            }
+            if (valid) {
+                double sn, cs;
+                sincos((double)p.z, &sn, &cs);
+                posx = dadd(x, dmul(P.laser_offset, (double)__double2float_rn(cs)));        // MC:644 (correctly rounded cosf)
+                posy = dadd(y, dmul(P.laser_offset, (double)__double2float_rn(sn)));        // MC:645
+                yawd = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);            // MC:351-352
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int slot = __popc(bal & ((1u << lane) - 1u)), nv = 0;
+        for (int w = 0; w < RU_TILE / 32; w++) { if (w < warp) slot += warp_cnt[w]; nv += warp_cnt[w]; }
+        if (valid) { S.vlist[slot] = threadIdx.x; S.posx[slot] = posx; S.posy[slot] = posy; S.yawd[slot] = yawd; }
+        __syncthreads();
+        // ---- phase B -------------------------------------------------------------------------------------------------
+        const int n_rays = nv * nb;
+        for (int r = threadIdx.x; r < n_rays; r += RU_TILE) {
+            const int v = (int)__umulhi((unsigned)r, div_magic);
+            const int b = r - v * nb;
+            const RefBeam bm = S.beams[b];
+            const double px = S.posx[v], py = S.posy[v];
+            const int k = ref_key_index(P, S.yawd[v], bm.off_deg);
+            const double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
+            double expected = P.max_range;                                               // MC:389
+            for (int s = 0; s < nr; s++) {                                               // MC:372
+                const double rr = S.radii[s];
+                int mx, my;
+                const int ex = cell_axis(dadd(px, dmul(rr, dir.x)), ox, res, inv_res, hx, W, mx);
+                const int ey = cell_axis(dadd(py, dmul(rr, dir.y)), oy, res, inv_res, hy, H, my);
+                if (ex | ey) break;                                                      // MC:376
+                if (occ[my * W + mx]) { expected = rr; break; }                          // MC:377-381
+            }
+            const double diff = fabs(dsub(bm.obs, expected));                            // MC:662
+            S.terms[v * stride + b] = dmul(P.w_hit, ref_gauss(P, diff));                 // MC:665
+        }
+        __syncthreads();
+        // ---- phase C -------------------------------------------------------------------------------------------------
+        if (j < n && !valid) { part[j].w = 0.f; w_dense[j] = 0.f; }
+        if ((int)threadIdx.x < nv) {
+            double prob = 0.0;
+            const double* t = S.terms + threadIdx.x * stride;
+            for (int b = 0; b < nb; b++) {
+                prob = dadd(prob, t[b]);                                                 // MC:665
+                prob = dadd(prob, S.beams[b].rand_term);                                 // MC:669
+            }
+            const float wf = __double2float_rn(prob);                                    // MC:673
+            const int64_t jj = tile * RU_TILE + S.vlist[threadIdx.x];
+            part[jj].w = wf;
+            w_dense[jj] = wf;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- sequential f64 accumulations (MC:675 and MC:496-505) --------------------------------------------------
 // The reference sums fp32 weights into an f64 total one by one, and builds the CDF the same way. fp addition is
 // not associative, so bit-identical results need the same roundings. The fast path is the parallel exact scan

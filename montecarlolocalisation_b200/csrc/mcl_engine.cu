@@ -28,7 +28,7 @@ Engine::~Engine() {
 }
 
 const char* Engine::kernel_name(int id) {
-    static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update",
+    static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
                                          "k_ref_seq_cdf", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_tile_offsets", "k_ns_weights_scan", "k_ns_resample", "k_ns_pose_partials", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
@@ -228,7 +228,7 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
     if (!force_sequential) {
         LAUNCH(K_XS_OFFSETS, xs::k_xs_offsets, 1, 32, 0, xs_tsum.p, nt, xs_toff.p, xs_flag.p);
         LAUNCH(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
-        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, 256, 0, nt, ws, d_total_out);
+        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out);
         if (want_cdf) LAUNCH(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
         CK(cudaGetLastError());
     }
@@ -535,8 +535,9 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
             const double off = -(all[i].angle) * 180.0 / M_PI;
             off_lo = std::min(off_lo, off); off_hi = std::max(off_hi, off);
         }
-        const int k_lo = std::max(0, (int)std::floor(-180.0 + off_lo) - 1 - key_min);
-        const int k_hi = std::min(n_keys - 1, (int)std::ceil(180.0 + off_hi) + 1 - key_min);
+        // yaw_deg lies in [-180, 180] up to an ulp; rounding is monotone, so these are the extreme reachable keys
+        const int k_lo = std::max(0, (int)std::round(-180.000001 + off_lo) - key_min);
+        const int k_hi = std::min(n_keys - 1, (int)std::round(180.000001 + off_hi) - key_min);
         for (int k = k_lo; k <= k_hi && !need_prepass; ++k) need_prepass = !h_lut_filled[k];
     }
     if (need_prepass) {
@@ -548,7 +549,22 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         int rc = ref_fill_ray_lut(all);
         if (rc) return rc;
     }
-    LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
+    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0);
+    if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024) {
+        if (!attr_set2) {
+            CK(cudaFuncSetAttribute(k_ref_update_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set2 = true;
+        }
+        int occ_blocks = 1, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, k_ref_update_v2, RU_TILE, smem2));
+        const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
+        const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));
+        const uint32_t div_magic = (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
+        LAUNCH(K_UPDATE_V2, k_ref_update_v2, grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic);
+    } else {
+        LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
+    }
     CK(cudaGetLastError());
     {
         int rc = exact_accumulate(false, d_scalars.p);

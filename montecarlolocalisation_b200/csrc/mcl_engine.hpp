@@ -77,13 +77,14 @@ public:
     int download_resample_draws(double* u_r, double* u_jit);
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
-    enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
+    enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
                     K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_TILEOFF, K_NS_WSCAN, K_NS_RESAMPLE, K_NS_POSE, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
 
     mcl_config cfg;
+    bool force_v1_update = false;       // tests: the one-thread-per-particle computeWeight kernel
     bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
     cudaStream_t stream = nullptr;
     int64_t n = 0;
@@ -102,7 +103,7 @@ private:
     void philox_host(uint32_t stream_id, uint64_t index, uint32_t out[4]) const;
 
     bool opened = false;
-    bool attr_set = false;
+    bool attr_set = false, attr_set2 = false;
     bool profiling = false;
     struct ProfEvent { int id; cudaEvent_t a, b; };
     std::vector<ProfEvent> prof_events;

@@ -216,7 +216,8 @@ class ParticleFilter:
         return cdf, total.value, fb.value
 
     def forceSequential(self, on):
-        self._ck(self.L.mcl_debug_force_sequential(self.h, int(bool(on))))
+        """bit 0: single-chain accumulation kernels; bit 1: per-particle computeWeight kernel (cross-checks)."""
+        self._ck(self.L.mcl_debug_force_sequential(self.h, int(on)))
 
     def benchGather(self, tier, table_bytes, iters=256):
         """Random 4-byte gathers per second from a table in shared memory (tier 0) or global memory (tier 1)."""

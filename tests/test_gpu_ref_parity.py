@@ -193,3 +193,55 @@ def test_philox_production_draws_run():
         P = pf.downloadParticles()
         idx = pf.ancestors()
         assert np.isfinite(P).all() and idx.min() >= -1 and idx.max() < 5000
+
+
+def test_ray_parallel_update_kernel_matches_per_particle_kernel_and_oracle():
+    """The restructured computeWeight kernel (rays as the unit of work, division-free cell lookup) against the plain
+    one-thread-per-particle kernel and the oracle, on particles that straddle walls, edges and the outside of the map."""
+    occ = load_map()
+    rng = np.random.default_rng(11)
+    n = 300_000
+    P = np.zeros((n, 4), np.float32)
+    P[:, 0] = rng.uniform(-0.4, 5.3, n)
+    P[:, 1] = rng.uniform(-0.4, 5.3, n)
+    P[:, 2] = rng.uniform(-9, 9, n)
+    # exact cell edges and exact integers stress the near-integer slow path
+    P[:5000, 0] = np.float32(0.1) * rng.integers(0, 50, 5000)
+    P[5000:10000, 1] = np.float32(0.1) * rng.integers(0, 50, 5000)
+    P[:, 3] = 1
+    sc = Scenario(1)
+    scan = sc.scans[0]
+    args = (scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    o, pf = make_pair(occ)
+    Po = P.copy()
+    total_o = o.compute_weight(Po, Scan(**scan))
+    pf.uploadParticles(P)
+    total_v2 = pf.computeWeight(*args)
+    w_v2 = pf.downloadParticles()[:, 3].copy()
+    pf2 = m.ParticleFilter()
+    pf2.setMap(occ, RES)
+    pf2.forceSequential(2)                  # bit 1: per-particle kernel
+    pf2.uploadParticles(P)
+    total_v1 = pf2.computeWeight(*args)
+    w_v1 = pf2.downloadParticles()[:, 3]
+    assert np.array_equal(w_v2, Po[:, 3]) and np.array_equal(w_v1, Po[:, 3])
+    assert total_v2 == total_o == total_v1
+    assert "k_ref_update_v2" not in pf2.profileRead()
+
+
+def test_large_map_not_in_shared_memory():
+    """REF mode on a 1025x1025 maze: the occupancy grid is read through L2 instead of shared memory."""
+    from montecarlolocalisation_b200 import synth
+    occ = synth.maze_occupancy(128, 3)
+    rng = np.random.default_rng(12)
+    n = 20000
+    P = np.zeros((n, 4), np.float32)
+    P[:, 0] = rng.uniform(0, 102.5, n); P[:, 1] = rng.uniform(0, 102.5, n); P[:, 2] = rng.uniform(-3.2, 3.2, n); P[:, 3] = 1
+    scan = synth.make_scan(occ, 0.1, (30.45, 40.45, 0.3), 360, 5)
+    o = Oracle(trig_mode=1); o.set_map(occ, RES); o.precompute_ray_directions()
+    pf = m.ParticleFilter(); pf.setMap(occ, RES)
+    Po = P.copy()
+    total_o = o.compute_weight(Po, Scan(**scan))
+    pf.uploadParticles(P)
+    total_g = pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    assert total_g == total_o and np.array_equal(pf.downloadParticles()[:, 3], Po[:, 3])
