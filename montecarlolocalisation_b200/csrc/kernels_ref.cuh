@@ -197,30 +197,38 @@ __global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, f
 //   phase B (thread = ray)        the (valid particle, beam) pairs are spread evenly over the block; each marches its ray
 //                                 and leaves w_hit*gauss in shared memory
 //   phase C (thread = particle)   the per-beam terms are added in the reference's order (f64, left to right) -> weight
-// Cell lookups avoid both the IEEE division and the XU-pipe conversions: q = a*(1/res) is rounded with the 2^52+2^51 magic
-// add, accepted when it is farther than 1e-6 from an integer (|q - a/res| <= 3.4e-16*q), and resolved by the exact
-// division only otherwise. Results are bit-identical to the kernel above (and to the CPU).
+// Cell lookups avoid both the IEEE division and the XU-pipe conversions, and their fast path is branch-free: q = a*(1/res)
+// is rounded with the 2^52+2^51 magic add, accepted when it is farther than 1e-6 from an integer
+// (|q - a/res| <= 3.4e-16*|q|), and resolved by the exact division only otherwise. Results are bit-identical to the kernel
+// above (and to the CPU).
 constexpr int RU_TILE = 256;
 constexpr double RU_MAGIC = 6755399441055744.0;       // 2^52 + 2^51
 
-// Cell along one axis: 0 = inside (cell set), 1 = outside the grid.
-__device__ __forceinline__ int cell_axis(double w, double o, double res, double inv_res, double hi_lim, int W, int& cell) {
-    const double a = dsub(w, o);
-    const double q = dmul(a, inv_res);
-    if (q > 1e-6 && q < hi_lim) {
-        const double t = dadd(q, RU_MAGIC);
-        const double d = dsub(q, dsub(t, RU_MAGIC));
-        if (fabs(d) > 1e-6) {
-            const int nn = __double2loint(t) - (d < 0.0 ? 1 : 0);
-            cell = nn;
-            return nn < W ? 0 : 1;
-        }
-    } else if (q >= hi_lim) {
-        return 1;
+// static_cast<int>((w - o) / res) along one axis, branch-free fast path. q = (w-o)*(1/res) differs from the correctly
+// rounded quotient by at most 3.4e-16*|q|; rounding q to the nearest integer with the magic add and looking at the
+// remainder d tells floor(q) whenever |d| > 1e-6, and truncation toward zero (what the reference's cast does, Q7) is
+// floor + 1 for negative non-integers. `ok` is false when the shortcut cannot be trusted (within 1e-6 of an integer,
+// |q| >= 1.9e9, NaN): the caller then redoes the probe with the IEEE division.
+__device__ __forceinline__ int cell_fast(double w, double o, double inv_res, bool& ok) {
+    const double q = dmul(dsub(w, o), inv_res);
+    const double t = dadd(q, RU_MAGIC);
+    const double d = dsub(q, dsub(t, RU_MAGIC));
+    ok = (fabs(d) > 1e-6) & (fabs(q) < 1.9e9);
+    const int fl = __double2loint(t) - (d < 0.0 ? 1 : 0);      // floor(q)
+    return fl + (int)((unsigned)fl >> 31);                      // trunc(q) for non-integers
+}
+// One map probe (worldToMap + bounds + getCell > 50, MC:298-319): 0 free, 1 occupied, -1 outside the grid.
+__device__ __forceinline__ int probe_fast(const uint8_t* __restrict__ occ, double wx, double wy, double ox, double oy, double res,
+                                          double inv_res, int W, int H) {
+    bool okx, oky;
+    int mx = cell_fast(wx, ox, inv_res, okx);
+    int my = cell_fast(wy, oy, inv_res, oky);
+    if (__builtin_expect(!(okx & oky), 0)) {                    // rare: exact path
+        mx = trunc_x86(ddiv(dsub(wx, ox), res));
+        my = trunc_x86(ddiv(dsub(wy, oy), res));
     }
-    const int nn = trunc_x86(ddiv(a, res));            // rare: near a cell edge, at or below the low edge, NaN
-    cell = nn;
-    return (nn >= 0 && nn < W) ? 0 : 1;
+    if ((unsigned)mx >= (unsigned)W || (unsigned)my >= (unsigned)H) return -1;
+    return occ[my * W + mx];
 }
 
 struct RuSmem {
@@ -265,7 +273,6 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     // constants in registers
     const double res = P.res, inv_res = P.inv_res, ox = P.ox, oy = P.oy;
     const int W = P.width, H = P.height;
-    const double hx = (double)W + 0.5, hy = (double)H + 0.5;
     const int nb = P.n_beams, nr = P.n_radii, stride = nb + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_tiles = (n + RU_TILE - 1) / RU_TILE;
@@ -279,19 +286,26 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
             const double x = (double)p.x, y = (double)p.y;
             if ((x >= ox && x < P.max_x) && (y >= oy && y < P.max_y)) {                  // isInsideMap, MC:685-692
                 const double o = P.validity_offset;
-                int cx[3], cy[3], sx[3], sy[3];
-                sx[0] = cell_axis(dadd(x, -o), ox, res, inv_res, hx, W, cx[0]);
-                sx[1] = cell_axis(x, ox, res, inv_res, hx, W, cx[1]);
-                sx[2] = cell_axis(dadd(x, o), ox, res, inv_res, hx, W, cx[2]);
-                sy[0] = cell_axis(dadd(y, -o), oy, res, inv_res, hy, H, cy[0]);
-                sy[1] = cell_axis(y, oy, res, inv_res, hy, H, cy[1]);
-                sy[2] = cell_axis(dadd(y, o), oy, res, inv_res, hy, H, cy[2]);
+                const double xs[3] = {dadd(x, -o), x, dadd(x, o)}, ys[3] = {dadd(y, -o), y, dadd(y, o)};
+                int cx[3], cy[3];
+                bool okall = true;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    bool k1, k2;
+                    cx[a] = cell_fast(xs[a], ox, inv_res, k1);
+                    cy[a] = cell_fast(ys[a], oy, inv_res, k2);
+                    okall = okall & k1 & k2;
+                }
+                if (__builtin_expect(!okall, 0)) {
+#pragma unroll
+                    for (int a = 0; a < 3; a++) { cx[a] = trunc_x86(ddiv(dsub(xs[a], ox), res)); cy[a] = trunc_x86(ddiv(dsub(ys[a], oy), res)); }
+                }
                 bool hit = false;                                                        // any of the 9 stencil points occupied
 #pragma unroll
                 for (int a = 0; a < 3; a++)
 #pragma unroll
                     for (int b = 0; b < 3; b++)
-                        if (sx[a] == 0 && sy[b] == 0 && occ[cy[b] * W + cx[a]]) hit = true;
+                        if ((unsigned)cx[a] < (unsigned)W && (unsigned)cy[b] < (unsigned)H && occ[cy[b] * W + cx[a]]) hit = true;
                 valid = !hit;
             }
             if (valid) {
@@ -321,11 +335,9 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
             double expected = P.max_range;                                               // MC:389
             for (int s = 0; s < nr; s++) {                                               // MC:372
                 const double rr = S.radii[s];
-                int mx, my;
-                const int ex = cell_axis(dadd(px, dmul(rr, dir.x)), ox, res, inv_res, hx, W, mx);
-                const int ey = cell_axis(dadd(py, dmul(rr, dir.y)), oy, res, inv_res, hy, H, my);
-                if (ex | ey) break;                                                      // MC:376
-                if (occ[my * W + mx]) { expected = rr; break; }                          // MC:377-381
+                const int c = probe_fast(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
+                if (c < 0) break;                                                        // MC:376
+                if (c) { expected = rr; break; }                                         // MC:377-381
             }
             const double diff = fabs(dsub(bm.obs, expected));                            // MC:662
             S.terms[v * stride + b] = dmul(P.w_hit, ref_gauss(P, diff));                 // MC:665
