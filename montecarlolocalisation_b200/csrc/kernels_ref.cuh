@@ -209,20 +209,25 @@ constexpr double RU_MAGIC = 6755399441055744.0;       // 2^52 + 2^51
 // remainder d tells floor(q) whenever |d| > 1e-6, and truncation toward zero (what the reference's cast does, Q7) is
 // floor + 1 for negative non-integers. `ok` is false when the shortcut cannot be trusted (within 1e-6 of an integer,
 // |q| >= 1.9e9, NaN): the caller then redoes the probe with the IEEE division.
+// BOUNDED: the caller guarantees |q| < 2^31 (a point within max_range of a particle that is inside the map), so only the
+// remainder test is needed; NaN fails it and takes the exact path. ZERO_ORIGIN: o == 0 (w - 0.0 == w except for -0.0,
+// whose cell is 0 either way).
+template <bool BOUNDED, bool ZERO_ORIGIN>
 __device__ __forceinline__ int cell_fast(double w, double o, double inv_res, bool& ok) {
-    const double q = dmul(dsub(w, o), inv_res);
+    const double q = dmul(ZERO_ORIGIN ? w : dsub(w, o), inv_res);
     const double t = dadd(q, RU_MAGIC);
     const double d = dsub(q, dsub(t, RU_MAGIC));
-    ok = (fabs(d) > 1e-6) & (fabs(q) < 1.9e9);
+    ok = BOUNDED ? (fabs(d) > 1e-6) : ((fabs(d) > 1e-6) & (fabs(q) < 1.9e9));
     const int fl = __double2loint(t) - (d < 0.0 ? 1 : 0);      // floor(q)
     return fl + (int)((unsigned)fl >> 31);                      // trunc(q) for non-integers
 }
 // One map probe (worldToMap + bounds + getCell > 50, MC:298-319): 0 free, 1 occupied, -1 outside the grid.
+template <bool ZERO_ORIGIN>
 __device__ __forceinline__ int probe_fast(const uint8_t* __restrict__ occ, double wx, double wy, double ox, double oy, double res,
                                           double inv_res, int W, int H) {
     bool okx, oky;
-    int mx = cell_fast(wx, ox, inv_res, okx);
-    int my = cell_fast(wy, oy, inv_res, oky);
+    int mx = cell_fast<true, ZERO_ORIGIN>(wx, ox, inv_res, okx);
+    int my = cell_fast<true, ZERO_ORIGIN>(wy, oy, inv_res, oky);
     if (__builtin_expect(!(okx & oky), 0)) {                    // rare: exact path
         mx = trunc_x86(ddiv(dsub(wx, ox), res));
         my = trunc_x86(ddiv(dsub(wy, oy), res));
@@ -247,6 +252,7 @@ __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_r
            RU_TILE * 4 + ((map_bytes + 15) & ~(size_t)15);
 }
 
+template <bool ZERO_ORIGIN>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
                                                            uint32_t div_magic /* ceil(2^32 / n_beams) */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -292,8 +298,8 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     bool k1, k2;
-                    cx[a] = cell_fast(xs[a], ox, inv_res, k1);
-                    cy[a] = cell_fast(ys[a], oy, inv_res, k2);
+                    cx[a] = cell_fast<false, false>(xs[a], ox, inv_res, k1);
+                    cy[a] = cell_fast<false, false>(ys[a], oy, inv_res, k2);
                     okall = okall & k1 & k2;
                 }
                 if (__builtin_expect(!okall, 0)) {
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
             double expected = P.max_range;                                               // MC:389
             for (int s = 0; s < nr; s++) {                                               // MC:372
                 const double rr = S.radii[s];
-                const int c = probe_fast(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
+                const int c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
                 if (c < 0) break;                                                        // MC:376
                 if (c) { expected = rr; break; }                                         // MC:377-381
             }

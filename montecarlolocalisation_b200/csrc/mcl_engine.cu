@@ -550,18 +550,23 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         if (rc) return rc;
     }
     const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0);
-    if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024) {
+    const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
+    if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024 && bounded_ok) {
         if (!attr_set2) {
-            CK(cudaFuncSetAttribute(k_ref_update_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_ref_update_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute(k_ref_update_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             attr_set2 = true;
         }
         int occ_blocks = 1, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, k_ref_update_v2, RU_TILE, smem2));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, k_ref_update_v2<false>, RU_TILE, smem2));
+        // the bounded fast path needs every probe quotient below 2^31: particle inside the map, ray at most max_range long
+        const bool zero_origin = origin_x == 0.0 && origin_y == 0.0;
         const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
         const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));
         const uint32_t div_magic = (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
-        LAUNCH(K_UPDATE_V2, k_ref_update_v2, grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic);
+        if (zero_origin) LAUNCH(K_UPDATE_V2, k_ref_update_v2<true>, grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic);
+        else LAUNCH(K_UPDATE_V2, k_ref_update_v2<false>, grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic);
     } else {
         LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
     }

@@ -245,3 +245,25 @@ def test_large_map_not_in_shared_memory():
     pf.uploadParticles(P)
     total_g = pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
     assert total_g == total_o and np.array_equal(pf.downloadParticles()[:, 3], Po[:, 3])
+
+
+def test_nonzero_map_origin():
+    """origin != (0,0): the reference subtracts it in worldToMap (MC:300-305) and isInsideMap (MC:686-689)."""
+    occ = load_map()
+    ox, oy = 1.5, -2.25
+    rng = np.random.default_rng(13)
+    n = 50_000
+    P = np.zeros((n, 4), np.float32)
+    P[:, 0] = rng.uniform(-0.4, 5.3, n) + ox
+    P[:, 1] = rng.uniform(-0.4, 5.3, n) + oy
+    P[:, 2] = rng.uniform(-4, 4, n)
+    P[:, 3] = 1
+    scan = Scenario(1).scans[0]
+    o = Oracle(trig_mode=1); o.set_map(occ, RES, ox, oy); o.precompute_ray_directions()
+    pf = m.ParticleFilter(); pf.setMap(occ, RES, ox, oy)
+    Po = P.copy()
+    total_o = o.compute_weight(Po, Scan(**scan))
+    pf.uploadParticles(P)
+    total_g = pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    assert (Po[:, 3] > 0).mean() > 0.3
+    assert total_g == total_o and np.array_equal(pf.downloadParticles()[:, 3], Po[:, 3])
