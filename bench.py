@@ -336,6 +336,9 @@ def ours(args):
         ns["map_txt_1M"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 6, 1_000_000, 360, "configs[1] shape", K, W)
         ns["grid4096"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, args.ns_cells, args.ns_particles, 720,
                                 "configs[3] per-GPU shape", K, W)
+        if not args.no_ns_large:
+            ns["grid8192"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 1024, args.ns_particles, 1080,
+                                    "configs[4] per-GPU shape (kidnapped robot)", K, W)
     if rank == 0:
         scan_bytes = int(sc.scans[0]["ranges"].nbytes) + 16 + 16         # ranges + 4 float32 scan fields + 2 encoder doubles
         line = {
@@ -478,6 +481,15 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
         step(2 * (W + K) + k, False)
     prof = shard.pf.profileRead()
     shard.pf.profileEnable(False)
+    # kidnapped-robot case: freshly uniform particles (no spatial locality in the field gathers)
+    shard.pf.profileEnable(True)
+    for k in range(3):
+        shard.pf.sampleParticles(n_global)
+        shard.pf.updateParticlePos(*motion)
+        shard.update_local_staged(0)
+    uni = shard.pf.profileRead().get("k_ns_update", (0.0, 1))
+    shard.pf.profileEnable(False)
+    uniform_ms = uni[0] / uni[1]
     t_res, t_e2e = sum(ms_res) * 1e-3, sum(ms_e2e) * 1e-3
     if world > 1:
         tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
@@ -513,6 +525,10 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
                      "share_of_step": kernels[top]["share"],
                      "note": "algorithmic bytes = 20 B/particle + 4 B per scored beam (table gather); the gathers are served by shared memory or L2, not HBM"},
         "kernels": kernels,
+        "uniform_particles": {"k_ns_update_ms": uniform_ms, "evals_per_s_per_gpu": per_gpu * valid_beams[0] / (uniform_ms * 1e-3),
+                              "note": "sensor-model kernel alone on freshly uniform particles (kidnapped robot): worst case for gather locality"},
+        "gather_microbench_reads_per_s": {"shared_memory_table": shard.pf.benchGather(0, min(field_bytes, 190 * 1024)),
+                                          "global_table_of_field_size": shard.pf.benchGather(1, field_bytes)},
     }
     del shard
     return out
@@ -527,6 +543,7 @@ def main():
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ns", action="store_true", help="skip the NS (north-star) leg")
+    ap.add_argument("--no-ns-large", action="store_true", help="skip the 8193x8193 / 1080-beam NS case")
     ap.add_argument("--ns-cells", type=int, default=512, help="NS leg: maze cells per side (512 -> 4097x4097 grid)")
     ap.add_argument("--ns-particles", type=int, default=12_500_000, help="NS leg: particles per GPU")
     args = ap.parse_args()
