@@ -205,7 +205,8 @@ int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitt
  * cdf[n] and/or total; *fell_back != 0 when the parallel path handed over to the single-chain kernel. */
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back);
 /* Cross-check switches (slow paths): bit 0 = single-chain sequential accumulation kernels instead of the parallel exact
- * scan; bit 1 = the one-thread-per-particle computeWeight kernel instead of the ray-parallel one. */
+ * scan; bit 1 = the one-thread-per-particle computeWeight kernel instead of the ray-parallel one; bit 2 = ray-parallel
+ * kernel without its fp32 pre-filter. */
 int mcl_debug_force_sequential(mcl_handle* h, int32_t on);
 /* Random 4-byte gather micro-benchmark: the roofline denominator of the sensor-model kernel.
  * tier 0 = table in shared memory (<= 200 KiB), tier 1 = table in global memory (L2- or HBM-resident by its size). */

@@ -236,6 +236,21 @@ __device__ __forceinline__ int probe_fast(const uint8_t* __restrict__ occ, doubl
     return occ[my * W + mx];
 }
 
+// fp32 pre-filter for the same lookup. The probe's cell coordinate q = ((p + r*dir) - o)/res is first evaluated in fp32
+// from per-ray fp32 copies (q0 = (p-o)/res, dq = dir/res) with one FFMA; its error against the f64 quantity the reference
+// truncates is below 2^-23*(W + 2*max_range/res + 2). When q sits farther than four times that from every integer, its
+// truncation IS the reference's cell and no f64 instruction is spent; otherwise (a fraction ~1e-4..1e-2 of the probes)
+// the f64 path above decides. Either way the result is the reference's, bit for bit.
+constexpr float RU_MAGICF = 12582912.0f;     // 1.5 * 2^23
+constexpr int RU_MAGICF_BITS = 0x4B400000;
+__device__ __forceinline__ int cell_fast32(float q, float tol, bool& ok) {
+    const float t = __fadd_rn(q, RU_MAGICF);
+    const float d = __fadd_rn(q, -__fadd_rn(t, -RU_MAGICF));
+    ok = fabsf(d) > tol;                                          // NaN fails
+    const int fl = (__float_as_int(t) - RU_MAGICF_BITS) - (d < 0.f ? 1 : 0);
+    return fl + (int)((unsigned)fl >> 31);
+}
+
 struct RuSmem {
     double2* lut;
     RefBeam* beams;
@@ -245,16 +260,17 @@ struct RuSmem {
     double* yawd;
     double* terms;
     int* vlist;
+    float* radii_f;
     uint8_t* occ;
 };
 __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes) {
     return (size_t)n_keys * 16 + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
-           RU_TILE * 4 + ((map_bytes + 15) & ~(size_t)15);
+           RU_TILE * 4 + (((size_t)n_radii * 4 + 15) & ~(size_t)15) + ((map_bytes + 15) & ~(size_t)15);
 }
 
-template <bool ZERO_ORIGIN>
+template <bool ZERO_ORIGIN, bool FAST32>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
-                                                           uint32_t div_magic /* ceil(2^32 / n_beams) */) {
+                                                           uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[RU_TILE / 32];
     RuSmem S;
@@ -266,7 +282,9 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     S.yawd = S.posy + RU_TILE;
     S.terms = S.yawd + RU_TILE;
     S.vlist = reinterpret_cast<int*>(S.terms + (size_t)RU_TILE * (P.n_beams + 1));
-    S.occ = reinterpret_cast<uint8_t*>(S.vlist + RU_TILE);
+    S.radii_f = reinterpret_cast<float*>(S.vlist + RU_TILE);
+    S.occ = reinterpret_cast<uint8_t*>(S.radii_f + ((P.n_radii + 3) & ~3));
+    for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii_f[i] = __double2float_rn(P.radii[i]);
     for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) S.lut[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = P.beams[i];
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii[i] = P.radii[i];
@@ -339,11 +357,31 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
             const int k = ref_key_index(P, S.yawd[v], bm.off_deg);
             const double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
             double expected = P.max_range;                                               // MC:389
-            for (int s = 0; s < nr; s++) {                                               // MC:372
-                const double rr = S.radii[s];
-                const int c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
-                if (c < 0) break;                                                        // MC:376
-                if (c) { expected = rr; break; }                                         // MC:377-381
+            if (FAST32) {
+                const float qx0 = __double2float_rn(dmul(dsub(px, ox), inv_res)), qy0 = __double2float_rn(dmul(dsub(py, oy), inv_res));
+                const float dqx = __double2float_rn(dmul(dir.x, inv_res)), dqy = __double2float_rn(dmul(dir.y, inv_res));
+                for (int s = 0; s < nr; s++) {                                           // MC:372
+                    const float rf = S.radii_f[s];
+                    bool okx, oky;
+                    int mx = cell_fast32(__fmaf_rn(rf, dqx, qx0), tol32, okx);
+                    int my = cell_fast32(__fmaf_rn(rf, dqy, qy0), tol32, oky);
+                    int c;
+                    if (__builtin_expect(!(okx & oky), 0)) {                             // near a cell edge: f64 decides
+                        const double rr = S.radii[s];
+                        c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
+                    } else {
+                        c = ((unsigned)mx >= (unsigned)W || (unsigned)my >= (unsigned)H) ? -1 : (int)occ[my * W + mx];
+                    }
+                    if (c < 0) break;                                                    // MC:376
+                    if (c) { expected = S.radii[s]; break; }                             // MC:377-381
+                }
+            } else {
+                for (int s = 0; s < nr; s++) {                                           // MC:372
+                    const double rr = S.radii[s];
+                    const int c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
+                    if (c < 0) break;                                                    // MC:376
+                    if (c) { expected = rr; break; }                                     // MC:377-381
+                }
             }
             const double diff = fabs(dsub(bm.obs, expected));                            // MC:662
             S.terms[v * stride + b] = dmul(P.w_hit, ref_gauss(P, diff));                 // MC:665

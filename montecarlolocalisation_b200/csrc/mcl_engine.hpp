@@ -84,6 +84,7 @@ public:
     int profile_read(int id, double* total_ms, int64_t* count);
 
     mcl_config cfg;
+    bool force_f64_probe = false;       // tests: ray-parallel kernel without the fp32 pre-filter
     bool force_v1_update = false;       // tests: the one-thread-per-particle computeWeight kernel
     bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
     cudaStream_t stream = nullptr;

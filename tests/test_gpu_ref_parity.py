@@ -224,8 +224,14 @@ def test_ray_parallel_update_kernel_matches_per_particle_kernel_and_oracle():
     pf2.uploadParticles(P)
     total_v1 = pf2.computeWeight(*args)
     w_v1 = pf2.downloadParticles()[:, 3]
-    assert np.array_equal(w_v2, Po[:, 3]) and np.array_equal(w_v1, Po[:, 3])
-    assert total_v2 == total_o == total_v1
+    pf3 = m.ParticleFilter()
+    pf3.setMap(occ, RES)
+    pf3.forceSequential(4)                  # bit 2: ray-parallel kernel, f64 probes only (no fp32 pre-filter)
+    pf3.uploadParticles(P)
+    total_v3 = pf3.computeWeight(*args)
+    w_v3 = pf3.downloadParticles()[:, 3]
+    assert np.array_equal(w_v2, Po[:, 3]) and np.array_equal(w_v1, Po[:, 3]) and np.array_equal(w_v3, Po[:, 3])
+    assert total_v2 == total_o == total_v1 == total_v3
     assert "k_ref_update_v2" not in pf2.profileRead()
 
 
