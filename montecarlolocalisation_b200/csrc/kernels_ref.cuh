@@ -370,7 +370,9 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                         const double rr = S.radii[s];
                         c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
                     } else {
-                        c = ((unsigned)mx >= (unsigned)W || (unsigned)my >= (unsigned)H) ? -1 : (int)occ[my * W + mx];
+                        const bool inb = (unsigned)mx < (unsigned)W && (unsigned)my < (unsigned)H;
+                        const int cell = occ[inb ? my * W + mx : 0];                     // unconditional load, clamped index
+                        c = inb ? cell : -1;
                     }
                     if (c < 0) break;                                                    // MC:376
                     if (c) { expected = S.radii[s]; break; }                             // MC:377-381
