@@ -287,7 +287,6 @@ def ours(args):
     launches0 = pf.kernelLaunches()
     ms_res, wall_res = timed(step_resident, 0)
     launches = pf.kernelLaunches() - launches0
-    clocks = sampler.stop()
     ms_e2e, wall_e2e = timed(step_e2e, W + K)
 
     # per-kernel durations (CUDA events around every launch on the engine's stream) over K more steps
@@ -339,6 +338,7 @@ def ours(args):
         if not args.no_ns_large:
             ns["grid8192"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 1024, args.ns_particles, 1080,
                                     "configs[4] per-GPU shape (kidnapped robot)", K, W)
+    clocks = sampler.stop()           # sampled over every timed region of this run (REF loop and NS legs)
     if rank == 0:
         scan_bytes = int(sc.scans[0]["ranges"].nbytes) + 16 + 16         # ranges + 4 float32 scan fields + 2 encoder doubles
         line = {
