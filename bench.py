@@ -40,6 +40,15 @@ ALGO_BYTES = {
 }
 
 
+def traffic_for(key, particles):
+    """DRAM bytes per launch from the committed ncu capture of this kernel at this workload size, else None."""
+    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(key)
+    return t["dram_bytes"] if t and t.get("particles") == particles else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,20 +333,22 @@ def ours(args):
                          "algo_bytes": algo, "gbs": (algo / (per_launch_ms * 1e-3) / 1e9) if algo else None}
     top = next(iter(kernels))
     roof = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None, "traffic": None, "peak_source": peak_src,
-            "share_of_step": kernels[top]["share"]}
+            "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None, "traffic": traffic_for(top, n), "peak_source": peak_src,
+            "share_of_step": kernels[top]["share"],
+            "note": "k_ref_update_v2 is instruction-issue bound (81% issue slots, ncu), not HBM bound: algorithmic bytes = 20 B/particle + "
+                    "one byte per map probe (<= 11 per scored beam); its DRAM traffic is the 16 B/particle particle stream"}
 
     ns = None
     if not args.no_ns:
         del flush
         torch.cuda.empty_cache()
         ns = {}
-        ns["map_txt_1M"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 6, 1_000_000, 360, "configs[1] shape", K, W)
+        ns["map_txt_1M"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 6, 1_000_000, 360, "configs[1] shape", K, W, "map_txt_1M")
         ns["grid4096"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, args.ns_cells, args.ns_particles, 720,
-                                "configs[3] per-GPU shape", K, W)
+                                "configs[3] per-GPU shape", K, W, "grid4096")
         if not args.no_ns_large:
             ns["grid8192"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 1024, args.ns_particles, 1080,
-                                    "configs[4] per-GPU shape (kidnapped robot)", K, W)
+                                    "configs[4] per-GPU shape (kidnapped robot)", K, W, "grid8192")
     clocks = sampler.stop()           # sampled over every timed region of this run (REF loop and NS legs)
     if rank == 0:
         scan_bytes = int(sc.scans[0]["ranges"].nbytes) + 16 + 16         # ranges + 4 float32 scan fields + 2 encoder doubles
@@ -386,7 +397,7 @@ def ns_workload(cells, n_beams, n_scans, seed):
     return occ, scans
 
 
-def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label, K, W):
+def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label, K, W, key=""):
     import montecarlolocalisation_b200 as m
     from montecarlolocalisation_b200 import NsShard
     n_global = per_gpu * world
@@ -521,7 +532,8 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
                    "l2": "per-GPU working set %.0f MB exceeds or displaces L2 between steps" % (per_gpu * 48 / 1e6)},
         "gpu_launches": launches, "scaling": "weak",
         "roofline": {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None,
+                     "traffic": traffic_for(top + "@" + key, per_gpu), "peak_source": peak_src,
                      "share_of_step": kernels[top]["share"],
                      "note": "algorithmic bytes = 20 B/particle + 4 B per scored beam (table gather); the gathers are served by shared memory or L2, not HBM"},
         "kernels": kernels,
