@@ -150,3 +150,69 @@ def test_200k_particles_bit_exact_and_systematic_properties():
     shards, P = run(1, 200_000, 1)
     anc = gather_anc(shards)
     assert (np.diff(anc) >= 0).all()
+
+
+def test_config3_full_size_properties_and_sharding():
+    """BASELINE.json configs[2] at full size: 1025x1025 grid, 10,000,000 particles, 720 beams. Too big for the oracle
+    in full, so: (1) a 4-shard run must equal the 1-shard run bit for bit (particles and ancestors); (2) log-likelihoods
+    of a random subsample are checked against the oracle; (3) systematic-resampling invariants hold: ancestors sorted,
+    every particle's offspring count within 1 of N*W_i/total, zero-weight particles never selected."""
+    occ = synth.maze_occupancy(128, 3)
+    n = 10_000_000
+    pose = (51.25, 51.25, 0.3)
+    scans = [synth.make_scan(occ, float(RES), pose, 720, 70 + i) for i in range(2)]
+    one = make_shards(1, n, occ)
+    four = make_shards(4, n, occ)
+    motion = (0.01, 0.02, -0.005)
+    o = NsOracle()
+    o.set_map(occ, RES)
+    rng = np.random.default_rng(3)
+    for step in range(2):
+        scan = scans[step]
+        # phase by phase on the single shard so intermediate products can be inspected
+        s = one[0]
+        s.pf.updateParticlePos(*motion)
+        Pp = s.pf.downloadParticles()
+        mx = s.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        ll = s.loglik()
+        idx = rng.integers(0, n, 3000)
+        assert np.array_equal(o.loglik(Pp[idx], o.beams(Scan(**scan))), ll[idx]), "log-likelihood subsample vs oracle"
+        assert mx == ll.max()
+        tot = s.weights_local(mx)
+        pre = s.prefix()
+        assert int(pre[-1]) == tot and (np.diff(pre.astype(np.int64)) >= 0).all()
+        s.resample_local(0, tot, s.u0())
+        s.end_step()
+        anc = s.pf.ancestors().astype(np.int64)
+        assert (np.diff(anc) >= 0).all()
+        W = np.diff(np.concatenate([[0], pre.astype(np.int64)]))
+        counts = np.bincount(anc, minlength=n)
+        assert (counts[W == 0] == 0).all()
+        expect = W.astype(np.float64) * (n / float(tot))
+        assert np.abs(counts - expect).max() < 1.0 + 1e-6
+        ns_step_in_process(four, scan, motion)
+        assert np.array_equal(gather_anc(four), anc), "4 shards vs 1 shard: ancestors"
+        assert np.array_equal(gather(four), s.pf.downloadParticles()), "4 shards vs 1 shard: particles"
+
+
+def test_no_valid_beams_and_particles_off_the_map():
+    """Every reading invalid -> zero beams -> all log-likelihoods 0 -> uniform weights -> ancestor(k) = k."""
+    sc = Scenario(1)
+    n = 1000
+    (s,) = make_shards(1, n, sc.occ)
+    bad = np.full(360, np.nan, np.float32)
+    mx = s.update_local(bad, -np.pi, 2 * np.pi / 360, 0.02, 5.6)
+    assert mx == 0.0 and (s.loglik() == 0).all()
+    tot = s.weights_local(mx)
+    assert tot == n << 32
+    s.resample_local(0, tot, 12345)
+    s.end_step()
+    assert np.array_equal(s.pf.ancestors(), np.arange(n))
+    # particles far outside the grid score the field's floor on every beam, identically in engine and oracle
+    o = NsOracle(); o.set_map(sc.occ, RES)
+    P = s.pf.downloadParticles()
+    P[:, 0] += 100.0
+    s.pf.uploadParticles(P)
+    scan = sc.scans[0]
+    s.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    assert np.array_equal(s.loglik(), o.loglik(P, o.beams(Scan(**scan))))
