@@ -178,6 +178,15 @@ int mcl_ns_resample_local(mcl_handle* h, uint64_t offset_q32, uint64_t total_q32
 int mcl_ns_end_step(mcl_handle* h);                   /* after every shard finished resampling: swap buffers */
 uint32_t mcl_ns_u0(mcl_handle* h);                    /* this step's systematic offset (same on every shard) */
 int mcl_ns_pose_partials(mcl_handle* h, double* out5);/* {sum w, sum w x, sum w y, sum w sin, sum w cos} of this shard */
+/* The same step driven entirely by the engine: NCCL (loaded at run time) on the handle's stream, resampling plan computed
+ * on the device, no host round trip. mcl_comm_unique_id on one shard -> hand the 128 bytes to every shard (any transport)
+ * -> mcl_comm_init on every shard (collective; also maps all peers' buffers through CUDA IPC) -> mcl_ns_step per tick on
+ * every shard. world == 1 needs no communicator. pose3 (optional) = {x, y, theta} weighted mean before resampling. */
+int mcl_comm_unique_id(mcl_handle* h, void* out128);
+int mcl_comm_init(mcl_handle* h, const void* id128);
+int mcl_ns_step(mcl_handle* h, double rot_1, double trans, double rot_2, const float* ranges, int32_t n_beams, float angle_min,
+                float angle_increment, float range_min, float range_max, double* pose3);
+int mcl_ns_step_staged(mcl_handle* h, double rot_1, double trans, double rot_2, int32_t slot, double* pose3);
 /* host-only planning helpers (no GPU touched) */
 int mcl_ns_first_slot(uint64_t offset_q32, uint64_t total_q32, uint64_t n_global, uint32_t u0, int64_t* slot);
 int mcl_ns_shard_range(int64_t n_global, int32_t world, int32_t rank, int64_t* begin, int64_t* count, int64_t* per_rank);

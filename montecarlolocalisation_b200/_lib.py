@@ -95,6 +95,10 @@ SYMBOLS = [
     ("mcl_ns_end_step", _i32, [_vp]),
     ("mcl_ns_u0", C.c_uint32, [_vp]),
     ("mcl_ns_pose_partials", _i32, [_vp, _dp]),
+    ("mcl_comm_unique_id", _i32, [_vp, _vp]),
+    ("mcl_comm_init", _i32, [_vp, _vp]),
+    ("mcl_ns_step", _i32, [_vp, _d, _d, _d, _fp, _i32, _f, _f, _f, _f, _dp]),
+    ("mcl_ns_step_staged", _i32, [_vp, _d, _d, _d, _i32, _dp]),
     ("mcl_ns_first_slot", _i32, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_i64)]),
     ("mcl_ns_shard_range", _i32, [_i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     ("mcl_peer_export", _i32, [_vp, _i32, _vp]),

@@ -11,6 +11,7 @@
 #pragma once
 #include "mcl_device.cuh"
 #include "ns_core.cuh"
+#include "ns_plan.hpp"
 
 namespace mcl {
 
@@ -238,6 +239,12 @@ constexpr int NS_SCAN_THREADS = 256;
 constexpr int NS_SCAN_ITEMS = 8;
 constexpr int NS_SCAN_TILE = NS_SCAN_THREADS * NS_SCAN_ITEMS;
 
+// the global maximum log-likelihood lives in device memory as an order-preserving int (so atomicMax / NCCL max work)
+__device__ __forceinline__ float ns_decode_max(const int* __restrict__ max_bits) {
+    int b = *max_bits;
+    b = b >= 0 ? b : b ^ 0x7fffffff;
+    return __int_as_float(b);
+}
 __device__ __forceinline__ uint64_t ns_weight(float ll, float max_ll, float temper) {
     return ns::det_exp_q32(ns::mulf(temper, ns::addf(ll, -max_ll)));
 }
@@ -257,9 +264,10 @@ __device__ __forceinline__ uint64_t block_scan_u64(uint64_t v, uint64_t* sm8, ui
     return pre + v;      // inclusive
 }
 // pass 1: per-tile sums of W
-__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float* __restrict__ ll, int64_t n, float max_ll, float temper,
-                                                                   uint64_t* __restrict__ tile_sums) {
+__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
+                                                                   float temper, uint64_t* __restrict__ tile_sums) {
     __shared__ uint64_t sm[8];
+    const float max_ll = ns_decode_max(max_bits);
     const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)threadIdx.x * NS_SCAN_ITEMS;
     uint64_t s = 0;
 #pragma unroll
@@ -291,10 +299,11 @@ __global__ void __launch_bounds__(1024) k_ns_tile_offsets(uint64_t* __restrict__
     if (threadIdx.x == 0) *total = carry;
 }
 // pass 3: inclusive prefix per particle (local to this shard), and the unnormalised weight into the particle record
-__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float* __restrict__ ll, int64_t n, float max_ll, float temper,
-                                                                    const uint64_t* __restrict__ tile_offsets, uint64_t* __restrict__ prefix,
-                                                                    float4* __restrict__ part) {
+__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
+                                                                    float temper, const uint64_t* __restrict__ tile_offsets,
+                                                                    uint64_t* __restrict__ prefix, float4* __restrict__ part) {
     __shared__ uint64_t sm[8];
+    const float max_ll = ns_decode_max(max_bits);
     const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)threadIdx.x * NS_SCAN_ITEMS;
     uint64_t w[NS_SCAN_ITEMS];
     uint64_t s = 0;
@@ -367,6 +376,54 @@ __global__ void __launch_bounds__(512) k_gather_bench(const float* __restrict__ 
         acc += SMEM ? t[idx] : __ldg(t + idx);
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// The resampling plan of this shard, computed on the device from the all-gathered Q32 totals (no host round trip).
+struct NsPlan {
+    uint64_t offset, total;
+    int64_t k_lo, k_hi;
+};
+__global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int rank, uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t off = 0, tot = 0;
+    for (int r = 0; r < world; r++) { if (r < rank) off += totals[r]; tot += totals[r]; }
+    NsPlan p;
+    p.offset = off; p.total = tot;
+    p.k_lo = tot ? ns::first_slot(off, tot, n_global, u0) : 0;
+    p.k_hi = tot ? ns::first_slot(off + totals[rank], tot, n_global, u0) : 0;
+    *plan = p;
+}
+// k_ns_resample with the plan read from device memory and a grid-stride loop (the slot count is not known on the host).
+__global__ void __launch_bounds__(256) k_ns_resample_planned(const float4* __restrict__ src, const uint64_t* __restrict__ prefix, int64_t n_local,
+                                                             int64_t g0, const NsPlan* __restrict__ plan, uint64_t n_global, uint32_t u0, NsDest D,
+                                                             float new_weight) {
+    const NsPlan P = *plan;
+    for (int64_t k = P.k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P.k_hi; k += (int64_t)gridDim.x * blockDim.x) {
+        const ns::U128 rhs = ns::rhs_of((uint64_t)k, u0, P.total);
+        int64_t lo = 0, len = n_local;
+        while (len > 0) {
+            const int64_t half = len >> 1;
+            if (!ns::selects(P.offset + prefix[lo + half], n_global, rhs)) { lo += half + 1; len -= half + 1; } else len = half;
+        }
+        if (lo >= n_local) lo = n_local - 1;
+        float4 p = src[lo];
+        p.w = new_weight;
+        int r = (int)(k / D.per_rank);
+        if (r >= D.world) r = D.world - 1;
+        const int64_t slot = k - (int64_t)r * D.per_rank;
+        D.part[r][slot] = p;
+        D.anc[r][slot] = (int)(g0 + lo);
+    }
+    __threadfence_system();        // peer stores must be visible before the step's closing collective lets anyone read them
+}
+// out[k] = sum over blocks of partials[b*5+k] (one warp per output, fixed order)
+__global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_blocks, double* __restrict__ out5) {
+    const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (o >= 5) return;
+    double s = 0;
+    for (int b = lane; b < n_blocks; b += 32) s += partials[(size_t)b * 5 + o];
+    s = warp_sum(s);
+    if (lane == 0) out5[o] = s;
 }
 
 // Weighted pose sums with the particle weights as they stand: {sum w, sum w x, sum w y, sum w sin, sum w cos} per block.

@@ -111,6 +111,18 @@ int mcl_ns_resample_local(mcl_handle* h, uint64_t off, uint64_t tot, uint32_t u0
 int mcl_ns_end_step(mcl_handle* h) { GUARD(h); TRY(h->engine.ns_end_step()) }
 uint32_t mcl_ns_u0(mcl_handle* h) { return h ? h->engine.ns_u0() : 0; }
 int mcl_ns_pose_partials(mcl_handle* h, double* out5) { GUARD(h); TRY(h->engine.ns_pose_partials(out5)) }
+int mcl_comm_unique_id(mcl_handle* h, void* out128) { GUARD(h); if (!out128) return MCL_ERR_ARG; TRY(h->engine.comm_unique_id(out128)) }
+int mcl_comm_init(mcl_handle* h, const void* id128) { GUARD(h); if (!id128) return MCL_ERR_ARG; TRY(h->engine.comm_init(id128)) }
+int mcl_ns_step(mcl_handle* h, double rot_1, double trans, double rot_2, const float* ranges, int32_t nb, float amin, float ainc, float rmin,
+                float rmax, double* pose3) {
+    GUARD(h);
+    if (nb < 0 || (nb > 0 && !ranges)) return MCL_ERR_ARG;
+    static const float none = 0.f;
+    TRY(h->engine.ns_step(rot_1, trans, rot_2, -1, ranges ? ranges : &none, nb, amin, ainc, rmin, rmax, pose3))
+}
+int mcl_ns_step_staged(mcl_handle* h, double rot_1, double trans, double rot_2, int32_t slot, double* pose3) {
+    GUARD(h); TRY(h->engine.ns_step(rot_1, trans, rot_2, slot, nullptr, 0, 0.f, 0.f, 0.f, 0.f, pose3))
+}
 int mcl_ns_first_slot(uint64_t off, uint64_t tot, uint64_t n, uint32_t u0, int64_t* slot) {
     if (!slot || tot == 0) return MCL_ERR_ARG;
     *slot = mcl::ns::first_slot(off, tot, n, u0);

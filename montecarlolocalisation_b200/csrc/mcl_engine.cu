@@ -19,7 +19,10 @@ Engine::~Engine() {
     if (!opened) return;
     cudaSetDevice(cfg.device);
     part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); d_lf.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
-    for (int w = 0; w < 3; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]); ancestors.release(); d_occ.release(); d_gauss.release();
+    for (int w = 0; w < 3; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
+    d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
+    if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
+    ns_comm_destroy(); ancestors.release(); d_occ.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
     d_beams.release(); for (auto& sc : staged) sc.d_used.release(); for (auto& sc : ns_staged) sc.d_pts.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
     d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();

@@ -64,6 +64,11 @@ public:
     int ns_end_step();
     uint32_t ns_u0() const;
     int ns_pose_partials(double* out5);
+    int comm_unique_id(void* out128);
+    void ns_comm_destroy();
+    int comm_init(const void* id128);
+    int ns_step(double rot1, double trans, double rot2, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc,
+                float range_min, float range_max, double* pose3);
     int ns_download_field(float* lf, uint16_t* d2);
     int ns_download_loglik(float* ll);
     int ns_download_prefix(uint64_t* prefix);
@@ -171,6 +176,18 @@ private:
     void ns_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
                           std::vector<float2>& pts) const;
     int ns_run_update(const float2* d_pts, int n_pts, float* local_max);
+    int ns_launch_update(const float2* d_pts, int n_pts);
+    int ns_launch_weights();
+    void* comm = nullptr;                 // ncclComm_t
+    DevBuf<uint64_t> d_totals;
+    DevBuf<unsigned char> d_plan;
+    DevBuf<double> d_pose;
+    DevBuf<int> d_bar;
+    static constexpr int RING = 8;
+    void* ring_base = nullptr; size_t ring_bytes = 0; int ring_pos = 0;
+    std::vector<cudaEvent_t> ring_events;
+    int ensure_pinned_ring(size_t bytes);
+    void* pinned_ring_next();
     struct NsStagedScan { DevBuf<float2> d_pts; int n = 0; bool valid = false; };
     std::vector<NsStagedScan> ns_staged;
     DevBuf<float> d_lf, d_lf_table, d_ll;

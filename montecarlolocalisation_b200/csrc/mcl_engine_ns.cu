@@ -7,6 +7,7 @@
 #include "mcl_engine.hpp"
 #include "engine_internal.hpp"
 #include "kernels_ns.cuh"
+#include "nccl_dyn.hpp"
 #include "ns_plan.hpp"
 
 namespace mcl {
@@ -150,6 +151,20 @@ int Engine::ns_update_local_staged(int slot, float* local_max) {
 
 // The likelihood-field kernel over this shard. Returns the shard's maximum log-likelihood.
 int Engine::ns_run_update(const float2* d_pts, int n_pts, float* local_max) {
+    int rc = ns_launch_update(d_pts, n_pts);
+    if (rc) return rc;
+    int bits = 0;
+    CK(cudaMemcpyAsync(&bits, d_maxbits.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
+    float mx;
+    memcpy(&mx, &bits, 4);
+    ns_last_max = mx;
+    if (local_max) *local_max = mx;
+    return MCL_OK;
+}
+
+int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
     if (!map_ready) return fail(MCL_ERR_ARG, "update: no map");
     if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
     ns_beams_n = n_pts;
@@ -184,16 +199,8 @@ int Engine::ns_run_update(const float2* d_pts, int n_pts, float* local_max) {
         LAUNCH(K_NS_UPDATE, k_ns_update<false>, std::max(1, grid), threads, beam_bytes, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
     }
     CK(cudaGetLastError());
-    int bits = 0;
-    CK(cudaMemcpyAsync(&bits, d_maxbits.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
-    float mx;
-    memcpy(&mx, &bits, 4);
-    ns_last_max = mx;
     ns_have_ll = true;
     have_weights = false;
-    if (local_max) *local_max = mx;
     return MCL_OK;
 }
 
@@ -201,18 +208,28 @@ int Engine::ns_weights_local(float global_max, uint64_t* local_total) {
     CK(cudaSetDevice(cfg.device));
     if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_weights_local: NS mode only");
     if (!ns_have_ll) return fail(MCL_ERR_ARG, "weights: run the update first");
-    const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
-    const float temper = (float)cfg.ns_temper;
-    LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, global_max, temper, d_tile_sums.p);
-    LAUNCH(K_NS_TILEOFF, k_ns_tile_offsets, 1, 1024, 0, d_tile_sums.p, nt, d_u64.p);
-    LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, global_max, temper, d_tile_sums.p, d_prefix.p, part[cur].p);
-    CK(cudaGetLastError());
+    int gbits;
+    memcpy(&gbits, &global_max, 4);
+    gbits = gbits >= 0 ? gbits : gbits ^ 0x7fffffff;
+    CK(cudaMemcpyAsync(d_maxbits.p, &gbits, sizeof(int), cudaMemcpyHostToDevice, stream));
+    int rc0 = ns_launch_weights();
+    if (rc0) return rc0;
     uint64_t tot = 0;
     CK(cudaMemcpyAsync(&tot, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     have_weights = true;
     last_total = (double)tot * 2.3283064365386963e-10;
     if (local_total) *local_total = tot;
+    return MCL_OK;
+}
+
+int Engine::ns_launch_weights() {
+    const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
+    const float temper = (float)cfg.ns_temper;
+    LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p);
+    LAUNCH(K_NS_TILEOFF, k_ns_tile_offsets, 1, 1024, 0, d_tile_sums.p, nt, d_u64.p);
+    LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, d_prefix.p, part[cur].p);
+    CK(cudaGetLastError());
     return MCL_OK;
 }
 
@@ -288,6 +305,156 @@ int Engine::ns_download_prefix(uint64_t* prefix) {
     CK(cudaMemcpyAsync(prefix, d_prefix.p, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
+}
+
+// ---- engine-native collectives: NCCL on the engine's stream ------------------------------------------------------------------
+#define NCK(call)                                                                                          \
+    do {                                                                                                   \
+        ncclResult_t r__ = (call);                                                                         \
+        if (r__ != ncclSuccess) { err = std::string("NCCL error: ") + nccl_api().GetErrorString(r__) + " at " #call; return MCL_ERR_COMM; } \
+    } while (0)
+
+void Engine::ns_comm_destroy() {
+    if (comm && nccl_api().lib) nccl_api().CommDestroy((ncclComm_t)comm);
+    comm = nullptr;
+}
+
+int Engine::comm_unique_id(void* out128) {
+    std::string e;
+    if (!nccl_api().load(e)) return fail(MCL_ERR_COMM, e);
+    ncclUniqueId id;
+    NCK(nccl_api().GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return MCL_OK;
+}
+
+// Joins the communicator (collective: every shard calls it), then maps every peer's particle / ancestor buffers through
+// CUDA IPC; the 64-byte handles travel by ncclAllGather, so no other transport is needed.
+int Engine::comm_init(const void* id128) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "comm_init: NS mode only");
+    if (n == 0) return fail(MCL_ERR_ARG, "comm_init: call mcl_ns_set_shard first");
+    std::string e;
+    if (!nccl_api().load(e)) return fail(MCL_ERR_COMM, e);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t c = nullptr;
+    NCK(nccl_api().CommInitRank(&c, shard_world, id, shard_rank));
+    comm = c;
+    CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
+    if (shard_world > 1) {
+        DevBuf<unsigned char> mine, all;
+        CK(mine.ensure(192)); CK(all.ensure((size_t)192 * shard_world));
+        unsigned char h[192];
+        for (int w = 0; w < 3; w++) { int rc = peer_export(w, h + 64 * w); if (rc) return rc; }
+        CK(cudaMemcpyAsync(mine.p, h, 192, cudaMemcpyHostToDevice, stream));
+        NCK(nccl_api().AllGather(mine.p, all.p, 192, ncclUint8, (ncclComm_t)comm, stream));
+        std::vector<unsigned char> hall((size_t)192 * shard_world);
+        CK(cudaMemcpyAsync(hall.data(), all.p, hall.size(), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (int r = 0; r < shard_world; r++) {
+            if (r == shard_rank) continue;
+            for (int w = 0; w < 3; w++) { int rc = peer_import(r, w, hall.data() + (size_t)192 * r + 64 * w); if (rc) return rc; }
+        }
+        mine.release(); all.release();
+    }
+    return MCL_OK;
+}
+
+// One whole filter step of a (possibly sharded) NS filter, enqueued on the engine's stream with no host round trip:
+//   predict -> likelihood field -> all-reduce(max) -> Q32 weights + prefix -> all-gather(totals) -> device plan ->
+//   resample straight into the owning shards -> closing all-reduce (barrier) -> swap.
+// pose3 != null additionally reduces the weighted pose (before resampling) and waits for it.
+int Engine::ns_step(double rot1, double trans, double rot2, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc,
+                    float range_min, float range_max, double* pose3) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_step: NS mode only");
+    if (shard_world > 1 && !comm) return fail(MCL_ERR_COMM, "ns_step: sharded filter without a communicator (mcl_comm_init)");
+    if (n == 0) return fail(MCL_ERR_ARG, "ns_step: no particles");
+    CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
+    Motion m; m.rot_1 = rot1; m.trans = trans; m.rot_2 = rot2;
+    int rc = ns_predict(m);
+    if (rc) return rc;
+    // sensor model (asynchronous variant of ns_run_update: the max stays on the device)
+    const float2* d_pts; int n_pts;
+    if (ranges) {
+        std::vector<float2> pts;
+        ns_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, pts);
+        CK(d_ns_beams.ensure(std::max<size_t>(1, pts.size())));
+        if (!pts.empty()) {
+            // a small ring of pinned slots so the host never overwrites a scan the GPU has not consumed yet
+            rc = ensure_pinned_ring(pts.size() * sizeof(float2));
+            if (rc) return rc;
+            void* hp = pinned_ring_next();
+            memcpy(hp, pts.data(), pts.size() * sizeof(float2));
+            CK(cudaMemcpyAsync(d_ns_beams.p, hp, pts.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(ring_events[ring_pos], stream));
+        }
+        d_pts = d_ns_beams.p; n_pts = (int)pts.size();
+    } else {
+        if (slot < 0 || (size_t)slot >= ns_staged.size() || !ns_staged[slot].valid) return fail(MCL_ERR_ARG, "ns_step: empty scan slot");
+        d_pts = ns_staged[slot].d_pts.p; n_pts = ns_staged[slot].n;
+    }
+    rc = ns_launch_update(d_pts, n_pts);
+    if (rc) return rc;
+    auto& N = nccl_api();
+    if (shard_world > 1) NCK(N.AllReduce(d_maxbits.p, d_maxbits.p, 1, ncclInt32, ncclMax, (ncclComm_t)comm, stream));
+    rc = ns_launch_weights();
+    if (rc) return rc;
+    if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
+    else CK(cudaMemcpyAsync(d_totals.p, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+    if (pose3) {
+        const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
+        CK(d_partials.ensure(5 * 512));
+        LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, d_partials.p);
+        LAUNCH(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
+        if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
+    }
+    const uint32_t u0 = ns_u0();
+    LAUNCH(K_NS_RESAMPLE, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
+    NsDest D;
+    D.per_rank = per_rank; D.world = shard_world;
+    const int next = cur ^ 1;
+    for (int r = 0; r < 8; ++r) { D.part[r] = nullptr; D.anc[r] = nullptr; }
+    for (int r = 0; r < shard_world; ++r) {
+        if (r == shard_rank) { D.part[r] = part[next].p; D.anc[r] = ancestors.p; }
+        else {
+            if (!peer_ptr[next][r] || !peer_ptr[2][r]) return fail(MCL_ERR_COMM, "ns_step: peer buffers are not mapped");
+            D.part[r] = (float4*)peer_ptr[next][r]; D.anc[r] = (int*)peer_ptr[2][r];
+        }
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    LAUNCH(K_NS_RESAMPLE, k_ns_resample_planned, sms * 8, 256, 0, part[cur].p, d_prefix.p, n, shard_begin, (const NsPlan*)d_plan.p,
+           (uint64_t)n_global, u0, D, (float)(1.0 / (double)n_global));
+    CK(cudaGetLastError());
+    if (shard_world > 1) NCK(N.AllReduce(d_bar.p, d_bar.p, 1, ncclInt32, ncclSum, (ncclComm_t)comm, stream));     // closing barrier
+    cur ^= 1;
+    have_weights = false; ns_have_ll = false;
+    ++step_counter;
+    if (pose3) {
+        double h[5];
+        CK(cudaMemcpyAsync(h, d_pose.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        pose3[0] = h[1] / h[0]; pose3[1] = h[2] / h[0]; pose3[2] = std::atan2(h[3], h[4]);
+    }
+    return MCL_OK;
+}
+
+int Engine::ensure_pinned_ring(size_t bytes) {
+    if (bytes <= ring_bytes && ring_base) return MCL_OK;
+    if (ring_base) { cudaStreamSynchronize(stream); cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); ring_events.clear(); }
+    ring_bytes = std::max<size_t>(bytes, 16 * 1024);
+    CK(cudaMallocHost(&ring_base, ring_bytes * RING));
+    ring_events.resize(RING);
+    for (auto& e : ring_events) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ring_pos = 0;
+    return MCL_OK;
+}
+void* Engine::pinned_ring_next() {
+    ring_pos = (ring_pos + 1) % RING;
+    cudaEventSynchronize(ring_events[ring_pos]);          // the copy that last used this slot has completed
+    return (char*)ring_base + ring_bytes * ring_pos;
 }
 
 // Random-gather micro-benchmark: reads/s for a table of `table_bytes` in shared memory (tier 0) or global

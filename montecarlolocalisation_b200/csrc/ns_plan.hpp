@@ -7,11 +7,17 @@
 #pragma once
 #include <stdint.h>
 
+#ifdef __CUDACC__
+#define NSP_HD __host__ __device__
+#else
+#define NSP_HD
+#endif
+
 namespace mcl {
 namespace ns {
 
 // min{ k in [0,N] : ((k<<32)+u0) * T >= O * (N<<32) }   (T > 0, O <= T)
-inline int64_t first_slot(uint64_t O, uint64_t T, uint64_t N, uint32_t u0) {
+NSP_HD inline int64_t first_slot(uint64_t O, uint64_t T, uint64_t N, uint32_t u0) {
     if (O == 0) return 0;
     if (O >= T) return (int64_t)N;
     const unsigned __int128 rhs = ((unsigned __int128)O * N) << 32;           // < 2^60 * 2^31 * 2^32

@@ -307,6 +307,25 @@ class NsShard:
         self.pf._ck(self.L.mcl_ns_download_prefix(self.h, p.ctypes.data_as(C.POINTER(C.c_uint64))))
         return p
 
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.pf._ck(self.L.mcl_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, raw128):
+        self.pf._ck(self.L.mcl_comm_init(self.h, C.create_string_buffer(raw128, 128)))
+
+    def step(self, motion, scan=None, slot=None, want_pose=False):
+        """One whole filter step inside the engine (NCCL + device-side plan, no host round trip)."""
+        pose = (C.c_double * 3)() if want_pose else None
+        if slot is not None:
+            self.pf._ck(self.L.mcl_ns_step_staged(self.h, motion[0], motion[1], motion[2], slot, pose))
+        else:
+            r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
+            self.pf._ck(self.L.mcl_ns_step(self.h, motion[0], motion[1], motion[2], r.ctypes.data_as(_fp), len(r), C.c_float(scan["angle_min"]),
+                                           C.c_float(scan["angle_inc"]), C.c_float(scan["range_min"]), C.c_float(scan["range_max"]), pose))
+        return np.array(pose) if want_pose else None
+
     def device_buffer(self, which):
         return self.L.mcl_device_buffer(self.h, which)
 

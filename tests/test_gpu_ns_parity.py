@@ -216,3 +216,54 @@ def test_no_valid_beams_and_particles_off_the_map():
     scan = sc.scans[0]
     s.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
     assert np.array_equal(s.loglik(), o.loglik(P, o.beams(Scan(**scan))))
+
+
+def test_engine_native_step_matches_phases():
+    """mcl_ns_step / mcl_ns_step_staged (whole step enqueued by the engine, plan computed on the device, no host round
+    trip) produce the same particles and ancestors as the phase-by-phase API, and the pose they return is the weighted
+    mean of the particles BEFORE resampling."""
+    sc = Scenario(4)
+    n = 30011
+    (a,) = make_shards(1, n, sc.occ)
+    (b,) = make_shards(1, n, sc.occ)
+    for i, scan in enumerate(sc.scans):
+        a.pf.stageScan(i, scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    for step in range(4):
+        motion = (0.01 * (step + 1), 0.02, -0.005)
+        scan = sc.scans[step]
+        # expected pose from the phases
+        b.pf.updateParticlePos(*motion)
+        mx = b.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        tot = b.weights_local(mx)
+        pp = b.pose_partials()
+        expect_pose = np.array([pp[1] / pp[0], pp[2] / pp[0], np.arctan2(pp[3], pp[4])])
+        b.resample_local(0, tot, b.u0())
+        b.end_step()
+        if step % 2 == 0:
+            pose = a.step(motion, scan=scan, want_pose=True)
+        else:
+            pose = a.step(motion, slot=step, want_pose=True)
+        assert np.allclose(pose, expect_pose, rtol=1e-12, atol=1e-12), (pose, expect_pose)
+        assert np.array_equal(a.pf.downloadParticles(), b.pf.downloadParticles()), "particles step %d" % step
+        assert np.array_equal(a.pf.ancestors(), b.pf.ancestors()), "ancestors step %d" % step
+    # without a pose the call does not wait for the GPU; results are the same
+    a.step((0.01, 0.02, 0.0), slot=0)
+    ns_step_in_process([b], sc.scans[0], (0.01, 0.02, 0.0))
+    assert np.array_equal(a.pf.downloadParticles(), b.pf.downloadParticles())
+
+
+def test_engine_native_step_multi_gpu_nccl(tmp_path):
+    """2+ GPUs, one process per GPU: the engine's own NCCL collectives + peer stores (tests/dist_ns_step_nccl.py) equal
+    the single-span oracle bit for bit. Skipped on a 1-GPU box (NCCL refuses two ranks on one device)."""
+    import subprocess
+    import sys
+    import os
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(g, 4)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", os.path.join(root, "tests", "dist_ns_step_nccl.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dist_ns_step ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
