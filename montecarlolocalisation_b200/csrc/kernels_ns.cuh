@@ -33,8 +33,13 @@ __global__ void k_ns_edt_cols(const uint8_t* __restrict__ occ, int W, int H, int
     }
 }
 // pass 2, one thread per cell: d2 = min over |dx| <= R of dx^2 + g^2, capped at R^2; field = table[d2].
+// The field is stored with a border of `pad` cells on every side (row pitch Wp = W + 2 pad) pre-filled with the
+// outside-the-grid value, so that the sensor-model kernel needs no bounds test for particles inside the map.
+__global__ void k_ns_fill_f32(float* __restrict__ dst, size_t n, float v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
 __global__ void k_ns_edt_rows(const uint16_t* __restrict__ g, int W, int H, int R, const float* __restrict__ lf_of_d2,
-                              uint16_t* __restrict__ d2_out, float* __restrict__ lf_out) {
+                              uint16_t* __restrict__ d2_out, float* __restrict__ lf_out, int pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const int cap = R * R;
@@ -50,7 +55,7 @@ __global__ void k_ns_edt_rows(const uint16_t* __restrict__ g, int W, int H, int 
     }
     size_t i = (size_t)y * W + x;
     if (d2_out) d2_out[i] = (uint16_t)best;
-    lf_out[i] = lf_of_d2[best];
+    lf_out[(size_t)(y + pad) * (W + 2 * pad) + (x + pad)] = lf_of_d2[best];
 }
 
 // ---- init / predict -------------------------------------------------------------------------------------------------------
@@ -102,8 +107,9 @@ __global__ void __launch_bounds__(256) k_ns_predict(float4* __restrict__ part, i
 
 // ---- update: likelihood field -----------------------------------------------------------------------------------------------
 struct NsField {
-    const float* lf;        // [H*W] log-likelihood per cell
-    int W, H;
+    const float* lf;        // [(H + 2 pad) * (W + 2 pad)] log-likelihood per cell, border = lf_out
+    int W, H;               // the grid proper
+    int pad, Wp;            // border width and row pitch (cells)
     float ox, oy, inv_res;
     float lf_out;           // value for endpoints outside the grid
     int bytes_padded;       // field bytes rounded up to 16 (TMA bulk copy granularity)
@@ -145,21 +151,91 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, uint
 // Particles are then taken four at a time: their poses are broadcast by shuffle and the 32 lanes take beams l, l+32, ...
 // (beam points are pre-scaled to cell units on the host), so one shared-memory beam load feeds four evaluations.
 // Cell index = round-to-nearest-even via the 1.5*2^23 magic add (FMA pipe) instead of F2I (XU pipe).
+// When all 32 particles of a batch lie inside the map (the overwhelmingly common case) no endpoint can leave the
+// bordered field (border >= longest beam), so the evaluation is 4 FFMA + 2 FADD + IMAD + LEA + load + FADD with no
+// bounds test: the magic-add bit patterns are fed to the address arithmetic as they are, their constant parts folded
+// into the base. Any batch with a particle outside the map takes the bounds-tested path; both give the same values.
 // Per-lane partial sums of the 32 particles are combined by a transpose-reduction: 31 shuffles per 32 particles, and
 // for every particle exactly the xor-butterfly (16,8,4,2,1) summation tree that DESIGN.md NS-3 specifies.
 constexpr float NS_MAGIC = 12582912.0f;          // 1.5 * 2^23
 constexpr int NS_MAGIC_BITS = 0x4B400000;
 
-__device__ __forceinline__ float ns_eval(const float* __restrict__ lf, float gx0, float gy0, float c, float s, float2 bm, unsigned W, unsigned H,
-                                         float lf_out, bool smem) {
+template <bool SMEM>
+struct NsFieldView {
+    const float* lf;        // generic pointer (global path, and the bounds-tested path)
+    uint32_t base;          // SMEM fast path: shared byte address of the field + folded constant; else folded cell constant
+    uint32_t Wp, Wp4;
+    unsigned W, H;
+    int pad;
+    float lf_out;
+};
+
+// bounds-tested evaluation (any particle position)
+template <bool SMEM>
+__device__ __forceinline__ float ns_eval_checked(const NsFieldView<SMEM>& V, float gx0, float gy0, float c, float s, float2 bm) {
     const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
     const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
     const unsigned ix = (unsigned)(__float_as_int(tx) - NS_MAGIC_BITS);
     const unsigned iy = (unsigned)(__float_as_int(ty) - NS_MAGIC_BITS);
-    const bool in = ix < W && iy < H;
-    const unsigned idx = in ? iy * W + ix : 0u;
-    const float v = smem ? lf[idx] : __ldg(lf + idx);
-    return in ? v : lf_out;
+    const bool in = ix < V.W && iy < V.H;
+    const unsigned idx = in ? (iy + V.pad) * V.Wp + ix + V.pad : 0u;
+    const float v = SMEM ? V.lf[idx] : __ldg(V.lf + idx);
+    return in ? v : V.lf_out;
+}
+// evaluation for a particle inside the map: the endpoint is inside the bordered field by construction
+template <bool SMEM>
+__device__ __forceinline__ float ns_eval_fast(const NsFieldView<SMEM>& V, float gx0, float gy0, float c, float s, float2 bm) {
+    const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
+    const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
+    if (SMEM) {
+        // byte address = field + 4 * ((iy + pad) * Wp + ix + pad), iy = bits(ty) - MAGIC_BITS (wrapping u32 arithmetic)
+        // (IMAD, LEA, LDS: written as PTX so the compiler does not re-associate it into three integer operations)
+        float v;
+        asm("{\n.reg .u32 t, u;\nmad.lo.u32 t, %1, %2, %3;\nshl.b32 u, %4, 2;\nadd.u32 t, t, u;\nld.shared.f32 %0, [t];\n}"
+            : "=f"(v)
+            : "r"(__float_as_uint(ty)), "r"(V.Wp4), "r"(V.base), "r"(__float_as_uint(tx)));
+        return v;
+    } else {
+        const uint32_t idx = __float_as_uint(ty) * V.Wp + V.base + __float_as_uint(tx);
+        return __ldg(V.lf + idx);
+    }
+}
+
+template <bool SMEM, bool FAST>
+__device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, const float2* __restrict__ s_beams, int n_beams, int lane, float gx0,
+                                                float gy0, float c, float s) {
+    float acc[32];
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+        float X[4], Y[4], C[4], S[4], a[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            X[q] = __shfl_sync(0xffffffffu, gx0, k0 + q); Y[q] = __shfl_sync(0xffffffffu, gy0, k0 + q);
+            C[q] = __shfl_sync(0xffffffffu, c, k0 + q); S[q] = __shfl_sync(0xffffffffu, s, k0 + q);
+            a[q] = 0.f;
+        }
+#pragma unroll 2
+        for (int b = lane; b < n_beams; b += 32) {
+            const float2 bm = s_beams[b];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                a[q] = ns::addf(a[q], FAST ? ns_eval_fast<SMEM>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<SMEM>(V, X[q], Y[q], C[q], S[q], bm));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
+    }
+    // transpose-reduction: after the stage with offset o, lanes with bit o set hold the upper half of the particles
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; j++) {
+            const float keep = up ? acc[j + o] : acc[j];
+            const float send = up ? acc[j] : acc[j + o];
+            acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+    }
+    return acc[0];
 }
 
 template <bool SMEM_FIELD>
@@ -174,9 +250,16 @@ __global__ void __launch_bounds__(512, 1) k_ns_update(const float4* __restrict__
     if (SMEM_FIELD) tma_stage(s_lf, F.lf, (uint32_t)F.bytes_padded, &bar);
     for (int b = threadIdx.x; b < n_beams; b += blockDim.x) s_beams[b] = beams[b];
     __syncthreads();
-    const float* lf = SMEM_FIELD ? s_lf : F.lf;
-    const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
-    const float lf_out = F.lf_out, ox = F.ox, oy = F.oy, inv_res = F.inv_res;
+    NsFieldView<SMEM_FIELD> V;
+    V.lf = SMEM_FIELD ? s_lf : F.lf;
+    V.Wp = (uint32_t)F.Wp; V.Wp4 = 4u * (uint32_t)F.Wp;
+    V.W = (unsigned)F.W; V.H = (unsigned)F.H; V.pad = F.pad; V.lf_out = F.lf_out;
+    // (pad - MAGIC_BITS) * (Wp + 1): turns the raw magic-add bit patterns into the bordered cell index (mod 2^32)
+    const uint32_t fold = (uint32_t)(F.pad - NS_MAGIC_BITS) * ((uint32_t)F.Wp + 1u);
+    V.base = SMEM_FIELD ? smem_u32(s_lf) + 4u * fold : fold;
+    const bool fast_ok = F.pad > 0;
+    const float ox = F.ox, oy = F.oy, inv_res = F.inv_res;
+    const float x_hi = (float)F.W - 0.5f, y_hi = (float)F.H - 0.5f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const int64_t n_batches = (n + 31) / 32;
     float best = -3.0e38f;
@@ -188,37 +271,11 @@ __global__ void __launch_bounds__(512, 1) k_ns_update(const float4* __restrict__
         ns::det_sincosf(p.z, s, c);
         const float gx0 = ns::fmaf_(ns::addf(p.x, -ox), inv_res, -0.5f);
         const float gy0 = ns::fmaf_(ns::addf(p.y, -oy), inv_res, -0.5f);
-        float acc[32];
-#pragma unroll
-        for (int k0 = 0; k0 < 32; k0 += 4) {
-            float X[4], Y[4], C[4], S[4], a[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                X[q] = __shfl_sync(0xffffffffu, gx0, k0 + q); Y[q] = __shfl_sync(0xffffffffu, gy0, k0 + q);
-                C[q] = __shfl_sync(0xffffffffu, c, k0 + q); S[q] = __shfl_sync(0xffffffffu, s, k0 + q);
-                a[q] = 0.f;
-            }
-#pragma unroll 2
-            for (int b = lane; b < n_beams; b += 32) {
-                const float2 bm = s_beams[b];
-#pragma unroll
-                for (int q = 0; q < 4; q++) a[q] = ns::addf(a[q], ns_eval(lf, X[q], Y[q], C[q], S[q], bm, W, H, lf_out, SMEM_FIELD));
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
-        }
-        // transpose-reduction: after the stage with offset o, lanes with bit o set hold the upper half of the particles
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int j = 0; j < o; j++) {
-                const float keep = up ? acc[j + o] : acc[j];
-                const float send = up ? acc[j] : acc[j + o];
-                acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
-            }
-        }
-        if (i < n) { ll_out[i] = acc[0]; best = fmaxf(best, acc[0]); }
+        const bool inside = gx0 >= -0.5f && gx0 <= x_hi && gy0 >= -0.5f && gy0 <= y_hi;        // false for NaN
+        float ll;
+        if (fast_ok && __all_sync(0xffffffffu, inside)) ll = ns_score_batch<SMEM_FIELD, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        else ll = ns_score_batch<SMEM_FIELD, false>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        if (i < n) { ll_out[i] = ll; best = fmaxf(best, ll); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));

@@ -197,6 +197,7 @@ private:
     DevBuf<int> d_maxbits;
     int ns_R = 0, ns_beams_n = 0;
     size_t lf_bytes_padded = 0;
+    int lf_pad = 0, lf_wp = 0, lf_hp = 0;      // bordered field: border width, row pitch, rows
     float lf_out = 0.f, ns_last_max = 0.f;
     bool ns_attr_set = false;
     bool ns_have_ll = false;

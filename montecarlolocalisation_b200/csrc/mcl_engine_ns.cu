@@ -39,12 +39,18 @@ int Engine::ns_build_field() {
     }
     lf_out = table[cap];
     const size_t cells = (size_t)map_w * map_h;
-    lf_bytes_padded = (cells * sizeof(float) + 15) & ~(size_t)15;
+    // border: no beam endpoint of a particle inside the map can leave the stored field (beams >= ns_max_range are dropped)
+    const double reach = (std::fabs(cfg.laser_offset) + cfg.ns_max_range) / (double)res_f;
+    lf_pad = reach < 4096.0 ? (int)std::ceil(reach) + 2 : 0;        // 0: absurd range, keep the bounds-tested path only
+    lf_wp = map_w + 2 * lf_pad; lf_hp = map_h + 2 * lf_pad;
+    const size_t cells_p = (size_t)lf_wp * lf_hp;
+    if (cells_p >= (1ull << 31)) return fail(MCL_ERR_ARG, "set_map: grid too large");
+    lf_bytes_padded = (cells_p * sizeof(float) + 15) & ~(size_t)15;
     CK(d_lf_table.ensure(table.size())); CK(d_lf.ensure(lf_bytes_padded / sizeof(float))); CK(d_d2.ensure(cells)); CK(d_g.ensure(cells));
     CK(cudaMemcpyAsync(d_lf_table.p, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemsetAsync(d_lf.p, 0, lf_bytes_padded, stream));
+    LAUNCH(K_NS_EDT_COLS, k_ns_fill_f32, 148 * 8, 256, 0, d_lf.p, lf_bytes_padded / sizeof(float), lf_out);
     LAUNCH(K_NS_EDT_COLS, k_ns_edt_cols, grid_for(map_w, 128), 128, 0, d_occ.p, map_w, map_h, ns_R, d_g.p);
-    LAUNCH(K_NS_EDT_ROWS, k_ns_edt_rows, dim3(grid_for(map_w, 128), map_h), 128, 0, d_g.p, map_w, map_h, ns_R, d_lf_table.p, d_d2.p, d_lf.p);
+    LAUNCH(K_NS_EDT_ROWS, k_ns_edt_rows, dim3(grid_for(map_w, 128), map_h), 128, 0, d_g.p, map_w, map_h, ns_R, d_lf_table.p, d_d2.p, d_lf.p, lf_pad);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
@@ -54,7 +60,8 @@ int Engine::ns_download_field(float* lf, uint16_t* d2) {
     CK(cudaSetDevice(cfg.device));
     if (!map_ready || cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "download_field: NS mode with a map only");
     const size_t cells = (size_t)map_w * map_h;
-    if (lf) CK(cudaMemcpyAsync(lf, d_lf.p, cells * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (lf) CK(cudaMemcpy2DAsync(lf, (size_t)map_w * sizeof(float), d_lf.p + (size_t)lf_pad * lf_wp + lf_pad, (size_t)lf_wp * sizeof(float),
+                                 (size_t)map_w * sizeof(float), map_h, cudaMemcpyDeviceToHost, stream));
     if (d2) CK(cudaMemcpyAsync(d2, d_d2.p, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
@@ -169,7 +176,7 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
     if (n == 0) return fail(MCL_ERR_ARG, "update: no particles");
     ns_beams_n = n_pts;
     NsField F;
-    F.lf = d_lf.p; F.W = map_w; F.H = map_h; F.ox = (float)origin_x; F.oy = (float)origin_y;
+    F.lf = d_lf.p; F.W = map_w; F.H = map_h; F.pad = lf_pad; F.Wp = lf_wp; F.ox = (float)origin_x; F.oy = (float)origin_y;
     F.inv_res = 1.0f / res_f; F.lf_out = lf_out; F.bytes_padded = (int)lf_bytes_padded;
     const int init_bits = INT32_MIN;
     CK(cudaMemcpyAsync(d_maxbits.p, &init_bits, sizeof(int), cudaMemcpyHostToDevice, stream));
