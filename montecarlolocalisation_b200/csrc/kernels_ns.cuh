@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_ns_predict(float4* __restrict__ part, i
     const float tr = ns::fmaf_(z1, m.sd_trans, m.trans);
     const float r2 = ns::fmaf_(z2, m.sd_rot2, m.rot2);
     float s, c;
-    ns::det_sincosf(ns::addf(p.z, r1), s, c);
+    ns::det_sincosf32(ns::addf(p.z, r1), s, c);
     p.x = ns::fmaf_(tr, c, p.x);
     p.y = ns::fmaf_(tr, s, p.y);
     p.z = ns::wrap_pi(ns::addf(p.z, ns::addf(r1, r2)));
@@ -201,50 +201,68 @@ __device__ __forceinline__ float ns_eval_fast(const NsFieldView<SMEM>& V, float 
     }
 }
 
-template <bool SMEM, bool FAST>
+// Scores the 32 particles of a warp batch in groups of P: partial sums acc[P] per lane, then per group the xor butterfly
+// stages 16 .. P as plain butterflies and stages P/2 .. 1 as a transpose-reduction, after which lane l holds the total of
+// particle (l mod P) of the group in acc[0]; lanes l with l / P == group keep it, so lane l ends with particle l.
+// Every particle's beams are summed by exactly the (16,8,4,2,1) xor-butterfly tree of DESIGN.md NS-3 whatever P is.
+// P trades shuffles (31 per 32 particles at P = 32, 2.9 per particle at P = 8) against registers (occupancy).
+template <bool SMEM, bool FAST, int P>
 __device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, const float2* __restrict__ s_beams, int n_beams, int lane, float gx0,
                                                 float gy0, float c, float s) {
-    float acc[32];
+    float mine = 0.f;
+#pragma unroll 1
+    for (int g0 = 0; g0 < 32; g0 += P) {
+        float acc[P];
 #pragma unroll
-    for (int k0 = 0; k0 < 32; k0 += 4) {
-        float X[4], Y[4], C[4], S[4], a[4];
+        for (int k0 = 0; k0 < P; k0 += 4) {
+            float X[4], Y[4], C[4], S[4], a[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            X[q] = __shfl_sync(0xffffffffu, gx0, k0 + q); Y[q] = __shfl_sync(0xffffffffu, gy0, k0 + q);
-            C[q] = __shfl_sync(0xffffffffu, c, k0 + q); S[q] = __shfl_sync(0xffffffffu, s, k0 + q);
-            a[q] = 0.f;
-        }
+            for (int q = 0; q < 4; q++) {
+                X[q] = __shfl_sync(0xffffffffu, gx0, g0 + k0 + q); Y[q] = __shfl_sync(0xffffffffu, gy0, g0 + k0 + q);
+                C[q] = __shfl_sync(0xffffffffu, c, g0 + k0 + q); S[q] = __shfl_sync(0xffffffffu, s, g0 + k0 + q);
+                a[q] = 0.f;
+            }
 #pragma unroll 2
-        for (int b = lane; b < n_beams; b += 32) {
-            const float2 bm = s_beams[b];
+            for (int b = lane; b < n_beams; b += 32) {
+                const float2 bm = s_beams[b];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                a[q] = ns::addf(a[q], FAST ? ns_eval_fast<SMEM>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<SMEM>(V, X[q], Y[q], C[q], S[q], bm));
+                for (int q = 0; q < 4; q++)
+                    a[q] = ns::addf(a[q], FAST ? ns_eval_fast<SMEM>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<SMEM>(V, X[q], Y[q], C[q], S[q], bm));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
-    }
-    // transpose-reduction: after the stage with offset o, lanes with bit o set hold the upper half of the particles
+        for (int o = 16; o >= P; o >>= 1) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int j = 0; j < o; j++) {
-            const float keep = up ? acc[j + o] : acc[j];
-            const float send = up ? acc[j] : acc[j + o];
-            acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            for (int j = 0; j < P; j++) acc[j] = ns::addf(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], o));
         }
+        // transpose-reduction: after the stage with offset o, lanes with bit o set hold the upper half of the particles
+#pragma unroll
+        for (int o = (P < 32 ? P / 2 : 16); o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; j++) {
+                const float keep = up ? acc[j + o] : acc[j];
+                const float send = up ? acc[j] : acc[j + o];
+                acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            }
+        }
+        if ((lane & ~(P - 1)) == g0) mine = acc[0];
     }
-    return acc[0];
+    return mine;
 }
 
+constexpr int NS_UPD_THREADS = 1024;
+constexpr int NS_UPD_P = 8;
+
 template <bool SMEM_FIELD>
-__global__ void __launch_bounds__(512, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
-                                                   const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
-                                                   int* __restrict__ max_bits /* ordered-int max of ll */) {
+__global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
+                                                                const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
+                                                                int* __restrict__ max_bits /* ordered-int max of ll */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    __shared__ float warp_max[16];
+    __shared__ float warp_max[NS_UPD_THREADS / 32];
     float* s_lf = reinterpret_cast<float*>(smem_raw);
     float2* s_beams = reinterpret_cast<float2*>(smem_raw + (SMEM_FIELD ? F.bytes_padded : 0));
     if (SMEM_FIELD) tma_stage(s_lf, F.lf, (uint32_t)F.bytes_padded, &bar);
@@ -273,8 +291,8 @@ __global__ void __launch_bounds__(512, 1) k_ns_update(const float4* __restrict__
         const float gy0 = ns::fmaf_(ns::addf(p.y, -oy), inv_res, -0.5f);
         const bool inside = gx0 >= -0.5f && gx0 <= x_hi && gy0 >= -0.5f && gy0 <= y_hi;        // false for NaN
         float ll;
-        if (fast_ok && __all_sync(0xffffffffu, inside)) ll = ns_score_batch<SMEM_FIELD, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
-        else ll = ns_score_batch<SMEM_FIELD, false>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        if (fast_ok && __all_sync(0xffffffffu, inside)) ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        else ll = ns_score_batch<SMEM_FIELD, false, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
         if (i < n) { ll_out[i] = ll; best = fmaxf(best, ll); }
     }
 #pragma unroll
@@ -292,9 +310,15 @@ __global__ void __launch_bounds__(512, 1) k_ns_update(const float4* __restrict__
 }
 
 // ---- weights + prefix sum -------------------------------------------------------------------------------------------------
+// W_i = Q32 weight of particle i, prefix[i] = W_0 + ... + W_i over this shard, in two passes: tile sums (with group sums
+// accumulated by integer atomics: exact, order-independent), then the prefix, every tile finding its own offset from the
+// sums before it. The log-likelihoods were just written by the sensor-model kernel and are re-read from L2; HBM sees the
+// 8-byte prefix writes. No spin-waits, no inter-block dependency inside a kernel.
 constexpr int NS_SCAN_THREADS = 256;
-constexpr int NS_SCAN_ITEMS = 8;
-constexpr int NS_SCAN_TILE = NS_SCAN_THREADS * NS_SCAN_ITEMS;
+constexpr int NS_SCAN_ITEMS = 16;                                    // per thread: 4 x float4
+constexpr int NS_SCAN_WARP_ITEMS = 32 * NS_SCAN_ITEMS;               // a warp owns 512 consecutive particles
+constexpr int NS_SCAN_TILE = NS_SCAN_THREADS * NS_SCAN_ITEMS;        // 4096
+constexpr int NS_SCAN_GROUP = 64;                                    // tiles per group sum
 
 // the global maximum log-likelihood lives in device memory as an order-preserving int (so atomicMax / NCCL max work)
 __device__ __forceinline__ float ns_decode_max(const int* __restrict__ max_bits) {
@@ -305,81 +329,115 @@ __device__ __forceinline__ float ns_decode_max(const int* __restrict__ max_bits)
 __device__ __forceinline__ uint64_t ns_weight(float ll, float max_ll, float temper) {
     return ns::det_exp_q32(ns::mulf(temper, ns::addf(ll, -max_ll)));
 }
-__device__ __forceinline__ uint64_t block_scan_u64(uint64_t v, uint64_t* sm8, uint64_t& block_total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ uint64_t warp_scan_u64(uint64_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint64_t t = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v += t;
     }
-    if (lane == 31) sm8[warp] = v;
-    __syncthreads();
-    uint64_t pre = 0, tot = 0;
-    for (int k = 0; k < NS_SCAN_THREADS / 32; k++) { if (k < warp) pre += sm8[k]; tot += sm8[k]; }
-    __syncthreads();
-    block_total = tot;
-    return pre + v;      // inclusive
+    return v;
 }
-// pass 1: per-tile sums of W
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// 32-byte store (sm_100: 256-bit global accesses)
+__device__ __forceinline__ void st_v4_u64(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+// Lane l of a warp holds the four float4 groups 4 (l + 32 j) .. + 3 (j = 0..3) of the warp's 512 particles: loads are
+// 512-byte and stores 1-KiB contiguous per warp instruction, and the scan needs no shared-memory transpose.
+__device__ __forceinline__ void ns_load_weights(const float* __restrict__ ll, int64_t n, int64_t base, float max_ll, float temper,
+                                                uint64_t (&w)[4][4], uint64_t (&s)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = base + j * 128;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i + 3 < n) { const float4 q = *reinterpret_cast<const float4*>(ll + i); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else { for (int e = 0; e < 4; e++) if (i + e < n) v[e] = ll[i + e]; }
+        s[j] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) { w[j][e] = (i + e < n) ? ns_weight(v[e], max_ll, temper) : 0ull; s[j] += w[j][e]; }
+    }
+}
+// pass 1: tile_sums[tile], group_sums[tile / 64] += (group_sums zeroed before the launch)
 __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
-                                                                   float temper, uint64_t* __restrict__ tile_sums) {
-    __shared__ uint64_t sm[8];
+                                                                   float temper, uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ group_sums) {
+    __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float max_ll = ns_decode_max(max_bits);
-    const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)threadIdx.x * NS_SCAN_ITEMS;
-    uint64_t s = 0;
+    const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)warp * NS_SCAN_WARP_ITEMS + lane * 4;
+    uint64_t w[4][4], s[4];
+    ns_load_weights(ll, n, base, max_ll, temper, w, s);
+    const uint64_t tot = warp_sum_u64(s[0] + s[1] + s[2] + s[3]);
+    if (lane == 0) s_warp[warp] = tot;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t t = 0;
 #pragma unroll
-    for (int j = 0; j < NS_SCAN_ITEMS; j++)
-        if (base + j < n) s += ns_weight(ll[base + j], max_ll, temper);
-    uint64_t tot;
-    block_scan_u64(s, sm, tot);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-}
-// pass 2: exclusive scan of tile sums (one block), grand total
-__global__ void __launch_bounds__(1024) k_ns_tile_offsets(uint64_t* __restrict__ tile_sums, int nt, uint64_t* __restrict__ total) {
-    __shared__ uint64_t sm[1024];
-    uint64_t carry = 0;
-    for (int c0 = 0; c0 < nt; c0 += 1024) {
-        const int i = c0 + threadIdx.x;
-        uint64_t v = i < nt ? tile_sums[i] : 0;
-        sm[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            uint64_t t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
-            __syncthreads();
-            sm[threadIdx.x] += t;
-            __syncthreads();
-        }
-        if (i < nt) tile_sums[i] = carry + sm[threadIdx.x] - v;      // exclusive
-        carry += sm[1023];
-        __syncthreads();
+        for (int k = 0; k < NS_SCAN_THREADS / 32; k++) t += s_warp[k];
+        tile_sums[blockIdx.x] = t;
+        atomicAdd((unsigned long long*)(group_sums + blockIdx.x / NS_SCAN_GROUP), (unsigned long long)t);
     }
-    if (threadIdx.x == 0) *total = carry;
 }
-// pass 3: inclusive prefix per particle (local to this shard), and the unnormalised weight into the particle record
+// pass 2: inclusive prefix per particle (local to this shard); block 0 also writes the shard total
 __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
-                                                                    float temper, const uint64_t* __restrict__ tile_offsets,
-                                                                    uint64_t* __restrict__ prefix, float4* __restrict__ part) {
-    __shared__ uint64_t sm[8];
+                                                                    float temper, const uint64_t* __restrict__ tile_sums,
+                                                                    const uint64_t* __restrict__ group_sums, int n_tiles,
+                                                                    uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out) {
+    __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32], s_offp[NS_SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, group = tile / NS_SCAN_GROUP;
+    // this tile's offset: whole groups before it + the tiles of its own group before it
+    uint64_t part = 0;
+    for (int g = tid; g < group; g += NS_SCAN_THREADS) part += group_sums[g];
+    if (tid < tile - group * NS_SCAN_GROUP) part += tile_sums[group * NS_SCAN_GROUP + tid];
+    part = warp_sum_u64(part);
+    if (lane == 0) s_offp[warp] = part;
+    if (tile == 0) {                                                 // shard total = all group sums
+        const int n_groups = (n_tiles + NS_SCAN_GROUP - 1) / NS_SCAN_GROUP;
+        uint64_t t = 0;
+        for (int g = tid; g < n_groups; g += NS_SCAN_THREADS) t += group_sums[g];
+        t = warp_sum_u64(t);
+        if (lane == 0) s_warp[warp] = t;
+        __syncthreads();
+        if (tid == 0) { uint64_t a = 0; for (int k = 0; k < NS_SCAN_THREADS / 32; k++) a += s_warp[k]; *total_out = a; }
+        __syncthreads();
+    }
     const float max_ll = ns_decode_max(max_bits);
-    const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)threadIdx.x * NS_SCAN_ITEMS;
-    uint64_t w[NS_SCAN_ITEMS];
-    uint64_t s = 0;
+    const int64_t base = (int64_t)tile * NS_SCAN_TILE + (int64_t)warp * NS_SCAN_WARP_ITEMS + lane * 4;
+    uint64_t w[4][4], s[4], incl[4];
+    ns_load_weights(ll, n, base, max_ll, temper, w, s);
+    uint64_t carry = 0;
 #pragma unroll
-    for (int j = 0; j < NS_SCAN_ITEMS; j++) {
-        w[j] = (base + j < n) ? ns_weight(ll[base + j], max_ll, temper) : 0;
-        s += w[j];
+    for (int j = 0; j < 4; j++) {
+        incl[j] = warp_scan_u64(s[j], lane) + carry;
+        carry = __shfl_sync(0xffffffffu, incl[j], 31);
     }
-    uint64_t tot;
-    uint64_t incl = block_scan_u64(s, sm, tot);
-    uint64_t run = tile_offsets[blockIdx.x] + incl - s;
+    if (lane == 31) s_warp[warp] = carry;                            // warp total
+    __syncthreads();
+    uint64_t off = 0;
 #pragma unroll
-    for (int j = 0; j < NS_SCAN_ITEMS; j++) {
-        run += w[j];
-        if (base + j < n) {
-            prefix[base + j] = run;
-            part[base + j].w = (float)((double)w[j] * 2.3283064365386963e-10);      // W * 2^-32, max particle = 1
-        }
+    for (int k = 0; k < NS_SCAN_THREADS / 32; k++) { off += s_offp[k]; if (k < warp) off += s_warp[k]; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = base + j * 128;
+        uint64_t run = off + incl[j] - s[j];
+        uint64_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { run += w[j][e]; o[e] = run; }
+        if (i + 3 < n) st_v4_u64(prefix + i, o[0], o[1], o[2], o[3]);
+        else { for (int e = 0; e < 4; e++) if (i + e < n) prefix[i + e] = o[e]; }
     }
+}
+// The unnormalised weight W * 2^-32 (max particle = 1) into the particle records: only when somebody asks for the
+// particles or the pose between update and resample (the filter loop itself never needs it).
+__global__ void __launch_bounds__(256) k_ns_materialise_w(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits, float temper,
+                                                          float4* __restrict__ part) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    part[i].w = (float)((double)ns_weight(ll[i], ns_decode_max(max_bits), temper) * 2.3283064365386963e-10);
 }
 
 // ---- systematic resampling ------------------------------------------------------------------------------------------------
@@ -389,27 +447,193 @@ struct NsDest {
     int64_t per_rank;       // slots [r*per_rank, (r+1)*per_rank) live on shard r
     int world;
 };
-// Output slot k (global) takes the first particle i of this shard with (offset + prefix[i]) selecting k. Slots
-// [k_lo, k_hi) are exactly those whose ancestor lives here (host plan, ns_plan.hpp).
-__global__ void __launch_bounds__(256) k_ns_resample(const float4* __restrict__ src, const uint64_t* __restrict__ prefix, int64_t n_local,
-                                                     int64_t g0, uint64_t offset, uint64_t total, uint64_t n_global, uint32_t u0,
-                                                     int64_t k_lo, int64_t k_hi, NsDest D, float new_weight) {
-    const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= k_hi) return;
-    const ns::U128 rhs = ns::rhs_of((uint64_t)k, u0, total);
-    int64_t lo = 0, len = n_local;
-    while (len > 0) {                       // first i with selects(offset + prefix[i])
+// The resampling plan of this shard: slots [k_lo, k_hi) are exactly those whose ancestor lives here (ns_plan.hpp).
+// Slot k selects the first particle i with offset + prefix[i] > thr(k), thr(k) = floor(((k << 32) + u0) * total / (N << 32))
+// (the integer form of u_k = (k + u0 / 2^32) / N against the normalised CDF). Moving one slot on adds total * 2^32 to the
+// numerator, i.e. (dq1, dr1 << 32) in (quotient, remainder) form; thresholds are advanced with that, exactly.
+struct NsPlan {
+    uint64_t offset, total;
+    int64_t k_lo, k_hi;
+    uint64_t dq1, dr1;      // total = dq1 * N + dr1
+    uint64_t dqs, drs;      // NS_RS_THREADS slots on: (NS_RS_THREADS * total) = dqs * N + drs
+};
+constexpr int NS_RS_THREADS = 256;
+constexpr int NS_RS_ITEMS = 4;
+constexpr int NS_RS_TILE = NS_RS_THREADS * NS_RS_ITEMS;             // output slots per tile
+constexpr int NS_RS_CAP = 2560;                                      // prefix entries staged in shared memory per tile (8 CTAs/SM fit)
+
+__device__ __forceinline__ void ns_plan_steps(NsPlan& p, uint64_t n_global) {
+    p.dq1 = p.total / n_global; p.dr1 = p.total % n_global;
+    // NS_RS_THREADS * total < 2^8 * 2^62: split so that nothing overflows
+    const uint64_t x = p.dr1 * NS_RS_THREADS;                         // < 2^39
+    p.dqs = p.dq1 * NS_RS_THREADS + x / n_global; p.drs = x % n_global;
+}
+// plan from the all-gathered Q32 totals, on the device (no host round trip)
+__global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int rank, uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t off = 0, tot = 0;
+    for (int r = 0; r < world; r++) { if (r < rank) off += totals[r]; tot += totals[r]; }
+    NsPlan p;
+    p.offset = off; p.total = tot;
+    p.k_lo = tot ? ns::first_slot(off, tot, n_global, u0) : 0;
+    p.k_hi = tot ? ns::first_slot(off + totals[rank], tot, n_global, u0) : 0;
+    ns_plan_steps(p, n_global);
+    *plan = p;
+}
+// plan handed in by the host (phase-by-phase API)
+__global__ void k_ns_plan_set(NsPlan p, uint64_t n_global, NsPlan* __restrict__ plan) { ns_plan_steps(p, n_global); *plan = p; }
+
+struct NsThr {
+    uint64_t q, r;          // ((k << 32) + u0) * total = q * (N << 32) + r
+};
+// by long division (once per output tile)
+__device__ __forceinline__ NsThr ns_thr_of(uint64_t k, uint32_t u0, uint64_t total, uint64_t n_global) {
+    const ns::U128 P = ns::mul64((k << 32) + u0, total);             // < 2^63 * 2^62
+    // floor(P / (N << 32)) = floor((P >> 32) / N), in 32-bit limbs; the top two limbs are P.hi itself (< 2^61)
+    const uint64_t lo = P.lo;
+    const uint64_t q1 = P.hi / n_global;
+    uint64_t rem = P.hi % n_global;
+    const uint64_t t = (rem << 32) | (lo >> 32);
+    const uint64_t q0 = t / n_global;
+    rem = t % n_global;
+    NsThr o;
+    o.q = (q1 << 32) + q0;
+    o.r = (rem << 32) | (lo & 0xffffffffull);
+    return o;
+}
+// threshold `steps` (< 2^9) slots after `t`: exact, one small quotient (<= steps) found with an f64 estimate and fixed up
+__device__ __forceinline__ NsThr ns_thr_ahead(const NsThr& t, uint32_t steps, uint64_t dq1, uint64_t dr1, uint64_t n_global, double inv_n) {
+    const uint64_t x = (t.r >> 32) + (uint64_t)steps * dr1;           // < 2^31 + 2^9 * 2^31
+    uint64_t c = (uint64_t)((double)x * inv_n);
+    if (c * n_global > x) --c;
+    else if ((c + 1) * n_global <= x) ++c;
+    NsThr o;
+    o.q = t.q + (uint64_t)steps * dq1 + c;
+    o.r = ((x - c * n_global) << 32) | (t.r & 0xffffffffull);
+    return o;
+}
+// first i in [lo, hi) with prefix[i] > v, else hi
+__device__ __forceinline__ int64_t ns_search_global(const uint64_t* __restrict__ prefix, uint64_t v, int64_t lo, int64_t hi) {
+    int64_t len = hi - lo;
+    while (len > 0) {
         const int64_t half = len >> 1;
-        if (!ns::selects(offset + prefix[lo + half], n_global, rhs)) { lo += half + 1; len -= half + 1; } else len = half;
+        if (!(prefix[lo + half] > v)) { lo += half + 1; len -= half + 1; } else len = half;
     }
-    if (lo >= n_local) lo = n_local - 1;    // cannot happen when the plan is right; keeps the access in range
-    float4 p = src[lo];
-    p.w = new_weight;
-    int r = (int)(k / D.per_rank);
-    if (r >= D.world) r = D.world - 1;
-    const int64_t slot = k - (int64_t)r * D.per_rank;
-    D.part[r][slot] = p;
-    D.anc[r][slot] = (int)(g0 + lo);
+    return lo;
+}
+struct NsTileHead {
+    uint64_t q, r;          // threshold of the tile's first slot
+    int i_lo;               // its ancestor (local index)
+    int pad;
+};
+
+// pass 1 (merge-path partition): head[t] = threshold and ancestor of the first slot of output tile t (t = 0 .. tiles;
+// the last entry describes the last slot instead)
+__global__ void __launch_bounds__(256) k_ns_resample_bounds(const uint64_t* __restrict__ prefix, int64_t n_local, const NsPlan* __restrict__ plan,
+                                                            uint64_t n_global, uint32_t u0, NsTileHead* __restrict__ head) {
+    const NsPlan P = *plan;
+    const int64_t tiles = (P.k_hi - P.k_lo + NS_RS_TILE - 1) / NS_RS_TILE;
+    if (tiles <= 0) return;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= tiles; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = P.k_lo + t * NS_RS_TILE;
+        if (k >= P.k_hi) k = P.k_hi - 1;
+        const NsThr th = ns_thr_of((uint64_t)k, u0, P.total, n_global);
+        // by the plan thr >= offset for every slot of this shard; a smaller one would select the first particle
+        int64_t i = th.q >= P.offset ? ns_search_global(prefix, th.q - P.offset, 0, n_local) : 0;
+        if (i >= n_local) i = n_local - 1;
+        NsTileHead h;
+        h.q = th.q; h.r = th.r; h.i_lo = (int)i; h.pad = 0;
+        head[t] = h;
+    }
+}
+// pass 2: every tile of NS_RS_TILE consecutive output slots stages the prefix range its ancestors lie in (coalesced).
+// Thread t resolves the four CONSECUTIVE slots 4t .. 4t+3: one branch-free binary search for the first, then short
+// forward walks (ancestors are non-decreasing in the slot index: a merge); the ancestors are exchanged through shared
+// memory so that gathers and stores run slot-strided (coalesced), each survivor going straight into the shard that owns
+// its slot (own memory or a peer GPU's over NVLink). Ranges too long for shared memory are searched in global memory.
+__global__ void __launch_bounds__(NS_RS_THREADS) k_ns_resample(const float4* __restrict__ src, const uint64_t* __restrict__ prefix, int64_t n_local,
+                                                               int64_t g0, const NsPlan* __restrict__ plan, const NsTileHead* __restrict__ head,
+                                                               uint64_t n_global, double inv_n, NsDest D, float new_weight) {
+    __shared__ uint64_t s_pre[NS_RS_CAP];
+    __shared__ __align__(16) int s_anc[NS_RS_TILE];
+    const NsPlan P = *plan;
+    const int64_t tiles = (P.k_hi - P.k_lo + NS_RS_TILE - 1) / NS_RS_TILE;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t k0 = P.k_lo + t * NS_RS_TILE;
+        const NsTileHead H = head[t];
+        const int i_lo = H.i_lo, i_hi = head[t + 1].i_lo;           // ancestors of this tile lie in [i_lo, i_hi]
+        const int range = i_hi - i_lo + 1;
+        const bool staged = range <= NS_RS_CAP;
+        if (staged)
+            for (int j = threadIdx.x; j < range; j += NS_RS_THREADS) s_pre[j] = prefix[i_lo + j];
+        __syncthreads();
+        NsThr th;
+        th.q = H.q; th.r = H.r;
+        th = ns_thr_ahead(th, NS_RS_ITEMS * threadIdx.x, P.dq1, P.dr1, n_global, inv_n);
+        const uint64_t* pre = prefix + i_lo;
+        int pos = 0;                                                  // entries of the range that do not select the current slot
+        int anc[NS_RS_ITEMS];
+#pragma unroll
+        for (int it = 0; it < NS_RS_ITEMS; it++) {
+            // by the plan thr >= offset for every slot of this shard; a smaller one would select the first particle
+            const bool none = th.q < P.offset;
+            const uint64_t v = th.q - P.offset;
+            if (staged) {
+                if (it == 0) {
+#pragma unroll
+                    for (int step = 2048; step > 0; step >>= 1) {    // NS_RS_CAP <= 4095
+                        const int np = pos + step;
+                        if (np <= range && !none && s_pre[np - 1] <= v) pos = np;
+                    }
+                } else {
+                    int walked = 0;
+                    while (pos < range && !none && s_pre[pos] <= v && walked < 8) { ++pos; ++walked; }
+                    if (walked == 8) {
+                        int len = range - pos;                        // long gap of (near-)weightless particles: search the rest
+                        while (len > 0) {
+                            const int half = len >> 1;
+                            if (s_pre[pos + half] <= v) { pos += half + 1; len -= half + 1; } else len = half;
+                        }
+                    }
+                }
+            } else if (!none) {
+                pos = (int)(ns_search_global(pre, v, pos, range));
+            }
+            anc[it] = i_lo + min(pos, range - 1);
+            th.q += P.dq1;                                            // one slot on
+            uint64_t rh = (th.r >> 32) + P.dr1;                       // < 2 N
+            if (rh >= n_global) { rh -= n_global; th.q += 1; }
+            th.r = (rh << 32) | (th.r & 0xffffffffull);
+        }
+        *reinterpret_cast<int4*>(s_anc + NS_RS_ITEMS * threadIdx.x) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+        __syncthreads();
+        const int r0 = (int)min((int64_t)(D.world - 1), k0 / D.per_rank);       // shard of the tile's first slot
+        const int64_t base0 = (int64_t)r0 * D.per_rank;
+        int a[NS_RS_ITEMS];
+        float4 p[NS_RS_ITEMS];
+#pragma unroll
+        for (int it = 0; it < NS_RS_ITEMS; it++) {
+            const int j = threadIdx.x + it * NS_RS_THREADS;
+            a[it] = (k0 + j < P.k_hi) ? s_anc[j] : -1;
+        }
+#pragma unroll
+        for (int it = 0; it < NS_RS_ITEMS; it++)
+            if (a[it] >= 0) p[it] = src[a[it]];
+#pragma unroll
+        for (int it = 0; it < NS_RS_ITEMS; it++) {
+            if (a[it] >= 0) {
+                const int64_t kk = k0 + threadIdx.x + it * NS_RS_THREADS;
+                int r = r0;
+                int64_t slot = kk - base0;
+                while (slot >= D.per_rank && r < D.world - 1) { slot -= D.per_rank; ++r; }
+                p[it].w = new_weight;
+                D.part[r][slot] = p[it];
+                D.anc[r][slot] = (int)(g0 + a[it]);
+            }
+        }
+        __syncthreads();
+    }
+    if (D.world > 1) __threadfence_system();        // peer stores visible before the step's closing collective lets anyone read them
 }
 
 // ---- gather micro-benchmark: the denominator for the sensor-model kernel ------------------------------------------------
@@ -435,44 +659,6 @@ __global__ void __launch_bounds__(512) k_gather_bench(const float* __restrict__ 
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
-// The resampling plan of this shard, computed on the device from the all-gathered Q32 totals (no host round trip).
-struct NsPlan {
-    uint64_t offset, total;
-    int64_t k_lo, k_hi;
-};
-__global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int rank, uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t off = 0, tot = 0;
-    for (int r = 0; r < world; r++) { if (r < rank) off += totals[r]; tot += totals[r]; }
-    NsPlan p;
-    p.offset = off; p.total = tot;
-    p.k_lo = tot ? ns::first_slot(off, tot, n_global, u0) : 0;
-    p.k_hi = tot ? ns::first_slot(off + totals[rank], tot, n_global, u0) : 0;
-    *plan = p;
-}
-// k_ns_resample with the plan read from device memory and a grid-stride loop (the slot count is not known on the host).
-__global__ void __launch_bounds__(256) k_ns_resample_planned(const float4* __restrict__ src, const uint64_t* __restrict__ prefix, int64_t n_local,
-                                                             int64_t g0, const NsPlan* __restrict__ plan, uint64_t n_global, uint32_t u0, NsDest D,
-                                                             float new_weight) {
-    const NsPlan P = *plan;
-    for (int64_t k = P.k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P.k_hi; k += (int64_t)gridDim.x * blockDim.x) {
-        const ns::U128 rhs = ns::rhs_of((uint64_t)k, u0, P.total);
-        int64_t lo = 0, len = n_local;
-        while (len > 0) {
-            const int64_t half = len >> 1;
-            if (!ns::selects(P.offset + prefix[lo + half], n_global, rhs)) { lo += half + 1; len -= half + 1; } else len = half;
-        }
-        if (lo >= n_local) lo = n_local - 1;
-        float4 p = src[lo];
-        p.w = new_weight;
-        int r = (int)(k / D.per_rank);
-        if (r >= D.world) r = D.world - 1;
-        const int64_t slot = k - (int64_t)r * D.per_rank;
-        D.part[r][slot] = p;
-        D.anc[r][slot] = (int)(g0 + lo);
-    }
-    __threadfence_system();        // peer stores must be visible before the step's closing collective lets anyone read them
-}
 // out[k] = sum over blocks of partials[b*5+k] (one warp per output, fixed order)
 __global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_blocks, double* __restrict__ out5) {
     const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -483,15 +669,19 @@ __global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_bloc
     if (lane == 0) out5[o] = s;
 }
 
-// Weighted pose sums with the particle weights as they stand: {sum w, sum w x, sum w y, sum w sin, sum w cos} per block.
-__global__ void __launch_bounds__(256) k_ns_pose_partials(const float4* __restrict__ part, int64_t n, double* __restrict__ partials) {
+// Weighted pose sums {sum w, sum w x, sum w y, sum w sin, sum w cos} per block, w = the unnormalised fp32 weight
+// W * 2^-32 recomputed from the log-likelihood (ll != null: between update and resample) or read from the particle record.
+__global__ void __launch_bounds__(256) k_ns_pose_partials(const float4* __restrict__ part, int64_t n, const float* __restrict__ ll,
+                                                          const int* __restrict__ max_bits, float temper, double* __restrict__ partials) {
     __shared__ double ws[8][5];
     double a[5] = {0, 0, 0, 0, 0};
+    const float max_ll = ll ? ns_decode_max(max_bits) : 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float4 p = part[i];
         float s, c;
         ns::det_sincosf(p.z, s, c);
-        const double w = (double)p.w;
+        const float wf = ll ? (float)((double)ns_weight(ll[i], max_ll, temper) * 2.3283064365386963e-10) : p.w;
+        const double w = (double)wf;
         a[0] += w; a[1] += w * (double)p.x; a[2] += w * (double)p.y; a[3] += w * (double)s; a[4] += w * (double)c;
     }
 #pragma unroll

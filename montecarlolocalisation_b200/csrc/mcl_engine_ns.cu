@@ -189,7 +189,7 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
         CK(cudaFuncSetAttribute(k_ns_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         ns_attr_set = true;
     }
-    const int threads = 512;
+    const int threads = NS_UPD_THREADS;
     const int64_t batches = (n + 31) / 32;
     const int64_t ctas_needed = (batches + threads / 32 - 1) / (threads / 32);
     if (in_smem) {
@@ -231,12 +231,24 @@ int Engine::ns_weights_local(float global_max, uint64_t* local_total) {
 }
 
 int Engine::ns_launch_weights() {
-    const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
     const float temper = (float)cfg.ns_temper;
-    LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p);
-    LAUNCH(K_NS_TILEOFF, k_ns_tile_offsets, 1, 1024, 0, d_tile_sums.p, nt, d_u64.p);
-    LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, d_prefix.p, part[cur].p);
+    const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
+    const int ng = (nt + NS_SCAN_GROUP - 1) / NS_SCAN_GROUP;
+    uint64_t* group_sums = d_tile_sums.p + nt;
+    CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
+    LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
+    LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
     CK(cudaGetLastError());
+    ns_w_in_records = false;
+    return MCL_OK;
+}
+
+// The fp32 weights into the particle records, for callers that look at the particles between update and resample.
+int Engine::ns_materialise_weights() {
+    if (cfg.mode != MCL_MODE_NS || !have_weights || ns_w_in_records) return MCL_OK;
+    LAUNCH(K_NS_WSCAN, k_ns_materialise_w, grid_for(n, 256), 256, 0, d_ll.p, n, d_maxbits.p, (float)cfg.ns_temper, part[cur].p);
+    CK(cudaGetLastError());
+    ns_w_in_records = true;
     return MCL_OK;
 }
 
@@ -254,8 +266,22 @@ int Engine::ns_resample_local(uint64_t offset, uint64_t total, uint32_t u0, int6
     uint64_t mine = 0;
     CK(cudaMemcpyAsync(&mine, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    const int64_t k_lo = ns::first_slot(offset, total, (uint64_t)n_global, u0);
-    const int64_t k_hi = ns::first_slot(offset + mine, total, (uint64_t)n_global, u0);
+    NsPlan P;
+    P.offset = offset; P.total = total; P.dq1 = P.dr1 = P.dqs = P.drs = 0;
+    P.k_lo = ns::first_slot(offset, total, (uint64_t)n_global, u0);
+    P.k_hi = ns::first_slot(offset + mine, total, (uint64_t)n_global, u0);
+    CK(d_plan.ensure(sizeof(NsPlan)));
+    LAUNCH(K_NS_PLAN, k_ns_plan_set, 1, 1, 0, P, (uint64_t)n_global, (NsPlan*)d_plan.p);
+    int rc = ns_launch_resample(u0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(stream));       // peers may only swap once every shard's stores have landed
+    if (k_lo_out) *k_lo_out = P.k_lo;
+    if (k_hi_out) *k_hi_out = P.k_hi;
+    return MCL_OK;
+}
+
+// Resampling proper, plan in d_plan: merge-path partition (ancestor of every output tile's first slot), then the tiles.
+int Engine::ns_launch_resample(uint32_t u0) {
     NsDest D;
     D.per_rank = per_rank; D.world = shard_world;
     const int next = cur ^ 1;
@@ -263,18 +289,24 @@ int Engine::ns_resample_local(uint64_t offset, uint64_t total, uint32_t u0, int6
     for (int r = 0; r < shard_world; ++r) {
         if (r == shard_rank) { D.part[r] = part[next].p; D.anc[r] = ancestors.p; }
         else {
-            if (!peer_ptr[next][r] || !peer_ptr[2][r]) return fail(MCL_ERR_COMM, "resample: peer buffers of a shard are not mapped (mcl_peer_import / mcl_peer_set)");
+            if (!peer_ptr[next][r] || !peer_ptr[2][r])
+                return fail(MCL_ERR_COMM, "resample: peer buffers of a shard are not mapped (mcl_comm_init, or mcl_peer_import / mcl_peer_set)");
             D.part[r] = (float4*)peer_ptr[next][r]; D.anc[r] = (int*)peer_ptr[2][r];
         }
     }
-    if (k_hi > k_lo) {
-        LAUNCH(K_NS_RESAMPLE, k_ns_resample, grid_for(k_hi - k_lo, 256), 256, 0, part[cur].p, d_prefix.p, n, shard_begin, offset, total,
-               (uint64_t)n_global, u0, k_lo, k_hi, D, (float)(1.0 / (double)n_global));
-        CK(cudaGetLastError());
-    }
-    CK(cudaStreamSynchronize(stream));       // peers may only swap once every shard's stores have landed
-    if (k_lo_out) *k_lo_out = k_lo;
-    if (k_hi_out) *k_hi_out = k_hi;
+    // a shard can own up to all n_global output slots
+    const int64_t max_tiles = (n_global + NS_RS_TILE - 1) / NS_RS_TILE;
+    CK(d_bounds.ensure(((size_t)max_tiles + 2) * sizeof(NsTileHead)));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    const int g1 = (int)std::min<int64_t>((max_tiles + 1 + 255) / 256, (int64_t)sms * 8);
+    LAUNCH(K_NS_BOUNDS, k_ns_resample_bounds, g1, 256, 0, d_prefix.p, n, (const NsPlan*)d_plan.p, (uint64_t)n_global, u0, (NsTileHead*)d_bounds.p);
+    int occ = 8;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_resample, NS_RS_THREADS, 0));
+    const int g2 = (int)std::min<int64_t>(max_tiles, (int64_t)sms * std::max(1, occ));      // resident CTAs only: tiles are taken grid-stride
+    LAUNCH(K_NS_RESAMPLE, k_ns_resample, g2, NS_RS_THREADS, 0, part[cur].p, d_prefix.p, n, shard_begin, (const NsPlan*)d_plan.p,
+           (const NsTileHead*)d_bounds.p, (uint64_t)n_global, 1.0 / (double)n_global, D, (float)(1.0 / (double)n_global));
+    CK(cudaGetLastError());
     return MCL_OK;
 }
 
@@ -290,7 +322,9 @@ int Engine::ns_pose_partials(double* out5) {
     if (n == 0 || !out5) return fail(MCL_ERR_ARG, "pose_partials: no particles");
     const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
     CK(d_partials.ensure(5 * 512));
-    LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, d_partials.p);
+    const bool from_ll = have_weights && !ns_w_in_records;
+    LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, from_ll ? (const float*)d_ll.p : (const float*)nullptr, (const int*)d_maxbits.p,
+           (float)cfg.ns_temper, d_partials.p);
     CK(cudaGetLastError());
     std::vector<double> h((size_t)blocks * 5);
     CK(cudaMemcpyAsync(h.data(), d_partials.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -413,28 +447,16 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (pose3) {
         const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
         CK(d_partials.ensure(5 * 512));
-        LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, d_partials.p);
+        LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
+               d_partials.p);
         LAUNCH(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
         if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
     }
     const uint32_t u0 = ns_u0();
-    LAUNCH(K_NS_RESAMPLE, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
-    NsDest D;
-    D.per_rank = per_rank; D.world = shard_world;
-    const int next = cur ^ 1;
-    for (int r = 0; r < 8; ++r) { D.part[r] = nullptr; D.anc[r] = nullptr; }
-    for (int r = 0; r < shard_world; ++r) {
-        if (r == shard_rank) { D.part[r] = part[next].p; D.anc[r] = ancestors.p; }
-        else {
-            if (!peer_ptr[next][r] || !peer_ptr[2][r]) return fail(MCL_ERR_COMM, "ns_step: peer buffers are not mapped");
-            D.part[r] = (float4*)peer_ptr[next][r]; D.anc[r] = (int*)peer_ptr[2][r];
-        }
-    }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-    LAUNCH(K_NS_RESAMPLE, k_ns_resample_planned, sms * 8, 256, 0, part[cur].p, d_prefix.p, n, shard_begin, (const NsPlan*)d_plan.p,
-           (uint64_t)n_global, u0, D, (float)(1.0 / (double)n_global));
-    CK(cudaGetLastError());
+    LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
+    have_weights = true;
+    rc = ns_launch_resample(u0);
+    if (rc) return rc;
     if (shard_world > 1) NCK(N.AllReduce(d_bar.p, d_bar.p, 1, ncclInt32, ncclSum, (ncclComm_t)comm, stream));     // closing barrier
     cur ^= 1;
     have_weights = false; ns_have_ll = false;

@@ -32,6 +32,8 @@ NS_HD double fmad(double a, double b, double c) { return __fma_rn(a, b, c); }
 NS_HD float mulf(float a, float b) { return __fmul_rn(a, b); }
 NS_HD float addf(float a, float b) { return __fadd_rn(a, b); }
 NS_HD float fmaf_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+NS_HD float divf(float a, float b) { return __fdiv_rn(a, b); }
+NS_HD float sqrtf_(float a) { return __fsqrt_rn(a); }
 #else
 // host translation units are built with -ffp-contract=off
 NS_HD double mul(double a, double b) { return a * b; }
@@ -40,6 +42,8 @@ NS_HD double fmad(double a, double b, double c) { return fma(a, b, c); }
 NS_HD float mulf(float a, float b) { return a * b; }
 NS_HD float addf(float a, float b) { return a + b; }
 NS_HD float fmaf_(float a, float b, float c) { return fmaf(a, b, c); }
+NS_HD float divf(float a, float b) { return a / b; }
+NS_HD float sqrtf_(float a) { return sqrtf(a); }
 #endif
 
 // ---- sin/cos of pi*r for |r| <= 1/4, Taylor in f64 (error < 1e-16) -------------------------------------------------------
@@ -118,43 +122,95 @@ NS_HD double det_log(double x) {
     return fmad((double)e, 0.69314718055994530942, mul(2.0, p));
 }
 
-// Two standard normals from two 32-bit words (Box-Muller): u = (word + 0.5) * 2^-32 in (0,1).
+// ---- fp32 elementary functions for the motion noise (NS-7): IEEE add/mul/div/sqrt/fma only, fixed order -------------------
+// sin/cos of an fp32 angle (|theta| up to a few turns): Cody-Waite reduction by pi/2 in three fp32 parts, degree-9/10
+// Taylor polynomials; within ~1 ulp of the exact value.
+NS_HD void sincos_poly_f(float x /* |x| <= pi/4 */, float& s, float& c) {
+    const float x2 = mulf(x, x);
+    float ps = 2.75573192e-06f;                                       //  1/9!
+    ps = fmaf_(ps, x2, -1.98412701e-04f);                             // -1/7!
+    ps = fmaf_(ps, x2, 8.33333377e-03f);                              //  1/5!
+    ps = fmaf_(ps, x2, -1.66666672e-01f);                             // -1/3!
+    s = fmaf_(mulf(ps, x2), x, x);
+    float pc = -2.75573200e-07f;                                      // -1/10!
+    pc = fmaf_(pc, x2, 2.48015876e-05f);                              //  1/8!
+    pc = fmaf_(pc, x2, -1.38888892e-03f);                             // -1/6!
+    pc = fmaf_(pc, x2, 4.16666679e-02f);                              //  1/4!
+    pc = fmaf_(pc, x2, -0.5f);
+    c = fmaf_(pc, x2, 1.0f);
+}
+NS_HD void quadrant_f(int k, float sr, float cr, float& s, float& c) {
+    switch (k & 3) {
+        case 0: s = sr; c = cr; break;
+        case 1: s = cr; c = -sr; break;
+        case 2: s = -sr; c = -cr; break;
+        default: s = -cr; c = sr; break;
+    }
+}
+NS_HD void det_sincosf32(float theta, float& s, float& c) {
+    const float kf = rintf(mulf(theta, 0.636619747f));               // theta * 2/pi
+    float r = fmaf_(-kf, 1.5703125f, theta);                          // pi/2 = 1.5703125 + 4.837512969970703125e-4 + 7.549789954891882e-8
+    r = fmaf_(-kf, 4.837512969970703125e-4f, r);
+    r = fmaf_(-kf, 7.54978995489188216e-8f, r);
+    float sr, cr;
+    sincos_poly_f(r, sr, cr);
+    quadrant_f((int)kf, sr, cr, s, c);
+}
+// sin/cos of 2*pi*u for u in [0,1): exact quadrant reduction in units of a turn
+NS_HD void det_sincos2pif(float u, float& s, float& c) {
+    const float q = rintf(mulf(u, 4.0f));
+    const float f = fmaf_(q, -0.25f, u);                              // exact, |f| <= 1/8
+    const float x = fmaf_(f, 6.28318548f, mulf(f, -1.74845553e-07f)); // 2 pi f (2 pi = 6.28318548 - 1.74845553e-07)
+    float sr, cr;
+    sincos_poly_f(x, sr, cr);
+    quadrant_f((int)q, sr, cr, s, c);
+}
+// natural log of a normal fp32 x in (0, 1]: x = m * 2^e, m in [sqrt(1/2), sqrt(2)), log m = 2 atanh((m-1)/(m+1))
+NS_HD float det_logf(float x) {
+    union { float f; uint32_t u; } v;
+    v.f = x;
+    int e = (int)(v.u >> 23) - 127;
+    v.u = (v.u & 0x007fffffu) | 0x3f800000u;                          // m in [1,2)
+    float m = v.f;
+    if (m > 1.41421354f) { m = mulf(m, 0.5f); e += 1; }
+    const float t = divf(addf(m, -1.0f), addf(m, 1.0f));
+    const float t2 = mulf(t, t);
+    float p = 0.111111112f;                                           // 1/9
+    p = fmaf_(p, t2, 0.142857149f);                                   // 1/7
+    p = fmaf_(p, t2, 0.200000003f);                                   // 1/5
+    p = fmaf_(p, t2, 0.333333343f);                                   // 1/3
+    p = fmaf_(mulf(p, t2), t, t);                                     // atanh(t)
+    return fmaf_((float)e, 0.693147182f, mulf(2.0f, p));
+}
+// Two standard normals from two 32-bit words (Box-Muller): u = ((word >> 9) + 0.5) * 2^-23 in (0,1), exact in fp32.
 NS_HD void det_normal_pair(uint32_t w1, uint32_t w2, float& z0, float& z1) {
-    const double u1 = mul(add((double)w1, 0.5), 2.3283064365386963e-10);
-    const double u2 = mul(add((double)w2, 0.5), 2.3283064365386963e-10);
-    const double r = sqrt(mul(-2.0, det_log(u1)));
-    double s, c;
-    det_sincos(mul(6.28318530717958647692, u2), s, c);
-    z0 = (float)mul(r, c);
-    z1 = (float)mul(r, s);
+    const float u1 = mulf(addf((float)(w1 >> 9), 0.5f), 1.1920929e-07f);
+    const float u2 = mulf(addf((float)(w2 >> 9), 0.5f), 1.1920929e-07f);
+    const float r = sqrtf_(mulf(-2.0f, det_logf(u1)));
+    float s, c;
+    det_sincos2pif(u2, s, c);
+    z0 = mulf(r, c);
+    z1 = mulf(r, s);
 }
 
-// W = floor(2^32 * exp(t)) for t <= 0 (fp32), as uint64 in [0, 2^32].
+// W = trunc(2^32 * e), e = exp(t) evaluated in fp32 (IEEE ops only, 24 significant bits), for t <= 0; uint64 in [0, 2^32].
 NS_HD uint64_t det_exp_q32(float t) {
     if (!(t > -22.5f)) return 0;                                      // below 2^-32 (also catches NaN)
     if (t >= 0.f) return 1ull << 32;
-    const double y = mul((double)t, 1.44269504088896340736);          // t * log2(e)
-    const double kf = floor(y);
-    const double g = mul(y - kf, 0.69314718055994530942);             // in [0, ln 2)
-    double p = 1.0 / 6227020800.0;                                    // 1/13!
-    p = fmad(p, g, 1.0 / 479001600.0);
-    p = fmad(p, g, 1.0 / 39916800.0);
-    p = fmad(p, g, 1.0 / 3628800.0);
-    p = fmad(p, g, 1.0 / 362880.0);
-    p = fmad(p, g, 1.0 / 40320.0);
-    p = fmad(p, g, 1.0 / 5040.0);
-    p = fmad(p, g, 1.0 / 720.0);
-    p = fmad(p, g, 1.0 / 120.0);
-    p = fmad(p, g, 1.0 / 24.0);
-    p = fmad(p, g, 1.0 / 6.0);
-    p = fmad(p, g, 0.5);
-    p = fmad(p, g, 1.0);
-    p = fmad(p, g, 1.0);                                              // exp(g) in [1, 2)
-    const int k = (int)kf;                                            // -33 .. -1
-    union { double d; uint64_t u; } sc;
-    sc.u = (uint64_t)(1023 + 32 + k) << 52;                           // 2^(32+k), exact
-    const double scaled = mul(p, sc.d);
-    uint64_t w = (uint64_t)scaled;                                    // truncation = floor for positives
+    const float kf = rintf(mulf(t, 1.44269502f));                     // -32 .. 0
+    float g = fmaf_(-kf, 0.693145752f, t);                            // ln 2 = 0.693145752 + 1.42860677e-06 (Cody-Waite)
+    g = fmaf_(-kf, 1.42860677e-06f, g);                               // |g| <= 0.347
+    float p = 1.98412701e-04f;                                        // 1/7!
+    p = fmaf_(p, g, 1.38888892e-03f);                                 // 1/6!
+    p = fmaf_(p, g, 8.33333377e-03f);                                 // 1/5!
+    p = fmaf_(p, g, 4.16666679e-02f);                                 // 1/4!
+    p = fmaf_(p, g, 1.66666672e-01f);                                 // 1/3!
+    p = fmaf_(p, g, 0.5f);
+    p = fmaf_(p, g, 1.0f);
+    p = fmaf_(p, g, 1.0f);                                            // exp(g) in [0.70, 1.42]
+    union { float f; uint32_t u; } sc;
+    sc.u = (uint32_t)(127 + 32 + (int)kf) << 23;                      // 2^(32+k), exact
+    const uint64_t w = (uint64_t)mulf(p, sc.f);                       // exact scaling, truncation
     return w > (1ull << 32) ? (1ull << 32) : w;
 }
 
@@ -186,11 +242,12 @@ NS_HD U128 rhs_of(uint64_t k, uint32_t u0, uint64_t total) { return mul64((k << 
 // slot k selects the first particle whose inclusive prefix c satisfies selects(c, ...)
 NS_HD bool selects(uint64_t c, uint64_t n, const U128& rhs) { return gt128(lhs_of(c, n), rhs); }
 
-// theta wrapped into [-pi, pi] with fp32 constants (at most a few turns off)
+// theta brought back towards [-pi, pi]: one conditional turn each way with fp32 constants (the per-step change of
+// theta is far below a turn; det_sincosf32 is accurate over several turns anyway)
 NS_HD float wrap_pi(float t) {
     const float PI_F = 3.14159274f, TWO_PI_F = 6.28318548f;
-    for (int i = 0; i < 4 && t > PI_F; i++) t = addf(t, -TWO_PI_F);
-    for (int i = 0; i < 4 && t < -PI_F; i++) t = addf(t, TWO_PI_F);
+    if (t > PI_F) t = addf(t, -TWO_PI_F);
+    if (t < -PI_F) t = addf(t, TWO_PI_F);
     return t;
 }
 

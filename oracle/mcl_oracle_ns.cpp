@@ -68,30 +68,78 @@ double det_log(double x) {
     p = fma(p * t2, t, t);
     return fma((double)e, 0.69314718055994530942, 2.0 * p);
 }
-void det_normal_pair(uint32_t w1, uint32_t w2, float& z0, float& z1) {
-    double u1 = ((double)w1 + 0.5) * 2.3283064365386963e-10, u2 = ((double)w2 + 0.5) * 2.3283064365386963e-10;
-    double r = sqrt(-2.0 * det_log(u1));
-    double s, c;
-    det_sincos(6.28318530717958647692 * u2, s, c);
-    z0 = (float)(r * c);
-    z1 = (float)(r * s);
+// fp32 elementary functions of the motion noise: IEEE +,*,/,sqrt,fma in fp32 only, fixed order.
+// Coefficient tables (Horner, highest power first); literals are the decimal strings of DESIGN.md.
+const float SIN_C[] = {2.75573192e-06f, -1.98412701e-04f, 8.33333377e-03f, -1.66666672e-01f};                 // 1/9! -1/7! 1/5! -1/3!
+const float COS_C[] = {-2.75573200e-07f, 2.48015876e-05f, -1.38888892e-03f, 4.16666679e-02f, -0.5f};           // -1/10! 1/8! -1/6! 1/4! -1/2!
+const float ATANH_C[] = {0.111111112f, 0.142857149f, 0.200000003f, 0.333333343f};                              // 1/9 1/7 1/5 1/3
+
+void sincos_small_f(float x, float& s, float& c) {
+    const float x2 = x * x;
+    float ps = SIN_C[0];
+    for (int i = 1; i < 4; i++) ps = fmaf(ps, x2, SIN_C[i]);
+    s = fmaf(ps * x2, x, x);
+    float pc = COS_C[0];
+    for (int i = 1; i < 5; i++) pc = fmaf(pc, x2, COS_C[i]);
+    c = fmaf(pc, x2, 1.0f);
 }
-uint64_t det_exp_q32(float t) {
+void rotate_quadrant_f(int q, float sr, float cr, float& s, float& c) {
+    q &= 3;
+    if (q == 0) { s = sr; c = cr; } else if (q == 1) { s = cr; c = -sr; } else if (q == 2) { s = -sr; c = -cr; } else { s = -cr; c = sr; }
+}
+void det_sincos_f32(float t, float& s, float& c) {                 // Cody-Waite by pi/2 = 1.5703125 + 4.8375129699707e-4 + 7.5497899548919e-8
+    const float kf = rintf(t * 0.636619747f);
+    float r = fmaf(-kf, 1.5703125f, t);
+    r = fmaf(-kf, 4.837512969970703125e-4f, r);
+    r = fmaf(-kf, 7.54978995489188216e-8f, r);
+    float sr, cr;
+    sincos_small_f(r, sr, cr);
+    rotate_quadrant_f((int)kf, sr, cr, s, c);
+}
+void det_sincos_turns_f32(float u, float& s, float& c) {           // sin, cos of 2 pi u, u in [0,1)
+    const float q = rintf(u * 4.0f);
+    const float f = fmaf(q, -0.25f, u);
+    const float x = fmaf(f, 6.28318548f, f * -1.74845553e-07f);
+    float sr, cr;
+    sincos_small_f(x, sr, cr);
+    rotate_quadrant_f((int)q, sr, cr, s, c);
+}
+float det_log_f32(float x) {
+    int e;
+    float m = frexpf(x, &e) * 2.0f;   // m in [1,2)
+    e -= 1;
+    if (m > 1.41421354f) { m *= 0.5f; e += 1; }
+    const float t = (m + -1.0f) / (m + 1.0f), t2 = t * t;
+    float p = ATANH_C[0];
+    for (int i = 1; i < 4; i++) p = fmaf(p, t2, ATANH_C[i]);
+    p = fmaf(p * t2, t, t);
+    return fmaf((float)e, 0.693147182f, 2.0f * p);
+}
+void det_normal_pair(uint32_t w1, uint32_t w2, float& z0, float& z1) {
+    const float u1 = ((float)(w1 >> 9) + 0.5f) * 1.1920929e-07f, u2 = ((float)(w2 >> 9) + 0.5f) * 1.1920929e-07f;
+    const float r = sqrtf(-2.0f * det_log_f32(u1));
+    float s, c;
+    det_sincos_turns_f32(u2, s, c);
+    z0 = r * c;
+    z1 = r * s;
+}
+const float EXP_C[] = {1.98412701e-04f, 1.38888892e-03f, 8.33333377e-03f, 4.16666679e-02f, 1.66666672e-01f, 0.5f, 1.0f, 1.0f};   // 1/7! .. 1/0!
+uint64_t det_exp_q32(float t) {                                // NS-4: trunc(2^32 * exp(t)), exp in fp32 (IEEE ops only)
     if (!(t > -22.5f)) return 0;
     if (t >= 0.f) return 1ull << 32;
-    double y = (double)t * 1.44269504088896340736;
-    double kf = floor(y);
-    double g = (y - kf) * 0.69314718055994530942;
-    double p = INV_FACT[13];
-    for (int n = 12; n >= 0; n--) p = fma(p, g, INV_FACT[n]);
-    double scaled = ldexp(p, 32 + (int)kf);
+    const float kf = rintf(t * 1.44269502f);
+    float g = fmaf(-kf, 0.693145752f, t);
+    g = fmaf(-kf, 1.42860677e-06f, g);
+    float p = EXP_C[0];
+    for (int i = 1; i < 8; i++) p = fmaf(p, g, EXP_C[i]);
+    const float scaled = ldexpf(p, 32 + (int)kf);
     uint64_t w = (uint64_t)scaled;
     return std::min<uint64_t>(w, 1ull << 32);
 }
-float wrap_pi(float t) {
+float wrap_pi(float t) {                                       // one conditional turn each way (NS-7)
     const float PI_F = 3.14159274f, TWO_PI_F = 6.28318548f;
-    for (int i = 0; i < 4 && t > PI_F; i++) t = t + -TWO_PI_F;
-    for (int i = 0; i < 4 && t < -PI_F; i++) t = t + TWO_PI_F;
+    if (t > PI_F) t = t - TWO_PI_F;
+    if (t < -PI_F) t = t + TWO_PI_F;
     return t;
 }
 
@@ -193,9 +241,8 @@ void ons_predict(void* h, float* P, int64_t g0, int64_t n, double rot1, double t
         det_normal_pair(r[2], r[3], z2, z3);
         float* p = P + 4 * i;
         float r1 = fmaf(z0, sd1, r1m), tr = fmaf(z1, sdt, trm), r2 = fmaf(z2, sd2, r2m);
-        double sd, cd;
-        det_sincos((double)(p[2] + r1), sd, cd);
-        float s = (float)sd, cs = (float)cd;
+        float s, cs;
+        det_sincos_f32(p[2] + r1, s, cs);
         p[0] = fmaf(tr, cs, p[0]);
         p[1] = fmaf(tr, s, p[1]);
         p[2] = wrap_pi(p[2] + (r1 + r2));
@@ -307,6 +354,12 @@ void ons_pose_partials(const float* P, int64_t n, double* out5) {
 // exposed for unit tests of the deterministic math
 void ons_det_sincos(double t, double* s, double* c) { det_sincos(t, *s, *c); }
 double ons_det_log(double x) { return det_log(x); }
+void ons_det_sincos_f32(float t, float* s, float* c) { det_sincos_f32(t, *s, *c); }
+void ons_det_sincos_turns_f32(float u, float* s, float* c) { det_sincos_turns_f32(u, *s, *c); }
+float ons_det_log_f32(float x) { return det_log_f32(x); }
+void ons_normal_pairs(const uint32_t* w1, const uint32_t* w2, int64_t n, float* z0, float* z1) {
+    for (int64_t i = 0; i < n; i++) det_normal_pair(w1[i], w2[i], z0[i], z1[i]);
+}
 uint64_t ons_det_exp_q32(float t) { return det_exp_q32(t); }
 void ons_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) { philox(c0, c1, c2, c3, k0, k1, out); }
 

@@ -25,9 +25,40 @@ def test_deterministic_math_is_accurate():
     for u in rng.uniform(1e-10, 1.0, 20000):
         assert abs(L.ons_det_log(C.c_double(u)) - np.log(u)) <= 4e-16 * max(1.0, abs(np.log(u)))
     for t in rng.uniform(-22.4, 0.0, 20000).astype(np.float32):
-        assert abs(int(L.ons_det_exp_q32(C.c_float(t))) - int(np.floor(np.exp(np.float64(t)) * 2.0**32))) <= 1
+        want = np.exp(np.float64(t)) * 2.0**32
+        assert abs(int(L.ons_det_exp_q32(C.c_float(t))) - want) <= 2.5e-7 * want + 1
     assert L.ons_det_exp_q32(C.c_float(0.0)) == 2**32 and L.ons_det_exp_q32(C.c_float(-23.0)) == 0
     assert L.ons_det_exp_q32(C.c_float(np.nan)) == 0
+
+
+def test_fp32_noise_functions_are_accurate_and_normal():
+    """NS-7's fp32 log / sincos (IEEE-only arithmetic) against libm, and the Box-Muller output against N(0,1) moments."""
+    L = oracle_lib()
+    L.ons_det_log_f32.restype = C.c_float
+    rng = np.random.default_rng(1)
+    s, c = C.c_float(), C.c_float()
+    for t in rng.uniform(-8, 8, 20000).astype(np.float32):
+        L.ons_det_sincos_f32(C.c_float(t), C.byref(s), C.byref(c))
+        assert abs(s.value - np.sin(np.float64(t))) < 2.5e-7 and abs(c.value - np.cos(np.float64(t))) < 2.5e-7
+    for u in rng.random(20000).astype(np.float32):
+        L.ons_det_sincos_turns_f32(C.c_float(u), C.byref(s), C.byref(c))
+        assert abs(s.value - np.sin(2 * np.pi * np.float64(u))) < 2.5e-7 and abs(c.value - np.cos(2 * np.pi * np.float64(u))) < 2.5e-7
+    us = np.concatenate([rng.uniform(2.0**-24, 1.0, 20000), [2.0**-24, 1.0 - 2.0**-24, 0.5, 0.70710678, 0.70710679]]).astype(np.float32)
+    for u in us:
+        got = L.ons_det_log_f32(C.c_float(u))
+        assert abs(got - np.log(np.float64(u))) <= 3e-7 * max(1.0, abs(np.log(np.float64(u)))), (u, got)
+    n = 400000
+    w1 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32); w2 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    z0 = np.zeros(n, np.float32); z1 = np.zeros(n, np.float32)
+    u32p, fp = C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    L.ons_normal_pairs(w1.ctypes.data_as(u32p), w2.ctypes.data_as(u32p), C.c_int64(n), z0.ctypes.data_as(fp), z1.ctypes.data_as(fp))
+    z = np.concatenate([z0, z1]).astype(np.float64)
+    assert np.isfinite(z).all() and abs(z.mean()) < 0.005 and abs(z.std() - 1.0) < 0.005
+    assert abs((z ** 4).mean() - 3.0) < 0.05 and abs(np.corrcoef(z0, z1)[0, 1]) < 0.005 and np.abs(z).max() < 5.8
+    # against the textbook formula evaluated in f64
+    u1 = ((w1 >> 9).astype(np.float64) + 0.5) * 2.0**-23; u2 = ((w2 >> 9).astype(np.float64) + 0.5) * 2.0**-23
+    ref0 = np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2)
+    assert np.abs(z0 - ref0).max() < 3e-6
 
 
 def test_philox_known_answer():

@@ -19,8 +19,8 @@ s.pf.setMap(occ, np.float32(0.1))
 s.pf.sampleParticles(n)
 sca = scans[0]
 s.pf.stageScan(0, sca["ranges"], sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
-s.pf.profileEnable(True)
 for i in range(steps):
+    s.pf.profileEnable(True)
     if uniform:
         s.pf.sampleParticles(n)
     s.pf.updateParticlePos(0.01, 0.02, 0.0)
@@ -28,8 +28,10 @@ for i in range(steps):
     t = s.weights_local(mx)
     s.resample_local(0, t, s.u0())
     s.end_step()
-for k, v in s.pf.profileRead().items():
-    print("%-22s %8.4f ms x %d" % (k, v[0] / v[1], v[1]))
+    print("step %d: " % i + "  ".join("%s %.1f us" % (k.replace("k_ns_", ""), 1e3 * v[0] / v[1]) for k, v in s.pf.profileRead().items()))
+    if os.environ.get("NS_PROFILE_ANC"):
+        anc = s.pf.ancestors()
+        print("   distinct ancestors: %d of %d" % (len(np.unique(anc)), n))
 fb = occ.size * 4
 print("gather bench: smem 9.6KB %.3e reads/s; global %d KB %.3e reads/s; global 64 MiB %.3e; global 1 GiB %.3e" % (
     s.pf.benchGather(0, 9604), fb // 1024, s.pf.benchGather(1, fb), s.pf.benchGather(1, 64 << 20), s.pf.benchGather(1, 1 << 30)))
