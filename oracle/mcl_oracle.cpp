@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -558,6 +559,126 @@ void orc_estimate_weighted_pose(void* h, const float* P, int N, double* out) {
     float x_mean = (float)sx, y_mean = (float)sy;
     float theta_mean = std::atan2((float)ss, (float)sc);
     out[0] = x_mean; out[1] = y_mean; out[2] = theta_mean;
+}
+
+// ---- k-means confidence estimate and output adapters ---------------------------------------------
+
+// kMeansClustering (MC:802-868). The reference seeds srand(time) (MC:808) and draws rand() % N for the K initial
+// centres (MC:812-815) and for every emptied cluster (MC:859-861); here those indices are INJECTED in consumption
+// order. assignments start at 0 (a fresh std::vector<int>::resize, MC:805 + MC:893). Centres accumulate in fp32,
+// sequentially over the particles (MC:851-853), then divide by the int count (MC:857-858).
+// Returns the number of assignment passes made; *reinit_used = how many re-initialisation draws were consumed.
+int orc_kmeans(const float* P, int N, int K, int max_iters, const int* init_idx, const int* reinit_idx, int n_reinit, int* assignments,
+               float* centers, int* reinit_used) {
+    for (int i = 0; i < N; i++) assignments[i] = 0;
+    for (int k = 0; k < K; k++) { centers[2 * k] = P[4 * (size_t)init_idx[k]]; centers[2 * k + 1] = P[4 * (size_t)init_idx[k] + 1]; }
+    int used = 0, passes = 0;
+    for (int iter = 0; iter < max_iters; ++iter) {
+        bool changed = false;
+        ++passes;
+        for (int i = 0; i < N; i++) {                                              // MC:821-840
+            float x = P[4 * (size_t)i], y = P[4 * (size_t)i + 1];
+            float min_dist = std::numeric_limits<float>::max();
+            int best = -1;
+            for (int k = 0; k < K; k++) {
+                float dx = x - centers[2 * k], dy = y - centers[2 * k + 1];
+                float dist = dx * dx + dy * dy;
+                if (dist < min_dist) { min_dist = dist; best = k; }
+            }
+            if (assignments[i] != best) { assignments[i] = best; changed = true; }
+        }
+        if (!changed) break;                                                       // MC:842-845
+        std::vector<int> counts(K, 0);
+        std::vector<float> nc(2 * (size_t)K, 0.0f);
+        for (int i = 0; i < N; i++) {                                              // MC:851-856
+            // best == -1 (all distances NaN) would index out of bounds in the reference; particles are finite here
+            int c = assignments[i];
+            nc[2 * c] += P[4 * (size_t)i];
+            nc[2 * c + 1] += P[4 * (size_t)i + 1];
+            counts[c]++;
+        }
+        for (int k = 0; k < K; k++) {                                              // MC:857-863
+            if (counts[k] > 0) { nc[2 * k] /= counts[k]; nc[2 * k + 1] /= counts[k]; }
+            else {
+                int idx = used < n_reinit ? reinit_idx[used] : 0;
+                ++used;
+                nc[2 * k] = P[4 * (size_t)idx]; nc[2 * k + 1] = P[4 * (size_t)idx + 1];
+            }
+        }
+        for (int k = 0; k < 2 * K; k++) centers[k] = nc[k];
+    }
+    if (reinit_used) *reinit_used = used;
+    return passes;
+}
+
+// countParticlesNearCluster (MC:869-884)
+int orc_count_near(const float* P, int N, float xc, float yc, float radius) {
+    int count = 0;
+    float radius_sq = radius * radius;
+    for (int i = 0; i < N; i++) {
+        float dx = P[4 * (size_t)i] - xc, dy = P[4 * (size_t)i + 1] - yc;
+        float d = dx * dx + dy * dy;
+        if (d <= radius_sq) ++count;
+    }
+    return count;
+}
+
+// isLocalizationLost_densitiy_cluster (MC:886-949), K = 3, 20 iterations, radius 0.4 (its cluster_distance argument is
+// unused). out = {x_best, y_best, theta_best} with the -1 sentinel (MC:938-940); info = {best_cluster, passes, reinit_used};
+// cluster_weights[K] optional. Returns the density ratio.
+double orc_kmeans_confidence(const float* P, int N, const int* init_idx, const int* reinit_idx, int n_reinit, double ratio_threshold,
+                             double* out, float* centers, int* assignments, int* info, double* cluster_weights) {
+    const int K = 3, max_iters = 20;
+    int used = 0;
+    int passes = orc_kmeans(P, N, K, max_iters, init_idx, reinit_idx, n_reinit, assignments, centers, &used);
+    double cw[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < N; i++) cw[assignments[i]] += P[4 * (size_t)i + 3];       // MC:903-907
+    int best = 0;
+    double max_w = cw[0];
+    for (int k = 1; k < K; k++) if (cw[k] > max_w) { max_w = cw[k]; best = k; }    // MC:910-917
+    double xb = centers[2 * best], yb = centers[2 * best + 1];                     // MC:920-921
+    double ss = 0.0, cs = 0.0;
+    for (int i = 0; i < N; i++) {                                                  // MC:924-931
+        if (assignments[i] == best) { double th = P[4 * (size_t)i + 2]; ss += std::sin(th); cs += std::cos(th); }
+    }
+    double tb = std::atan2(ss, cs);
+    double ratio = static_cast<double>(orc_count_near(P, N, (float)xb, (float)yb, 0.4f)) / N;      // MC:933 (float parameters)
+    if (ratio > ratio_threshold) { out[0] = xb; out[1] = yb; out[2] = tb; } else { out[0] = -1; out[1] = -1; out[2] = -1; }
+    if (info) { info[0] = best; info[1] = passes; info[2] = used; }
+    if (cluster_weights) for (int k = 0; k < K; k++) cluster_weights[k] = cw[k];
+    return ratio;
+}
+
+// publishPosMsg (MC:958-994): world pose -> maze cell (row, column) and 4-way direction; out = {row, column, orientation},
+// all -1 for the "not localised" sentinel (negative coordinates). RIGHT=0, UP=1, LEFT=2, DOWN=3 (MC:130-135, msg/Pose.msg).
+void orc_pose_to_cell(double wx, double wy, double angle, int* out) {
+    const double CELL_METERS = 0.8;
+    if (wx < 0 || wy < 0) { out[0] = out[1] = out[2] = -1; return; }
+    double col_wx = (wx - 0.5 * CELL_METERS) / CELL_METERS;
+    double row_wx = (wy - 0.5 * CELL_METERS) / CELL_METERS;
+    int col = static_cast<int>(std::floor(col_wx + 0.5));
+    int row = static_cast<int>(std::floor(row_wx + 0.5));
+    const double TWO_PI = 2.0 * M_PI;                                              // wrapTo2Pi, MC:951-957
+    double wrapped = std::fmod(angle, TWO_PI);
+    if (wrapped < 0) wrapped += TWO_PI;
+    double deg = wrapped * 180.0 / M_PI;
+    int dir;
+    if (deg >= 45 && deg < 135) dir = 3;
+    else if (deg >= 135 && deg < 225) dir = 2;
+    else if (deg >= 225 && deg < 315) dir = 1;
+    else dir = 0;
+    out[0] = row; out[1] = col; out[2] = dir;
+}
+// publishExactPose (MC:995-1008): float32 narrowing of the message fields (msg/ExactPose.msg)
+void orc_exact_pose(double x, double y, double theta, float* out) { out[0] = (float)x; out[1] = (float)y; out[2] = (float)theta; }
+// publishParticles (MC:563-579): pose i = (x, y, quaternion of yaw); tf::createQuaternionMsgFromYaw = setRPY(0,0,yaw):
+// qz = sin(yaw/2), qw = cos(yaw/2), qx = qy = 0 (restated from the tf formulas: PARITY UNPINNED at this boundary)
+void orc_particle_poses(const float* P, int N, double* out) {
+    for (int i = 0; i < N; i++) {
+        double yaw = P[4 * (size_t)i + 2], h = yaw * 0.5;
+        out[4 * (size_t)i] = P[4 * (size_t)i]; out[4 * (size_t)i + 1] = P[4 * (size_t)i + 1];
+        out[4 * (size_t)i + 2] = std::sin(h); out[4 * (size_t)i + 3] = std::cos(h);
+    }
 }
 
 }  // extern "C"

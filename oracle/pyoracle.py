@@ -26,8 +26,9 @@ def build(force=False):
     stale = force or not os.path.exists(ORACLE_SO) or any(
         os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
     ref_src = "/root/reference/pink_fundamentals/src/monte_carlo.cpp"
+    ref_deps = [os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "shim", "shim_prelude.h"), os.path.join(HERE, "shim", "ros", "ros.h")]
     ref_stale = os.path.exists(ref_src) and (force or not os.path.exists(REF_SO) or
-                                             os.path.getmtime(os.path.join(HERE, "ref_harness.cpp")) > os.path.getmtime(REF_SO))
+                                             any(os.path.getmtime(d) > os.path.getmtime(REF_SO) for d in ref_deps))
     if stale or ref_stale:
         subprocess.run(["make", "-s", "-C", HERE, "-B"], check=True)
 
@@ -212,6 +213,65 @@ class Oracle:
         return out
 
 
+def _P32(P):
+    P = np.ascontiguousarray(P, dtype=np.float32)
+    assert P.ndim == 2 and P.shape[1] == 4
+    return P
+
+
+def kmeans(P, init_idx, reinit_idx=(), K=3, max_iters=20):
+    """kMeansClustering (MC:802-868) with the rand() draws injected. Returns (assignments, centers[K,2], passes, reinit_used)."""
+    L = oracle_lib(); P = _P32(P)
+    a = np.zeros(len(P), np.int32); c = np.zeros((K, 2), np.float32); used = C.c_int()
+    ii = _i32(init_idx); ri = _i32(reinit_idx if len(reinit_idx) else [0])
+    passes = L.orc_kmeans(_p(P, c_fp), len(P), K, max_iters, _p(ii, c_ip), _p(ri, c_ip), len(reinit_idx), _p(a, c_ip), _p(c, c_fp), C.byref(used))
+    return a, c, passes, used.value
+
+
+def kmeans_confidence(P, init_idx, reinit_idx=(), ratio_threshold=0.6):
+    """isLocalizationLost_densitiy_cluster (MC:886-949). Returns dict(ratio, best[3], centers, assignments, best_cluster, passes, ...)."""
+    L = oracle_lib(); P = _P32(P)
+    L.orc_kmeans_confidence.restype = C.c_double
+    a = np.zeros(len(P), np.int32); c = np.zeros((3, 2), np.float32); out = np.zeros(3); info = np.zeros(3, np.int32); cw = np.zeros(3)
+    ii = _i32(init_idx); ri = _i32(reinit_idx if len(reinit_idx) else [0])
+    ratio = L.orc_kmeans_confidence(_p(P, c_fp), len(P), _p(ii, c_ip), _p(ri, c_ip), len(reinit_idx), C.c_double(ratio_threshold), _p(out, c_dp),
+                                    _p(c, c_fp), _p(a, c_ip), _p(info, c_ip), _p(cw, c_dp))
+    return dict(ratio=ratio, best=out, centers=c, assignments=a, best_cluster=int(info[0]), passes=int(info[1]), reinit_used=int(info[2]),
+                cluster_weights=cw)
+
+
+def count_near(P, x, y, radius=0.4):
+    P = _P32(P)
+    return oracle_lib().orc_count_near(_p(P, c_fp), len(P), C.c_float(x), C.c_float(y), C.c_float(radius))
+
+
+def pose_to_cell(wx, wy, angle):
+    """publishPosMsg (MC:958-994): (row, column, orientation)."""
+    out = np.zeros(3, np.int32)
+    oracle_lib().orc_pose_to_cell(C.c_double(wx), C.c_double(wy), C.c_double(angle), _p(out, c_ip))
+    return tuple(int(v) for v in out)
+
+
+def exact_pose(x, y, theta):
+    out = np.zeros(3, np.float32)
+    oracle_lib().orc_exact_pose(C.c_double(x), C.c_double(y), C.c_double(theta), _p(out, c_fp))
+    return out
+
+
+def particle_poses(P):
+    """publishParticles (MC:563-579): [N,4] = x, y, qz, qw."""
+    P = _P32(P); out = np.zeros((len(P), 4))
+    oracle_lib().orc_particle_poses(_p(P, c_fp), len(P), _p(out, c_dp))
+    return out
+
+
+def libc_rand_sequence(seed, count):
+    """What srand(seed); rand() ... yields in this process's libc: the draws kMeansClustering makes after srand(time) (MC:808)."""
+    libc = C.CDLL(None)
+    libc.srand(C.c_uint(int(seed)))
+    return [int(libc.rand()) for _ in range(count)]
+
+
 # ------------------------------------------------------------------------------------------------------
 # Compiled reference (oracle/_ref). Process-global state, exactly like the reference node.
 # ------------------------------------------------------------------------------------------------------
@@ -261,6 +321,42 @@ class Ref:
 
     def stream_minstd_normal(self, seed, n):
         out = np.zeros(n); self.L.ref_stream_minstd_normal(C.c_uint(int(seed)), n, _p(out, c_dp)); return out
+
+    # -- SURVEY §8f rows
+    def set_time(self, t):
+        """The value std::time(nullptr) returns inside the reference (it seeds srand with it, MC:808)."""
+        self.L.ref_set_time(C.c_long(int(t)))
+
+    def kmeans_confidence(self, P, ratio_threshold=0.6, cluster_distance=0.5):
+        P = _P32(P); out = np.zeros(3)
+        self.L.ref_kmeans_confidence.restype = C.c_double
+        ratio = self.L.ref_kmeans_confidence(_p(P, c_fp), len(P), C.c_double(cluster_distance), C.c_double(ratio_threshold), _p(out, c_dp))
+        return ratio, out
+
+    def kmeans(self, P, K=3, max_iters=20):
+        P = _P32(P); a = np.zeros(len(P), np.int32); c = np.zeros((K, 2), np.float32)
+        self.L.ref_kmeans(_p(P, c_fp), len(P), K, max_iters, _p(a, c_ip), _p(c, c_fp))
+        return a, c
+
+    def count_near(self, P, x, y, radius=0.4):
+        P = _P32(P)
+        return self.L.ref_count_near(_p(P, c_fp), len(P), C.c_float(x), C.c_float(y), C.c_float(radius))
+
+    def publish_pos_msg(self, wx, wy, angle):
+        out = np.zeros(3, np.int32)
+        self.L.ref_publish_pos_msg(C.c_double(wx), C.c_double(wy), C.c_double(angle), _p(out, c_ip))
+        return tuple(int(v) for v in out)
+
+    def publish_exact_pose(self, x, y, theta):
+        out = np.zeros(3, np.float32)
+        self.L.ref_publish_exact_pose(C.c_double(x), C.c_double(y), C.c_double(theta), _p(out, c_fp))
+        return out
+
+    def publish_particles(self, P):
+        P = _P32(P); out = np.zeros((len(P), 4))
+        n = self.L.ref_publish_particles(_p(P, c_fp), len(P), _p(out, c_dp))
+        assert n == len(P)
+        return out
 
     def named_sample_draws(self, seed, n_rows, n_cols, count):
         uy = np.zeros(count); r = np.zeros(count, np.int32); c = np.zeros(count, np.int32); ux = np.zeros(count); uyy = np.zeros(count)

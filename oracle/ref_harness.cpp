@@ -137,4 +137,47 @@ void ref_estimate_weighted_pose(const float* P, int N, double* out) {
     RobotPosition r = estimateWeightedPose(m);
     out[0] = r.x; out[1] = r.y; out[2] = r.theta;
 }
+// ---- confidence estimate and output adapters ----------------------------------------
+void ref_set_time(long t) { mclshim::fake_time() = (time_t)t; }
+// isLocalizationLost_densitiy_cluster (MC:886-949) on P; out = {x_best, y_best, theta_best} (the globals it sets)
+double ref_kmeans_confidence(const float* P, int N, double cluster_distance, double ratio_threshold, double* out) {
+    Eigen::MatrixXf m; load(m, P, N);
+    double ratio = isLocalizationLost_densitiy_cluster(m, cluster_distance, ratio_threshold);
+    out[0] = x_best; out[1] = y_best; out[2] = theta_best;
+    return ratio;
+}
+// kMeansClustering alone (MC:802-868): assignments[N], centers[2K]
+void ref_kmeans(const float* P, int N, int K, int max_iters, int* assignments, float* centers) {
+    Eigen::MatrixXf m; load(m, P, N);
+    std::vector<int> a; std::vector<std::pair<float, float>> c;
+    kMeansClustering(m, K, max_iters, a, c);
+    for (int i = 0; i < N; i++) assignments[i] = a[i];
+    for (int k = 0; k < K; k++) { centers[2 * k] = c[k].first; centers[2 * k + 1] = c[k].second; }
+}
+int ref_count_near(const float* P, int N, float x, float y, float radius) { Eigen::MatrixXf m; load(m, P, N); return countParticlesNearCluster(m, x, y, radius); }
+// publishPosMsg (MC:958-994): out = {row, column, orientation} of the message it published
+void ref_publish_pos_msg(double wx, double wy, double angle, int* out) {
+    publishPosMsg(wx, wy, angle);
+    const pink_fundamentals::Pose& p = mclshim::last_published<pink_fundamentals::Pose>();
+    out[0] = p.row; out[1] = p.column; out[2] = p.orientation;
+}
+// publishExactPose (MC:995-1008): out = {x, y, theta} as float32 message fields
+void ref_publish_exact_pose(double x, double y, double theta, float* out) {
+    ros::Publisher pub;
+    publishExactPose(x, y, theta, pub);
+    const pink_fundamentals::ExactPose& p = mclshim::last_published<pink_fundamentals::ExactPose>();
+    out[0] = p.x; out[1] = p.y; out[2] = p.theta;
+}
+// publishParticles (MC:563-579): out[i] = {x, y, qz, qw} of pose i (qx = qy = 0)
+int ref_publish_particles(const float* P, int N, double* out) {
+    Eigen::MatrixXf m; load(m, P, N);
+    ros::Publisher pub;
+    publishParticles(m, pub);
+    const geometry_msgs::PoseArray& a = mclshim::last_published<geometry_msgs::PoseArray>();
+    for (size_t i = 0; i < a.poses.size(); i++) {
+        out[4 * i] = a.poses[i].position.x; out[4 * i + 1] = a.poses[i].position.y;
+        out[4 * i + 2] = a.poses[i].orientation.z; out[4 * i + 3] = a.poses[i].orientation.w;
+    }
+    return (int)a.poses.size();
+}
 }  // extern "C"

@@ -14,6 +14,11 @@
 #include <string>
 #include <vector>
 #include <deque>
+#include <ctime>
+#include <cstdlib>
+#include <thread>
+#include <unordered_map>
+#include <utility>
 
 namespace mclshim {
 struct SeedQueue {
@@ -37,5 +42,9 @@ namespace std {
 typedef ::mclshim::fixed_random_device mclshim_random_device;
 typedef ::mclshim::registered_engine mclshim_default_engine;
 }
+// std::time(nullptr) seeds srand at MC:808 (k-means): the harness sets the value it returns
+namespace mclshim { inline time_t& fake_time() { static time_t t = 1; return t; } }
+namespace std { inline time_t mclshim_time(time_t*) { return ::mclshim::fake_time(); } }
+#define time mclshim_time
 #define random_device mclshim_random_device
 #define default_random_engine mclshim_default_engine
