@@ -87,6 +87,8 @@ typedef struct mcl_config {
     int32_t ns_beam_stride;      /* 1 = score every beam */
     int32_t ns_use_fov;          /* 0 = full circle, 1 = apply fov_lower/upper like the reference */
     double ns_temper;            /* weight = exp(ns_temper * (loglik - max loglik)); 1 = plain product of beam likelihoods */
+    /* confidence estimate, MC:889-890, 933 */
+    double kmeans_radius;        /* 0.4: density radius around the best cluster (countParticlesNearCluster) */
 } mcl_config;
 
 /* Named draws for sampleParticles (MC:427-440): per particle yaw~U[0,1) canonical, row, col, dx, dy canonical. */
@@ -200,6 +202,39 @@ void* mcl_device_buffer(mcl_handle* h, int32_t which);
 int mcl_ns_download_field(mcl_handle* h, float* loglik_field, uint16_t* d2);
 int mcl_ns_download_loglik(mcl_handle* h, float* loglik);
 int mcl_ns_download_prefix(mcl_handle* h, uint64_t* prefix_q32);
+
+/* ---- the rows either side of the hot path ------------------------------------------------- */
+#define MCL_KMEANS_K 3
+#define MCL_KMEANS_EXACT_MAX 65536   /* up to this many particles the centre sums are accumulated sequentially in fp32 like
+                                        the reference's loop (MC:851-856): results bit-exact with the CPU */
+typedef struct mcl_kmeans_result {
+    double ratio;                /* return value of isLocalizationLost_densitiy_cluster (MC:933, 948) */
+    double x_best, y_best, theta_best;        /* globals x_best.. (MC:934-940); all -1 when ratio <= threshold */
+    double cluster_weight[MCL_KMEANS_K];      /* MC:903-907 */
+    float centers[2 * MCL_KMEANS_K];          /* x0,y0,x1,y1,x2,y2 */
+    int64_t counts[MCL_KMEANS_K];
+    int32_t best_cluster, passes, reinit_used, exact;
+} mcl_kmeans_result;
+/* replaces isLocalizationLost_densitiy_cluster(particles, cluster_distance, cluster_ratio_threshold) (MC:886-949, call
+ * site MC:1090) incl. kMeansClustering (MC:802-868, K = 3, <= 20 iterations) and countParticlesNearCluster (MC:869-884).
+ * The reference seeds srand(time) and draws rand() % N for the 3 initial centres and for every emptied cluster: pass those
+ * indices (init_idx[3], reinit_idx[n_reinit], consumption order) for reproducible/parity runs, or NULL to draw them from
+ * the handle's Philox stream. cluster_distance is unused by the reference and therefore absent. */
+int mcl_kmeans_confidence(mcl_handle* h, const int32_t* init_idx, const int32_t* reinit_idx, int32_t n_reinit,
+                          double cluster_ratio_threshold, mcl_kmeans_result* out);
+int mcl_download_assignments(mcl_handle* h, int32_t* cluster_of_particle);     /* assignments of the last call */
+/* replaces publishPosMsg (MC:958-994): world pose -> msg/Pose.msg fields {row, column, orientation}; RIGHT=0 UP=1 LEFT=2
+ * DOWN=3; all -1 for the "not localised" sentinel (wx < 0 or wy < 0). Host only. cell_meters = 0.8 in the reference. */
+int mcl_pose_to_cell(double wx, double wy, double angle, double cell_meters, int32_t* row, int32_t* column, int32_t* orientation);
+/* replaces publishExactPose (MC:995-1008): msg/ExactPose.msg float32 fields {x, y, theta}. Host only. */
+int mcl_exact_pose(double x, double y, double theta, float* out3);
+/* replaces the loop of publishParticles (MC:563-579) for particles first, first+stride, ...: out[4*j..] =
+ * {position.x, position.y, orientation.z, orientation.w} (position.z = orientation.x = orientation.y = 0), quaternions
+ * built on the device; stride > 1 streams a subsample instead of 16 B x N every tick. */
+int mcl_download_pose_array(mcl_handle* h, int64_t first, int64_t stride, int64_t count, double* out);
+/* config presets: "reference" (= mcl_config_default) or "playground" = the knobs of the earlier, unbuilt variant
+ * src/playground.cpp that the config can express (ray step 0.05 :328, every 3rd beam :604, FOV +-90 :601). */
+int mcl_config_preset(mcl_config* cfg, const char* name);
 
 /* ---- state the reference keeps in globals (MC:189-192), for checkpoint/resume and tests ---------------- */
 int mcl_get_injection_state(mcl_handle* h, double* weight_slow, double* weight_fast);

@@ -5,4 +5,4 @@ Python host mirror used by the tests and bench.py; it never falls back to a CPU 
 """
 from ._lib import MODE_NS, MODE_REF, MclError, build, load  # noqa: F401
 from .particle_filter import (NsShard, ParticleFilter, default_config, ns_first_slot, ns_shard_range,  # noqa: F401
-                              ns_step_in_process, rasterise_map_txt)
+                              ns_step_in_process, rasterise_map_txt, pose_to_cell, exact_pose)

@@ -32,6 +32,7 @@ class Config(C.Structure):
         ("jitter_xy_lost", C.c_double), ("jitter_theta_lost", C.c_double), ("jitter_xy_conf", C.c_double),
         ("seed", C.c_uint64), ("ns_sigma_hit", C.c_double), ("ns_z_hit", C.c_double), ("ns_z_rand", C.c_double),
         ("ns_max_range", C.c_double), ("ns_beam_stride", C.c_int32), ("ns_use_fov", C.c_int32), ("ns_temper", C.c_double),
+        ("kmeans_radius", C.c_double),
     ]
 
 
@@ -48,6 +49,12 @@ class ResampleDraws(C.Structure):
 class ResampleStats(C.Structure):
     _fields_ = [("injected", C.c_int32), ("clamped", C.c_int32), ("p_inject", C.c_double), ("weight_slow", C.c_double),
                 ("weight_fast", C.c_double), ("total_weight", C.c_double)]
+
+
+class KmeansResult(C.Structure):
+    _fields_ = [("ratio", C.c_double), ("x_best", C.c_double), ("y_best", C.c_double), ("theta_best", C.c_double),
+                ("cluster_weight", C.c_double * 3), ("centers", C.c_float * 6), ("counts", C.c_int64 * 3),
+                ("best_cluster", C.c_int32), ("passes", C.c_int32), ("reinit_used", C.c_int32), ("exact", C.c_int32)]
 
 
 # every symbol include/mcl.h declares: (name, restype, argtypes)
@@ -76,6 +83,12 @@ SYMBOLS = [
     ("mcl_download_ancestors", _i32, [_vp, _ip]),
     ("mcl_download_cdf", _i32, [_vp, _dp]),
     ("mcl_estimate", _i32, [_vp, _dp, _dp, _dp]),
+    ("mcl_kmeans_confidence", _i32, [_vp, _ip, _ip, _i32, _d, C.POINTER(KmeansResult)]),
+    ("mcl_download_assignments", _i32, [_vp, _ip]),
+    ("mcl_pose_to_cell", _i32, [_d, _d, _d, _d, _ip, _ip, _ip]),
+    ("mcl_exact_pose", _i32, [_d, _d, _d, _fp]),
+    ("mcl_download_pose_array", _i32, [_vp, _i64, _i64, _i64, _dp]),
+    ("mcl_config_preset", _i32, [C.POINTER(Config), C.c_char_p]),
     ("mcl_get_injection_state", _i32, [_vp, _dp, _dp]),
     ("mcl_set_injection_state", _i32, [_vp, _d, _d]),
     ("mcl_get_ray_lut", _i32, [_vp, _ip, _dp, _dp, _i32, _ip]),

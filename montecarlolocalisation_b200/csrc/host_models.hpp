@@ -167,4 +167,21 @@ inline double tf_yaw_roundtrip(double theta) {
     return std::atan2(m10, m00);
 }
 
+// publishPosMsg (MC:958-994) with wrapTo2Pi (MC:951-957): maze cell and 4-way direction of a world pose.
+inline void pose_to_cell(double wx, double wy, double angle, double cell_meters, int& row, int& col, int& dir) {
+    if (wx < 0 || wy < 0) { row = col = dir = -1; return; }                       // "not localised" sentinel, MC:964-971
+    const double col_wx = (wx - 0.5 * cell_meters) / cell_meters;                 // MC:973-974
+    const double row_wx = (wy - 0.5 * cell_meters) / cell_meters;
+    col = static_cast<int>(std::floor(col_wx + 0.5));                             // MC:976-977
+    row = static_cast<int>(std::floor(row_wx + 0.5));
+    const double two_pi = 2.0 * M_PI;
+    double wrapped = std::fmod(angle, two_pi);
+    if (wrapped < 0) wrapped += two_pi;
+    const double deg = wrapped * 180.0 / M_PI;                                    // MC:978
+    if (deg >= 45 && deg < 135) dir = 3;                                          // DOWN   (MC:980-987; msg/Pose.msg constants)
+    else if (deg >= 135 && deg < 225) dir = 2;                                    // LEFT
+    else if (deg >= 225 && deg < 315) dir = 1;                                    // UP
+    else dir = 0;                                                                 // RIGHT
+}
+
 }  // namespace mcl

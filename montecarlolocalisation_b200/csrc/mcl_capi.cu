@@ -41,6 +41,7 @@ void mcl_config_default(mcl_config* c) {
     c->seed = 0x9E3779B97F4A7C15ull;
     c->ns_sigma_hit = 0.1; c->ns_z_hit = 0.8; c->ns_z_rand = 0.2; c->ns_max_range = 5.6;
     c->ns_beam_stride = 1; c->ns_use_fov = 0; c->ns_temper = 0.05;
+    c->kmeans_radius = 0.4;                                                                         // MC:933
 }
 
 int mcl_create(const mcl_config* cfg, mcl_handle** out) {
@@ -122,6 +123,39 @@ int mcl_ns_step(mcl_handle* h, double rot_1, double trans, double rot_2, const f
 }
 int mcl_ns_step_staged(mcl_handle* h, double rot_1, double trans, double rot_2, int32_t slot, double* pose3) {
     GUARD(h); TRY(h->engine.ns_step(rot_1, trans, rot_2, slot, nullptr, 0, 0.f, 0.f, 0.f, 0.f, pose3))
+}
+int mcl_kmeans_confidence(mcl_handle* h, const int32_t* init_idx, const int32_t* reinit_idx, int32_t n_reinit, double thr, mcl_kmeans_result* out) {
+    GUARD(h); TRY(h->engine.kmeans_confidence(init_idx, reinit_idx, n_reinit, thr, out))
+}
+int mcl_download_assignments(mcl_handle* h, int32_t* a) { GUARD(h); TRY(h->engine.download_assignments(a)) }
+int mcl_pose_to_cell(double wx, double wy, double angle, double cell_meters, int32_t* row, int32_t* column, int32_t* orientation) {
+    if (!row || !column || !orientation || !(cell_meters > 0)) return MCL_ERR_ARG;
+    int r, c, o;
+    mcl::pose_to_cell(wx, wy, angle, cell_meters, r, c, o);
+    *row = r; *column = c; *orientation = o;
+    return MCL_OK;
+}
+int mcl_exact_pose(double x, double y, double theta, float* out3) {
+    if (!out3) return MCL_ERR_ARG;
+    out3[0] = (float)x; out3[1] = (float)y; out3[2] = (float)theta;       // float32 message fields (msg/ExactPose.msg)
+    return MCL_OK;
+}
+int mcl_download_pose_array(mcl_handle* h, int64_t first, int64_t stride, int64_t count, double* out) {
+    GUARD(h); TRY(h->engine.download_pose_array(first, stride, count, out))
+}
+int mcl_config_preset(mcl_config* cfg, const char* name) {
+    if (!cfg || !name) return MCL_ERR_ARG;
+    const std::string n(name);
+    const int32_t mode = cfg->mode, device = cfg->device;
+    if (n == "reference") { mcl_config_default(cfg); cfg->mode = mode; cfg->device = device; return MCL_OK; }
+    if (n == "playground") {
+        mcl_config_default(cfg); cfg->mode = mode; cfg->device = device;
+        cfg->ray_step = 0.05;            // playground.cpp:328
+        cfg->beam_stride = 3;            // playground.cpp:604
+        cfg->fov_lower_deg = -90.0; cfg->fov_upper_deg = 90.0;       // playground.cpp:601
+        return MCL_OK;
+    }
+    return MCL_ERR_ARG;
 }
 int mcl_ns_first_slot(uint64_t off, uint64_t tot, uint64_t n, uint32_t u0, int64_t* slot) {
     if (!slot || tot == 0) return MCL_ERR_ARG;

@@ -72,6 +72,13 @@ public:
     int ns_download_field(float* lf, uint16_t* d2);
     int ns_download_loglik(float* ll);
     int ns_download_prefix(uint64_t* prefix);
+    // rows either side of the hot path
+    int kmeans_confidence(const int32_t* init_idx, const int32_t* reinit_idx, int n_reinit, double ratio_threshold, mcl_kmeans_result* out);
+    int download_assignments(int32_t* a);
+    int download_pose_array(int64_t first, int64_t stride, int64_t count, double* out);
+    DevBuf<int> d_assign, d_km_reinit;
+    DevBuf<unsigned char> d_km;
+    DevBuf<double> d_posearr;
     int gather_bench(int tier, size_t table_bytes, int iters, double* reads_per_s);
     int peer_export(int which, void* out64);
     int peer_import(int rank, int which, const void* in64);
@@ -83,7 +90,7 @@ public:
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);

@@ -201,6 +201,33 @@ class ParticleFilter:
         self._ck(self.L.mcl_get_ray_lut(self.h, k.ctypes.data_as(_ip), dx.ctypes.data_as(_dp), dy.ctypes.data_as(_dp), cnt.value, C.byref(cnt)))
         return k, dx, dy
 
+    # -- rows either side of the hot path ------------------------------------------------------
+    def isLocalizationLost_densitiy_cluster(self, cluster_ratio_threshold, init_idx=None, reinit_idx=None):
+        """MC:886-949 (sic). Returns dict(ratio, best=(x,y,theta) with the -1 sentinel, centers, counts, ...). init_idx /
+        reinit_idx: the rand() % N draws of kMeansClustering (MC:813, 860) for reproducible runs; None = Philox."""
+        res = _lib.KmeansResult()
+        ii = np.ascontiguousarray(init_idx, dtype=np.int32) if init_idx is not None else None
+        ri = np.ascontiguousarray(reinit_idx, dtype=np.int32) if reinit_idx is not None and len(reinit_idx) else None
+        self._ck(self.L.mcl_kmeans_confidence(self.h, ii.ctypes.data_as(_ip) if ii is not None else None,
+                                              ri.ctypes.data_as(_ip) if ri is not None else None, len(ri) if ri is not None else 0,
+                                              C.c_double(cluster_ratio_threshold), C.byref(res)))
+        return dict(ratio=res.ratio, best=np.array([res.x_best, res.y_best, res.theta_best]), centers=np.array(res.centers, np.float32).reshape(3, 2),
+                    counts=np.array(res.counts), cluster_weights=np.array(res.cluster_weight), best_cluster=res.best_cluster, passes=res.passes,
+                    reinit_used=res.reinit_used, exact=bool(res.exact))
+
+    def clusterAssignments(self):
+        a = np.zeros(self.num_particles, np.int32)
+        self._ck(self.L.mcl_download_assignments(self.h, a.ctypes.data_as(_ip)))
+        return a
+
+    def poseArray(self, first=0, stride=1, count=None):
+        """publishParticles (MC:563-579): [count, 4] = position.x, position.y, orientation.z, orientation.w."""
+        if count is None:
+            count = (self.num_particles - first + stride - 1) // stride
+        out = np.zeros((count, 4))
+        self._ck(self.L.mcl_download_pose_array(self.h, first, stride, count, out.ctypes.data_as(_dp)))
+        return out
+
     # -- instrumentation ----------------------------------------------------------------------------------------
     def lastResampleDraws(self, jitter_state):
         n = self.num_particles
@@ -339,6 +366,24 @@ class NsShard:
 
     def peer_import(self, rank, which, raw64):
         self.pf._ck(self.L.mcl_peer_import(self.h, rank, which, C.create_string_buffer(raw64, 64)))
+
+
+def pose_to_cell(wx, wy, angle, cell_meters=0.8):
+    """publishPosMsg (MC:958-994): (row, column, orientation); RIGHT=0 UP=1 LEFT=2 DOWN=3, all -1 = not localised."""
+    r, c, o = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = _lib.load().mcl_pose_to_cell(wx, wy, angle, cell_meters, C.byref(r), C.byref(c), C.byref(o))
+    if rc:
+        raise MclError(rc, "mcl_pose_to_cell")
+    return r.value, c.value, o.value
+
+
+def exact_pose(x, y, theta):
+    """publishExactPose (MC:995-1008): the float32 message fields."""
+    out = np.zeros(3, np.float32)
+    rc = _lib.load().mcl_exact_pose(x, y, theta, out.ctypes.data_as(_fp))
+    if rc:
+        raise MclError(rc, "mcl_exact_pose")
+    return out
 
 
 def ns_first_slot(offset, total, n_global, u0):

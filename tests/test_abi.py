@@ -14,6 +14,16 @@ from montecarlolocalisation_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def gpu_present():
+    """A usable CUDA device in this process (driver API; no torch import needed)."""
+    try:
+        cu = C.CDLL("libcuda.so.1")
+        n = C.c_int(0)
+        return cu.cuInit(0) == 0 and cu.cuDeviceGetCount(C.byref(n)) == 0 and n.value > 0
+    except OSError:
+        return False
+
+
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "mcl.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
@@ -37,7 +47,7 @@ def test_config_struct_matches_header_defaults():
     assert list(cfg.alpha) == [0.001, 0.001, 0.0001, 0.0001]
     assert (cfg.wheel_size, cfg.wheel_space, cfg.cell_size_px, cfg.cell_meters) == (0.062, 0.265, 8, 0.8)
     assert (cfg.inject_max_lost, cfg.inject_max_conf, cfg.jitter_xy_lost, cfg.jitter_xy_conf) == (200, 50, 0.05, 0.01)
-    assert cfg.ns_beam_stride == 1           # last fields land where the C struct puts them
+    assert cfg.ns_beam_stride == 1 and cfg.kmeans_radius == 0.4      # last fields land where the C struct puts them
     assert b"sm_100a" in _lib.load().mcl_version()
 
 
@@ -51,7 +61,7 @@ def test_host_rasteriser_matches_kat_and_oracle(map_txt):
         m.rasterise_map_txt("[[[Q]]]")
 
 
-@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
+@pytest.mark.skipif(gpu_present(), reason="GPU present")
 def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(m.MclError) as e:
         m.ParticleFilter()
@@ -67,7 +77,29 @@ def test_cxx_host_class_compiles_and_links(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "native", "cxx_binding_check.cpp"),
                     "-L" + libdir, "-lmcl_b200", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
-    if os.path.exists("/dev/nvidia0"):
+    if gpu_present():
         assert r.returncode == 0 and "gpu ok" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def test_host_only_pose_adapters_match_oracle():
+    """mcl_pose_to_cell / mcl_exact_pose (publishPosMsg / publishExactPose, MC:958-1008) need no GPU."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(3)
+    pts = [(-0.1, 1.0, 0.3), (1.0, -1e-9, 0.0), (-1, -1, -1), (0.0, 0.0, 0.0), (0.4, 0.4, 0.0), (0.79999, 0.8, np.pi / 4), (1.2, 3.6, -7.0),
+           (1.2, 3.6, 100.0), (1.2, 3.6, np.deg2rad(135.0)), (1.2, 3.6, np.deg2rad(225.0)), (1.2, 3.6, np.deg2rad(315.0)), (1.2, 3.6, np.deg2rad(45.0))]
+    pts += [(rng.uniform(-0.2, 4.8), rng.uniform(-0.2, 4.8), rng.uniform(-10, 10)) for _ in range(3000)]
+    for wx, wy, th in pts:
+        assert m.pose_to_cell(wx, wy, th) == pyoracle.pose_to_cell(wx, wy, th)
+        assert np.array_equal(m.exact_pose(wx, wy, th), pyoracle.exact_pose(wx, wy, th))
+
+
+def test_config_presets():
+    cfg = m.default_config()
+    L = _lib.load()
+    assert L.mcl_config_preset(C.byref(cfg), b"playground") == 0
+    assert (cfg.ray_step, cfg.beam_stride, cfg.fov_lower_deg, cfg.fov_upper_deg) == (0.05, 3, -90.0, 90.0)
+    assert L.mcl_config_preset(C.byref(cfg), b"reference") == 0
+    assert (cfg.ray_step, cfg.beam_stride, cfg.kmeans_radius) == (0.1, 20, 0.4)
+    assert L.mcl_config_preset(C.byref(cfg), b"nope") != 0
