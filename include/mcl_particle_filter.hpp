@@ -13,6 +13,9 @@
 //     particles = resampleParticles(particles, lost)  ->  resampleParticles(latest_scan..., lost)   (computeWeight inside)
 //     estimateWeightedPose(particles)       MC:782    ->  estimateWeightedPose()
 //     particles (Eigen::MatrixXf 4xN)                 ->  downloadParticles(float*)  (same column-major 4xN layout)
+//     isLocalizationLost_densitiy_cluster(...) MC:1090 ->  isLocalizationLost_densitiy_cluster(threshold)  (sets x_best.. below)
+//     publishPosMsg / publishExactPose      MC:958-1008 ->  poseMsg(x, y, theta) / exactPoseMsg(x, y, theta)  (message fields)
+//     publishParticles(particles, pub)      MC:563-579  ->  poseArray(stride)  (x, y, qz, qw per pose, quaternions built on the GPU)
 //
 // Header-only, no ROS or Eigen dependency; link with -lmcl_b200. Errors throw std::runtime_error on this side of the ABI.
 #pragma once
@@ -102,6 +105,39 @@ public:
         return p;
     }
 
+    // ---- confidence estimate (MC:886-949): returns the density ratio; x_best / y_best / theta_best carry the reference's
+    // globals of the same names (MC:73-75), -1 when the ratio does not exceed the threshold (MC:938-940) ----
+    double isLocalizationLost_densitiy_cluster(double cluster_ratio_threshold) {
+        mcl_kmeans_result r;
+        check(mcl_kmeans_confidence(h_, nullptr, nullptr, 0, cluster_ratio_threshold, &r));
+        x_best = r.x_best; y_best = r.y_best; theta_best = r.theta_best;
+        last_kmeans_ = r;
+        return r.ratio;
+    }
+    double x_best = -1, y_best = -1, theta_best = -1;
+    const mcl_kmeans_result& lastKmeans() const { return last_kmeans_; }
+
+    // ---- output adapters ----
+    struct PoseMsg { int32_t row, column, orientation; };          // msg/Pose.msg
+    struct ExactPoseMsg { float x, y, theta; };                    // msg/ExactPose.msg (the fields publishExactPose fills)
+    static PoseMsg poseMsg(double wx, double wy, double angle, double cell_meters = 0.8) {      // publishPosMsg, MC:958-994
+        PoseMsg m;
+        if (mcl_pose_to_cell(wx, wy, angle, cell_meters, &m.row, &m.column, &m.orientation)) throw std::runtime_error("mcl_pose_to_cell: bad argument");
+        return m;
+    }
+    static ExactPoseMsg exactPoseMsg(double x, double y, double theta) {                        // publishExactPose, MC:995-1008
+        float o[3];
+        mcl_exact_pose(x, y, theta, o);
+        return ExactPoseMsg{o[0], o[1], o[2]};
+    }
+    // publishParticles (MC:563-579): every stride-th particle as {position.x, position.y, orientation.z, orientation.w}
+    std::vector<double> poseArray(int64_t stride = 1) {
+        const int64_t count = (cols() + stride - 1) / stride;
+        std::vector<double> out((size_t)count * 4);
+        check(mcl_download_pose_array(h_, 0, stride, count, out.data()));
+        return out;
+    }
+
     mcl_handle* handle() { return h_; }
     const mcl_config& config() const { return cfg_; }
 
@@ -116,6 +152,7 @@ private:
     mcl_config cfg_;
     mcl_handle* h_ = nullptr;
     mcl_resample_stats last_stats_{};
+    mcl_kmeans_result last_kmeans_{};
 };
 
 }  // namespace mcl

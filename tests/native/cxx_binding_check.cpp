@@ -23,7 +23,11 @@ int main() {
         mcl::RobotPosition p = pf.estimateWeightedPose();
         std::vector<float> P(4 * pf.cols());
         pf.downloadParticles(P.data());
-        printf("gpu ok: injected %d pose %.3f %.3f %.3f\n", injected, p.x, p.y, p.theta);
+        double confident_level = pf.isLocalizationLost_densitiy_cluster(0.6);
+        mcl::ParticleFilter::PoseMsg cell = mcl::ParticleFilter::poseMsg(p.x, p.y, p.theta);
+        std::vector<double> poses = pf.poseArray(10);
+        if (poses.size() != 4 * 150 || cell.row < -1 || confident_level < 0 || confident_level > 1) return 4;
+        printf("gpu ok: injected %d pose %.3f %.3f %.3f confidence %.3f best %.3f %.3f\n", injected, p.x, p.y, p.theta, confident_level, pf.x_best, pf.y_best);
         return 0;
     } catch (const std::exception& e) {
         printf("threw: %s\n", e.what());
