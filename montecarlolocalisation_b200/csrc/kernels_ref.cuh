@@ -480,11 +480,26 @@ struct RefResampleParams {
     double cell_meters, half_cell, init_a, init_w, yaw_a, yaw_w, init_shift;
 };
 
+// Production draws: the u_r / u_jitter streams come from Philox4x32-10, counter = (2i | 2i+1, stream 0x30, step):
+//   u_r[i] = c53(A.0, A.1), u_jitter[i*per + 0] = c53(A.2, A.3), [+1] = c53(B.0, B.1), [+2] = c53(B.2, B.3),  A = philox(2i), B = philox(2i+1)
+// Generated inside the kernels that consume them (GEN = true); k_fill_resample_draws materialises the same streams when a
+// checker asks for them (mcl_debug_download_resample_draws).
+struct RefDrawGen { uint32_t step, k0, k1; };
+__device__ __forceinline__ void ref_philox_draws(uint64_t counter, const RefDrawGen& G, uint32_t (&o)[4]) {
+    Philox::gen((uint32_t)counter, (uint32_t)(counter >> 32), 0x30u, G.step, G.k0, G.k1, o);
+}
+
 // flags[i] = (u_r[i] < p_inject); block_counts[b] = number of flags in block b.
+template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
-                                                          int* __restrict__ block_counts) {
+                                                          int* __restrict__ block_counts, RefDrawGen G) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int f = (i < n && u_r[i] < p_inject) ? 1 : 0;
+    double r = 2.0;
+    if (i < n) {
+        if (GEN) { uint32_t a[4]; ref_philox_draws(2 * (uint64_t)i, G, a); r = canonical53(a[0], a[1]); }
+        else r = u_r[i];
+    }
+    int f = (r < p_inject) ? 1 : 0;
     int c = __syncthreads_count(f);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
@@ -497,6 +512,7 @@ __global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, 
     }
 }
 
+template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n,
                                                       const double* __restrict__ cdf, const double* __restrict__ u_r,
                                                       const double* __restrict__ u_jit,
@@ -505,11 +521,16 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       const double* __restrict__ inj_u_dy,
                                                       const int* __restrict__ block_flag_offsets,   // null when p_inject == 0
                                                       RefResampleParams R, int* __restrict__ ancestors,
-                                                      int* __restrict__ counters /* [0]=injected, [1]=clamped */) {
+                                                      int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G) {
     __shared__ int warp_counts[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
-    double r = live ? u_r[i] : 2.0;
+    uint32_t A[4] = {0, 0, 0, 0};
+    double r = 2.0;
+    if (live) {
+        if (GEN) { ref_philox_draws(2 * (uint64_t)i, G, A); r = canonical53(A[0], A[1]); }
+        else r = u_r[i];
+    }
     // rank of this slot among the slots whose draw fell below p_inject (sequential injection counter, MC:518,525)
     int flag = (block_flag_offsets != nullptr && r < R.p_inject) ? 1 : 0;
     int rank = 0;
@@ -547,11 +568,23 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
         if (lo >= n) { lo = n - 1; atomicAdd(&counters[1], 1); }
         float4 a = src[lo];
         int64_t inj_before = rank < R.max_inject ? rank : R.max_inject;
-        int64_t jpos = (i - inj_before) * (R.jitter_state ? 3 : 2);
-        double jx = dadd(dmul(u_jit[jpos], R.jit_xy_w), R.jit_xy_a);
-        double jy = dadd(dmul(u_jit[jpos + 1], R.jit_xy_w), R.jit_xy_a);
+        // jitter draws are consumed in slot order by non-injected slots only: this slot takes stream entry i - inj_before
+        double ux, uy, ut = 0.0;
+        if (GEN) {
+            const uint64_t j = (uint64_t)(i - inj_before);
+            uint32_t B[4];
+            if (inj_before != 0) ref_philox_draws(2 * j, G, A);
+            ref_philox_draws(2 * j + 1, G, B);
+            ux = canonical53(A[2], A[3]); uy = canonical53(B[0], B[1]); ut = canonical53(B[2], B[3]);
+        } else {
+            const int64_t jpos = (i - inj_before) * (R.jitter_state ? 3 : 2);
+            ux = u_jit[jpos]; uy = u_jit[jpos + 1];
+            if (R.jitter_state) ut = u_jit[jpos + 2];
+        }
+        double jx = dadd(dmul(ux, R.jit_xy_w), R.jit_xy_a);
+        double jy = dadd(dmul(uy, R.jit_xy_w), R.jit_xy_a);
         double jt = (double)a.z;
-        if (R.jitter_state) jt = dadd(jt, dadd(dmul(u_jit[jpos + 2], R.jit_th_w), R.jit_th_a));
+        if (R.jitter_state) jt = dadd(jt, dadd(dmul(ut, R.jit_th_w), R.jit_th_a));
         o.x = __double2float_rn(dadd((double)a.x, jx));          // MC:548
         o.y = __double2float_rn(dadd((double)a.y, jy));          // MC:549
         double sn, cs;
@@ -563,7 +596,7 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
     dst[i] = o;
 }
 
-// ---- production draws: the u_r / u_jitter streams from Philox4x32-10, counter = (2i | 2i+1, stream 0x30, step) -------
+// ---- the production draw streams materialised (for checkers) ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fill_resample_draws(double* __restrict__ u_r, double* __restrict__ u_jit, int64_t n, int per,
                                                              uint32_t step, uint32_t k0, uint32_t k1) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -631,10 +664,14 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n_par
     s = warp_sum(s);
     if (lane == 0) out[o] = s;
 }
-__global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum,
-                                                   double* __restrict__ partials /* [grid][4] */) {
+// weight_sum by value (known on the host after update / resample / init, else from k_pose_wsum + k_reduce_partials). The last
+// block to finish adds the per-block partials in block order (deterministic) and leaves the four sums in out4.
+__global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum_dev, double wsum_host,
+                                                   double* __restrict__ partials /* [grid][4] */, unsigned* __restrict__ ticket,
+                                                   double* __restrict__ out4) {
     __shared__ double ws[8][4];
-    const float weight_sum = __double2float_rn(*wsum);
+    __shared__ bool last;
+    const float weight_sum = __double2float_rn(wsum_dev ? *wsum_dev : wsum_host);
     double a[4] = {0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float4 p = part[i];
@@ -650,6 +687,21 @@ __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ pa
         for (int k = 0; k < 4; k++) ws[threadIdx.x >> 5][k] = a[k];
     __syncthreads();
     if (threadIdx.x < 4) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w][threadIdx.x]; partials[(size_t)blockIdx.x * 4 + threadIdx.x] = s; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (o < 4) {
+            double s = 0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 4 + o);
+            s = warp_sum(s);
+            if (lane == 0) out4[o] = s;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
 }
 
 }  // namespace mcl

@@ -114,7 +114,8 @@ int Engine::open() {
     CK(d_lut.ensure(n_keys)); CK(d_lut_filled.ensure(n_keys)); CK(d_touch.ensure(n_keys)); CK(d_touch_theta.ensure(n_keys));
     CK(cudaMemcpyAsync(d_lut.p, h_lut.data(), n_keys * sizeof(double2), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
-    CK(d_counters.ensure(4)); CK(d_scalars.ensure(8));
+    CK(d_counters.ensure(8)); CK(d_scalars.ensure(8));
+    CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4] = ticket of k_pose_sums (resets itself)
     CK(d_partials.ensure(4 * 1024));
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
@@ -335,6 +336,7 @@ int Engine::init(int64_t count, const mcl_init_draws* d) {
     CK(cudaStreamSynchronize(stream));
     n = count;
     have_weights = false;
+    wsum_known = true; known_wsum = (double)count;                 // every weight is 1 (MC:445)
     return MCL_OK;
 }
 
@@ -347,6 +349,7 @@ int Engine::upload(const float* p, int64_t count) {
     CK(cudaStreamSynchronize(stream));
     n = count;
     have_weights = false;
+    wsum_known = false;
     return MCL_OK;
 }
 
@@ -371,6 +374,12 @@ int Engine::download_ancestors(int32_t* idx) {
 int Engine::download_resample_draws(double* u_r, double* u_jit) {
     CK(cudaSetDevice(cfg.device));
     if (!u_r || !u_jit || n == 0) return fail(MCL_ERR_ARG, "download_resample_draws: nothing to download");
+    if (draws_generated) {        // the last resample generated its draws inside the kernels: materialise the same streams
+        CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3));
+        LAUNCH(K_FILL_DRAWS, k_fill_resample_draws, grid_for(n, 256), 256, 0, d_u_r.p, d_u_jit.p, n, last_per, draws_step, (uint32_t)cfg.seed,
+               (uint32_t)(cfg.seed >> 32));
+        CK(cudaGetLastError());
+    }
     CK(cudaMemcpyAsync(u_r, d_u_r.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(u_jit, d_u_jit.p, (size_t)n * last_per * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -593,6 +602,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
     CK(cudaMemcpyAsync(&last_total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     have_weights = true;
+    wsum_known = true; known_wsum = last_total;                    // the f64 sum of the fp32 weights just written (MC:675)
     if (total) *total = last_total;
     return MCL_OK;
 }
@@ -657,7 +667,7 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const int per = jitter_state ? 3 : 2;
     const int max_inj = R.max_inject;
     // stage draws
-    CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3));
+    if (d) { CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3)); }
     CK(d_inj_f64.ensure(3 * (size_t)std::max(1, max_inj))); CK(d_inj_i32.ensure(2 * (size_t)std::max(1, max_inj)));
     const size_t inj_f64 = 3 * (size_t)max_inj, inj_i32 = 2 * (size_t)max_inj;
     int rc = ensure_pinned(((size_t)(d ? n : 0) * (1 + per) + inj_f64) * sizeof(double) + inj_i32 * sizeof(int));
@@ -700,11 +710,11 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     if (d) {
         CK(cudaMemcpyAsync(d_u_r.p, hr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_u_jit.p, hj, (size_t)n * per * sizeof(double), cudaMemcpyHostToDevice, stream));
-    } else {
-        LAUNCH(K_FILL_DRAWS, k_fill_resample_draws, grid_for(n, 256), 256, 0, d_u_r.p, d_u_jit.p, n, per, (uint32_t)step_counter,
-               (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
-        CK(cudaGetLastError());
     }
+    // no injected draws: the kernels generate the Philox streams themselves (k_fill_resample_draws materialises them on request)
+    draws_generated = d == nullptr;
+    draws_step = (uint32_t)step_counter;
+    const RefDrawGen G{(uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)};
     if (max_inj > 0) {
         CK(cudaMemcpyAsync(d_inj_f64.p, hif, inj_f64 * sizeof(double), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_inj_i32.p, hii, inj_i32 * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -714,16 +724,22 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const bool inject_possible = p_inject > 0.0 && max_inj > 0;      // NaN p_inject compares false (MC:492, std::max(0.0, NaN) = 0.0)
     if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
-        LAUNCH(K_INJECT_COUNT, k_ref_inject_count, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p);
+        if (d) LAUNCH(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G);
+        else LAUNCH(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G);
         LAUNCH(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2);
         CK(cudaGetLastError());
     }
     // normalise + sequential CDF (MC:496-505)
     rc = exact_accumulate(true, nullptr);
     if (rc) return rc;
-    LAUNCH(K_RESAMPLE, k_ref_resample, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
-           d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-           inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p);
+    if (d)
+        LAUNCH(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
+               d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G);
+    else
+        LAUNCH(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
+               d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G);
     CK(cudaGetLastError());
     int counters[4];
     CK(cudaMemcpyAsync(counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
@@ -731,6 +747,7 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     cur ^= 1;
     have_weights = false;
     ++step_counter;
+    wsum_known = true; known_wsum = (double)n * (double)R.new_weight;        // every new particle weighs (float)(1/N), MC:524,551
     if (st) {
         st->injected = counters[0]; st->clamped = counters[1]; st->p_inject = p_inject;
         st->weight_slow = inj_slow; st->weight_fast = inj_fast; st->total_weight = last_total;
@@ -744,10 +761,14 @@ int Engine::estimate(double* x, double* y, double* th) {
     if (n == 0) return fail(MCL_ERR_ARG, "estimate: no particles");
     { int rc = ns_materialise_weights(); if (rc) return rc; }
     const int blocks = (int)std::min<int64_t>(1024, grid_for(n, 256));
-    LAUNCH(K_POSE_WSUM, k_pose_wsum, blocks, 256, 0, part[cur].p, n, d_partials.p);
-    LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
-    LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, d_scalars.p + 1, d_partials.p);
-    LAUNCH(K_REDUCE, k_reduce_partials, 1, 128, 0, d_partials.p, blocks, 4, 4, d_scalars.p + 2);
+    CK(d_partials.ensure(4 * 1024));
+    const double* wsum_dev = nullptr;
+    if (!(wsum_known && cfg.mode == MCL_MODE_REF)) {            // weights of unknown provenance (uploaded, NS records): sum them first
+        LAUNCH(K_POSE_WSUM, k_pose_wsum, blocks, 256, 0, part[cur].p, n, d_partials.p);
+        LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
+        wsum_dev = d_scalars.p + 1;
+    }
+    LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2);
     CK(cudaGetLastError());
     double s[4];
     CK(cudaMemcpyAsync(s, d_scalars.p + 2, sizeof(s), cudaMemcpyDeviceToHost, stream));

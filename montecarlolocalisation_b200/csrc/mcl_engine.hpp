@@ -176,6 +176,10 @@ private:
     DevBuf<double> d_partials;
     double last_total = 0;
     bool have_weights = false;
+    bool wsum_known = false;                    // sum of the particle weights known on the host (skips a reduction pass in estimate)
+    double known_wsum = 0;
+    bool draws_generated = false;               // the last resample generated its draws in-kernel (Philox)
+    uint32_t draws_step = 0;
     // NS state
     int ns_build_field();
     int ns_init(int64_t count);

@@ -1,5 +1,5 @@
 """Join an ncu SASS source page with nvdisasm line info: executed instructions per CUDA source line.
-usage: python tools/ncu_lines.py <report.ncu-rep> <mangled-kernel-substring> [top]"""
+usage: python tools/ncu_lines.py <report.ncu-rep> <mangled-kernel-substring> [top] [ncu kernel-name regex if the report holds several kernels]"""
 import collections, csv, glob, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kern = sys.argv[1], sys.argv[2]
@@ -24,7 +24,8 @@ for cub in glob.glob(tmp + "/*.cubin"):
             mm = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
             if mm:
                 m[int(mm.group(1), 16)] = line
-csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["-k", "regex:" + sys.argv[4], "-c", "1"] if len(sys.argv) > 4 else []
+csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(csvtxt.splitlines()))
 hi = [i for i, r in enumerate(rows) if "Source" in r][0]
 h = rows[hi]
