@@ -20,6 +20,10 @@ struct RefParams {
     const uint8_t* occ;
     int width, height;
     int map_in_smem;           // stage occ into shared memory (w*h small enough)
+    // bordered ray-march table (k_ref_update_v2's fp32 path): (width + 2 pad) x (height + 2 pad) bytes, 0 free, 1 occupied,
+    // 2 outside the grid; row/column -1 replicate row/column 0 (the reference's cast truncates (-1,0) to cell 0, Q7)
+    const uint8_t* occ_pad;
+    int pad, wp;
     double res, inv_res;       // (double)float32 resolution (Q10) and its rounded reciprocal
     double ox, oy;             // origin (MC:300-301)
     double max_x, max_y;       // isInsideMap upper bounds (MC:688-689)
@@ -262,13 +266,20 @@ struct RuSmem {
     int* vlist;
     float* radii_f;
     uint8_t* occ;
+    uint8_t* occ_pad;
+    float2* dq;           // per ray-table key: fp32 direction in cells per metre (dir / res)
+    float2* q0;           // per valid particle: fp32 laser origin in cell units, minus 0.5
+    double* gterm;        // [beam][hit index 0..n_radii]: w_hit * GaussianLookup(|obs - expected|), last = no hit (max range)
 };
-__host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes) {
+// map_bytes = plain + bordered table bytes when they are staged in shared memory, else 0
+__host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes, size_t pad_bytes) {
     return (size_t)n_keys * 16 + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
-           RU_TILE * 4 + (((size_t)n_radii * 4 + 15) & ~(size_t)15) + ((map_bytes + 15) & ~(size_t)15);
+           RU_TILE * 4 + (((size_t)n_radii * 4 + 15) & ~(size_t)15) + ((map_bytes + 15) & ~(size_t)15) + ((pad_bytes + 15) & ~(size_t)15) +
+           (size_t)n_keys * 8 + RU_TILE * 8 + (size_t)n_beams * (n_radii + 1) * 8;
 }
 
-template <bool ZERO_ORIGIN, bool FAST32>
+// NR: number of ray steps known at compile time (11 for the reference's 1.0 m / 0.1 m), 0 = run-time count (<= 16)
+template <bool ZERO_ORIGIN, bool FAST32, int NR>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
                                                            uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -284,6 +295,10 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     S.vlist = reinterpret_cast<int*>(S.terms + (size_t)RU_TILE * (P.n_beams + 1));
     S.radii_f = reinterpret_cast<float*>(S.vlist + RU_TILE);
     S.occ = reinterpret_cast<uint8_t*>(S.radii_f + ((P.n_radii + 3) & ~3));
+    S.occ_pad = S.occ + ((P.map_in_smem ? (size_t)P.width * P.height + 15 : 0) & ~(size_t)15);
+    S.dq = reinterpret_cast<float2*>(S.occ_pad + ((P.map_in_smem ? (size_t)P.wp * (P.height + 2 * P.pad) + 15 : 0) & ~(size_t)15));
+    S.q0 = S.dq + P.n_keys;
+    S.gterm = reinterpret_cast<double*>(S.q0 + RU_TILE);
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii_f[i] = __double2float_rn(P.radii[i]);
     for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) S.lut[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = P.beams[i];
@@ -291,9 +306,30 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     if (P.map_in_smem) {
         const int cells = P.width * P.height;
         for (int i = threadIdx.x; i < cells; i += RU_TILE) S.occ[i] = P.occ[i];
+        const int cells_p = P.wp * (P.height + 2 * P.pad);
+        for (int i = threadIdx.x; i < cells_p; i += RU_TILE) S.occ_pad[i] = P.occ_pad[i];
     }
     __syncthreads();
+    if (FAST32) {
+        // per key: the direction in fp32 cell units; per (beam, step at which the ray ended): the beam's score term. A ray
+        // ends at one of n_radii + 1 distances, so GaussianLookup::get (MC:154-168) is evaluated here once per pair.
+        for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE)
+            S.dq[i] = make_float2(__double2float_rn(dmul(S.lut[i].x, P.inv_res)), __double2float_rn(dmul(S.lut[i].y, P.inv_res)));
+        const int per = P.n_radii + 1;
+        for (int i = threadIdx.x; i < P.n_beams * per; i += RU_TILE) {
+            const int b = i / per, k = i - b * per;
+            const double expected = k < P.n_radii ? S.radii[k] : P.max_range;            // MC:379 / MC:389
+            S.gterm[i] = dmul(P.w_hit, ref_gauss(P, fabs(dsub(S.beams[b].obs, expected))));   // MC:662-665
+        }
+        __syncthreads();
+    }
     const uint8_t* occ = P.map_in_smem ? S.occ : P.occ;
+    const uint8_t* occ_pad = P.map_in_smem ? S.occ_pad : P.occ_pad;
+    // raw magic-add bit patterns -> bordered index: (by - MB + pad) * wp + (bx - MB + pad), constants folded (mod 2^32)
+    const uint32_t pad_fold = (uint32_t)(P.pad - RU_MAGICF_BITS) * ((uint32_t)P.wp + 1u);
+    const uint32_t wp_u = (uint32_t)P.wp;
+    const float lim32 = 0.5f - tol32;
+    const uint32_t pad_last = (uint32_t)P.wp * (uint32_t)(P.height + 2 * P.pad) - 1u;
     // constants in registers
     const double res = P.res, inv_res = P.inv_res, ox = P.ox, oy = P.oy;
     const int W = P.width, H = P.height;
@@ -345,48 +381,74 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
         __syncthreads();
         int slot = __popc(bal & ((1u << lane) - 1u)), nv = 0;
         for (int w = 0; w < RU_TILE / 32; w++) { if (w < warp) slot += warp_cnt[w]; nv += warp_cnt[w]; }
-        if (valid) { S.vlist[slot] = threadIdx.x; S.posx[slot] = posx; S.posy[slot] = posy; S.yawd[slot] = yawd; }
+        if (valid) {
+            S.vlist[slot] = threadIdx.x; S.posx[slot] = posx; S.posy[slot] = posy; S.yawd[slot] = yawd;
+            if (FAST32) S.q0[slot] = make_float2(__double2float_rn(dsub(dmul(dsub(posx, ox), inv_res), 0.5)), __double2float_rn(dsub(dmul(dsub(posy, oy), inv_res), 0.5)));
+        }
         __syncthreads();
         // ---- phase B -------------------------------------------------------------------------------------------------
         const int n_rays = nv * nb;
+        const int nrr = NR ? NR : nr;
         for (int r = threadIdx.x; r < n_rays; r += RU_TILE) {
             const int v = (int)__umulhi((unsigned)r, div_magic);
             const int b = r - v * nb;
-            const RefBeam bm = S.beams[b];
-            const double px = S.posx[v], py = S.posy[v];
-            const int k = ref_key_index(P, S.yawd[v], bm.off_deg);
-            const double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
-            double expected = P.max_range;                                               // MC:389
+            const int k = ref_key_index(P, S.yawd[v], S.beams[b].off_deg);
             if (FAST32) {
-                const float qx0 = __double2float_rn(dmul(dsub(px, ox), inv_res)), qy0 = __double2float_rn(dmul(dsub(py, oy), inv_res));
-                const float dqx = __double2float_rn(dmul(dir.x, inv_res)), dqy = __double2float_rn(dmul(dir.y, inv_res));
-                for (int s = 0; s < nr; s++) {                                           // MC:372
+                // All probes of the ray at once, branch-free, in fp32: q' = cell coordinate - 0.5, so that round-to-nearest
+                // (magic add) gives floor(q) and e = q' - RN(q') = frac(q) - 0.5. A probe whose q lies within tol of a cell
+                // edge in either axis (|e| >= 0.5 - tol) is marked undecided. Codes from the bordered table: 1 = occupied
+                // (MC:377), 2 = left the grid (MC:376); the first non-zero code ends the march. Only if an undecided probe
+                // comes at or before it does the f64 march decide (a fraction ~1e-3 of the rays).
+                const float2 q0 = S.q0[v];
+                const float2 dq = (k >= 0) ? S.dq[k] : make_float2(0.f, 0.f);
+                uint32_t codes = 0, undecided = 0;
+#pragma unroll
+                for (int s = 0; s < (NR ? NR : 16); s++) {                              // MC:372
+                    if (!NR && s >= nr) break;
                     const float rf = S.radii_f[s];
-                    bool okx, oky;
-                    int mx = cell_fast32(__fmaf_rn(rf, dqx, qx0), tol32, okx);
-                    int my = cell_fast32(__fmaf_rn(rf, dqy, qy0), tol32, oky);
-                    int c;
-                    if (__builtin_expect(!(okx & oky), 0)) {                             // near a cell edge: f64 decides
-                        const double rr = S.radii[s];
-                        c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
-                    } else {
-                        const bool inb = (unsigned)mx < (unsigned)W && (unsigned)my < (unsigned)H;
-                        const int cell = occ[inb ? my * W + mx : 0];                     // unconditional load, clamped index
-                        c = inb ? cell : -1;
-                    }
-                    if (c < 0) break;                                                    // MC:376
-                    if (c) { expected = S.radii[s]; break; }                             // MC:377-381
+                    const float qx = __fmaf_rn(rf, dq.x, q0.x), qy = __fmaf_rn(rf, dq.y, q0.y);
+                    const float tx = __fadd_rn(qx, RU_MAGICF), ty = __fadd_rn(qy, RU_MAGICF);
+                    const float ex = __fadd_rn(qx, -__fadd_rn(tx, -RU_MAGICF)), ey = __fadd_rn(qy, -__fadd_rn(ty, -RU_MAGICF));
+                    const bool decided = (fabsf(ex) < lim32) & (fabsf(ey) < lim32);      // NaN fails
+                    // a valid particle is inside the map and its rays end inside the border, so the index is in range;
+                    // an undecided probe's code is never used (the f64 march takes over if it matters)
+                    const uint32_t idx = __float_as_uint(ty) * wp_u + __float_as_uint(tx) + pad_fold;
+                    codes |= (uint32_t)occ_pad[min(idx, pad_last)] << (2 * s);
+                    if (!decided) undecided |= 3u << (2 * s);
                 }
+                const uint32_t events = codes | undecided;
+                const int first = events ? (__ffs((int)events) - 1) >> 1 : nrr;          // probe index of the first event
+                double term;
+                if (__builtin_expect(first < nrr && ((undecided >> (2 * first)) & 1u), 0)) {
+                    const double px = S.posx[v], py = S.posy[v];
+                    const double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
+                    double expected = P.max_range;                                       // MC:389
+                    for (int s = 0; s < nrr; s++) {                                      // exact march
+                        const double rr = S.radii[s];
+                        const int c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
+                        if (c < 0) break;                                                // MC:376
+                        if (c) { expected = rr; break; }                                 // MC:377-381
+                    }
+                    term = dmul(P.w_hit, ref_gauss(P, fabs(dsub(S.beams[b].obs, expected))));
+                } else {
+                    const bool hit = first < nrr && ((codes >> (2 * first)) & 3u) == 1u;
+                    term = S.gterm[b * (nrr + 1) + (hit ? first : nrr)];
+                }
+                S.terms[v * stride + b] = term;                                          // MC:665
             } else {
+                const RefBeam bm = S.beams[b];
+                const double px = S.posx[v], py = S.posy[v];
+                const double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
+                double expected = P.max_range;                                           // MC:389
                 for (int s = 0; s < nr; s++) {                                           // MC:372
                     const double rr = S.radii[s];
                     const int c = probe_fast<ZERO_ORIGIN>(occ, dadd(px, dmul(rr, dir.x)), dadd(py, dmul(rr, dir.y)), ox, oy, res, inv_res, W, H);
                     if (c < 0) break;                                                    // MC:376
                     if (c) { expected = rr; break; }                                     // MC:377-381
                 }
+                const double diff = fabs(dsub(bm.obs, expected));                        // MC:662
+                S.terms[v * stride + b] = dmul(P.w_hit, ref_gauss(P, diff));             // MC:665
             }
-            const double diff = fabs(dsub(bm.obs, expected));                            // MC:662
-            S.terms[v * stride + b] = dmul(P.w_hit, ref_gauss(P, diff));                 // MC:665
         }
         __syncthreads();
         // ---- phase C -------------------------------------------------------------------------------------------------

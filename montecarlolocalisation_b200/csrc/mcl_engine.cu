@@ -22,7 +22,7 @@ Engine::~Engine() {
     for (int w = 0; w < 3; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
     if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
-    ns_comm_destroy(); ancestors.release(); d_occ.release(); d_gauss.release();
+    ns_comm_destroy(); ancestors.release(); d_occ.release(); d_occ_pad.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
     d_beams.release(); for (auto& sc : staged) sc.d_used.release(); for (auto& sc : ns_staged) sc.d_pts.release(); d_u_r.release(); d_u_jit.release(); d_inj_f64.release(); d_inj_i32.release();
     d_block_counts.release(); d_counters.release(); d_scalars.release(); d_partials.release();
@@ -135,6 +135,21 @@ int Engine::set_map(const int8_t* occ, int w, int h, float res, double ox, doubl
     for (size_t i = 0; i < flags.size(); ++i) flags[i] = occ[i] > 50 ? 1 : 0;    // MC:327,377
     CK(d_occ.ensure(flags.size()));
     CK(cudaMemcpyAsync(d_occ.p, flags.data(), flags.size(), cudaMemcpyHostToDevice, stream));
+    // bordered ray-march table: 0 free, 1 occupied, 2 outside; row/column -1 replicate row/column 0 (truncation quirk, Q7).
+    // Border = longest ray (max range + laser offset) in cells + 3, so a ray from a particle inside the map never leaves it.
+    {
+        const double reach = (cfg.max_laser_range + std::fabs(cfg.laser_offset)) / (double)res;
+        occ_pad = reach < 1024.0 ? (int)std::ceil(reach) + 3 : 0;
+        occ_wp = w + 2 * occ_pad;
+        std::vector<uint8_t> padded((size_t)occ_wp * (h + 2 * occ_pad), 2);
+        if (occ_pad > 0) {
+            for (int y = -1; y < h; ++y)
+                for (int x = -1; x < w; ++x)
+                    padded[(size_t)(y + occ_pad) * occ_wp + (x + occ_pad)] = flags[(size_t)std::max(y, 0) * w + std::max(x, 0)];
+        }
+        CK(d_occ_pad.ensure(std::max<size_t>(1, padded.size())));
+        CK(cudaMemcpyAsync(d_occ_pad.p, padded.data(), padded.size(), cudaMemcpyHostToDevice, stream));
+    }
     CK(cudaStreamSynchronize(stream));
     map_ready = true;
     if (cfg.mode == MCL_MODE_NS) return ns_build_field();
@@ -521,8 +536,10 @@ int Engine::ref_prepare_beams(const float* ranges, int n_beams, float angle_min,
 int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total) {
     RefParams P;
     P.occ = d_occ.p; P.width = map_w; P.height = map_h;
+    P.occ_pad = d_occ_pad.p; P.pad = occ_pad; P.wp = occ_wp;
     const size_t map_bytes = (size_t)map_w * map_h;
-    P.map_in_smem = map_bytes <= 64 * 1024 ? 1 : 0;
+    const size_t pad_bytes = (size_t)occ_wp * (map_h + 2 * occ_pad);
+    P.map_in_smem = map_bytes + pad_bytes <= 64 * 1024 ? 1 : 0;
     P.res = (double)res_f; P.inv_res = 1.0 / (double)res_f;
     P.ox = origin_x; P.oy = origin_y; P.max_x = max_x; P.max_y = max_y;
     P.laser_offset = cfg.laser_offset; P.validity_offset = cfg.validity_offset; P.max_range = cfg.max_laser_range;
@@ -562,19 +579,21 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         int rc = ref_fill_ray_lut(all);
         if (rc) return rc;
     }
-    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0);
+    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0);
     const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
     if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024 && bounded_ok) {
         if (!attr_set2) {
-            CK(cudaFuncSetAttribute(k_ref_update_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_ref_update_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_ref_update_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute(k_ref_update_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute((k_ref_update_v2<true, true, 11>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute((k_ref_update_v2<false, true, 11>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute((k_ref_update_v2<true, true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute((k_ref_update_v2<false, true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute((k_ref_update_v2<true, false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CK(cudaFuncSetAttribute((k_ref_update_v2<false, false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             attr_set2 = true;
         }
         int occ_blocks = 1, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, k_ref_update_v2<false, true>, RU_TILE, smem2));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<false, true, 0>), RU_TILE, smem2));
         // the bounded fast path needs every probe quotient below 2^31: particle inside the map, ray at most max_range long
         const bool zero_origin = origin_x == 0.0 && origin_y == 0.0;
         const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
@@ -583,13 +602,16 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         // fp32 pre-filter tolerance: 4x the bound 2^-23*(cells + 2*max_range/res + 2) on the fp32 cell coordinate's error
         const double span = (double)std::max(map_w, map_h) + 2.0 * cfg.max_laser_range / (double)res_f + 2.0;
         const float tol32 = (float)(span * 4.76837158203125e-07);                  // 2^-21
-        const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f;
-        if (fast32) {
-            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, true>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, true>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+        const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f && occ_pad > 0 && P.n_radii <= 16;
+        if (fast32 && P.n_radii == 11) {
+            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+        } else if (fast32) {
+            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
         } else {
-            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, false>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, false>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
         }
     } else {
         LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);

@@ -147,6 +147,8 @@ private:
     double origin_x = 0, origin_y = 0, max_x = 0, max_y = 0;
     std::vector<int8_t> h_occ;
     DevBuf<uint8_t> d_occ;            // 1 = occupied (value > 50)
+    DevBuf<uint8_t> d_occ_pad;        // bordered ray-march table (0 free, 1 occupied, 2 outside)
+    int occ_pad = 0, occ_wp = 0;
     // tables
     GaussTable gauss;
     DevBuf<double> d_gauss;
