@@ -1,8 +1,8 @@
 // exact_scan.cuh — CUDA kernels for the parallel, bit-exact sequential f64 accumulation (see exact_scan_core.cuh).
 //
 // Tiles of 2048 fp32 weights (256 threads x 8 consecutive items). Per accumulation:
-//   k_xs_tilesum   tile sums of the weights (optionally normalising them first: w <- (float)((double)w / total))
-//   k_xs_offsets   exclusive scan of the tile sums (one warp)                      -> P~ at every tile edge
+//   k_xs_tilesum   tile sums of the weights (optionally normalising them first: w <- (float)((double)w / total)); the last
+//                  block to finish scans them with one warp                         -> P~ at every tile edge
 //   k_xs_scan<0>   per tile: P~_i, binade prediction, parity-monoid segmented scan  -> tile composites + SEQ entries
 //   k_xs_chain     one thread: carries across tiles, the SEQ elements with the hardware adder, the grand total
 //   k_xs_scan<1>   per tile again: same scan, now applying run-start values         -> exact s_i for every i (the CDF)
@@ -41,7 +41,7 @@ struct Workspace {
     Par* carry;           // [nt+1]
     int* seq_base;        // [nt+1]
     double* seq_s;        // [nt * XS_SEQ_CAP]
-    int* flag;            // != 0: fall back to the sequential kernel
+    int* flag;            // != 0: fall back to the sequential kernel; flag[1] = ticket of k_xs_tilesum (resets itself)
 };
 
 __device__ __forceinline__ void load_items(const float* __restrict__ w, int64_t base, int64_t n, float (&x)[XS_ITEMS]) {
@@ -71,12 +71,31 @@ __device__ __forceinline__ double block_scan_incl(double v, double* smem8) {
     return dadd(pre, v);
 }
 
-// ---- pass 1: tile sums (and normalisation) -------------------------------------------------------------------------
+// Exclusive scan of the tile sums by one warp, contiguous chunks (fixed association) -> P~ at every tile edge.
+__device__ __forceinline__ void tile_offsets_warp(const double* __restrict__ tsum, int nt, double* __restrict__ toff, int lane) {
+    const int chunk = (nt + 31) / 32;
+    const int a = min(nt, lane * chunk), b = min(nt, a + chunk);
+    double s = 0.0;
+    for (int t = a; t < b; t++) s = dadd(s, __ldcg(tsum + t));
+    double incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = dadd(up, incl);
+    }
+    double run = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) run = 0.0;
+    for (int t = a; t < b; t++) { toff[t] = run; run = dadd(run, __ldcg(tsum + t)); }
+    if (lane == 31) toff[nt] = run;          // lane 31's chunk always ends at nt
+}
+
+// ---- pass 1: tile sums (and normalisation); the last block to finish also scans them (pass 2) ---------------------------
 template <bool NORMALISE>
 __global__ void __launch_bounds__(XS_THREADS) k_xs_tilesum(const float* __restrict__ w_in, float* __restrict__ w_out,
                                                            float4* __restrict__ part, int64_t n, const double* __restrict__ total,
-                                                           double* __restrict__ tsum) {
+                                                           double* __restrict__ tsum, double* __restrict__ toff, int* __restrict__ flag) {
     __shared__ double sm[8];
+    __shared__ bool last;
     const int64_t base = (int64_t)blockIdx.x * XS_TILE + (int64_t)threadIdx.x * XS_ITEMS;
     float x[XS_ITEMS];
     load_items(w_in, base, n, x);
@@ -94,27 +113,17 @@ __global__ void __launch_bounds__(XS_THREADS) k_xs_tilesum(const float* __restri
 #pragma unroll
     for (int j = 0; j < XS_ITEMS; j++) s = dadd(s, (double)x[j]);
     double incl = block_scan_incl(s, sm);
-    if (threadIdx.x == XS_THREADS - 1) tsum[blockIdx.x] = incl;
-}
-
-// ---- pass 2: exclusive scan of tile sums, one warp, contiguous chunks -------------------------------------------------
-__global__ void k_xs_offsets(const double* __restrict__ tsum, int nt, double* __restrict__ toff, int* __restrict__ flag) {
-    const int lane = threadIdx.x;
-    if (lane == 0) *flag = 0;
-    const int chunk = (nt + 31) / 32;
-    const int a = min(nt, lane * chunk), b = min(nt, a + chunk);
-    double s = 0.0;
-    for (int t = a; t < b; t++) s = dadd(s, tsum[t]);
-    double incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl = dadd(up, incl);
+    if (threadIdx.x == XS_THREADS - 1) {
+        tsum[blockIdx.x] = incl;
+        __threadfence();
+        last = atomicAdd(flag + 1, 1) == (int)gridDim.x - 1;
     }
-    double run = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) run = 0.0;
-    for (int t = a; t < b; t++) { toff[t] = run; run = dadd(run, tsum[t]); }
-    if (lane == 31) toff[nt] = run;          // lane 31's chunk always ends at nt
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        if (threadIdx.x == 0) { flag[0] = 0; flag[1] = 0; }
+        tile_offsets_warp(tsum, (int)gridDim.x, toff, threadIdx.x);
+    }
 }
 
 // ---- passes 3 and 5 ---------------------------------------------------------------------------------------------------
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(XS_THREADS) k_xs_scan(const float* __restrict_
     __shared__ ScanState sm_st[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x;
+    if (APPLY && *ws.flag) return;            // uniform: the sequential kernel redoes the whole job
     const int64_t base = (int64_t)t * XS_TILE + (int64_t)tid * XS_ITEMS;
     float x[XS_ITEMS];
     load_items(w, base, n, x);
@@ -265,18 +275,49 @@ __global__ void __launch_bounds__(XS_THREADS) k_xs_scan(const float* __restrict_
 // between them need the hardware adder in order; one thread walks those.
 constexpr int XS_CHAIN_THREADS = 512;
 constexpr int XS_CHAIN_LIST = 2048;
-__global__ void __launch_bounds__(XS_CHAIN_THREADS) k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out) {
+constexpr int XS_CHAIN_PRE = 32;              // listed tiles whose SEQ entries are prefetched into shared memory
+constexpr int XS_SEQ_TILE = 1024;
+
+// The always-correct fallback for the total: one thread adds left to right (MC:675) while the rest of the block stages
+// the next 1024 weights in shared memory.
+__device__ __forceinline__ double seq_total_block(const float* __restrict__ w, int64_t n, float (*tile)[XS_SEQ_TILE]) {
+    double acc = 0.0;
+    const int64_t n_tiles = (n + XS_SEQ_TILE - 1) / XS_SEQ_TILE;
+    for (int i = threadIdx.x; i < XS_SEQ_TILE; i += blockDim.x) { int64_t g = i; tile[0][i] = g < n ? w[g] : 0.f; }
+    __syncthreads();
+    for (int64_t t = 0; t < n_tiles; t++) {
+        const int cur = t & 1;
+        if (threadIdx.x == 0) {
+            const int64_t cnt = min((int64_t)XS_SEQ_TILE, n - t * XS_SEQ_TILE);
+            for (int i = 0; i < cnt; i++) acc = dadd(acc, (double)tile[cur][i]);
+        } else if (t + 1 < n_tiles) {
+            const int64_t base = (t + 1) * XS_SEQ_TILE;
+            for (int i = threadIdx.x - 1; i < XS_SEQ_TILE; i += blockDim.x - 1) { int64_t g = base + i; tile[cur ^ 1][i] = g < n ? w[g] : 0.f; }
+        }
+        __syncthreads();
+    }
+    return acc;      // valid in thread 0
+}
+
+// w / n: the accumulated terms, for the in-kernel sequential fallback of the total (the CDF has its own fallback kernel
+// after the apply pass).
+__global__ void __launch_bounds__(XS_CHAIN_THREADS) k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out, const float* __restrict__ w,
+                                                               int64_t n) {
     __shared__ ScanState sm_warp[XS_CHAIN_THREADS / 32];
     __shared__ ScanState sm_carry_in;          // running state entering the current chunk of tiles
     __shared__ int sm_fail;
     __shared__ int sm_list[XS_CHAIN_LIST];     // tiles that contain SEQ elements, in order
     __shared__ int sm_list_n;
     __shared__ int sm_wcount[XS_CHAIN_THREADS / 32];
-    if (*ws.flag) return;                      // uniform: every thread reads the same word
+    __shared__ SeqEntry sm_entries[XS_CHAIN_PRE * XS_SEQ_CAP];
+    __shared__ Par sm_pcarry[XS_CHAIN_PRE];
+    __shared__ int sm_pcnt[XS_CHAIN_PRE], sm_pbase[XS_CHAIN_PRE];
+    __shared__ float sm_seq[2][XS_SEQ_TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0; sm_fail = 0; sm_list_n = 0; }
+    if (tid == 0) { sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0; sm_fail = *ws.flag ? 1 : 0; sm_list_n = 0; }
     __syncthreads();
-    for (int c0 = 0; c0 < nt; c0 += XS_CHAIN_THREADS) {
+    const bool skip = sm_fail != 0;            // uniform: an earlier pass already gave up
+    for (int c0 = 0; c0 < nt && !skip; c0 += XS_CHAIN_THREADS) {
         const int t = c0 + tid;
         ScanState mine;
         mine.v = par_identity(); mine.reset = 0; mine.cnt = 0;
@@ -296,16 +337,22 @@ __global__ void __launch_bounds__(XS_CHAIN_THREADS) k_xs_chain(int nt, Workspace
         if (lane == 31) sm_warp[warp] = inc;
         if (lane == 0) sm_wcount[warp] = __popc(has);
         __syncthreads();
-        {
-            int pos = sm_list_n;
-            for (int k = 0; k < warp; k++) pos += sm_wcount[k];
-            pos += __popc(has & ((1u << lane) - 1u));
-            if (mine.cnt > 0) { if (pos < XS_CHAIN_LIST) sm_list[pos] = t; else sm_fail = 1; }
-        }
         ScanState pre = sm_carry_in;
         for (int k = 0; k < warp; k++) pre = st_combine(pre, sm_warp[k]);
         ScanState lane_excl = st_shfl_up(inc, 1);
         if (lane > 0) pre = st_combine(pre, lane_excl);          // state entering tile t
+        {
+            int pos = sm_list_n;
+            for (int k = 0; k < warp; k++) pos += sm_wcount[k];
+            pos += __popc(has & ((1u << lane) - 1u));
+            if (mine.cnt > 0) {
+                if (pos < XS_CHAIN_LIST) sm_list[pos] = t; else sm_fail = 1;
+                if (pos < XS_CHAIN_PRE) {                        // keep what the sequential walk will need on chip
+                    sm_pcarry[pos] = pre.v; sm_pcnt[pos] = mine.cnt; sm_pbase[pos] = pre.cnt;
+                    for (int k = 0; k < mine.cnt && k < XS_SEQ_CAP; k++) sm_entries[pos * XS_SEQ_CAP + k] = ws.entries[(size_t)t * XS_SEQ_CAP + k];
+                }
+            }
+        }
         if (t < nt) { ws.carry[t] = pre.v; ws.seq_base[t] = pre.cnt; }
         __syncthreads();
         if (tid == XS_CHAIN_THREADS - 1) {
@@ -316,32 +363,39 @@ __global__ void __launch_bounds__(XS_CHAIN_THREADS) k_xs_chain(int nt, Workspace
         }
         __syncthreads();
     }
-    if (tid != 0) return;
-    const ScanState fin = sm_carry_in;
-    ws.carry[nt] = fin.v;
-    ws.seq_base[nt] = fin.cnt;
-    bool ok = sm_fail == 0;
-    double s = 0.0;
-    if (ok) {
-        const int n_list = min(sm_list_n, XS_CHAIN_LIST);
-        for (int li = 0; li < n_list; li++) {
-            const int t = sm_list[li];
-            const int cnt = ws.tiles[t].seq_count;
-            const Par carry = ws.carry[t];
-            const int base = ws.seq_base[t];
-            for (int k = 0; k < cnt; k++) {
-                const SeqEntry e = ws.entries[(size_t)t * XS_SEQ_CAP + k];
-                const Par comp = e.first_in_tile ? par_compose(carry, e.pre) : e.pre;
-                s = par_apply(s, comp, e.E_prev, ok);
-                s = dadd(s, (double)e.w);            // the hardware adder: exactly the reference's rounding
-                ws.seq_s[base + k] = s;
+    if (tid == 0 && !skip) {
+        const ScanState fin = sm_carry_in;
+        ws.carry[nt] = fin.v;
+        ws.seq_base[nt] = fin.cnt;
+        bool ok = sm_fail == 0;
+        double s = 0.0;
+        if (ok) {
+            const int n_list = min(sm_list_n, XS_CHAIN_LIST);
+            for (int li = 0; li < n_list; li++) {
+                const bool pre = li < XS_CHAIN_PRE;
+                const int t = sm_list[li];
+                const int cnt = pre ? sm_pcnt[li] : ws.tiles[t].seq_count;
+                const Par carry = pre ? sm_pcarry[li] : ws.carry[t];
+                const int base = pre ? sm_pbase[li] : ws.seq_base[t];
+                for (int k = 0; k < cnt; k++) {
+                    const SeqEntry e = pre ? sm_entries[li * XS_SEQ_CAP + k] : ws.entries[(size_t)t * XS_SEQ_CAP + k];
+                    const Par comp = e.first_in_tile ? par_compose(carry, e.pre) : e.pre;
+                    s = par_apply(s, comp, e.E_prev, ok);
+                    s = dadd(s, (double)e.w);            // the hardware adder: exactly the reference's rounding
+                    ws.seq_s[base + k] = s;
+                }
             }
+            // the run after the last SEQ element: its binade is that of P~_{n-1} = toff[nt]
+            if (ok) s = par_apply(s, fin.v, f64_exponent(ws.toff[nt]), ok);
         }
-        // the run after the last SEQ element: its binade is that of P~_{n-1} = toff[nt]
-        if (ok) s = par_apply(s, fin.v, f64_exponent(ws.toff[nt]), ok);
+        if (!ok) { atomicOr(ws.flag, 1); sm_fail = 1; }
+        else if (total_out) *total_out = s;
     }
-    if (!ok) { atomicOr(ws.flag, 1); return; }
-    if (total_out) *total_out = s;
+    __syncthreads();
+    if (sm_fail && total_out) {                  // uniform: redo the total with the single chain
+        const double s = seq_total_block(w, n, sm_seq);
+        if (tid == 0) *total_out = s;
+    }
 }
 
 }  // namespace xs

@@ -216,7 +216,8 @@ int Engine::ensure_particles(int64_t count) {
 
 int Engine::ensure_xs(int64_t count) {
     const int nt = (int)((count + xs::XS_TILE - 1) / xs::XS_TILE);
-    CK(xs_flag.ensure(1));
+    CK(xs_flag.ensure(2));
+    CK(cudaMemsetAsync(xs_flag.p, 0, 2 * sizeof(int), stream));      // [0] fallback flag, [1] ticket of k_xs_tilesum
     if (nt <= xs_tiles_cap) return MCL_OK;
     CK(xs_tsum.ensure(nt)); CK(xs_toff.ensure(nt + 1)); CK(xs_seq_s.ensure((size_t)nt * xs::XS_SEQ_CAP));
     CK(xs_tiles.ensure((size_t)nt * sizeof(xs::TileSummary))); CK(xs_entries.ensure((size_t)nt * xs::XS_SEQ_CAP * sizeof(xs::SeqEntry)));
@@ -238,22 +239,24 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
     xs::Workspace ws;
     ws.tsum = xs_tsum.p; ws.toff = xs_toff.p; ws.tiles = (xs::TileSummary*)xs_tiles.p; ws.entries = (xs::SeqEntry*)xs_entries.p;
     ws.carry = (xs::Par*)xs_carry.p; ws.seq_base = xs_seq_base.p; ws.seq_s = xs_seq_s.p; ws.flag = xs_flag.p;
-    if (normalise)
-        LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p);
-    else if (!force_sequential)
-        LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<false>, nt, xs::XS_THREADS, 0, w, (float*)nullptr, (float4*)nullptr, n,
-               (const double*)nullptr, xs_tsum.p);
-    CK(cudaGetLastError());
     if (!force_sequential) {
-        LAUNCH(K_XS_OFFSETS, xs::k_xs_offsets, 1, 32, 0, xs_tsum.p, nt, xs_toff.p, xs_flag.p);
+        if (normalise)
+            LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
+        else
+            LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<false>, nt, xs::XS_THREADS, 0, w, (float*)nullptr, (float4*)nullptr, n, (const double*)nullptr,
+                   xs_tsum.p, xs_toff.p, xs_flag.p);
         LAUNCH(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
-        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out);
-        if (want_cdf) LAUNCH(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
-        CK(cudaGetLastError());
+        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out, w, n);     // total: falls back in-kernel
+        if (want_cdf) {
+            LAUNCH(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
+            LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)xs_flag.p);            // runs only if flagged
+        }
+    } else {
+        if (normalise)
+            LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
+        if (want_cdf) LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)nullptr);
+        if (d_total_out) LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, w, n, d_total_out, (const int*)nullptr);
     }
-    const int* run_if = force_sequential ? nullptr : xs_flag.p;
-    if (want_cdf) LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, run_if);
-    if (d_total_out) LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, w, n, d_total_out, run_if);
     CK(cudaGetLastError());
     return MCL_OK;
 }
