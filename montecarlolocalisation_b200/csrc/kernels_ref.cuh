@@ -574,6 +574,23 @@ __global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, 
     }
 }
 
+// (float)atan2(sin(t), cos(t)) (MC:550). For |t| < 3 pi the mathematical value is t, t - 2 pi or t + 2 pi; libm's composed
+// result differs from it by a few 1e-16, so the float rounding agrees unless the value sits within 1e-14 of a float
+// rounding boundary: only then (or near +-pi, or for larger |t|) is the libm chain evaluated.
+__device__ __forceinline__ float ref_wrap_theta(double t) {
+    const double PI = 3.14159265358979323846, TWO_PI_HI = 6.283185307179586, TWO_PI_LO = 2.4492935982947064e-16;
+    if (fabs(t) < 9.42) {
+        double z = t;
+        if (t > PI) z = dsub(dsub(t, TWO_PI_HI), TWO_PI_LO);
+        else if (t < -PI) z = dadd(dadd(t, TWO_PI_HI), TWO_PI_LO);
+        const float f = __double2float_rn(z);
+        if (__double2float_rn(z - 1e-14) == f && __double2float_rn(z + 1e-14) == f && fabs(fabs(t) - PI) > 1e-12) return f;
+    }
+    double sn, cs;
+    sincos(t, &sn, &cs);
+    return __double2float_rn(atan2(sn, cs));
+}
+
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n,
                                                       const double* __restrict__ cdf, const double* __restrict__ u_r,
@@ -649,9 +666,7 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
         if (R.jitter_state) jt = dadd(jt, dadd(dmul(ut, R.jit_th_w), R.jit_th_a));
         o.x = __double2float_rn(dadd((double)a.x, jx));          // MC:548
         o.y = __double2float_rn(dadd((double)a.y, jy));          // MC:549
-        double sn, cs;
-        sincos(jt, &sn, &cs);
-        o.z = __double2float_rn(atan2(sn, cs));                  // MC:550
+        o.z = ref_wrap_theta(jt);                                // MC:550
         o.w = R.new_weight;                                      // MC:551
         ancestors[i] = (int)lo;
     }
