@@ -163,6 +163,7 @@ constexpr int NS_MAGIC_BITS = 0x4B400000;
 template <bool SMEM>
 struct NsFieldView {
     const float* lf;        // generic pointer (global path, and the bounds-tested path)
+    const float* lf_shifted;   // global fast path: lf - (2^32 - fold) cells, valid when every cell index wraps alike
     uint32_t base;          // SMEM fast path: shared byte address of the field + folded constant; else folded cell constant
     uint32_t Wp, Wp4;
     unsigned W, H;
@@ -183,7 +184,7 @@ __device__ __forceinline__ float ns_eval_checked(const NsFieldView<SMEM>& V, flo
     return in ? v : V.lf_out;
 }
 // evaluation for a particle inside the map: the endpoint is inside the bordered field by construction
-template <bool SMEM>
+template <bool SMEM, bool SHIFT>
 __device__ __forceinline__ float ns_eval_fast(const NsFieldView<SMEM>& V, float gx0, float gy0, float c, float s, float2 bm) {
     const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
     const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
@@ -196,17 +197,14 @@ __device__ __forceinline__ float ns_eval_fast(const NsFieldView<SMEM>& V, float 
             : "r"(__float_as_uint(ty)), "r"(V.Wp4), "r"(V.base), "r"(__float_as_uint(tx)));
         return v;
     } else {
-        const uint32_t idx = __float_as_uint(ty) * V.Wp + V.base + __float_as_uint(tx);
-        return __ldg(V.lf + idx);
+        // t = raw bits combined (mod 2^32); the folded constant lives in the (shifted) base pointer when it cannot wrap
+        // differently for different cells (V.lf_shifted != null), else it is added explicitly
+        const uint32_t t = __float_as_uint(ty) * V.Wp + __float_as_uint(tx);
+        return SHIFT ? __ldg(V.lf_shifted + t) : __ldg(V.lf + (uint32_t)(t + V.base));
     }
 }
 
-// Scores the 32 particles of a warp batch in groups of P: partial sums acc[P] per lane, then per group the xor butterfly
-// stages 16 .. P as plain butterflies and stages P/2 .. 1 as a transpose-reduction, after which lane l holds the total of
-// particle (l mod P) of the group in acc[0]; lanes l with l / P == group keep it, so lane l ends with particle l.
-// Every particle's beams are summed by exactly the (16,8,4,2,1) xor-butterfly tree of DESIGN.md NS-3 whatever P is.
-// P trades shuffles (31 per 32 particles at P = 32, 2.9 per particle at P = 8) against registers (occupancy).
-template <bool SMEM, bool FAST, int P>
+template <bool SMEM, bool FAST, int P, bool SHIFT = false>
 __device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, const float2* __restrict__ s_beams, int n_beams, int lane, float gx0,
                                                 float gy0, float c, float s) {
     float mine = 0.f;
@@ -227,7 +225,7 @@ __device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, cons
                 const float2 bm = s_beams[b];
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    a[q] = ns::addf(a[q], FAST ? ns_eval_fast<SMEM>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<SMEM>(V, X[q], Y[q], C[q], S[q], bm));
+                    a[q] = ns::addf(a[q], FAST ? ns_eval_fast<SMEM, SHIFT>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<SMEM>(V, X[q], Y[q], C[q], S[q], bm));
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
@@ -275,6 +273,11 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
     // (pad - MAGIC_BITS) * (Wp + 1): turns the raw magic-add bit patterns into the bordered cell index (mod 2^32)
     const uint32_t fold = (uint32_t)(F.pad - NS_MAGIC_BITS) * ((uint32_t)F.Wp + 1u);
     V.base = SMEM_FIELD ? smem_u32(s_lf) + 4u * fold : fold;
+    // cell index = (t + fold) mod 2^32 with t = bits(ty) * Wp + bits(tx). If fold >= number of cells, t + fold always
+    // wraps exactly once, so index = t - (2^32 - fold) and the subtraction can live in the pointer.
+    V.lf_shifted = nullptr;
+    if (!SMEM_FIELD && (uint64_t)fold >= (uint64_t)F.Wp * (uint64_t)(F.H + 2 * F.pad))
+        V.lf_shifted = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(F.lf) - 4ull * (0x100000000ull - (uint64_t)fold));
     const bool fast_ok = F.pad > 0;
     const float ox = F.ox, oy = F.oy, inv_res = F.inv_res;
     const float x_hi = (float)F.W - 0.5f, y_hi = (float)F.H - 0.5f;
@@ -291,7 +294,10 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
         const float gy0 = ns::fmaf_(ns::addf(p.y, -oy), inv_res, -0.5f);
         const bool inside = gx0 >= -0.5f && gx0 <= x_hi && gy0 >= -0.5f && gy0 <= y_hi;        // false for NaN
         float ll;
-        if (fast_ok && __all_sync(0xffffffffu, inside)) ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        if (fast_ok && __all_sync(0xffffffffu, inside)) {
+            if (!SMEM_FIELD && V.lf_shifted) ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+            else ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        }
         else ll = ns_score_batch<SMEM_FIELD, false, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
         if (i < n) { ll_out[i] = ll; best = fmaxf(best, ll); }
     }
