@@ -220,7 +220,7 @@ __device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, cons
                 C[q] = __shfl_sync(0xffffffffu, c, g0 + k0 + q); S[q] = __shfl_sync(0xffffffffu, s, g0 + k0 + q);
                 a[q] = 0.f;
             }
-#pragma unroll 2
+#pragma unroll (SMEM ? 2 : 4)
             for (int b = lane; b < n_beams; b += 32) {
                 const float2 bm = s_beams[b];
 #pragma unroll
