@@ -163,7 +163,7 @@ constexpr int NS_MAGIC_BITS = 0x4B400000;
 template <bool SMEM>
 struct NsFieldView {
     const float* lf;        // generic pointer (global path, and the bounds-tested path)
-    const float* lf_shifted;   // global fast path: lf - (2^32 - fold) cells, valid when every cell index wraps alike
+    uint32_t win_hi;           // global fast path: high address word when the field lies inside one 4 GiB window
     uint32_t base;          // SMEM fast path: shared byte address of the field + folded constant; else folded cell constant
     uint32_t Wp, Wp4;
     unsigned W, H;
@@ -197,10 +197,16 @@ __device__ __forceinline__ float ns_eval_fast(const NsFieldView<SMEM>& V, float 
             : "r"(__float_as_uint(ty)), "r"(V.Wp4), "r"(V.base), "r"(__float_as_uint(tx)));
         return v;
     } else {
-        // t = raw bits combined (mod 2^32); the folded constant lives in the (shifted) base pointer when it cannot wrap
-        // differently for different cells (V.lf_shifted != null), else it is added explicitly
-        const uint32_t t = __float_as_uint(ty) * V.Wp + __float_as_uint(tx);
-        return SHIFT ? __ldg(V.lf_shifted + t) : __ldg(V.lf + (uint32_t)(t + V.base));
+        // SHIFT: the field lies inside one 4 GiB-aligned window, so only the low address word depends on the cell:
+        // lo = field_lo + 4 * ((iy + pad) * Wp + ix + pad) (mod 2^32; constants folded) is one IMAD (FMA pipe) + one LEA
+        // (ALU pipe) like the shared-memory path, and the high word is a constant. The FMA pipe is this kernel's busiest
+        // unit, which is why the 64-bit IMAD.WIDE address form is avoided.
+        if (SHIFT) {
+            const uint32_t lo = __float_as_uint(ty) * V.Wp4 + V.base + (__float_as_uint(tx) << 2);
+            return __ldg(reinterpret_cast<const float*>(((uint64_t)V.win_hi << 32) | (uint64_t)lo));
+        }
+        const uint32_t idx = __float_as_uint(ty) * V.Wp + V.base + __float_as_uint(tx);
+        return __ldg(V.lf + idx);
     }
 }
 
@@ -273,11 +279,11 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
     // (pad - MAGIC_BITS) * (Wp + 1): turns the raw magic-add bit patterns into the bordered cell index (mod 2^32)
     const uint32_t fold = (uint32_t)(F.pad - NS_MAGIC_BITS) * ((uint32_t)F.Wp + 1u);
     V.base = SMEM_FIELD ? smem_u32(s_lf) + 4u * fold : fold;
-    // cell index = (t + fold) mod 2^32 with t = bits(ty) * Wp + bits(tx). If fold >= number of cells, t + fold always
-    // wraps exactly once, so index = t - (2^32 - fold) and the subtraction can live in the pointer.
-    V.lf_shifted = nullptr;
-    if (!SMEM_FIELD && (uint64_t)fold >= (uint64_t)F.Wp * (uint64_t)(F.H + 2 * F.pad))
-        V.lf_shifted = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(F.lf) - 4ull * (0x100000000ull - (uint64_t)fold));
+    // global field inside one 4 GiB-aligned window: 32-bit address arithmetic, constant high word
+    const uint64_t f_lo = reinterpret_cast<uint64_t>(F.lf), f_hi = f_lo + (uint64_t)F.bytes_padded - 1;
+    const bool one_window = !SMEM_FIELD && (f_lo >> 32) == (f_hi >> 32);
+    V.win_hi = (uint32_t)(f_lo >> 32);
+    if (one_window) V.base = (uint32_t)f_lo + 4u * fold;
     const bool fast_ok = F.pad > 0;
     const float ox = F.ox, oy = F.oy, inv_res = F.inv_res;
     const float x_hi = (float)F.W - 0.5f, y_hi = (float)F.H - 0.5f;
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
         const bool inside = gx0 >= -0.5f && gx0 <= x_hi && gy0 >= -0.5f && gy0 <= y_hi;        // false for NaN
         float ll;
         if (fast_ok && __all_sync(0xffffffffu, inside)) {
-            if (!SMEM_FIELD && V.lf_shifted) ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+            if (one_window) ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
             else ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
         }
         else ll = ns_score_batch<SMEM_FIELD, false, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);

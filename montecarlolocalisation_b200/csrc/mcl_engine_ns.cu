@@ -47,6 +47,16 @@ int Engine::ns_build_field() {
     if (cells_p >= (1ull << 31)) return fail(MCL_ERR_ARG, "set_map: grid too large");
     lf_bytes_padded = (cells_p * sizeof(float) + 15) & ~(size_t)15;
     CK(d_lf_table.ensure(table.size())); CK(d_lf.ensure(lf_bytes_padded / sizeof(float))); CK(d_d2.ensure(cells)); CK(d_g.ensure(cells));
+    // the sensor-model kernel addresses the field with 32-bit arithmetic when it lies inside one 4 GiB-aligned window
+    // (else it falls back to 64-bit address arithmetic): if this allocation straddles a boundary, try for another one
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const uint64_t a = (uint64_t)(uintptr_t)d_lf.p, b = a + lf_bytes_padded - 1;
+        if ((a >> 32) == (b >> 32) || lf_bytes_padded > (1ull << 32)) break;
+        DevBuf<float> other;
+        if (other.ensure(lf_bytes_padded / sizeof(float)) != cudaSuccess) { cudaGetLastError(); break; }
+        std::swap(other.p, d_lf.p); std::swap(other.n, d_lf.n);
+        other.release();
+    }
     CK(cudaMemcpyAsync(d_lf_table.p, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
     LAUNCH(K_NS_EDT_COLS, k_ns_fill_f32, 148 * 8, 256, 0, d_lf.p, lf_bytes_padded / sizeof(float), lf_out);
     LAUNCH(K_NS_EDT_COLS, k_ns_edt_cols, grid_for(map_w, 128), 128, 0, d_occ.p, map_w, map_h, ns_R, d_g.p);
