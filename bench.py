@@ -464,13 +464,16 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
     prof = shard.pf.profileRead()
     shard.pf.profileEnable(False)
     # kidnapped-robot case: freshly uniform particles (no spatial locality in the field gathers)
-    shard.pf.profileEnable(True)
-    for k in range(3):
+    steady_form = shard.field_form()
+    for k in range(6):
+        if k == 2:          # two untimed launches first: fields larger than L2 settle on their field form by measurement
+            shard.pf.profileEnable(True)
         shard.pf.sampleParticles(n_global)
         shard.pf.updateParticlePos(*motion)
         shard.update_local_staged(0)
     uni = shard.pf.profileRead().get("k_ns_update", (0.0, 1))
     shard.pf.profileEnable(False)
+    uniform_form = shard.field_form()
     uniform_ms = uni[0] / uni[1]
     t_res, t_e2e = sum(ms_res) * 1e-3, sum(ms_e2e) * 1e-3
     if world > 1:
@@ -498,7 +501,8 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
         "config": {"workload": "%s: %dx%d occupancy grid, %d particles per GPU x %d GPU(s) = %d, %d-beam scan (%d valid beams scored per particle), "
                                "NS mode: Philox motion noise -> likelihood field -> Q32 systematic resampling" % (
                                    label, occ.shape[1], occ.shape[0], per_gpu, world, n_global, n_beams, nb),
-                   "field": "%d KiB log-likelihood field, %s" % (field_bytes // 1024, "TMA-staged into shared memory" if field_bytes <= 190 * 1024 else "gathered through L2"),
+                   "field": "%d KiB log-likelihood field, %s" % (field_bytes // 1024, {"smem-f32": "TMA-staged into shared memory", "global-f32": "fp32, gathered through L1/L2",
+                                                                       "global-u8": "as one-byte codes (%d KiB) gathered through L1/L2 + shared-memory code table" % (field_bytes // 4096)}[steady_form]),
                    "collectives": "none (1 GPU)" if world == 1 else "engine-enqueued NCCL on the filter's stream, no host round trip: all-reduce(max), all-gather(Q32 totals), all-reduce(pose, e2e only), closing all-reduce as barrier; resampled particles stored into peer shards over NVLink (CUDA IPC)",
                    "l2": "per-GPU working set %.0f MB exceeds or displaces L2 between steps" % (per_gpu * 48 / 1e6)},
         "gpu_launches": launches, "scaling": "weak",
@@ -508,7 +512,7 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
                      "share_of_step": kernels[top]["share"],
                      "note": "algorithmic bytes = 20 B/particle + 4 B per scored beam (table gather); the gathers are served by shared memory or L2, not HBM"},
         "kernels": kernels,
-        "uniform_particles": {"k_ns_update_ms": uniform_ms, "evals_per_s_per_gpu": per_gpu * valid_beams[0] / (uniform_ms * 1e-3),
+        "uniform_particles": {"k_ns_update_ms": uniform_ms, "field_form": uniform_form, "evals_per_s_per_gpu": per_gpu * valid_beams[0] / (uniform_ms * 1e-3),
                               "note": "sensor-model kernel alone on freshly uniform particles (kidnapped robot): worst case for gather locality"},
         "gather_microbench_reads_per_s": {"shared_memory_table": shard.pf.benchGather(0, min(field_bytes, 190 * 1024)),
                                           "global_table_of_field_size": shard.pf.benchGather(1, field_bytes)},

@@ -202,6 +202,10 @@ void* mcl_device_buffer(mcl_handle* h, int32_t which);
 int mcl_ns_download_field(mcl_handle* h, float* loglik_field, uint16_t* d2);
 int mcl_ns_download_loglik(mcl_handle* h, float* loglik);
 int mcl_ns_download_prefix(mcl_handle* h, uint64_t* prefix_q32);
+/* Where the last sensor-model launch read the likelihood field from: 0 = fp32 field staged into shared memory by TMA,
+ * 1 = fp32 field through L1/L2, 2 = one-byte coded field through L1/L2 + shared-memory code table (fields too large for
+ * L2 as fp32; chosen by measured time against form 1). All three give identical values. -1 before the first update. */
+int mcl_ns_field_form(mcl_handle* h);
 
 /* ---- the rows either side of the hot path ------------------------------------------------- */
 #define MCL_KMEANS_K 3
@@ -250,7 +254,9 @@ int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitt
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back);
 /* Cross-check switches (slow paths): bit 0 = single-chain sequential accumulation kernels instead of the parallel exact
  * scan; bit 1 = the one-thread-per-particle computeWeight kernel instead of the ray-parallel one; bit 2 = ray-parallel
- * kernel without its fp32 pre-filter. */
+ * kernel without its fp32 pre-filter; bit 3 = NS sensor model reads the one-byte coded field, bit 4 = the fp32 field
+ * through global memory (each regardless of the field's size; all three forms give identical values); bit 5 = NS sensor
+ * model in scalar FFMA form on every path. */
 int mcl_debug_force_sequential(mcl_handle* h, int32_t on);
 /* Random 4-byte gather micro-benchmark: the roofline denominator of the sensor-model kernel.
  * tier 0 = table in shared memory (<= 200 KiB), tier 1 = table in global memory (L2- or HBM-resident by its size). */

@@ -38,8 +38,14 @@ __global__ void k_ns_edt_cols(const uint8_t* __restrict__ occ, int W, int H, int
 __global__ void k_ns_fill_f32(float* __restrict__ dst, size_t n, float v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
 }
+__global__ void k_ns_fill_u8(uint8_t* __restrict__ dst, size_t n, uint8_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+// code_of_d2 / code_out (both or neither): the same field as one byte per cell, the rank of d2 among the attainable
+// squared distances; k_ns_update turns the code back into table[d2] through a <= 256-entry shared-memory table
 __global__ void k_ns_edt_rows(const uint16_t* __restrict__ g, int W, int H, int R, const float* __restrict__ lf_of_d2,
-                              uint16_t* __restrict__ d2_out, float* __restrict__ lf_out, int pad) {
+                              uint16_t* __restrict__ d2_out, float* __restrict__ lf_out, int pad,
+                              const uint8_t* __restrict__ code_of_d2, uint8_t* __restrict__ code_out) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const int cap = R * R;
@@ -56,6 +62,7 @@ __global__ void k_ns_edt_rows(const uint16_t* __restrict__ g, int W, int H, int 
     size_t i = (size_t)y * W + x;
     if (d2_out) d2_out[i] = (uint16_t)best;
     lf_out[(size_t)(y + pad) * (W + 2 * pad) + (x + pad)] = lf_of_d2[best];
+    if (code_out) code_out[(size_t)(y + pad) * (W + 2 * pad) + (x + pad)] = code_of_d2[best];
 }
 
 // ---- init / predict -------------------------------------------------------------------------------------------------------
@@ -113,7 +120,15 @@ struct NsField {
     float ox, oy, inv_res;
     float lf_out;           // value for endpoints outside the grid
     int bytes_padded;       // field bytes rounded up to 16 (TMA bulk copy granularity)
+    const uint8_t* lf8;     // NS_FIELD_U8: one code per cell, same bordered layout; value = codes[code]
+    const float* codes;     // NS_FIELD_U8: code -> log-likelihood (n_codes <= 256 entries, global)
+    int n_codes;
 };
+// where k_ns_update reads the field from
+constexpr int NS_FIELD_SMEM = 0;     // fp32 field staged into shared memory by TMA
+constexpr int NS_FIELD_GLOBAL = 1;   // fp32 field through L1/L2
+constexpr int NS_FIELD_U8 = 2;       // one-byte codes through L1/L2 (a quarter of the footprint: fields too large for L2 as fp32)
+                                     // + code table in shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -160,9 +175,11 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, uint
 constexpr float NS_MAGIC = 12582912.0f;          // 1.5 * 2^23
 constexpr int NS_MAGIC_BITS = 0x4B400000;
 
-template <bool SMEM>
+template <int KIND>
 struct NsFieldView {
     const float* lf;        // generic pointer (global path, and the bounds-tested path)
+    const uint8_t* lf8;     // NS_FIELD_U8: the code field
+    const float* codes;     // NS_FIELD_U8: shared-memory code table
     uint32_t win_hi;           // global fast path: high address word when the field lies inside one 4 GiB window
     uint32_t base;          // SMEM fast path: shared byte address of the field + folded constant; else folded cell constant
     uint32_t Wp, Wp4;
@@ -172,46 +189,83 @@ struct NsFieldView {
 };
 
 // bounds-tested evaluation (any particle position)
-template <bool SMEM>
-__device__ __forceinline__ float ns_eval_checked(const NsFieldView<SMEM>& V, float gx0, float gy0, float c, float s, float2 bm) {
+template <int KIND>
+__device__ __forceinline__ float ns_eval_checked(const NsFieldView<KIND>& V, float gx0, float gy0, float c, float s, float2 bm) {
     const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
     const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
     const unsigned ix = (unsigned)(__float_as_int(tx) - NS_MAGIC_BITS);
     const unsigned iy = (unsigned)(__float_as_int(ty) - NS_MAGIC_BITS);
     const bool in = ix < V.W && iy < V.H;
     const unsigned idx = in ? (iy + V.pad) * V.Wp + ix + V.pad : 0u;
-    const float v = SMEM ? V.lf[idx] : __ldg(V.lf + idx);
+    const float v = KIND == NS_FIELD_U8 ? V.codes[__ldg(V.lf8 + idx)] : KIND == NS_FIELD_SMEM ? V.lf[idx] : __ldg(V.lf + idx);
     return in ? v : V.lf_out;
 }
-// evaluation for a particle inside the map: the endpoint is inside the bordered field by construction
-template <bool SMEM, bool SHIFT>
-__device__ __forceinline__ float ns_eval_fast(const NsFieldView<SMEM>& V, float gx0, float gy0, float c, float s, float2 bm) {
-    const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
-    const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
-    if (SMEM) {
+// The field value for a particle inside the map from the raw magic-add bit patterns of the endpoint's cell coordinates:
+// the endpoint is inside the bordered field by construction, the constant parts of the bit patterns are folded into the
+// base. SHIFT (global fields): the field lies inside one 4 GiB-aligned window, so only the low address word depends on
+// the cell (IMAD + LEA/IADD like the shared-memory path, constant high word) and the 64-bit IMAD.WIDE address form is
+// avoided - the FMA pipe is this kernel's busiest unit.
+template <int KIND, bool SHIFT>
+__device__ __forceinline__ float ns_load_fast(const NsFieldView<KIND>& V, uint32_t tx_bits, uint32_t ty_bits) {
+    if (KIND == NS_FIELD_SMEM) {
         // byte address = field + 4 * ((iy + pad) * Wp + ix + pad), iy = bits(ty) - MAGIC_BITS (wrapping u32 arithmetic)
         // (IMAD, LEA, LDS: written as PTX so the compiler does not re-associate it into three integer operations)
         float v;
         asm("{\n.reg .u32 t, u;\nmad.lo.u32 t, %1, %2, %3;\nshl.b32 u, %4, 2;\nadd.u32 t, t, u;\nld.shared.f32 %0, [t];\n}"
             : "=f"(v)
-            : "r"(__float_as_uint(ty)), "r"(V.Wp4), "r"(V.base), "r"(__float_as_uint(tx)));
+            : "r"(ty_bits), "r"(V.Wp4), "r"(V.base), "r"(tx_bits));
         return v;
-    } else {
-        // SHIFT: the field lies inside one 4 GiB-aligned window, so only the low address word depends on the cell:
-        // lo = field_lo + 4 * ((iy + pad) * Wp + ix + pad) (mod 2^32; constants folded) is one IMAD (FMA pipe) + one LEA
-        // (ALU pipe) like the shared-memory path, and the high word is a constant. The FMA pipe is this kernel's busiest
-        // unit, which is why the 64-bit IMAD.WIDE address form is avoided.
+    } else if (KIND == NS_FIELD_GLOBAL) {
         if (SHIFT) {
-            const uint32_t lo = __float_as_uint(ty) * V.Wp4 + V.base + (__float_as_uint(tx) << 2);
+            const uint32_t lo = ty_bits * V.Wp4 + V.base + (tx_bits << 2);
             return __ldg(reinterpret_cast<const float*>(((uint64_t)V.win_hi << 32) | (uint64_t)lo));
         }
-        const uint32_t idx = __float_as_uint(ty) * V.Wp + V.base + __float_as_uint(tx);
+        const uint32_t idx = ty_bits * V.Wp + V.base + tx_bits;
         return __ldg(V.lf + idx);
+    } else {
+        uint32_t code;
+        if (SHIFT) {
+            const uint32_t lo = ty_bits * V.Wp + V.base + tx_bits;
+            code = __ldg(reinterpret_cast<const uint8_t*>(((uint64_t)V.win_hi << 32) | (uint64_t)lo));
+        } else {
+            const uint32_t idx = ty_bits * V.Wp + V.base + tx_bits;
+            code = __ldg(V.lf8 + idx);
+        }
+        return V.codes[code];
     }
 }
+template <int KIND, bool SHIFT>
+__device__ __forceinline__ float ns_eval_fast(const NsFieldView<KIND>& V, float gx0, float gy0, float c, float s, float2 bm) {
+    const float tx = ns::addf(ns::fmaf_(c, bm.x, ns::fmaf_(-s, bm.y, gx0)), NS_MAGIC);
+    const float ty = ns::addf(ns::fmaf_(s, bm.x, ns::fmaf_(c, bm.y, gy0)), NS_MAGIC);
+    return ns_load_fast<KIND, SHIFT>(V, __float_as_uint(tx), __float_as_uint(ty));
+}
 
-template <bool SMEM, bool FAST, int P, bool SHIFT = false>
-__device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, const float2* __restrict__ s_beams, int n_beams, int lane, float gx0,
+// per-lane partial sums of P particles -> lane (g0 + j) holds particle j's total: the xor-butterfly (16,8,4,2,1) tree of
+// DESIGN.md NS-3 for every particle, as a transpose-reduction (31 shuffles per 32 particles)
+template <int P>
+__device__ __forceinline__ float ns_transpose_reduce(float (&acc)[P], int lane) {
+#pragma unroll
+    for (int o = 16; o >= P; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < P; j++) acc[j] = ns::addf(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], o));
+    }
+    // after the stage with offset o, lanes with bit o set hold the upper half of the particles
+#pragma unroll
+    for (int o = (P < 32 ? P / 2 : 16); o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; j++) {
+            const float keep = up ? acc[j + o] : acc[j];
+            const float send = up ? acc[j] : acc[j + o];
+            acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+    }
+    return acc[0];
+}
+
+template <int KIND, bool FAST, int P, bool SHIFT = false>
+__device__ __forceinline__ float ns_score_batch(const NsFieldView<KIND>& V, const float2* __restrict__ s_beams, int n_beams, int lane, float gx0,
                                                 float gy0, float c, float s) {
     float mine = 0.f;
 #pragma unroll 1
@@ -226,41 +280,88 @@ __device__ __forceinline__ float ns_score_batch(const NsFieldView<SMEM>& V, cons
                 C[q] = __shfl_sync(0xffffffffu, c, g0 + k0 + q); S[q] = __shfl_sync(0xffffffffu, s, g0 + k0 + q);
                 a[q] = 0.f;
             }
-#pragma unroll (SMEM ? 2 : 4)
+#pragma unroll (KIND == NS_FIELD_SMEM ? 2 : 4)
             for (int b = lane; b < n_beams; b += 32) {
                 const float2 bm = s_beams[b];
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    a[q] = ns::addf(a[q], FAST ? ns_eval_fast<SMEM, SHIFT>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<SMEM>(V, X[q], Y[q], C[q], S[q], bm));
+                    a[q] = ns::addf(a[q], FAST ? ns_eval_fast<KIND, SHIFT>(V, X[q], Y[q], C[q], S[q], bm) : ns_eval_checked<KIND>(V, X[q], Y[q], C[q], S[q], bm));
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[k0 + q] = a[q];
         }
+        const float total = ns_transpose_reduce<P>(acc, lane);
+        if ((lane & ~(P - 1)) == g0) mine = total;
+    }
+    return mine;
+}
+
+// ---- packed fp32 (sm_100 FFMA2 / FADD2) form of the fast path ---------------------------------------------------------------
+// fma.rn.f32x2 / add.rn.f32x2 perform two independent IEEE fp32 operations on a 64-bit register pair per issue slot; the
+// values are bit-identical to the scalar form. Two particles share a pair: (pose_q, pose_q+1) against the same beam point
+// (a scalar operand broadcast to both halves). Measured (profiles/): FFMA2 occupies the FMA pipe for two cycles, so it
+// saves issue slots, not pipe time: +4 % on the global-field path (issue bound), nothing on the shared-memory path (FMA
+// pipe and LDS bound), which therefore keeps the scalar form.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void upk2u(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// same summation order, same values as ns_score_batch<KIND, true, P, SHIFT>
+template <int KIND, int P, bool SHIFT>
+__device__ __forceinline__ float ns_score_batch_packed(const NsFieldView<KIND>& V, const float2* __restrict__ s_beams, int n_beams, int lane,
+                                                       float gx0, float gy0, float c, float s) {
+    float mine = 0.f;
+    const f32x2 magic2 = pk2(NS_MAGIC, NS_MAGIC);
+    const float ns_ = -s;
+#pragma unroll 1
+    for (int g0 = 0; g0 < 32; g0 += P) {
+        float acc[P];
 #pragma unroll
-        for (int o = 16; o >= P; o >>= 1) {
+        for (int k0 = 0; k0 < P; k0 += 4) {
+            f32x2 X[2], Y[2], C[2], S[2], NSn[2], a[2];
 #pragma unroll
-            for (int j = 0; j < P; j++) acc[j] = ns::addf(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], o));
-        }
-        // transpose-reduction: after the stage with offset o, lanes with bit o set hold the upper half of the particles
-#pragma unroll
-        for (int o = (P < 32 ? P / 2 : 16); o > 0; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int j = 0; j < o; j++) {
-                const float keep = up ? acc[j + o] : acc[j];
-                const float send = up ? acc[j] : acc[j + o];
-                acc[j] = ns::addf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            for (int h = 0; h < 2; h++) {
+                const int q = g0 + k0 + 2 * h;
+                X[h] = pk2(__shfl_sync(0xffffffffu, gx0, q), __shfl_sync(0xffffffffu, gx0, q + 1));
+                Y[h] = pk2(__shfl_sync(0xffffffffu, gy0, q), __shfl_sync(0xffffffffu, gy0, q + 1));
+                C[h] = pk2(__shfl_sync(0xffffffffu, c, q), __shfl_sync(0xffffffffu, c, q + 1));
+                S[h] = pk2(__shfl_sync(0xffffffffu, s, q), __shfl_sync(0xffffffffu, s, q + 1));
+                NSn[h] = pk2(__shfl_sync(0xffffffffu, ns_, q), __shfl_sync(0xffffffffu, ns_, q + 1));
+                a[h] = pk2(0.f, 0.f);
             }
+#pragma unroll (KIND == NS_FIELD_SMEM ? 2 : 4)
+            for (int b = lane; b < n_beams; b += 32) {
+                const float2 bm = s_beams[b];
+                const f32x2 bx2 = pk2(bm.x, bm.x), by2 = pk2(bm.y, bm.y);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const f32x2 tx2 = add2(fma2(C[h], bx2, fma2(NSn[h], by2, X[h])), magic2);
+                    const f32x2 ty2 = add2(fma2(S[h], bx2, fma2(C[h], by2, Y[h])), magic2);
+                    uint32_t tx0, tx1, ty0, ty1;
+                    upk2u(tx2, tx0, tx1); upk2u(ty2, ty0, ty1);
+                    const float v0 = ns_load_fast<KIND, SHIFT>(V, tx0, ty0);
+                    const float v1 = ns_load_fast<KIND, SHIFT>(V, tx1, ty1);
+                    a[h] = add2(a[h], pk2(v0, v1));
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) upk2(a[h], acc[k0 + 2 * h], acc[k0 + 2 * h + 1]);
         }
-        if ((lane & ~(P - 1)) == g0) mine = acc[0];
+        const float total = ns_transpose_reduce<P>(acc, lane);
+        if ((lane & ~(P - 1)) == g0) mine = total;
     }
     return mine;
 }
 
 constexpr int NS_UPD_THREADS = 1024;
 constexpr int NS_UPD_P = 8;
+constexpr int NS_MAX_CODES = 256;
 
-template <bool SMEM_FIELD>
+// dynamic shared memory: [field (NS_FIELD_SMEM) | code table, NS_MAX_CODES floats (NS_FIELD_U8)] [beam points]
+template <int KIND, bool PACKED>
 __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
                                                                 const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
                                                                 int* __restrict__ max_bits /* ordered-int max of ll */) {
@@ -268,22 +369,28 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
     __shared__ uint64_t bar;
     __shared__ float warp_max[NS_UPD_THREADS / 32];
     float* s_lf = reinterpret_cast<float*>(smem_raw);
-    float2* s_beams = reinterpret_cast<float2*>(smem_raw + (SMEM_FIELD ? F.bytes_padded : 0));
-    if (SMEM_FIELD) tma_stage(s_lf, F.lf, (uint32_t)F.bytes_padded, &bar);
+    const size_t front = KIND == NS_FIELD_SMEM ? (size_t)F.bytes_padded : KIND == NS_FIELD_U8 ? NS_MAX_CODES * sizeof(float) : 0;
+    float2* s_beams = reinterpret_cast<float2*>(smem_raw + front);
+    if (KIND == NS_FIELD_SMEM) tma_stage(s_lf, F.lf, (uint32_t)F.bytes_padded, &bar);
+    if (KIND == NS_FIELD_U8)
+        for (int k = threadIdx.x; k < NS_MAX_CODES; k += blockDim.x) s_lf[k] = k < F.n_codes ? F.codes[k] : F.lf_out;
     for (int b = threadIdx.x; b < n_beams; b += blockDim.x) s_beams[b] = beams[b];
     __syncthreads();
-    NsFieldView<SMEM_FIELD> V;
-    V.lf = SMEM_FIELD ? s_lf : F.lf;
+    NsFieldView<KIND> V;
+    V.lf = KIND == NS_FIELD_SMEM ? s_lf : F.lf;
+    V.lf8 = F.lf8; V.codes = s_lf;
     V.Wp = (uint32_t)F.Wp; V.Wp4 = 4u * (uint32_t)F.Wp;
     V.W = (unsigned)F.W; V.H = (unsigned)F.H; V.pad = F.pad; V.lf_out = F.lf_out;
     // (pad - MAGIC_BITS) * (Wp + 1): turns the raw magic-add bit patterns into the bordered cell index (mod 2^32)
     const uint32_t fold = (uint32_t)(F.pad - NS_MAGIC_BITS) * ((uint32_t)F.Wp + 1u);
-    V.base = SMEM_FIELD ? smem_u32(s_lf) + 4u * fold : fold;
+    V.base = KIND == NS_FIELD_SMEM ? smem_u32(s_lf) + 4u * fold : fold;
     // global field inside one 4 GiB-aligned window: 32-bit address arithmetic, constant high word
-    const uint64_t f_lo = reinterpret_cast<uint64_t>(F.lf), f_hi = f_lo + (uint64_t)F.bytes_padded - 1;
-    const bool one_window = !SMEM_FIELD && (f_lo >> 32) == (f_hi >> 32);
+    const uint64_t cell_bytes = KIND == NS_FIELD_U8 ? 1 : 4;
+    const uint64_t f_lo = KIND == NS_FIELD_U8 ? reinterpret_cast<uint64_t>(F.lf8) : reinterpret_cast<uint64_t>(F.lf);
+    const uint64_t f_hi = f_lo + (uint64_t)F.Wp * (uint64_t)(F.H + 2 * F.pad) * cell_bytes - 1;
+    const bool one_window = KIND != NS_FIELD_SMEM && (f_lo >> 32) == (f_hi >> 32);
     V.win_hi = (uint32_t)(f_lo >> 32);
-    if (one_window) V.base = (uint32_t)f_lo + 4u * fold;
+    if (one_window) V.base = (uint32_t)f_lo + (uint32_t)cell_bytes * fold;
     const bool fast_ok = F.pad > 0;
     const float ox = F.ox, oy = F.oy, inv_res = F.inv_res;
     const float x_hi = (float)F.W - 0.5f, y_hi = (float)F.H - 0.5f;
@@ -301,10 +408,15 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
         const bool inside = gx0 >= -0.5f && gx0 <= x_hi && gy0 >= -0.5f && gy0 <= y_hi;        // false for NaN
         float ll;
         if (fast_ok && __all_sync(0xffffffffu, inside)) {
-            if (one_window) ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
-            else ll = ns_score_batch<SMEM_FIELD, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+            if (PACKED) {
+                if (one_window) ll = ns_score_batch_packed<KIND, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+                else ll = ns_score_batch_packed<KIND, NS_UPD_P, false>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+            } else {
+                if (one_window) ll = ns_score_batch<KIND, true, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+                else ll = ns_score_batch<KIND, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+            }
         }
-        else ll = ns_score_batch<SMEM_FIELD, false, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+        else ll = ns_score_batch<KIND, false, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
         if (i < n) { ll_out[i] = ll; best = fmaxf(best, ll); }
     }
 #pragma unroll

@@ -97,7 +97,8 @@ int mcl_set_injection_state(mcl_handle* h, double s, double f) { GUARD(h); h->en
 int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count) { GUARD(h); TRY(h->engine.get_ray_lut(keys, dx, dy, cap, count)) }
 int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter) { GUARD(h); TRY(h->engine.download_resample_draws(u_r, u_jitter)) }
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back) { GUARD(h); TRY(h->engine.debug_exact_scan(w, n, cdf, total, fell_back)) }
-int mcl_debug_force_sequential(mcl_handle* h, int32_t on) { GUARD(h); h->engine.force_sequential = (on & 1) != 0; h->engine.force_v1_update = (on & 2) != 0; h->engine.force_f64_probe = (on & 4) != 0; return MCL_OK; }
+int mcl_debug_force_sequential(mcl_handle* h, int32_t on) { GUARD(h); h->engine.force_sequential = (on & 1) != 0; h->engine.force_v1_update = (on & 2) != 0; h->engine.force_f64_probe = (on & 4) != 0;
+    h->engine.ns_force_field = (on & 8) ? 2 : (on & 16) ? 1 : -1; h->engine.ns_force_scalar = (on & 32) != 0; return MCL_OK; }
 int mcl_profile_enable(mcl_handle* h, int32_t on) { GUARD(h); h->engine.profile_enable(on != 0); return MCL_OK; }
 int mcl_profile_kernel_count(void) { return mcl::Engine::K_COUNT; }
 const char* mcl_profile_kernel_name(int32_t id) { return mcl::Engine::kernel_name(id); }
@@ -175,6 +176,7 @@ void* mcl_device_buffer(mcl_handle* h, int32_t which) { return h ? h->engine.dev
 int mcl_ns_download_field(mcl_handle* h, float* lf, uint16_t* d2) { GUARD(h); TRY(h->engine.ns_download_field(lf, d2)) }
 int mcl_ns_download_loglik(mcl_handle* h, float* ll) { GUARD(h); TRY(h->engine.ns_download_loglik(ll)) }
 int mcl_ns_download_prefix(mcl_handle* h, uint64_t* p) { GUARD(h); TRY(h->engine.ns_download_prefix(p)) }
+int mcl_ns_field_form(mcl_handle* h) { return h ? h->engine.ns_field_kind : -1; }
 void* mcl_stream(mcl_handle* h) { return h ? (void*)h->engine.stream : nullptr; }
 int mcl_synchronize(mcl_handle* h) { GUARD(h); TRY(h->engine.synchronize()) }
 int64_t mcl_kernel_launches(mcl_handle* h) { return h ? h->engine.launches : 0; }

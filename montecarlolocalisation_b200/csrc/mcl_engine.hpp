@@ -98,6 +98,9 @@ public:
     mcl_config cfg;
     bool force_f64_probe = false;       // tests: ray-parallel kernel without the fp32 pre-filter
     bool force_v1_update = false;       // tests: the one-thread-per-particle computeWeight kernel
+    int ns_field_kind = -1;             // NS_FIELD_* the last sensor-model launch used
+    int ns_force_field = -1;            // tests: NS_FIELD_* to use regardless of size (-1 = by size)
+    bool ns_force_scalar = false;       // tests: scalar FFMA form of the sensor model on every path
     bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
     cudaStream_t stream = nullptr;
     int64_t n = 0;
@@ -207,7 +210,17 @@ private:
     void* pinned_ring_next();
     struct NsStagedScan { DevBuf<float2> d_pts; int n = 0; bool valid = false; };
     std::vector<NsStagedScan> ns_staged;
-    DevBuf<float> d_lf, d_lf_table, d_ll;
+    DevBuf<float> d_lf, d_lf_table, d_ll, d_codes;
+    DevBuf<uint8_t> d_lf8, d_code_of_d2;      // the field as one-byte codes (NS_FIELD_U8), same bordered layout
+    int ns_n_codes = 0;                        // 0: more than 256 attainable squared distances, no code field
+    // fields too large for L2 as fp32: the sensor model alternates between the fp32 and the coded form on measured time
+    // (spread-out particles favour the small coded field, converged ones the cheaper fp32 lookup; same values either way)
+    cudaEvent_t ns_tune_ev[2] = {nullptr, nullptr};
+    bool ns_tune_pending = false;
+    int ns_tune_kind = -1, ns_tune_beams = 1;
+    int64_t ns_tune_launches = 0;
+    double ns_tune_cost[3] = {-1.0, -1.0, -1.0};   // last measured ms per beam, by NS_FIELD_*
+
     DevBuf<uint16_t> d_d2, d_g;
     DevBuf<float2> d_ns_beams;
     DevBuf<uint64_t> d_prefix, d_tile_sums, d_u64;      // d_u64[0] = local total

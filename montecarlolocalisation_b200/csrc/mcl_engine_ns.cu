@@ -28,6 +28,7 @@ int Engine::ns_set_shard(int rank, int world, int64_t ng) {
 // Exact capped squared distance transform -> log-likelihood field.
 int Engine::ns_build_field() {
     const double max_dist = 2.0;                                   // metres beyond which the field is flat
+    ns_tune_cost[0] = ns_tune_cost[1] = ns_tune_cost[2] = -1.0; ns_tune_launches = 0;       // a new field: measure afresh
     ns_R = std::min(255, std::max(1, (int)std::ceil(max_dist / (double)res_f)));
     const int cap = ns_R * ns_R;
     std::vector<float> table(cap + 1);
@@ -57,10 +58,44 @@ int Engine::ns_build_field() {
         std::swap(other.p, d_lf.p); std::swap(other.n, d_lf.n);
         other.release();
     }
+    // The same field as one byte per cell: d2 takes only the values a^2 + b^2 <= R^2 (and the cap), 125 of them for R = 20,
+    // so its rank fits a byte whenever there are <= 256. A quarter of the footprint: an 8193 x 8193 field is 66 MiB instead
+    // of 264 MiB and stays L2-resident. k_ns_update maps code -> table[d2] through shared memory: identical values.
+    std::vector<uint8_t> code_of_d2(cap + 1, 0);
+    std::vector<float> codes;
+    {
+        std::vector<char> attainable(cap + 1, 0);
+        attainable[cap] = 1;
+        for (int a = 0; a <= ns_R; ++a)
+            for (int b = a; a * a + b * b <= cap; ++b) attainable[a * a + b * b] = 1;
+        int count = 0;
+        for (int d2 = 0; d2 <= cap; ++d2) count += attainable[d2];
+        ns_n_codes = count <= NS_MAX_CODES ? count : 0;
+        if (ns_n_codes) {
+            for (int d2 = 0; d2 <= cap; ++d2)
+                if (attainable[d2]) { code_of_d2[d2] = (uint8_t)codes.size(); codes.push_back(table[d2]); }
+        }
+    }
     CK(cudaMemcpyAsync(d_lf_table.p, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
     LAUNCH(K_NS_EDT_COLS, k_ns_fill_f32, 148 * 8, 256, 0, d_lf.p, lf_bytes_padded / sizeof(float), lf_out);
+    if (ns_n_codes) {
+        const size_t bytes8 = (cells_p + 15) & ~(size_t)15;
+        CK(d_codes.ensure(codes.size())); CK(d_code_of_d2.ensure(code_of_d2.size())); CK(d_lf8.ensure(bytes8));
+        for (int attempt = 0; attempt < 3; ++attempt) {            // inside one 4 GiB window, like the fp32 field
+            const uint64_t a = (uint64_t)(uintptr_t)d_lf8.p, b = a + bytes8 - 1;
+            if ((a >> 32) == (b >> 32)) break;
+            DevBuf<uint8_t> other;
+            if (other.ensure(bytes8) != cudaSuccess) { cudaGetLastError(); break; }
+            std::swap(other.p, d_lf8.p); std::swap(other.n, d_lf8.n);
+            other.release();
+        }
+        CK(cudaMemcpyAsync(d_codes.p, codes.data(), codes.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_code_of_d2.p, code_of_d2.data(), code_of_d2.size(), cudaMemcpyHostToDevice, stream));
+        LAUNCH(K_NS_EDT_COLS, k_ns_fill_u8, 148 * 8, 256, 0, d_lf8.p, bytes8, code_of_d2[cap]);
+    }
     LAUNCH(K_NS_EDT_COLS, k_ns_edt_cols, grid_for(map_w, 128), 128, 0, d_occ.p, map_w, map_h, ns_R, d_g.p);
-    LAUNCH(K_NS_EDT_ROWS, k_ns_edt_rows, dim3(grid_for(map_w, 128), map_h), 128, 0, d_g.p, map_w, map_h, ns_R, d_lf_table.p, d_d2.p, d_lf.p, lf_pad);
+    LAUNCH(K_NS_EDT_ROWS, k_ns_edt_rows, dim3(grid_for(map_w, 128), map_h), 128, 0, d_g.p, map_w, map_h, ns_R, d_lf_table.p, d_d2.p, d_lf.p, lf_pad,
+           ns_n_codes ? d_code_of_d2.p : nullptr, ns_n_codes ? d_lf8.p : nullptr);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
@@ -192,29 +227,66 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
     CK(cudaMemcpyAsync(d_maxbits.p, &init_bits, sizeof(int), cudaMemcpyHostToDevice, stream));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    F.lf8 = d_lf8.p; F.codes = d_codes.p; F.n_codes = ns_n_codes;
     const size_t beam_bytes = (size_t)ns_beams_n * sizeof(float2);
-    const bool in_smem = lf_bytes_padded + beam_bytes <= 200 * 1024;
+    // Where the field is read from. Shared memory (TMA-staged) when it fits; else fp32 through L1/L2 while that stays
+    // L2-resident next to the particle stream; else the one-byte coded field (same values, a quarter of the footprint).
+    const size_t l2_budget = 96ull << 20;
+    int kind = lf_bytes_padded + beam_bytes <= 200 * 1024 ? NS_FIELD_SMEM : NS_FIELD_GLOBAL;
+    bool tuning = false;
+    if (kind == NS_FIELD_GLOBAL && lf_bytes_padded > l2_budget && ns_n_codes && ns_force_field < 0) {
+        // both global forms are candidates: keep the faster one by measurement, re-trying the other every 32nd launch
+        tuning = true;
+        if (!ns_tune_ev[0]) { CK(cudaEventCreate(&ns_tune_ev[0])); CK(cudaEventCreate(&ns_tune_ev[1])); }
+        if (ns_tune_pending && cudaEventQuery(ns_tune_ev[1]) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ns_tune_ev[0], ns_tune_ev[1]) == cudaSuccess && ns_beams_n > 0) ns_tune_cost[ns_tune_kind] = ms / ns_tune_beams;
+            ns_tune_pending = false;
+        }
+        cudaGetLastError();
+        const double cu8 = ns_tune_cost[NS_FIELD_U8], cf32 = ns_tune_cost[NS_FIELD_GLOBAL];
+        if (cu8 < 0) kind = NS_FIELD_U8;                                  // uniform start: the coded field first
+        else if (cf32 < 0) kind = NS_FIELD_GLOBAL;
+        else {
+            kind = cu8 <= cf32 ? NS_FIELD_U8 : NS_FIELD_GLOBAL;
+            if (ns_tune_launches % 32 == 31) kind = kind == NS_FIELD_U8 ? NS_FIELD_GLOBAL : NS_FIELD_U8;
+        }
+        ++ns_tune_launches;
+    }
+    if (ns_force_field == NS_FIELD_U8 && ns_n_codes) kind = NS_FIELD_U8;
+    if (ns_force_field == NS_FIELD_GLOBAL) kind = NS_FIELD_GLOBAL;
+    // packed FFMA2 form where it pays (issue-bound global paths); MCL_NS_SCALAR=1 / debug bit 5: scalar form everywhere
+    static const bool env_scalar = [] { const char* e = getenv("MCL_NS_SCALAR"); return e && e[0] == '1'; }();
+    const bool packed = kind != NS_FIELD_SMEM && !env_scalar && !ns_force_scalar;
     if (!ns_attr_set) {
-        CK(cudaFuncSetAttribute(k_ns_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_ns_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_U8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_U8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         ns_attr_set = true;
     }
     const int threads = NS_UPD_THREADS;
     const int64_t batches = (n + 31) / 32;
     const int64_t ctas_needed = (batches + threads / 32 - 1) / (threads / 32);
-    if (in_smem) {
-        const size_t smem = lf_bytes_padded + beam_bytes;
+    const size_t smem = beam_bytes + (kind == NS_FIELD_SMEM ? lf_bytes_padded : kind == NS_FIELD_U8 ? NS_MAX_CODES * sizeof(float) : 0);
+    if (kind != NS_FIELD_SMEM && smem > 64 * 1024) return fail(MCL_ERR_ARG, "update: too many beams");
+    auto launch = [&](auto kernel) -> int {
         int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_update<true>, threads, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
         const int grid = (int)std::min<int64_t>((int64_t)sms * std::max(1, occ), ctas_needed);     // persistent: resident CTAs only
-        LAUNCH(K_NS_UPDATE, k_ns_update<true>, std::max(1, grid), threads, smem, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
-    } else {
-        if (beam_bytes > 64 * 1024) return fail(MCL_ERR_ARG, "update: too many beams");
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_update<false>, threads, beam_bytes));
-        const int grid = (int)std::min<int64_t>((int64_t)sms * std::max(1, occ), ctas_needed);
-        LAUNCH(K_NS_UPDATE, k_ns_update<false>, std::max(1, grid), threads, beam_bytes, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
-    }
+        const bool measure = tuning && !ns_tune_pending && ns_beams_n > 0;
+        if (measure) CK(cudaEventRecord(ns_tune_ev[0], stream));
+        LAUNCH(K_NS_UPDATE, kernel, std::max(1, grid), threads, smem, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
+        if (measure) { CK(cudaEventRecord(ns_tune_ev[1], stream)); ns_tune_pending = true; ns_tune_kind = kind; ns_tune_beams = ns_beams_n; }
+        return MCL_OK;
+    };
+    int lrc;
+    if (kind == NS_FIELD_SMEM) lrc = launch(k_ns_update<NS_FIELD_SMEM, false>);
+    else if (kind == NS_FIELD_GLOBAL) lrc = packed ? launch(k_ns_update<NS_FIELD_GLOBAL, true>) : launch(k_ns_update<NS_FIELD_GLOBAL, false>);
+    else lrc = packed ? launch(k_ns_update<NS_FIELD_U8, true>) : launch(k_ns_update<NS_FIELD_U8, false>);
+    if (lrc != MCL_OK) return lrc;
+    ns_field_kind = kind;
     CK(cudaGetLastError());
     ns_have_ll = true;
     have_weights = false;

@@ -329,6 +329,10 @@ class NsShard:
         self.pf._ck(self.L.mcl_ns_download_loglik(self.h, ll.ctypes.data_as(_fp)))
         return ll
 
+    def field_form(self):
+        """Where the last sensor-model launch read the field: 'smem-f32', 'global-f32' or 'global-u8' (mcl_ns_field_form)."""
+        return {0: "smem-f32", 1: "global-f32", 2: "global-u8"}.get(self.L.mcl_ns_field_form(self.h), "none")
+
     def prefix(self):
         p = np.zeros(self.pf.num_particles, np.uint64)
         self.pf._ck(self.L.mcl_ns_download_prefix(self.h, p.ctypes.data_as(C.POINTER(C.c_uint64))))

@@ -126,6 +126,27 @@ def test_field_through_l2_1024_map():
     run(1, 20000, 2, occ=occ, scenario=sc)
 
 
+def test_field_forms_give_identical_loglik():
+    """The sensor model has three homes for the field (fp32 in shared memory, fp32 through L1/L2, one-byte codes through
+    L1/L2 + a shared-memory code table) and a scalar and a packed (FFMA2) arithmetic form: identical values from all of
+    them and from the oracle, for particles inside the map, near its edge and outside (bounds-tested path)."""
+    for occ, pose, n_beams in ((Scenario(1).occ, (2.45, 2.45, 0.3), 360), (synth.maze_occupancy(128, 3), (30.45, 40.45, 0.3), 1080)):
+        scan = synth.make_scan(occ, float(RES), pose, n_beams, 7)
+        n = 4096 + 37
+        (s,) = make_shards(1, n, occ)
+        P = s.pf.downloadParticles()
+        P[::7, 0] -= 3.0                       # a seventh of the particles shifted, many of them off the map
+        P[5::11, 1] += 2.5
+        s.pf.uploadParticles(P)
+        o = NsOracle(); o.set_map(occ, RES)
+        want = o.loglik(P, o.beams(Scan(**scan)))
+        for bits in (0, 32, 8, 8 | 32, 16, 16 | 32):
+            s.pf.forceSequential(bits)
+            s.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+            assert np.array_equal(s.loglik(), want), "debug bits %d, map %s" % (bits, occ.shape)
+        s.pf.forceSequential(0)
+
+
 def test_one_shard_api_matches_phases():
     """mcl_update + mcl_resample (world == 1 convenience path) give the same particles as the explicit phases."""
     sc = Scenario(3)

@@ -17,6 +17,8 @@ else:
 s = NsShard(0, 1, n)
 s.pf.setMap(occ, np.float32(0.1))
 s.pf.sampleParticles(n)
+if os.environ.get("NS_FORCE"):
+    s.pf.forceSequential(int(os.environ["NS_FORCE"]))      # 8: coded field, 16: fp32 global field, 32: scalar form
 sca = scans[0]
 s.pf.stageScan(0, sca["ranges"], sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
 for i in range(steps):
@@ -28,7 +30,7 @@ for i in range(steps):
     t = s.weights_local(mx)
     s.resample_local(0, t, s.u0())
     s.end_step()
-    print("step %d: " % i + "  ".join("%s %.1f us" % (k.replace("k_ns_", ""), 1e3 * v[0] / v[1]) for k, v in s.pf.profileRead().items()))
+    print("step %d [%s]: " % (i, s.field_form()) + "  ".join("%s %.1f us" % (k.replace("k_ns_", ""), 1e3 * v[0] / v[1]) for k, v in s.pf.profileRead().items()))
     if os.environ.get("NS_PROFILE_ANC"):
         anc = s.pf.ancestors()
         print("   distinct ancestors: %d of %d" % (len(np.unique(anc)), n))
