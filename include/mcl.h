@@ -192,8 +192,17 @@ int mcl_ns_step_staged(mcl_handle* h, double rot_1, double trans, double rot_2, 
 /* host-only planning helpers (no GPU touched) */
 int mcl_ns_first_slot(uint64_t offset_q32, uint64_t total_q32, uint64_t n_global, uint32_t u0, int64_t* slot);
 int mcl_ns_shard_range(int64_t n_global, int32_t world, int32_t rank, int64_t* begin, int64_t* count, int64_t* per_rank);
-/* peer memory. which: 0/1 = the two particle buffers, 2 = ancestors. export/import move a 64-byte CUDA IPC handle
- * between processes; mcl_peer_set wires two handles of one process (tests, single-process multi-GPU). */
+/* How mcl_ns_step does the step's collectives (all-reduce of the maximum log-likelihood, all-gather of the Q32 totals,
+ * pose all-reduce, closing barrier): 1 = peer-memory mailboxes (each shard stores {payload, tag} straight into the other
+ * shards' mailboxes over NVLink and polls its own; four 32-thread kernels, no NCCL on the data path; the default once
+ * every peer's mailbox is mapped, which mcl_comm_init does), 0 = NCCL collectives on the handle's stream, -1 = default.
+ * Results are identical. Environment override for the default: MCL_NS_EXCHANGE=nccl|peer.
+ * mcl_ns_exchange_used: what the last sharded step used (-1: none yet). */
+int mcl_ns_set_exchange(mcl_handle* h, int32_t mode);
+int mcl_ns_exchange_used(mcl_handle* h);
+/* peer memory. which: 0/1 = the two particle buffers, 2 = ancestors, 3 = the exchange mailbox. export/import move a
+ * 64-byte CUDA IPC handle between processes; mcl_peer_set wires two handles of one process (tests, single-process
+ * multi-GPU). */
 int mcl_peer_export(mcl_handle* h, int32_t which, void* out64);
 int mcl_peer_import(mcl_handle* h, int32_t rank, int32_t which, const void* in64);
 int mcl_peer_set(mcl_handle* h, int32_t rank, int32_t which, void* device_ptr);

@@ -122,6 +122,8 @@ SYMBOLS = [
     ("mcl_ns_download_loglik", _i32, [_vp, _fp]),
     ("mcl_ns_download_prefix", _i32, [_vp, C.POINTER(C.c_uint64)]),
     ("mcl_ns_field_form", _i32, [_vp]),
+    ("mcl_ns_set_exchange", _i32, [_vp, _i32]),
+    ("mcl_ns_exchange_used", _i32, [_vp]),
     ("mcl_stream", _vp, [_vp]),
     ("mcl_synchronize", _i32, [_vp]),
     ("mcl_kernel_launches", _i64, [_vp]),

@@ -593,8 +593,7 @@ __device__ __forceinline__ void ns_plan_steps(NsPlan& p, uint64_t n_global) {
     p.dqs = p.dq1 * NS_RS_THREADS + x / n_global; p.drs = x % n_global;
 }
 // plan from the all-gathered Q32 totals, on the device (no host round trip)
-__global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int rank, uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ NsPlan ns_make_plan(const uint64_t* totals, int world, int rank, uint64_t n_global, uint32_t u0) {
     uint64_t off = 0, tot = 0;
     for (int r = 0; r < world; r++) { if (r < rank) off += totals[r]; tot += totals[r]; }
     NsPlan p;
@@ -602,8 +601,141 @@ __global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int ra
     p.k_lo = tot ? ns::first_slot(off, tot, n_global, u0) : 0;
     p.k_hi = tot ? ns::first_slot(off + totals[rank], tot, n_global, u0) : 0;
     ns_plan_steps(p, n_global);
-    *plan = p;
+    return p;
 }
+__global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int rank, uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    *plan = ns_make_plan(totals, world, rank, n_global, u0);
+}
+
+// ---- peer-memory exchange: the step's collectives without NCCL on the data path ---------------------------------------------
+// Every shard owns a mailbox in its own HBM, mapped into the other shards (CUDA IPC, like the particle buffers). A shard
+// POSTS by storing {payload, tag} into slot [its rank] of every peer's mailbox over NVLink (payload, then a system-scope
+// release store of the tag) and COMPLETES by polling its own mailbox (system-scope acquire loads of local memory) until
+// all `world` slots carry this step's tag. One 32-thread kernel per exchange: lane r talks to shard r. What an NCCL
+// all-reduce(max) + all-gather + all-reduce(sum) + barrier cost in launches and protocol latency becomes four tiny
+// kernels, two of them fused with work the step needs anyway (the resampling plan, the pose reduction).
+// Value slots are double-buffered by step parity and a shard cannot start step s+1's exchange before every shard posted
+// step s's closing barrier, so a slot is never overwritten before it is read. Polls are bounded: a shard that never
+// posts makes the others give up after ~20 s and raise the mailbox status instead of hanging the GPU.
+struct NsMailSlot {
+    unsigned long long v[5];
+    unsigned tag, pad[5];
+};
+static_assert(sizeof(NsMailSlot) == 64, "one slot per 64-byte line pair");
+struct NsMailbox {
+    NsMailSlot max_ll[2][8], total[2][8], pose[2][8];
+    unsigned barrier[8];            // monotonic step tags
+    int status;                     // != 0: an exchange timed out
+    int pad[7];
+};
+struct NsPeers {
+    NsMailbox* box[8];              // box[rank] = this shard's own mailbox
+    int world, rank;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ns_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long NS_MAIL_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+template <int WORDS>
+__device__ __forceinline__ void ns_mail_post(NsMailSlot* slot_on_peer, const unsigned long long* payload, unsigned tag) {
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) st_relaxed_sys(&slot_on_peer->v[w], payload[w]);
+    st_release_sys(&slot_on_peer->tag, tag);
+}
+// wait until *flag reaches `tag` (AT_LEAST: monotonic barrier tags, compared modulo 2^32; else equality)
+template <bool AT_LEAST>
+__device__ __forceinline__ bool ns_mail_wait(const unsigned* flag, unsigned tag, int* status) {
+    const unsigned long long t0 = ns_globaltimer();
+    for (unsigned spins = 0;; ++spins) {
+        const unsigned seen = ld_acquire_sys(flag);
+        if (AT_LEAST ? (int)(seen - tag) >= 0 : seen == tag) return true;
+        if ((spins & 1023u) == 1023u && ns_globaltimer() - t0 > NS_MAIL_TIMEOUT_NS) { atomicExch(status, 1); return false; }
+        __nanosleep(32);
+    }
+}
+
+// all-reduce(max) of the ordered-int maximum log-likelihood
+__global__ void k_ns_xchg_max(int* __restrict__ max_bits, NsPeers P, unsigned tag, int parity) {
+    const int r = threadIdx.x;
+    int v = INT32_MIN;
+    if (r < P.world) {
+        NsMailbox* mine = P.box[P.rank];
+        unsigned long long pay = (unsigned long long)(unsigned)(*max_bits);
+        ns_mail_post<1>(&P.box[r]->max_ll[parity][P.rank], &pay, tag);
+        if (ns_mail_wait<false>(&mine->max_ll[parity][r].tag, tag, &mine->status)) v = (int)(unsigned)ld_relaxed_sys(&mine->max_ll[parity][r].v[0]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (r == 0) *max_bits = v;
+}
+// all-gather of the shards' Q32 totals fused with the resampling plan they determine
+__global__ void k_ns_plan_xchg(const uint64_t* __restrict__ local_total, NsPeers P, unsigned tag, int parity, uint64_t n_global, uint32_t u0,
+                               NsPlan* __restrict__ plan, uint64_t* __restrict__ totals_out) {
+    __shared__ uint64_t s_tot[8];
+    const int r = threadIdx.x;
+    if (r < P.world) {
+        NsMailbox* mine = P.box[P.rank];
+        unsigned long long pay = *local_total;
+        ns_mail_post<1>(&P.box[r]->total[parity][P.rank], &pay, tag);
+        uint64_t t = 0;
+        if (ns_mail_wait<false>(&mine->total[parity][r].tag, tag, &mine->status)) t = ld_relaxed_sys(&mine->total[parity][r].v[0]);
+        s_tot[r] = t;
+        totals_out[r] = t;
+    }
+    __syncwarp();
+    if (r == 0) *plan = ns_make_plan(s_tot, P.world, P.rank, n_global, u0);
+}
+// all-reduce(sum) of the five weighted pose sums, added in rank order: the same bits on every shard.
+// pose5[5] receives the mailbox status (0 = every exchange so far completed).
+__global__ void k_ns_pose_xchg(double* __restrict__ pose5, NsPeers P, unsigned tag, int parity) {
+    const int r = threadIdx.x;
+    NsMailbox* mine = P.box[P.rank];
+    bool ok = true;
+    if (r < P.world) {
+        unsigned long long pay[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) pay[k] = (unsigned long long)__double_as_longlong(pose5[k]);
+        ns_mail_post<5>(&P.box[r]->pose[parity][P.rank], pay, tag);
+        ok = ns_mail_wait<false>(&mine->pose[parity][r].tag, tag, &mine->status);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (r == 0) {
+        for (int k = 0; k < 5; k++) {
+            double s = 0.0;
+            for (int q = 0; q < P.world; q++) s += __longlong_as_double((long long)ld_relaxed_sys(&mine->pose[parity][q].v[k]));
+            pose5[k] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
+        }
+        pose5[5] = (double)(*(volatile int*)&mine->status);
+    }
+}
+// closing barrier: every shard's resampled particles have landed in their owners' buffers before anybody swaps
+__global__ void k_ns_xchg_barrier(NsPeers P, unsigned tag) {
+    const int r = threadIdx.x;
+    if (r < P.world) {
+        NsMailbox* mine = P.box[P.rank];
+        __threadfence_system();
+        st_release_sys(&P.box[r]->barrier[P.rank], tag);
+        ns_mail_wait<true>(&mine->barrier[r], tag, &mine->status);
+    }
+}
+
 // plan handed in by the host (phase-by-phase API)
 __global__ void k_ns_plan_set(NsPlan p, uint64_t n_global, NsPlan* __restrict__ plan) { ns_plan_steps(p, n_global); *plan = p; }
 

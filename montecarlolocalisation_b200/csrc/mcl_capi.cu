@@ -169,6 +169,8 @@ int mcl_ns_shard_range(int64_t ng, int32_t world, int32_t rank, int64_t* b, int6
     return MCL_OK;
 }
 int mcl_bench_gather(mcl_handle* h, int32_t tier, int64_t table_bytes, int32_t iters, double* reads_per_s) { GUARD(h); TRY(h->engine.gather_bench(tier, (size_t)table_bytes, iters, reads_per_s)) }
+int mcl_ns_set_exchange(mcl_handle* h, int32_t mode) { GUARD(h); if (mode < -1 || mode > 1) return MCL_ERR_ARG; h->engine.ns_exchange = mode; return MCL_OK; }
+int mcl_ns_exchange_used(mcl_handle* h) { return h ? h->engine.ns_exchange_used : -1; }
 int mcl_peer_export(mcl_handle* h, int32_t which, void* out64) { GUARD(h); TRY(h->engine.peer_export(which, out64)) }
 int mcl_peer_import(mcl_handle* h, int32_t rank, int32_t which, const void* in64) { GUARD(h); TRY(h->engine.peer_import(rank, which, in64)) }
 int mcl_peer_set(mcl_handle* h, int32_t rank, int32_t which, void* p) { GUARD(h); TRY(h->engine.peer_set(rank, which, p)) }

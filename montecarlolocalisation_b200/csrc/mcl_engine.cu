@@ -19,8 +19,8 @@ Engine::~Engine() {
     if (!opened) return;
     cudaSetDevice(cfg.device);
     part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); for (auto& e : ns_tune_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
-    d_lf.release(); d_lf8.release(); d_codes.release(); d_code_of_d2.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
-    for (int w = 0; w < 3; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
+    d_mbox.release(); d_lf.release(); d_lf8.release(); d_codes.release(); d_code_of_d2.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
+    for (int w = 0; w < 4; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
     if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
     ns_comm_destroy(); ancestors.release(); d_occ.release(); d_occ_pad.release(); d_gauss.release();
@@ -122,7 +122,17 @@ int Engine::open() {
     return MCL_OK;
 }
 
-int Engine::synchronize() { CK(cudaSetDevice(cfg.device)); CK(cudaStreamSynchronize(stream)); return MCL_OK; }
+int Engine::synchronize() {
+    CK(cudaSetDevice(cfg.device));
+    CK(cudaStreamSynchronize(stream));
+    if (ns_exchange_used == 1 && d_mbox.p) {
+        // last word group of the mailbox: {barrier[8], status, pad}
+        int status = 0;
+        CK(cudaMemcpy(&status, d_mbox.p + d_mbox.n - 8 * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost));
+        if (status) return fail(MCL_ERR_COMM, "a peer-memory exchange timed out (a shard never posted)");
+    }
+    return MCL_OK;
+}
 
 // ---- map ----------------------------------------------------------------------------------------------------
 int Engine::set_map(const int8_t* occ, int w, int h, float res, double ox, double oy) {

@@ -98,6 +98,8 @@ public:
     mcl_config cfg;
     bool force_f64_probe = false;       // tests: ray-parallel kernel without the fp32 pre-filter
     bool force_v1_update = false;       // tests: the one-thread-per-particle computeWeight kernel
+    int ns_exchange = -1;               // sharded step's collectives: 0 = NCCL, 1 = peer-memory mailboxes, -1 = mailboxes when mapped
+    int ns_exchange_used = -1;          // what the last sharded step used
     int ns_field_kind = -1;             // NS_FIELD_* the last sensor-model launch used
     int ns_force_field = -1;            // tests: NS_FIELD_* to use regardless of size (-1 = by size)
     bool ns_force_scalar = false;       // tests: scalar FFMA form of the sensor model on every path
@@ -231,8 +233,12 @@ private:
     float lf_out = 0.f, ns_last_max = 0.f;
     bool ns_attr_set = false;
     bool ns_have_ll = false;
-    void* peer_ptr[3][8] = {{nullptr}};    // [0],[1]: particle ping-pong buffers of shard r; [2]: ancestors
-    bool peer_ipc[3][8] = {{false}};
+    void* peer_ptr[4][8] = {{nullptr}};    // [0],[1]: particle ping-pong buffers of shard r; [2]: ancestors; [3]: mailbox
+    bool peer_ipc[4][8] = {{false}};
+    DevBuf<unsigned char> d_mbox;          // this shard's NsMailbox (peer-memory exchange)
+    uint32_t xchg_seq = 0;                 // exchange tag: sharded steps taken by this handle (never reset; same on every shard)
+    int ensure_mailbox();
+    bool peers_have_mailboxes() const;
     // pinned staging
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;

@@ -22,7 +22,35 @@ int Engine::ns_set_shard(int rank, int world, int64_t ng) {
     int rc = ensure_particles(cnt);
     if (rc) return rc;
     n = cnt;
+    return world > 1 ? ensure_mailbox() : MCL_OK;
+}
+
+int Engine::ensure_mailbox() {
+    if (d_mbox.p) return MCL_OK;
+    CK(d_mbox.ensure(sizeof(NsMailbox)));
+    CK(cudaMemset(d_mbox.p, 0, sizeof(NsMailbox)));
+    // everything mcl_ns_step needs, allocated now: cudaMalloc waits for the device, and a shard whose stream already holds
+    // an exchange kernel waiting for its peers must not be waited on by a peer living in the same process
+    CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1)); CK(d_partials.ensure(5 * 512));
+    const int64_t max_tiles = (n_global + NS_RS_TILE - 1) / NS_RS_TILE;
+    CK(d_bounds.ensure(((size_t)max_tiles + 2) * sizeof(NsTileHead)));
+    // ... and every kernel of the step loaded now: with lazy module loading the first launch of a kernel synchronises
+    // the context, which would wait for exchange kernels already spinning on this device
+    cudaFuncAttributes fa;
+#define PRELOAD(k) CK(cudaFuncGetAttributes(&fa, k))
+    PRELOAD(k_ns_predict); PRELOAD((k_ns_update<NS_FIELD_SMEM, false>)); PRELOAD((k_ns_update<NS_FIELD_GLOBAL, true>));
+    PRELOAD((k_ns_update<NS_FIELD_GLOBAL, false>)); PRELOAD((k_ns_update<NS_FIELD_U8, true>)); PRELOAD((k_ns_update<NS_FIELD_U8, false>));
+    PRELOAD(k_ns_weights_sum); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
+    PRELOAD(k_ns_pose_partials); PRELOAD(k_ns_pose_reduce); PRELOAD(k_ns_pose_xchg); PRELOAD(k_ns_xchg_barrier);
+    PRELOAD(k_ns_resample_bounds); PRELOAD(k_ns_resample);
+#undef PRELOAD
     return MCL_OK;
+}
+bool Engine::peers_have_mailboxes() const {
+    if (!d_mbox.p) return false;
+    for (int r = 0; r < shard_world; ++r)
+        if (r != shard_rank && !peer_ptr[3][r]) return false;
+    return true;
 }
 
 // Exact capped squared distance transform -> log-likelihood field.
@@ -467,17 +495,19 @@ int Engine::comm_init(const void* id128) {
     CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
     if (shard_world > 1) {
         DevBuf<unsigned char> mine, all;
-        CK(mine.ensure(192)); CK(all.ensure((size_t)192 * shard_world));
-        unsigned char h[192];
-        for (int w = 0; w < 3; w++) { int rc = peer_export(w, h + 64 * w); if (rc) return rc; }
-        CK(cudaMemcpyAsync(mine.p, h, 192, cudaMemcpyHostToDevice, stream));
-        NCK(nccl_api().AllGather(mine.p, all.p, 192, ncclUint8, (ncclComm_t)comm, stream));
-        std::vector<unsigned char> hall((size_t)192 * shard_world);
+        int mrc = ensure_mailbox();
+        if (mrc) return mrc;
+        CK(mine.ensure(256)); CK(all.ensure((size_t)256 * shard_world));
+        unsigned char h[256];
+        for (int w = 0; w < 4; w++) { int rc = peer_export(w, h + 64 * w); if (rc) return rc; }
+        CK(cudaMemcpyAsync(mine.p, h, 256, cudaMemcpyHostToDevice, stream));
+        NCK(nccl_api().AllGather(mine.p, all.p, 256, ncclUint8, (ncclComm_t)comm, stream));
+        std::vector<unsigned char> hall((size_t)256 * shard_world);
         CK(cudaMemcpyAsync(hall.data(), all.p, hall.size(), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         for (int r = 0; r < shard_world; r++) {
             if (r == shard_rank) continue;
-            for (int w = 0; w < 3; w++) { int rc = peer_import(r, w, hall.data() + (size_t)192 * r + 64 * w); if (rc) return rc; }
+            for (int w = 0; w < 4; w++) { int rc = peer_import(r, w, hall.data() + (size_t)256 * r + 64 * w); if (rc) return rc; }
         }
         mine.release(); all.release();
     }
@@ -492,7 +522,18 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
                     float range_min, float range_max, double* pose3) {
     CK(cudaSetDevice(cfg.device));
     if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "ns_step: NS mode only");
-    if (shard_world > 1 && !comm) return fail(MCL_ERR_COMM, "ns_step: sharded filter without a communicator (mcl_comm_init)");
+    // the step's collectives: peer-memory mailboxes (default once every peer's mailbox is mapped) or NCCL
+    static const int env_exchange = [] { const char* e = getenv("MCL_NS_EXCHANGE"); return !e ? -1 : !strcmp(e, "nccl") ? 0 : !strcmp(e, "peer") ? 1 : -1; }();
+    const int want = ns_exchange >= 0 ? ns_exchange : env_exchange;
+    const bool mail = shard_world > 1 && want != 0 && peers_have_mailboxes();
+    if (shard_world > 1 && want == 1 && !mail) return fail(MCL_ERR_COMM, "ns_step: peer-memory exchange asked for but a peer mailbox is not mapped");
+    if (shard_world > 1 && !mail && !comm) return fail(MCL_ERR_COMM, "ns_step: sharded filter without a communicator (mcl_comm_init)");
+    NsPeers PX;
+    PX.world = shard_world; PX.rank = shard_rank;
+    for (int r = 0; r < 8; ++r) PX.box[r] = r >= shard_world ? nullptr : r == shard_rank ? (NsMailbox*)d_mbox.p : (NsMailbox*)peer_ptr[3][r];
+    const unsigned tag = mail ? ++xchg_seq : 0u;
+    const int parity = (int)(tag & 1u);
+    if (shard_world > 1) ns_exchange_used = mail ? 1 : 0;
     if (n == 0) return fail(MCL_ERR_ARG, "ns_step: no particles");
     CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
     Motion m; m.rot_1 = rot1; m.trans = trans; m.rot_2 = rot2;
@@ -521,10 +562,12 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     rc = ns_launch_update(d_pts, n_pts);
     if (rc) return rc;
     auto& N = nccl_api();
-    if (shard_world > 1) NCK(N.AllReduce(d_maxbits.p, d_maxbits.p, 1, ncclInt32, ncclMax, (ncclComm_t)comm, stream));
+    if (mail) LAUNCH(K_NS_PLAN, k_ns_xchg_max, 1, 32, 0, d_maxbits.p, PX, tag, parity);
+    else if (shard_world > 1) NCK(N.AllReduce(d_maxbits.p, d_maxbits.p, 1, ncclInt32, ncclMax, (ncclComm_t)comm, stream));
     rc = ns_launch_weights();
     if (rc) return rc;
-    if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
+    if (mail) {}                                                              // gathered inside k_ns_plan_xchg
+    else if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
     else CK(cudaMemcpyAsync(d_totals.p, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
     if (pose3) {
         const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
@@ -532,21 +575,25 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
         LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
                d_partials.p);
         LAUNCH(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
-        if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
+        if (mail) LAUNCH(K_NS_POSE, k_ns_pose_xchg, 1, 32, 0, d_pose.p, PX, tag, parity);
+        else if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
     }
     const uint32_t u0 = ns_u0();
-    LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
+    if (mail) LAUNCH(K_NS_PLAN, k_ns_plan_xchg, 1, 32, 0, d_u64.p, PX, tag, parity, (uint64_t)n_global, u0, (NsPlan*)d_plan.p, d_totals.p);
+    else LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
     have_weights = true;
     rc = ns_launch_resample(u0);
     if (rc) return rc;
-    if (shard_world > 1) NCK(N.AllReduce(d_bar.p, d_bar.p, 1, ncclInt32, ncclSum, (ncclComm_t)comm, stream));     // closing barrier
+    if (mail) LAUNCH(K_NS_PLAN, k_ns_xchg_barrier, 1, 32, 0, PX, tag);                                            // closing barrier
+    else if (shard_world > 1) NCK(N.AllReduce(d_bar.p, d_bar.p, 1, ncclInt32, ncclSum, (ncclComm_t)comm, stream));
     cur ^= 1;
     have_weights = false; ns_have_ll = false;
     ++step_counter;
     if (pose3) {
-        double h[5];
-        CK(cudaMemcpyAsync(h, d_pose.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        double h[6] = {0, 0, 0, 0, 0, 0};
+        CK(cudaMemcpyAsync(h, d_pose.p, (mail ? 6 : 5) * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        if (mail && h[5] != 0.0) return fail(MCL_ERR_COMM, "ns_step: a peer-memory exchange timed out (a shard never posted)");
         pose3[0] = h[1] / h[0]; pose3[1] = h[2] / h[0]; pose3[2] = std::atan2(h[3], h[4]);
     }
     return MCL_OK;
@@ -612,6 +659,7 @@ int Engine::gather_bench(int tier, size_t table_bytes, int iters, double* reads_
 void* Engine::device_buffer(int which) {
     if (which == 0 || which == 1) return part[which].p;
     if (which == 2) return ancestors.p;
+    if (which == 3) return d_mbox.p;
     return nullptr;
 }
 int Engine::peer_export(int which, void* out64) {
@@ -626,7 +674,7 @@ int Engine::peer_export(int which, void* out64) {
 }
 int Engine::peer_import(int rank, int which, const void* in64) {
     CK(cudaSetDevice(cfg.device));
-    if (rank < 0 || rank >= 8 || which < 0 || which > 2 || !in64) return fail(MCL_ERR_ARG, "peer_import: bad argument");
+    if (rank < 0 || rank >= 8 || which < 0 || which > 3 || !in64) return fail(MCL_ERR_ARG, "peer_import: bad argument");
     cudaIpcMemHandle_t hnd;
     memcpy(&hnd, in64, 64);
     void* p = nullptr;
@@ -636,7 +684,7 @@ int Engine::peer_import(int rank, int which, const void* in64) {
     return MCL_OK;
 }
 int Engine::peer_set(int rank, int which, void* devptr) {
-    if (rank < 0 || rank >= 8 || which < 0 || which > 2) return fail(MCL_ERR_ARG, "peer_set: bad argument");
+    if (rank < 0 || rank >= 8 || which < 0 || which > 3) return fail(MCL_ERR_ARG, "peer_set: bad argument");
     peer_ptr[which][rank] = devptr; peer_ipc[which][rank] = false;
     return MCL_OK;
 }

@@ -329,6 +329,13 @@ class NsShard:
         self.pf._ck(self.L.mcl_ns_download_loglik(self.h, ll.ctypes.data_as(_fp)))
         return ll
 
+    def set_exchange(self, mode):
+        """Collectives of the sharded step: 'peer' (mailboxes in peer memory), 'nccl', or None for the default."""
+        self.pf._ck(self.L.mcl_ns_set_exchange(self.h, {None: -1, "nccl": 0, "peer": 1}[mode]))
+
+    def exchange_used(self):
+        return {0: "nccl", 1: "peer"}.get(self.L.mcl_ns_exchange_used(self.h), "none")
+
     def field_form(self):
         """Where the last sensor-model launch read the field: 'smem-f32', 'global-f32' or 'global-u8' (mcl_ns_field_form)."""
         return {0: "smem-f32", 1: "global-f32", 2: "global-u8"}.get(self.L.mcl_ns_field_form(self.h), "none")

@@ -1,5 +1,6 @@
-"""torchrun script (one process per GPU): the engine-native sharded NS step (mcl_comm_init + mcl_ns_step: NCCL on the
-engine's stream, device-side plan, resampled particles stored straight into the owning shard over NVLink) against the
+"""torchrun script (one process per GPU): the engine-native sharded NS step (mcl_comm_init + mcl_ns_step: collectives
+through peer-memory mailboxes or, with MCL_NS_EXCHANGE=nccl, NCCL on the engine's stream; device-side plan; resampled
+particles stored straight into the owning shard over NVLink) against the
 single-span NS oracle, bit for bit. torch.distributed (gloo) only carries the NCCL unique id and the final gather.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 tests/dist_ns_step_nccl.py
@@ -54,7 +55,7 @@ def main():
         for p in allpose[1:]:
             assert np.array_equal(p, allpose[0]), "pose differs between ranks"
         assert np.isfinite(allpose[0]).all()
-        print("dist_ns_step ok: world %d, %d particles, pose %s" % (world, n, allpose[0]))
+        print("dist_ns_step ok: world %d, %d particles, exchange %s, pose %s" % (world, n, shard.exchange_used(), allpose[0]))
     dist.barrier()
     del shard
     dist.destroy_process_group()

@@ -20,7 +20,7 @@ def make_shards(world, n, occ, **cfg):
     for a in shards:
         for b in shards:
             if a is not b:
-                for which in (0, 1, 2):
+                for which in (0, 1, 2, 3):        # particle buffers, ancestors, exchange mailbox
                     a.peer_set(b.rank, which, b.device_buffer(which))
     for s in shards:
         s.pf.sampleParticles(n)
@@ -273,9 +273,36 @@ def test_engine_native_step_matches_phases():
     assert np.array_equal(a.pf.downloadParticles(), b.pf.downloadParticles())
 
 
-def test_engine_native_step_multi_gpu_nccl(tmp_path):
-    """2+ GPUs, one process per GPU: the engine's own NCCL collectives + peer stores (tests/dist_ns_step_nccl.py) equal
-    the single-span oracle bit for bit. Skipped on a 1-GPU box (NCCL refuses two ranks on one device)."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_engine_native_step_peer_memory_exchange_in_process(world):
+    """mcl_ns_step of a sharded filter with the collectives done through peer-memory mailboxes (no NCCL): `world` shards
+    of one process on one GPU, each on its own stream, every step enqueued without a host round trip. Same particles and
+    ancestors as the phase-by-phase path whose collectives are plain Python."""
+    sc = Scenario(3)
+    n = 20011
+    a = make_shards(world, n, sc.occ)
+    b = make_shards(world, n, sc.occ)
+    for s in a:
+        s.set_exchange("peer")
+        for i, scan in enumerate(sc.scans):     # scans parked on the device: enqueueing a step then never waits for the GPU,
+            s.pf.stageScan(i, scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    for step in range(3):                       # which shards sharing one process (and one host thread) depend on
+        motion = (0.01 * (step + 1), 0.02, -0.005)
+        for s in a:
+            s.step(motion, slot=step)
+        ns_step_in_process(b, sc.scans[step], motion)
+    for s in a:
+        s.pf.synchronize()
+        assert s.exchange_used() == "peer"
+    assert np.array_equal(gather(a), gather(b))
+    assert np.array_equal(gather_anc(a), gather_anc(b))
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_engine_native_step_multi_gpu(exchange):
+    """2+ GPUs, one process per GPU: the engine-enqueued sharded step - collectives through peer-memory mailboxes, or
+    through the engine's NCCL communicator - + peer stores (tests/dist_ns_step_nccl.py) equals the single-span oracle bit
+    for bit. Skipped on a 1-GPU box."""
     import subprocess
     import sys
     import os
@@ -285,6 +312,8 @@ def test_engine_native_step_multi_gpu_nccl(tmp_path):
         pytest.skip("needs >= 2 GPUs")
     world = min(g, 4)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MCL_NS_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-                        "--master-port", "29631", os.path.join(root, "tests", "dist_ns_step_nccl.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "dist_ns_step ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+                        "--master-port", "29631", os.path.join(root, "tests", "dist_ns_step_nccl.py")], capture_output=True, text=True, timeout=600,
+                       env=env)
+    assert r.returncode == 0 and "dist_ns_step ok" in r.stdout and "exchange %s" % exchange in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
