@@ -450,8 +450,34 @@ __device__ __forceinline__ float ns_decode_max(const int* __restrict__ max_bits)
     b = b >= 0 ? b : b ^ 0x7fffffff;
     return __int_as_float(b);
 }
+// ns::det_exp_q32 (NS-4) for the device, same value for every input, without the three conversion (XU pipe) operations of
+// the plain form: rintf + (int) become a magic-add whose bit pattern holds k, and the exact power-of-two scaling followed
+// by the float -> uint64 truncation becomes a shift of the polynomial's significand.
+__device__ __forceinline__ uint64_t ns_exp_q32_dev(float t) {
+    const float tc = fminf(fmaxf(t, -30.f), 0.f);                     // keeps the bit tricks in range; NaN -> -30 (selected away below)
+    const float km = ns::addf(ns::mulf(tc, 1.44269502f), NS_MAGIC);   // nearest-even integer k = rintf(tc * log2 e), in the low bits
+    const float kf = ns::addf(km, -NS_MAGIC);
+    float g = ns::fmaf_(-kf, 0.693145752f, tc);
+    g = ns::fmaf_(-kf, 1.42860677e-06f, g);
+    float p = 1.98412701e-04f;
+    p = ns::fmaf_(p, g, 1.38888892e-03f);
+    p = ns::fmaf_(p, g, 8.33333377e-03f);
+    p = ns::fmaf_(p, g, 4.16666679e-02f);
+    p = ns::fmaf_(p, g, 1.66666672e-01f);
+    p = ns::fmaf_(p, g, 0.5f);
+    p = ns::fmaf_(p, g, 1.0f);
+    p = ns::fmaf_(p, g, 1.0f);                                        // exp(g) in [0.70, 1.42]
+    // trunc(p * 2^(32+k)): p = m * 2^(e-23) with the 24-bit significand m, so the value is (m << 9) >> (32 - e - k)
+    const uint32_t pb = __float_as_uint(p);
+    const int sh = 127 + NS_MAGIC_BITS - (int)(pb >> 23) - __float_as_int(km);     // 32 - ((pb >> 23) - 127 + 32 + k), 0 .. 45
+    const uint64_t m9 = (uint64_t)((pb & 0x007fffffu) | 0x00800000u) << 9;
+    uint64_t w = m9 >> sh;
+    w = w > (1ull << 32) ? (1ull << 32) : w;
+    w = t >= 0.f ? (1ull << 32) : w;
+    return t > -22.5f ? w : 0ull;                                     // below 2^-32, and NaN
+}
 __device__ __forceinline__ uint64_t ns_weight(float ll, float max_ll, float temper) {
-    return ns::det_exp_q32(ns::mulf(temper, ns::addf(ll, -max_ll)));
+    return ns_exp_q32_dev(ns::mulf(temper, ns::addf(ll, -max_ll)));
 }
 __device__ __forceinline__ uint64_t warp_scan_u64(uint64_t v, int lane) {
 #pragma unroll
@@ -544,6 +570,77 @@ __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float
     uint64_t off = 0;
 #pragma unroll
     for (int k = 0; k < NS_SCAN_THREADS / 32; k++) { off += s_offp[k]; if (k < warp) off += s_warp[k]; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = base + j * 128;
+        uint64_t run = off + incl[j] - s[j];
+        uint64_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { run += w[j][e]; o[e] = run; }
+        if (i + 3 < n) st_v4_u64(prefix + i, o[0], o[1], o[2], o[3]);
+        else { for (int e = 0; e < 4; e++) if (i + e < n) prefix[i + e] = o[e]; }
+    }
+}
+// Single pass (decoupled look-back): every tile computes its weights once, publishes its aggregate, finds its offset from
+// the tiles before it and writes its prefix; tiles are taken in ticket order, so a tile only ever waits for tiles that
+// are already running. State word per tile = status in bits 63:62 (0 none, 1 aggregate, 2 inclusive) | value (< 2^62):
+// one 64-bit store/load, no fence needed. HBM sees the log-likelihoods once (4 B) and the prefix once (8 B).
+constexpr uint64_t NS_LB_AGG = 1ull << 62, NS_LB_INC = 2ull << 62, NS_LB_VAL = (1ull << 62) - 1;
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan1(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
+                                                                     float temper, uint64_t* __restrict__ tile_state /* n_tiles + 1, zeroed */,
+                                                                     int n_tiles, uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out) {
+    __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32];
+    __shared__ uint64_t s_excl;
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd((unsigned long long*)(tile_state + n_tiles), 1ull);
+    __syncthreads();
+    const int tile = s_tile;
+    const float max_ll = ns_decode_max(max_bits);
+    const int64_t base = (int64_t)tile * NS_SCAN_TILE + (int64_t)warp * NS_SCAN_WARP_ITEMS + lane * 4;
+    uint64_t w[4][4], s[4], incl[4];
+    ns_load_weights(ll, n, base, max_ll, temper, w, s);
+    uint64_t carry = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        incl[j] = warp_scan_u64(s[j], lane) + carry;
+        carry = __shfl_sync(0xffffffffu, incl[j], 31);
+    }
+    if (lane == 31) s_warp[warp] = carry;                            // warp total
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t agg = 0;
+#pragma unroll
+        for (int k = 0; k < NS_SCAN_THREADS / 32; k++) agg += s_warp[k];
+        uint64_t excl = 0;
+        if (tile > 0) {
+            if (lane == 0) st_volatile_u64(tile_state + tile, NS_LB_AGG | agg);
+            for (int j = tile - 1;; j -= 32) {                       // look back 32 tiles at a time
+                const int idx = j - lane;
+                uint64_t v;
+                do { v = idx >= 0 ? ld_volatile_u64(tile_state + idx) : NS_LB_INC; } while (__any_sync(0xffffffffu, (v >> 62) == 0));
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int stop = inc_mask ? __ffs((int)inc_mask) - 1 : 32;      // nearest tile with an inclusive prefix
+                excl += warp_sum_u64(lane <= stop ? (v & NS_LB_VAL) : 0ull);
+                if (inc_mask) break;
+            }
+        }
+        if (lane == 0) {
+            st_volatile_u64(tile_state + tile, NS_LB_INC | (excl + agg));
+            s_excl = excl;
+            if (tile == n_tiles - 1) *total_out = excl + agg;
+        }
+    }
+    __syncthreads();
+    uint64_t off = s_excl;
+#pragma unroll
+    for (int k = 0; k < NS_SCAN_THREADS / 32; k++) if (k < warp) off += s_warp[k];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int64_t i = base + j * 128;

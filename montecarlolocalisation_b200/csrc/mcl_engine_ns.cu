@@ -40,7 +40,7 @@ int Engine::ensure_mailbox() {
 #define PRELOAD(k) CK(cudaFuncGetAttributes(&fa, k))
     PRELOAD(k_ns_predict); PRELOAD((k_ns_update<NS_FIELD_SMEM, false>)); PRELOAD((k_ns_update<NS_FIELD_GLOBAL, true>));
     PRELOAD((k_ns_update<NS_FIELD_GLOBAL, false>)); PRELOAD((k_ns_update<NS_FIELD_U8, true>)); PRELOAD((k_ns_update<NS_FIELD_U8, false>));
-    PRELOAD(k_ns_weights_sum); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
+    PRELOAD(k_ns_weights_sum); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_weights_scan1); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
     PRELOAD(k_ns_pose_partials); PRELOAD(k_ns_pose_reduce); PRELOAD(k_ns_pose_xchg); PRELOAD(k_ns_xchg_barrier);
     PRELOAD(k_ns_resample_bounds); PRELOAD(k_ns_resample);
 #undef PRELOAD
@@ -344,10 +344,21 @@ int Engine::ns_launch_weights() {
     const float temper = (float)cfg.ns_temper;
     const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
     const int ng = (nt + NS_SCAN_GROUP - 1) / NS_SCAN_GROUP;
-    uint64_t* group_sums = d_tile_sums.p + nt;
-    CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
-    LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
-    LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
+    // One wave of tiles or less: single pass with decoupled look-back (one launch, weights computed once). More: the
+    // look-back frontier (32 tiles per L2 round trip) would cap the rate below HBM speed (measured 1.7 TB/s), so the
+    // dependency-free two-pass form takes over (tile sums, then the prefix with offsets read from the sums).
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+    const bool two_pass = force_sequential || nt > sms * (2048 / NS_SCAN_THREADS);
+    if (two_pass) {
+        uint64_t* group_sums = d_tile_sums.p + nt;
+        CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
+        LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
+        LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
+    } else {
+        CK(cudaMemsetAsync(d_tile_sums.p, 0, (size_t)(nt + 1) * sizeof(uint64_t), stream));      // tile states + ticket
+        LAUNCH(K_NS_WSCAN, k_ns_weights_scan1, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p);
+    }
     CK(cudaGetLastError());
     ns_w_in_records = false;
     return MCL_OK;
