@@ -302,13 +302,6 @@ __device__ __forceinline__ float ns_score_batch(const NsFieldView<KIND>& V, cons
 // (a scalar operand broadcast to both halves). Measured (profiles/): FFMA2 occupies the FMA pipe for two cycles, so it
 // saves issue slots, not pipe time: +4 % on the global-field path (issue bound), nothing on the shared-memory path (FMA
 // pipe and LDS bound), which therefore keeps the scalar form.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ void upk2u(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-
 // same summation order, same values as ns_score_batch<KIND, true, P, SHIFT>
 template <int KIND, int P, bool SHIFT>
 __device__ __forceinline__ float ns_score_batch_packed(const NsFieldView<KIND>& V, const float2* __restrict__ s_beams, int n_beams, int lane,
@@ -467,14 +460,15 @@ __device__ __forceinline__ uint64_t ns_exp_q32_dev(float t) {
     p = ns::fmaf_(p, g, 0.5f);
     p = ns::fmaf_(p, g, 1.0f);
     p = ns::fmaf_(p, g, 1.0f);                                        // exp(g) in [0.70, 1.42]
-    // trunc(p * 2^(32+k)): p = m * 2^(e-23) with the 24-bit significand m, so the value is (m << 9) >> (32 - e - k)
+    // trunc(p * 2^(32+k)): p = m * 2^(e-23) with the 24-bit significand m, so the value is (m << 9) >> sh, sh = 32 - e - k.
+    // m << 9 is the 33-bit number {1, m << 9 (32 bits)}; sh is 0 (p = 1, k = 0: the value 2^32) .. 33 (k = -32, p < 1: 0)
     const uint32_t pb = __float_as_uint(p);
-    const int sh = 127 + NS_MAGIC_BITS - (int)(pb >> 23) - __float_as_int(km);     // 32 - ((pb >> 23) - 127 + 32 + k), 0 .. 45
-    const uint64_t m9 = (uint64_t)((pb & 0x007fffffu) | 0x00800000u) << 9;
-    uint64_t w = m9 >> sh;
-    w = w > (1ull << 32) ? (1ull << 32) : w;
-    w = t >= 0.f ? (1ull << 32) : w;
-    return t > -22.5f ? w : 0ull;                                     // below 2^-32, and NaN
+    const int sh = 127 + NS_MAGIC_BITS - (int)(pb >> 23) - __float_as_int(km);
+    uint32_t lo = __funnelshift_rc(pb << 9, 1u, (unsigned)sh);       // low word of (2^32 + (m << 9 mod 2^32)) >> min(sh, 32)
+    lo = sh > 32 ? 0u : lo;
+    const bool one = (sh == 0) | (t >= 0.f);                          // exactly 2^32
+    lo = (one | !(t > -22.5f)) ? 0u : lo;                             // t <= -22.5 and NaN: below 2^-32
+    return ((uint64_t)(one ? 1u : 0u) << 32) | lo;
 }
 __device__ __forceinline__ uint64_t ns_weight(float ll, float max_ll, float temper) {
     return ns_exp_q32_dev(ns::mulf(temper, ns::addf(ll, -max_ll)));

