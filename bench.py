@@ -260,19 +260,29 @@ def ours(args):
     evals_per_step = [n * used_beams(sc.scans[s]) for s in range(total_steps)]
 
     def step_resident(s):
-        pf.diffDriveModel(sc.enc_left[s], sc.enc_right[s])
-        pf.computeWeightStaged(s)
-        pf.resampleParticles(1)
-        return pf.estimateWeightedPose()
+        """One tick through mcl_step_staged (predict, computeWeight, resample, estimate enqueued as one piece; the scan is
+        already parked in HBM). --separate-calls: the four per-function calls, which wait for the GPU three times."""
+        if args.separate_calls:
+            pf.diffDriveModel(sc.enc_left[s], sc.enc_right[s])
+            pf.computeWeightStaged(s)
+            pf.resampleParticles(1)
+            return pf.estimateWeightedPose()
+        return pf.executeParticleFilter(sc.enc_left[s], sc.enc_right[s], 1, slot=s)[0]
 
     pinned = [torch.from_numpy(np.ascontiguousarray(sc.scans[s]["ranges"])).pin_memory() for s in range(total_steps)]
 
     def step_e2e(s):
+        """The same tick through mcl_step with the scan in (pinned) host memory: H2D of the scored beams, D2H of the weight
+        total, the counters and the pose inside the timed region."""
         sca = sc.scans[s]
-        pf.diffDriveModel(sc.enc_left[s], sc.enc_right[s])
-        pf.computeWeight(pinned[s].numpy(), sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
-        pf.resampleParticles(1)
-        return pf.estimateWeightedPose()
+        if args.separate_calls:
+            pf.diffDriveModel(sc.enc_left[s], sc.enc_right[s])
+            pf.computeWeight(pinned[s].numpy(), sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
+            pf.resampleParticles(1)
+            return pf.estimateWeightedPose()
+        sca = dict(sca)
+        sca["ranges"] = pinned[s].numpy()
+        return pf.executeParticleFilter(sc.enc_left[s], sc.enc_right[s], 1, scan=sca)[0]
 
     def timed(fn, first):
         """W warm-up + K timed steps; each timed step bracketed by CUDA events on the engine's stream, L2 flushed
@@ -355,7 +365,9 @@ def ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_dict(n, "B200 x%d%s" % (world, ", independent replicas" if world > 1 else "")),
+            "data": "synthetic", "config": dict(config_dict(n, "B200 x%d%s" % (world, ", independent replicas" if world > 1 else "")),
+                                                api="four calls per tick: mcl_predict_encoders, mcl_update[_staged], mcl_resample, mcl_estimate" if args.separate_calls
+                                                else "one call per tick: mcl_step_staged (value) / mcl_step (e2e)"),
             "steps_per_s": world * K / t_res,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": scan_bytes, "d2h_bytes_per_step": 24 + 8 + 48,
                     "ms_per_step": 1e3 * t_e2e / K, "wall_ms_per_step": 1e3 * wall_e2e / K},
@@ -532,6 +544,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=N_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--separate-calls", action="store_true", help="REF loop through the four per-function calls instead of mcl_step")
     ap.add_argument("--no-ns", action="store_true", help="skip the NS (north-star) leg")
     ap.add_argument("--no-ns-large", action="store_true", help="skip the 8193x8193 / 1080-beam NS case")
     ap.add_argument("--ns-cells", type=int, default=512, help="NS leg: maze cells per side (512 -> 4097x4097 grid)")

@@ -166,6 +166,18 @@ int mcl_download_cdf(mcl_handle* h, double* cdf);          /* REF: the f64 CDF o
 /* ---- estimate: estimateWeightedPose(particles) (MC:782-800) ------------------------------------------- */
 int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
 
+/* ---- one tick of the node's loop: executeParticleFilter (MC:1084-1092) = diffDriveModel + updateParticlePos,
+ *      resampleParticles (computeWeight inside, MC:468), estimateWeightedPose --------------------------------
+ * The same kernels and results as mcl_predict_encoders + mcl_update + mcl_resample + mcl_estimate with the engine's own
+ * draw streams, enqueued as one piece: the host waits for the GPU once at the end instead of three times (the weight
+ * total it needs for the adaptive injection, MC:469-492, arrives while the CDF kernels run). MCL_MODE_REF only (NS
+ * filters: mcl_ns_step). pose3 = {x, y, theta} of the resampled particles; stats as mcl_resample. Both optional.
+ * mcl_step_staged takes a scan parked by mcl_scan_stage. */
+int mcl_step(mcl_handle* h, double enc_left, double enc_right, const float* ranges, int32_t n_beams, float angle_min,
+             float angle_increment, float range_min, float range_max, int32_t jitter_state, double* pose3, mcl_resample_stats* stats);
+int mcl_step_staged(mcl_handle* h, double enc_left, double enc_right, int32_t slot, int32_t jitter_state, double* pose3,
+                    mcl_resample_stats* stats);
+
 /* ---- NS mode across GPUs: particles shard by contiguous global index; one handle per GPU. A driver sequences the
  *      *_local phases around three tiny collectives (max of the local maxima; all-gather of the local totals; a barrier),
  *      which keeps systematic resampling globally exact and bit-identical for any GPU count. Each shard stores its

@@ -105,6 +105,21 @@ public:
         return p;
     }
 
+    // ---- one tick: executeParticleFilter (MC:1084-1092) as a single engine call (mcl_step) ----
+    // = diffDriveModel + updateParticlePos + resampleParticles (computeWeight inside) + estimateWeightedPose with one wait for
+    // the GPU instead of three; same results as the separate calls. Returns the weighted pose of the resampled particles.
+    template <class LaserScanMsg>
+    RobotPosition executeParticleFilter(double current_encoderLeft, double current_encoderRight, const LaserScanMsg& latest_scan, bool jitterState) {
+        double pose[3];
+        mcl_resample_stats st;
+        check(mcl_step(h_, current_encoderLeft, current_encoderRight, latest_scan.ranges.data(), (int)latest_scan.ranges.size(), latest_scan.angle_min,
+                       latest_scan.angle_increment, latest_scan.range_min, latest_scan.range_max, jitterState ? 1 : 0, pose, &st));
+        last_stats_ = st;
+        RobotPosition p;
+        p.x = pose[0]; p.y = pose[1]; p.theta = pose[2];
+        return p;
+    }
+
     // ---- confidence estimate (MC:886-949): returns the density ratio; x_best / y_best / theta_best carry the reference's
     // globals of the same names (MC:73-75), -1 when the ratio does not exceed the threshold (MC:938-940) ----
     double isLocalizationLost_densitiy_cluster(double cluster_ratio_threshold) {

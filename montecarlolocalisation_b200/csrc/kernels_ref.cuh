@@ -597,6 +597,32 @@ __device__ __forceinline__ float ref_wrap_theta(double t) {
     return __double2float_rn(atan2(sn, cs));
 }
 
+// Guide table for the CDF search: guide[b] = std::lower_bound(cdf, b / buckets) for b = 0..buckets (buckets a power of two, so
+// b / buckets and floor(r * buckets) are exact). lower_bound is monotone in its argument, hence for r in [b, b+1) / buckets
+// the answer lies in [guide[b], guide[b+1]]: each particle's search shrinks from log2(N) dependent loads to one guide load
+// plus log2(N / buckets) on a few neighbouring lines. Valid when the CDF is non-decreasing, i.e. the total weight is finite
+// and positive (the host knows it); otherwise (NaN CDF, MC:492/530) the full-range search reproduces std::lower_bound's walk.
+// One warp per bucket edge, 32-ary search (4-5 dependent loads instead of log2 N): the predicate is monotone here, so
+// the ballot of 32 evenly spaced probes is a prefix mask and its population count selects the sub-range.
+__global__ void __launch_bounds__(256) k_ref_guide(const double* __restrict__ cdf, int64_t n, int buckets, int* __restrict__ guide) {
+    const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (b > buckets) return;                                          // whole warps leave together
+    const double t = (double)b / (double)buckets;
+    int64_t lo = 0, len = n;                                          // the answer lies in [lo, lo + len]
+    while (len > 0) {
+        if (len <= 32) {
+            const bool below = lane < len && cdf[lo + lane] < t;
+            lo += __popc(__ballot_sync(0xffffffffu, below));
+            break;
+        }
+        const int64_t step = len >> 5;
+        const int c = __popc(__ballot_sync(0xffffffffu, cdf[lo + (lane + 1) * step - 1] < t));
+        lo += c * step;
+        len = c < 32 ? step - 1 : len - 32 * step;
+    }
+    if (lane == 0) guide[b] = (int)lo;
+}
+
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n,
                                                       const double* __restrict__ cdf, const double* __restrict__ u_r,
@@ -606,7 +632,8 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       const double* __restrict__ inj_u_dy,
                                                       const int* __restrict__ block_flag_offsets,   // null when p_inject == 0
                                                       RefResampleParams R, int* __restrict__ ancestors,
-                                                      int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G) {
+                                                      int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G,
+                                                      const int* __restrict__ guide /* null: full-range search */, int buckets) {
     __shared__ int warp_counts[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
@@ -646,6 +673,10 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
     } else {
         // std::lower_bound(cdf, r): first idx with !(cdf[idx] < r) (MC:530); NaN entries compare false.
         int64_t lo = 0, len = n;
+        if (guide && r >= 0.0 && r < 1.0) {                           // (injected draws outside [0, 1): full-range search)
+            const int b = (int)(r * (double)buckets);                // exact: power-of-two scaling, r in [0, 1)
+            lo = guide[b]; len = (int64_t)guide[b + 1] - lo;         // answer in [guide[b], guide[b+1]]
+        }
         while (len > 0) {
             int64_t half = len >> 1;
             if (cdf[lo + half] < r) { lo += half + 1; len -= half + 1; } else { len = half; }

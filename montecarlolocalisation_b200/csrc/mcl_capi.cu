@@ -92,6 +92,16 @@ int mcl_resample(mcl_handle* h, int32_t js, const mcl_resample_draws* d, mcl_res
 int mcl_download_ancestors(mcl_handle* h, int32_t* idx) { GUARD(h); TRY(h->engine.download_ancestors(idx)) }
 int mcl_download_cdf(mcl_handle* h, double* cdf) { GUARD(h); TRY(h->engine.download_cdf(cdf)) }
 int mcl_estimate(mcl_handle* h, double* x, double* y, double* th) { GUARD(h); TRY(h->engine.estimate(x, y, th)) }
+int mcl_step(mcl_handle* h, double el, double er, const float* ranges, int32_t nb, float amin, float ainc, float rmin, float rmax, int32_t js,
+             double* pose3, mcl_resample_stats* st) {
+    GUARD(h);
+    TRY(h->engine.ref_step(el, er, -1, ranges, nb, amin, ainc, rmin, rmax, js, pose3, st))
+}
+int mcl_step_staged(mcl_handle* h, double el, double er, int32_t slot, int32_t js, double* pose3, mcl_resample_stats* st) {
+    GUARD(h);
+    if (slot < 0) return MCL_ERR_ARG;
+    TRY(h->engine.ref_step(el, er, slot, nullptr, 0, 0.f, 0.f, 0.f, 0.f, js, pose3, st))
+}
 int mcl_get_injection_state(mcl_handle* h, double* s, double* f) { GUARD(h); if (s) *s = h->engine.inj_slow; if (f) *f = h->engine.inj_fast; return MCL_OK; }
 int mcl_set_injection_state(mcl_handle* h, double s, double f) { GUARD(h); h->engine.inj_slow = s; h->engine.inj_fast = f; return MCL_OK; }
 int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count) { GUARD(h); TRY(h->engine.get_ray_lut(keys, dx, dy, cap, count)) }

@@ -19,9 +19,10 @@ Engine::~Engine() {
     if (!opened) return;
     cudaSetDevice(cfg.device);
     part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); for (auto& e : ns_tune_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
-    d_mbox.release(); d_lf.release(); d_lf8.release(); d_codes.release(); d_code_of_d2.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
+    d_guide.release(); d_mbox.release(); d_lf.release(); d_lf8.release(); d_codes.release(); d_code_of_d2.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
     for (int w = 0; w < 4; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
+    if (h_step) { cudaFreeHost(h_step); cudaEventDestroy(ev_total); }
     if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
     ns_comm_destroy(); ancestors.release(); d_occ.release(); d_occ_pad.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
@@ -34,7 +35,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
-                                         "k_ref_seq_cdf", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
@@ -547,7 +548,7 @@ int Engine::ref_prepare_beams(const float* ranges, int n_beams, float angle_min,
     return MCL_OK;
 }
 
-int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total) {
+int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync) {
     RefParams P;
     P.occ = d_occ.p; P.width = map_w; P.height = map_h;
     P.occ_pad = d_occ_pad.p; P.pad = occ_pad; P.wp = occ_wp;
@@ -635,6 +636,12 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         int rc = exact_accumulate(false, d_scalars.p);
         if (rc) return rc;
     }
+    if (defer_sync) {            // ref_step: the total travels through pinned memory while the GPU goes on with the CDF
+        CK(cudaMemcpyAsync(&h_step->total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(ev_total, stream));
+        have_weights = true;
+        return MCL_OK;
+    }
     CK(cudaMemcpyAsync(&last_total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     have_weights = true;
@@ -690,7 +697,23 @@ int Engine::resample(int jitter_state, const mcl_resample_draws* d, mcl_resample
     return MCL_OK;
 }
 
-int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st) {
+// normalise + sequential CDF (MC:496-505) and the guide table of the CDF search: everything resampling needs that does not
+// depend on a host decision, so mcl_step can enqueue it before it waits for the weight total.
+int Engine::ref_resample_front() {
+    int rc = exact_accumulate(true, nullptr);
+    if (rc) return rc;
+    guide_built = false;
+    if (n >= 4096 && !force_sequential) {
+        int buckets = 1024;
+        while ((int64_t)buckets * 64 < n && buckets < (1 << 20)) buckets <<= 1;
+        CK(d_guide.ensure((size_t)buckets + 2));
+        LAUNCH(K_GUIDE, k_ref_guide, grid_for((int64_t)(buckets + 1) * 32, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
+        guide_built = true; guide_buckets = buckets;
+    }
+    return MCL_OK;
+}
+
+int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done, bool defer_sync) {
     jitter_state = jitter_state ? 1 : 0;
     // adaptive injection EMA (MC:469-492)
     const double weight_avg = last_total / (double)n;
@@ -765,21 +788,26 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
         LAUNCH(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2);
         CK(cudaGetLastError());
     }
-    // normalise + sequential CDF (MC:496-505)
-    rc = exact_accumulate(true, nullptr);
-    if (rc) return rc;
+    if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
+    // the guide table is used whenever the CDF is known to be non-decreasing: finite positive total weight
+    const bool use_guide = guide_built && std::isfinite(last_total) && last_total > 0.0;
+    const int* guide = use_guide ? d_guide.p : nullptr;
+    const int buckets = use_guide ? guide_buckets : 0;
     if (d)
         LAUNCH(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
                d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets);
     else
         LAUNCH(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
                d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets);
     CK(cudaGetLastError());
-    int counters[4];
-    CK(cudaMemcpyAsync(counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
+    int counters[4] = {0, 0, 0, 0};
+    if (defer_sync) CK(cudaMemcpyAsync(h_step->counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+    else {
+        CK(cudaMemcpyAsync(counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
     cur ^= 1;
     have_weights = false;
     ++step_counter;
@@ -792,9 +820,7 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
 }
 
 // ---- estimate -----------------------------------------------------------------------------------------------------
-int Engine::estimate(double* x, double* y, double* th) {
-    CK(cudaSetDevice(cfg.device));
-    if (n == 0) return fail(MCL_ERR_ARG, "estimate: no particles");
+int Engine::estimate_enqueue(double* h_sums4) {
     { int rc = ns_materialise_weights(); if (rc) return rc; }
     const int blocks = (int)std::min<int64_t>(1024, grid_for(n, 256));
     CK(d_partials.ensure(4 * 1024));
@@ -806,14 +832,73 @@ int Engine::estimate(double* x, double* y, double* th) {
     }
     LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2);
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    return MCL_OK;
+}
+
+int Engine::estimate(double* x, double* y, double* th) {
+    CK(cudaSetDevice(cfg.device));
+    if (n == 0) return fail(MCL_ERR_ARG, "estimate: no particles");
     double s[4];
-    CK(cudaMemcpyAsync(s, d_scalars.p + 2, sizeof(s), cudaMemcpyDeviceToHost, stream));
+    { int rc = estimate_enqueue(s); if (rc) return rc; }
     CK(cudaStreamSynchronize(stream));
     const float xm = (float)s[0], ym = (float)s[1];
     const float tm = std::atan2((float)s[2], (float)s[3]);      // MC:796 (fp32 atan2)
     if (x) *x = xm;
     if (y) *y = ym;
     if (th) *th = tm;
+    return MCL_OK;
+}
+
+// ---- one whole step of the reference loop (MC:1084-1092) with a single wait at its end ---------------------------------------
+// predict -> computeWeight -> [total starts travelling to the host] -> normalise + CDF + guide table -> (host: adaptive
+// injection from the total, MC:469-492, while those kernels run) -> resample -> pose sums -> one synchronisation for the
+// counters and the pose. Same kernels, same results as mcl_predict_encoders + mcl_update + mcl_resample + mcl_estimate,
+// which wait for the GPU three times. Draws come from the engine's Philox streams (parity runs inject theirs per call).
+int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min,
+                     float range_max, int jitter_state, double* pose3, mcl_resample_stats* st) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "step: MCL_MODE_REF only (NS filters use mcl_ns_step)");
+    if (!map_ready) return fail(MCL_ERR_ARG, "step: no map");
+    if (n == 0) return fail(MCL_ERR_ARG, "step: no particles");
+    if (!h_step) { CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars))); CK(cudaEventCreateWithFlags(&ev_total, cudaEventDisableTiming)); }
+    int rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
+    if (rc) return rc;
+    if (ranges || slot < 0) {
+        if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "step: bad scan");
+        std::vector<RefBeam> used;
+        rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, beams_all, used);
+        if (rc) return rc;
+        CK(d_beams.ensure(std::max<size_t>(1, used.size())));
+        if (!used.empty()) {
+            rc = ensure_pinned(used.size() * sizeof(RefBeam));
+            if (rc) return rc;
+            memcpy(h_pinned, used.data(), used.size() * sizeof(RefBeam));
+            CK(cudaMemcpyAsync(d_beams.p, h_pinned, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+        }
+        rc = ref_run_update(d_beams.p, (int)used.size(), beams_all, nullptr, true);
+    } else {
+        if ((size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "step: empty scan slot");
+        rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true);
+    }
+    if (rc) return rc;
+    rc = ref_resample_front();
+    if (rc) return rc;
+    CK(cudaEventSynchronize(ev_total));                         // the GPU is busy with the CDF meanwhile
+    last_total = h_step->total;
+    wsum_known = true; known_wsum = last_total;
+    mcl_resample_stats local;
+    rc = ref_resample(jitter_state, nullptr, &local, true, true);
+    if (rc) return rc;
+    rc = estimate_enqueue(h_step->pose);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(stream));
+    local.injected = h_step->counters[0]; local.clamped = h_step->counters[1];
+    if (st) *st = local;
+    if (pose3) {
+        pose3[0] = (double)(float)h_step->pose[0]; pose3[1] = (double)(float)h_step->pose[1];
+        pose3[2] = (double)std::atan2((float)h_step->pose[2], (float)h_step->pose[3]);      // MC:796 (fp32 atan2)
+    }
     return MCL_OK;
 }
 

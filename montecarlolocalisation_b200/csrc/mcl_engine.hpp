@@ -52,6 +52,8 @@ public:
     int download_ancestors(int32_t* idx);
     int download_cdf(double* cdf);
     int estimate(double* x, double* y, double* th);
+    int ref_step(double enc_l, double enc_r, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min,
+                 float range_max, int jitter_state, double* pose3, mcl_resample_stats* st);
     int get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
     int synchronize();
     // NS mode (north-star formulation); the *_local phases are what a multi-GPU driver sequences around its collectives
@@ -90,7 +92,7 @@ public:
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
@@ -115,8 +117,16 @@ private:
     int ensure_particles(int64_t count);
     int ref_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
                           std::vector<HostBeam>& all, std::vector<RefBeam>& used);
-    int ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total);
-    int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st);
+    int ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync = false);
+    int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done = false, bool defer_sync = false);
+    int ref_resample_front();               // normalise + CDF + guide table: needs nothing from the host
+    int estimate_enqueue(double* h_sums4);
+    // whole-step entry (mcl_step / mcl_step_staged): scalars the host needs travel through this pinned block
+    struct StepScalars { double total; double pose[4]; int counters[4]; };
+    StepScalars* h_step = nullptr;
+    cudaEvent_t ev_total = nullptr;
+    bool guide_built = false;
+    int guide_buckets = 0;
     int ref_fill_ray_lut(const std::vector<HostBeam>& all);
     void philox_host(uint32_t stream_id, uint64_t index, uint32_t out[4]) const;
 
@@ -235,6 +245,7 @@ private:
     bool ns_have_ll = false;
     void* peer_ptr[4][8] = {{nullptr}};    // [0],[1]: particle ping-pong buffers of shard r; [2]: ancestors; [3]: mailbox
     bool peer_ipc[4][8] = {{false}};
+    DevBuf<int> d_guide;                   // REF resampling: guide table of the CDF search
     DevBuf<unsigned char> d_mbox;          // this shard's NsMailbox (peer-memory exchange)
     uint32_t xchg_seq = 0;                 // exchange tag: sharded steps taken by this handle (never reset; same on every shard)
     int ensure_mailbox();

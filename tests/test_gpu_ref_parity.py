@@ -273,3 +273,37 @@ def test_nonzero_map_origin():
     total_g = pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
     assert (Po[:, 3] > 0).mean() > 0.3
     assert total_g == total_o and np.array_equal(pf.downloadParticles()[:, 3], Po[:, 3])
+
+
+def test_whole_step_call_equals_separate_calls():
+    """mcl_step / mcl_step_staged (one tick enqueued as one piece, the host waiting once) against the four separate calls
+    on a twin filter with the same seed: same particles, ancestors, injection state, stats and pose, over steps that
+    include injections (lost mode after a weight collapse) and both scan paths."""
+    sc = Scenario(6, n_beams=360, seed=3)
+    n = 30011
+    a = m.ParticleFilter(max_particles=n, seed=77)
+    b = m.ParticleFilter(max_particles=n, seed=77)
+    for pf in (a, b):
+        pf.setMap(sc.occ, RES)
+        pf.sampleParticles(n)
+    for i, scan in enumerate(sc.scans):
+        a.stageScan(i, scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    for step in range(6):
+        scan = dict(sc.scans[step])
+        if step == 3:                       # a scan that fits nothing: weights collapse, the injection EMA reacts on the next steps
+            scan["ranges"] = np.full_like(scan["ranges"], 0.05)
+            a.stageScan(step, scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        lost = step >= 2
+        if step % 2 == 0:
+            pose_a, st_a = a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, slot=step)
+        else:
+            pose_a, st_a = a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, scan=scan)
+        b.diffDriveModel(sc.enc_left[step], sc.enc_right[step])
+        total = b.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        st_b = b.resampleParticles(lost)
+        pose_b = b.estimateWeightedPose()
+        assert st_a == st_b and st_a["total_weight"] == total, (step, st_a, st_b)
+        assert np.array_equal(pose_a, pose_b), (step, pose_a, pose_b)
+        assert np.array_equal(a.downloadParticles(), b.downloadParticles()), step
+        assert np.array_equal(a.ancestors(), b.ancestors()), step
+    assert np.array_equal(a.injectionState(), b.injectionState())
