@@ -61,15 +61,17 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device = device
+    def __init__(self, devices):
+        """devices: the GPU indices of this job. ONE sampler per job (rank 0): eight nvidia-smi pollers would contend with
+        the filters' own driver calls."""
+        self.devices = list(devices)
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(d) for d in self.devices), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -88,7 +90,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        per_gpu = {}
+        for r in self.rows:
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                per_gpu.setdefault(r[0], []).append(float(r[1]))
+        sm = [statistics.median(v) for v in per_gpu.values()]           # the slowest GPU's median is what is reported
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
@@ -97,8 +103,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": sum(len(v) for v in per_gpu.values()), "gpus_sampled": len(per_gpu)}
 
 
 def workload(n_steps):
@@ -301,8 +307,9 @@ def ours(args):
         wall = time.perf_counter() - wall0
         return [a.elapsed_time(b) for a, b in ev], wall
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(range(world)) if rank == 0 else None      # rank 0 samples every GPU of the job
+    if sampler:
+        sampler.start()
     launches0 = pf.kernelLaunches()
     ms_res, wall_res = timed(step_resident, 0)
     launches = pf.kernelLaunches() - launches0
@@ -359,7 +366,7 @@ def ours(args):
         if not args.no_ns_large:
             ns["grid8192"] = ns_leg(args, torch, dist if world > 1 else None, rank, world, local, 1024, args.ns_particles, 1080,
                                     "configs[4] per-GPU shape (kidnapped robot)", K, W, "grid8192")
-    clocks = sampler.stop()           # sampled over every timed region of this run (REF loop and NS legs)
+    clocks = sampler.stop() if sampler else None           # sampled over every timed region of this run (REF loop and NS legs)
     if rank == 0:
         scan_bytes = int(sc.scans[0]["ranges"].nbytes) + 16 + 16         # ranges + 4 float32 scan fields + 2 encoder doubles
         line = {

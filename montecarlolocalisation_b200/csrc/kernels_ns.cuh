@@ -349,12 +349,59 @@ __device__ __forceinline__ float ns_score_batch_packed(const NsFieldView<KIND>& 
     return mine;
 }
 
+// Mixed form: the four FFMAs per evaluation stay scalar (they can issue on either half of the FMA pipe), the two magic adds
+// of an evaluation travel as one FADD2 on the (x, y) pair and the running sums of two particles as one FADD2. FFMA2/FADD2
+// occupy the heavy half of the FMA pipe for two cycles (measured), so packing everything moves the bound from the issue
+// slots to that half-pipe; packing only the adds balances the two halves and still saves 3 of 13 issue slots.
+template <int KIND, int P, bool SHIFT>
+__device__ __forceinline__ float ns_score_batch_mixed(const NsFieldView<KIND>& V, const float2* __restrict__ s_beams, int n_beams, int lane,
+                                                      float gx0, float gy0, float c, float s) {
+    float mine = 0.f;
+    const f32x2 magic2 = pk2(NS_MAGIC, NS_MAGIC);
+#pragma unroll 1
+    for (int g0 = 0; g0 < 32; g0 += P) {
+        float acc[P];
+#pragma unroll
+        for (int k0 = 0; k0 < P; k0 += 4) {
+            float X[4], Y[4], C[4], S[4];
+            f32x2 a[2];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                X[q] = __shfl_sync(0xffffffffu, gx0, g0 + k0 + q); Y[q] = __shfl_sync(0xffffffffu, gy0, g0 + k0 + q);
+                C[q] = __shfl_sync(0xffffffffu, c, g0 + k0 + q); S[q] = __shfl_sync(0xffffffffu, s, g0 + k0 + q);
+            }
+            a[0] = a[1] = pk2(0.f, 0.f);
+#pragma unroll (KIND == NS_FIELD_SMEM ? 2 : 4)
+            for (int b = lane; b < n_beams; b += 32) {
+                const float2 bm = s_beams[b];
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float ex = ns::fmaf_(C[q], bm.x, ns::fmaf_(-S[q], bm.y, X[q]));
+                    const float ey = ns::fmaf_(S[q], bm.x, ns::fmaf_(C[q], bm.y, Y[q]));
+                    uint32_t tx, ty;
+                    upk2u(add2(pk2(ex, ey), magic2), tx, ty);
+                    v[q] = ns_load_fast<KIND, SHIFT>(V, tx, ty);
+                }
+                a[0] = add2(a[0], pk2(v[0], v[1]));
+                a[1] = add2(a[1], pk2(v[2], v[3]));
+            }
+            upk2(a[0], acc[k0], acc[k0 + 1]);
+            upk2(a[1], acc[k0 + 2], acc[k0 + 3]);
+        }
+        const float total = ns_transpose_reduce<P>(acc, lane);
+        if ((lane & ~(P - 1)) == g0) mine = total;
+    }
+    return mine;
+}
+
 constexpr int NS_UPD_THREADS = 1024;
 constexpr int NS_UPD_P = 8;
 constexpr int NS_MAX_CODES = 256;
 
 // dynamic shared memory: [field (NS_FIELD_SMEM) | code table, NS_MAX_CODES floats (NS_FIELD_U8)] [beam points]
-template <int KIND, bool PACKED>
+// PACK: 0 scalar arithmetic, 1 everything packed (FFMA2/FADD2), 2 only the adds packed
+template <int KIND, int PACK>
 __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
                                                                 const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
                                                                 int* __restrict__ max_bits /* ordered-int max of ll */) {
@@ -401,9 +448,12 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
         const bool inside = gx0 >= -0.5f && gx0 <= x_hi && gy0 >= -0.5f && gy0 <= y_hi;        // false for NaN
         float ll;
         if (fast_ok && __all_sync(0xffffffffu, inside)) {
-            if (PACKED) {
+            if (PACK == 1) {
                 if (one_window) ll = ns_score_batch_packed<KIND, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
                 else ll = ns_score_batch_packed<KIND, NS_UPD_P, false>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+            } else if (PACK == 2) {
+                if (one_window) ll = ns_score_batch_mixed<KIND, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
+                else ll = ns_score_batch_mixed<KIND, NS_UPD_P, false>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
             } else {
                 if (one_window) ll = ns_score_batch<KIND, true, NS_UPD_P, true>(V, s_beams, n_beams, lane, gx0, gy0, c, s);
                 else ll = ns_score_batch<KIND, true, NS_UPD_P>(V, s_beams, n_beams, lane, gx0, gy0, c, s);

@@ -249,6 +249,7 @@ private:
     DevBuf<unsigned char> d_mbox;          // this shard's NsMailbox (peer-memory exchange)
     uint32_t xchg_seq = 0;                 // exchange tag: sharded steps taken by this handle (never reset; same on every shard)
     int ensure_mailbox();
+    int ns_preload_update(int kind, int pack);
     bool peers_have_mailboxes() const;
     // pinned staging
     void* h_pinned = nullptr;

@@ -25,6 +25,16 @@ int Engine::ns_set_shard(int rank, int world, int64_t ng) {
     return world > 1 ? ensure_mailbox() : MCL_OK;
 }
 
+#define NS_UPD_FOR_ALL(X) X(NS_FIELD_SMEM, 0) X(NS_FIELD_SMEM, 1) X(NS_FIELD_SMEM, 2) X(NS_FIELD_GLOBAL, 0) X(NS_FIELD_GLOBAL, 1) X(NS_FIELD_GLOBAL, 2) \
+                          X(NS_FIELD_U8, 0) X(NS_FIELD_U8, 1) X(NS_FIELD_U8, 2)
+int Engine::ns_preload_update(int kind, int pack) {
+    cudaFuncAttributes fa;
+#define X(K, P) if (kind == K && pack == P) CK(cudaFuncGetAttributes(&fa, k_ns_update<K, P>));
+    NS_UPD_FOR_ALL(X)
+#undef X
+    return MCL_OK;
+}
+
 int Engine::ensure_mailbox() {
     if (d_mbox.p) return MCL_OK;
     CK(d_mbox.ensure(sizeof(NsMailbox)));
@@ -38,8 +48,8 @@ int Engine::ensure_mailbox() {
     // the context, which would wait for exchange kernels already spinning on this device
     cudaFuncAttributes fa;
 #define PRELOAD(k) CK(cudaFuncGetAttributes(&fa, k))
-    PRELOAD(k_ns_predict); PRELOAD((k_ns_update<NS_FIELD_SMEM, false>)); PRELOAD((k_ns_update<NS_FIELD_GLOBAL, true>));
-    PRELOAD((k_ns_update<NS_FIELD_GLOBAL, false>)); PRELOAD((k_ns_update<NS_FIELD_U8, true>)); PRELOAD((k_ns_update<NS_FIELD_U8, false>));
+    PRELOAD(k_ns_predict);
+    for (int kk = 0; kk < 3; ++kk) for (int pp = 0; pp < 3; ++pp) { int rc = ns_preload_update(kk, pp); if (rc) return rc; }
     PRELOAD(k_ns_weights_sum); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_weights_scan1); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
     PRELOAD(k_ns_pose_partials); PRELOAD(k_ns_pose_reduce); PRELOAD(k_ns_pose_xchg); PRELOAD(k_ns_xchg_barrier);
     PRELOAD(k_ns_resample_bounds); PRELOAD(k_ns_resample);
@@ -283,15 +293,16 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
     }
     if (ns_force_field == NS_FIELD_U8 && ns_n_codes) kind = NS_FIELD_U8;
     if (ns_force_field == NS_FIELD_GLOBAL) kind = NS_FIELD_GLOBAL;
-    // packed FFMA2 form where it pays (issue-bound global paths); MCL_NS_SCALAR=1 / debug bit 5: scalar form everywhere
-    static const bool env_scalar = [] { const char* e = getenv("MCL_NS_SCALAR"); return e && e[0] == '1'; }();
-    const bool packed = kind != NS_FIELD_SMEM && !env_scalar && !ns_force_scalar;
+    // arithmetic form (identical values): 0 scalar, 1 everything packed (FFMA2/FADD2), 2 only the adds packed. Defaults by
+    // measurement (profiles/); MCL_NS_PACK=<smem><global><u8> digits override (experiments), debug bit 5 forces scalar.
+    static const char* env_pack = getenv("MCL_NS_PACK");
+    int pack = kind == NS_FIELD_SMEM ? 0 : kind == NS_FIELD_GLOBAL ? 1 : 2;      // measured: 158/158/161 us, 3416/3341/3286 us, 4472/4294/4428 us
+    if (env_pack && strlen(env_pack) == 3 && env_pack[kind] >= '0' && env_pack[kind] <= '2') pack = env_pack[kind] - '0';
+    if (ns_force_scalar) pack = 0;
     if (!ns_attr_set) {
-        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_U8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CK(cudaFuncSetAttribute(k_ns_update<NS_FIELD_U8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+#define X(K, P) CK(cudaFuncSetAttribute(k_ns_update<K, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (K == NS_FIELD_SMEM ? 200 : 64) * 1024));
+        NS_UPD_FOR_ALL(X)
+#undef X
         ns_attr_set = true;
     }
     const int threads = NS_UPD_THREADS;
@@ -309,10 +320,10 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
         if (measure) { CK(cudaEventRecord(ns_tune_ev[1], stream)); ns_tune_pending = true; ns_tune_kind = kind; ns_tune_beams = ns_beams_n; }
         return MCL_OK;
     };
-    int lrc;
-    if (kind == NS_FIELD_SMEM) lrc = launch(k_ns_update<NS_FIELD_SMEM, false>);
-    else if (kind == NS_FIELD_GLOBAL) lrc = packed ? launch(k_ns_update<NS_FIELD_GLOBAL, true>) : launch(k_ns_update<NS_FIELD_GLOBAL, false>);
-    else lrc = packed ? launch(k_ns_update<NS_FIELD_U8, true>) : launch(k_ns_update<NS_FIELD_U8, false>);
+    int lrc = MCL_ERR_ARG;
+#define X(K, P) if (kind == K && pack == P) lrc = launch(k_ns_update<K, P>);
+    NS_UPD_FOR_ALL(X)
+#undef X
     if (lrc != MCL_OK) return lrc;
     ns_field_kind = kind;
     CK(cudaGetLastError());
