@@ -274,7 +274,7 @@ def ours(args):
             pf.computeWeightStaged(s)
             pf.resampleParticles(1)
             return pf.estimateWeightedPose()
-        return pf.executeParticleFilter(sc.enc_left[s], sc.enc_right[s], 1, slot=s)[0]
+        return pf.executeParticleFilter(sc.enc_left[s], sc.enc_right[s], 1, slot=s, want_result=False)      # queued: nothing read back
 
     pinned = [torch.from_numpy(np.ascontiguousarray(sc.scans[s]["ranges"])).pin_memory() for s in range(total_steps)]
 

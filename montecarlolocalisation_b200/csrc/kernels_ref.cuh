@@ -558,9 +558,26 @@ __device__ __forceinline__ void ref_philox_draws(uint64_t counter, const RefDraw
 }
 
 // flags[i] = (u_r[i] < p_inject); block_counts[b] = number of flags in block b.
+// Adaptive injection (MC:469-492) on the device, for mcl_step: the same IEEE operations in the same order as the host
+// form in Engine::ref_resample, so both give the same bits. inj = {weight_slow, weight_fast, p_inject, cdf_is_monotone}.
+__global__ void k_ref_ema(const double* __restrict__ total, double n, double a_slow, double a_fast, double* __restrict__ inj) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double t = *total;
+    const double avg = ddiv(t, n);
+    const double slow = dadd(inj[0], dmul(a_slow, dsub(avg, inj[0])));
+    const double fast = dadd(inj[1], dmul(a_fast, dsub(avg, inj[1])));
+    const double p = dsub(1.0, ddiv(fast, slow));
+    inj[0] = slow; inj[1] = fast;
+    inj[2] = (0.0 < p) ? p : 0.0;                                   // std::max(0.0, p): NaN gives 0.0 (MC:492)
+    inj[3] = (t > 0.0 && t < 1.0e300) ? 1.0 : 0.0;                  // finite positive total: the CDF is non-decreasing
+    inj[4] = t;
+}
+
+// inj_dev (mcl_step): p_inject lives in device memory (inj_dev[2]); nothing to do when it is zero
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
-                                                          int* __restrict__ block_counts, RefDrawGen G) {
+                                                          int* __restrict__ block_counts, RefDrawGen G, const double* __restrict__ inj_dev) {
+    if (inj_dev) { p_inject = inj_dev[2]; if (!(p_inject > 0.0)) return; }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double r = 2.0;
     if (i < n) {
@@ -572,7 +589,8 @@ __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restri
     if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
 // exclusive scan of block counts in place (single block, sequential chunks; n_blocks is small).
-__global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total) {
+__global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total, const double* __restrict__ inj_dev) {
+    if (inj_dev && !(inj_dev[2] > 0.0)) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int acc = 0;
         for (int b = 0; b < n_blocks; b++) { int c = block_counts[b]; block_counts[b] = acc; acc += c; }
@@ -633,7 +651,8 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       const int* __restrict__ block_flag_offsets,   // null when p_inject == 0
                                                       RefResampleParams R, int* __restrict__ ancestors,
                                                       int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G,
-                                                      const int* __restrict__ guide /* null: full-range search */, int buckets) {
+                                                      const int* __restrict__ guide /* null: full-range search */, int buckets,
+                                                      const double* __restrict__ inj_dev /* mcl_step: {.., p_inject, cdf_is_monotone} on the device */) {
     __shared__ int warp_counts[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
@@ -643,8 +662,13 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
         if (GEN) { ref_philox_draws(2 * (uint64_t)i, G, A); r = canonical53(A[0], A[1]); }
         else r = u_r[i];
     }
+    const double p_inject = inj_dev ? inj_dev[2] : R.p_inject;
+    if (inj_dev) {
+        if (!(p_inject > 0.0)) block_flag_offsets = nullptr;       // block-uniform: no slot can be injected
+        if (inj_dev[3] == 0.0) guide = nullptr;                    // NaN CDF: std::lower_bound's full-range walk
+    }
     // rank of this slot among the slots whose draw fell below p_inject (sequential injection counter, MC:518,525)
-    int flag = (block_flag_offsets != nullptr && r < R.p_inject) ? 1 : 0;
+    int flag = (block_flag_offsets != nullptr && r < p_inject) ? 1 : 0;
     int rank = 0;
     if (block_flag_offsets != nullptr) {
         unsigned ballot = __ballot_sync(0xffffffffu, flag);

@@ -102,8 +102,21 @@ int mcl_step_staged(mcl_handle* h, double el, double er, int32_t slot, int32_t j
     if (slot < 0) return MCL_ERR_ARG;
     TRY(h->engine.ref_step(el, er, slot, nullptr, 0, 0.f, 0.f, 0.f, 0.f, js, pose3, st))
 }
-int mcl_get_injection_state(mcl_handle* h, double* s, double* f) { GUARD(h); if (s) *s = h->engine.inj_slow; if (f) *f = h->engine.inj_fast; return MCL_OK; }
-int mcl_set_injection_state(mcl_handle* h, double s, double f) { GUARD(h); h->engine.inj_slow = s; h->engine.inj_fast = f; return MCL_OK; }
+int mcl_get_injection_state(mcl_handle* h, double* s, double* f) {
+    GUARD(h);
+    int rc = h->engine.inj_sync_to_host();
+    if (rc) return rc;
+    if (s) *s = h->engine.inj_slow;
+    if (f) *f = h->engine.inj_fast;
+    return MCL_OK;
+}
+int mcl_set_injection_state(mcl_handle* h, double s, double f) {
+    GUARD(h);
+    int rc = h->engine.inj_sync_to_host();
+    if (rc) return rc;
+    h->engine.inj_slow = s; h->engine.inj_fast = f;
+    return MCL_OK;
+}
 int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count) { GUARD(h); TRY(h->engine.get_ray_lut(keys, dx, dy, cap, count)) }
 int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter) { GUARD(h); TRY(h->engine.download_resample_draws(u_r, u_jitter)) }
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back) { GUARD(h); TRY(h->engine.debug_exact_scan(w, n, cdf, total, fell_back)) }

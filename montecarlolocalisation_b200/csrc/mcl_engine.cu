@@ -22,7 +22,8 @@ Engine::~Engine() {
     d_guide.release(); d_mbox.release(); d_lf.release(); d_lf8.release(); d_codes.release(); d_code_of_d2.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
     for (int w = 0; w < 4; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
-    if (h_step) { cudaFreeHost(h_step); cudaEventDestroy(ev_total); }
+    if (h_step) cudaFreeHost(h_step);
+    d_inj.release();
     if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
     ns_comm_destroy(); ancestors.release(); d_occ.release(); d_occ_pad.release(); d_gauss.release();
     d_radii.release(); d_lut.release(); d_lut_filled.release(); d_touch.release(); d_touch_theta.release();
@@ -636,10 +637,9 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         int rc = exact_accumulate(false, d_scalars.p);
         if (rc) return rc;
     }
-    if (defer_sync) {            // ref_step: the total travels through pinned memory while the GPU goes on with the CDF
-        CK(cudaMemcpyAsync(&h_step->total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaEventRecord(ev_total, stream));
+    if (defer_sync) {            // mcl_step: the total stays on the device (k_ref_ema reads it there)
         have_weights = true;
+        wsum_known = false;
         return MCL_OK;
     }
     CK(cudaMemcpyAsync(&last_total, d_scalars.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -713,15 +713,26 @@ int Engine::ref_resample_front() {
     return MCL_OK;
 }
 
-int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done, bool defer_sync) {
+// dev_ema (mcl_step): the adaptive-injection state lives in device memory (d_inj, advanced by k_ref_ema) and the kernels
+// read p_inject from there, so nothing here waits for the weight total; draws are staged through the pinned ring because
+// several steps may be in flight; counters travel to the pinned step block and the call does not synchronise.
+int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done, bool dev_ema) {
     jitter_state = jitter_state ? 1 : 0;
-    // adaptive injection EMA (MC:469-492)
-    const double weight_avg = last_total / (double)n;
     const double a_slow = jitter_state ? cfg.inject_alpha_slow_lost : cfg.inject_alpha_slow_conf;
     const double a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
-    inj_slow = inj_slow + a_slow * (weight_avg - inj_slow);
-    inj_fast = inj_fast + a_fast * (weight_avg - inj_fast);
-    const double p_inject = std::max(0.0, 1.0 - (inj_fast / inj_slow));
+    double p_inject = 0.0;
+    if (dev_ema) {
+        LAUNCH(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p);
+    } else {
+        int rc0 = inj_sync_to_host();
+        if (rc0) return rc0;
+        // adaptive injection EMA (MC:469-492)
+        const double weight_avg = last_total / (double)n;
+        inj_slow = inj_slow + a_slow * (weight_avg - inj_slow);
+        inj_fast = inj_fast + a_fast * (weight_avg - inj_fast);
+        p_inject = std::max(0.0, 1.0 - (inj_fast / inj_slow));
+    }
+    const double* inj_dev = dev_ema ? (const double*)d_inj.p : (const double*)nullptr;
     RefResampleParams R = make_resample_params(cfg, n, jitter_state, p_inject);
     const int per = jitter_state ? 3 : 2;
     const int max_inj = R.max_inject;
@@ -729,9 +740,18 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     if (d) { CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3)); }
     CK(d_inj_f64.ensure(3 * (size_t)std::max(1, max_inj))); CK(d_inj_i32.ensure(2 * (size_t)std::max(1, max_inj)));
     const size_t inj_f64 = 3 * (size_t)max_inj, inj_i32 = 2 * (size_t)max_inj;
-    int rc = ensure_pinned(((size_t)(d ? n : 0) * (1 + per) + inj_f64) * sizeof(double) + inj_i32 * sizeof(int));
-    if (rc) return rc;
-    double* hr = (double*)h_pinned;
+    const size_t stage_bytes = ((size_t)(d ? n : 0) * (1 + per) + inj_f64) * sizeof(double) + inj_i32 * sizeof(int);
+    int rc;
+    double* hr;
+    if (dev_ema) {
+        rc = ensure_pinned_ring(std::max<size_t>(stage_bytes, 64));
+        if (rc) return rc;
+        hr = (double*)pinned_ring_next();
+    } else {
+        rc = ensure_pinned(stage_bytes);
+        if (rc) return rc;
+        hr = (double*)h_pinned;
+    }
     double* hj = hr + (d ? n : 0);
     double* hif = hj + (size_t)(d ? n : 0) * per;
     int* hii = (int*)(hif + inj_f64);
@@ -778,33 +798,34 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
         CK(cudaMemcpyAsync(d_inj_f64.p, hif, inj_f64 * sizeof(double), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_inj_i32.p, hii, inj_i32 * sizeof(int), cudaMemcpyHostToDevice, stream));
     }
+    if (dev_ema) CK(cudaEventRecord(ring_events[ring_pos], stream));
     CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(int), stream));
     const unsigned blocks = grid_for(n, 256);
-    const bool inject_possible = p_inject > 0.0 && max_inj > 0;      // NaN p_inject compares false (MC:492, std::max(0.0, NaN) = 0.0)
+    // NaN p_inject compares false (MC:492, std::max(0.0, NaN) = 0.0); dev_ema: the kernels decide from inj_dev[2]
+    const bool inject_possible = max_inj > 0 && (dev_ema || p_inject > 0.0);
     if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
-        if (d) LAUNCH(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G);
-        else LAUNCH(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G);
-        LAUNCH(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2);
+        if (d) LAUNCH(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G, inj_dev);
+        else LAUNCH(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G, inj_dev);
+        LAUNCH(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2, inj_dev);
         CK(cudaGetLastError());
     }
     if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
-    // the guide table is used whenever the CDF is known to be non-decreasing: finite positive total weight
-    const bool use_guide = guide_built && std::isfinite(last_total) && last_total > 0.0;
+    // the guide table is used whenever the CDF is known to be non-decreasing: finite positive total weight (dev_ema: inj_dev[3])
+    const bool use_guide = guide_built && (dev_ema || (std::isfinite(last_total) && last_total > 0.0));
     const int* guide = use_guide ? d_guide.p : nullptr;
     const int buckets = use_guide ? guide_buckets : 0;
     if (d)
         LAUNCH(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
                d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev);
     else
         LAUNCH(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
                d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev);
     CK(cudaGetLastError());
     int counters[4] = {0, 0, 0, 0};
-    if (defer_sync) CK(cudaMemcpyAsync(h_step->counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
-    else {
+    if (!dev_ema) {
         CK(cudaMemcpyAsync(counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
     }
@@ -812,10 +833,30 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     have_weights = false;
     ++step_counter;
     wsum_known = true; known_wsum = (double)n * (double)R.new_weight;        // every new particle weighs (float)(1/N), MC:524,551
-    if (st) {
+    if (st && !dev_ema) {
         st->injected = counters[0]; st->clamped = counters[1]; st->p_inject = p_inject;
         st->weight_slow = inj_slow; st->weight_fast = inj_fast; st->total_weight = last_total;
     }
+    return MCL_OK;
+}
+
+// The adaptive-injection state has two homes: the host (per-function calls, mcl_get/set_injection_state) and device memory
+// (mcl_step). Whoever advanced it last is the owner; the other side is refreshed on demand.
+int Engine::inj_sync_to_host() {
+    if (!inj_on_device) return MCL_OK;
+    double h[5];
+    CK(cudaMemcpyAsync(h, d_inj.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    inj_slow = h[0]; inj_fast = h[1];
+    inj_on_device = false;
+    return MCL_OK;
+}
+int Engine::inj_sync_to_device() {
+    if (inj_on_device) return MCL_OK;
+    CK(d_inj.ensure(8));
+    const double h[5] = {inj_slow, inj_fast, 0.0, 0.0, last_total};
+    CK(cudaMemcpyAsync(d_inj.p, h, sizeof(h), cudaMemcpyHostToDevice, stream));      // pageable source: staged before the call returns
+    inj_on_device = true;
     return MCL_OK;
 }
 
@@ -861,8 +902,10 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "step: MCL_MODE_REF only (NS filters use mcl_ns_step)");
     if (!map_ready) return fail(MCL_ERR_ARG, "step: no map");
     if (n == 0) return fail(MCL_ERR_ARG, "step: no particles");
-    if (!h_step) { CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars))); CK(cudaEventCreateWithFlags(&ev_total, cudaEventDisableTiming)); }
-    int rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
+    if (!h_step) CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars)));
+    int rc = inj_sync_to_device();
+    if (rc) return rc;
+    rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
     if (rc) return rc;
     if (ranges || slot < 0) {
         if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "step: bad scan");
@@ -871,10 +914,13 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
         if (rc) return rc;
         CK(d_beams.ensure(std::max<size_t>(1, used.size())));
         if (!used.empty()) {
-            rc = ensure_pinned(used.size() * sizeof(RefBeam));
+            // a ring of pinned slots: earlier steps may still be in flight, their scans must not be overwritten
+            rc = ensure_pinned_ring(used.size() * sizeof(RefBeam));
             if (rc) return rc;
-            memcpy(h_pinned, used.data(), used.size() * sizeof(RefBeam));
-            CK(cudaMemcpyAsync(d_beams.p, h_pinned, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+            void* hp = pinned_ring_next();
+            memcpy(hp, used.data(), used.size() * sizeof(RefBeam));
+            CK(cudaMemcpyAsync(d_beams.p, hp, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(ring_events[ring_pos], stream));
         }
         rc = ref_run_update(d_beams.p, (int)used.size(), beams_all, nullptr, true);
     } else {
@@ -882,19 +928,18 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
         rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true);
     }
     if (rc) return rc;
-    rc = ref_resample_front();
+    rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;
-    CK(cudaEventSynchronize(ev_total));                         // the GPU is busy with the CDF meanwhile
-    last_total = h_step->total;
-    wsum_known = true; known_wsum = last_total;
-    mcl_resample_stats local;
-    rc = ref_resample(jitter_state, nullptr, &local, true, true);
-    if (rc) return rc;
-    rc = estimate_enqueue(h_step->pose);
-    if (rc) return rc;
+    if (!pose3 && !st) return MCL_OK;                           // nothing asked for: the tick is queued, the host moves on
+    if (pose3) { rc = estimate_enqueue(h_step->pose); if (rc) return rc; }
+    CK(cudaMemcpyAsync(h_step->counters, d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_step->inj, d_inj.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    local.injected = h_step->counters[0]; local.clamped = h_step->counters[1];
-    if (st) *st = local;
+    last_total = h_step->inj[4];
+    if (st) {
+        st->injected = h_step->counters[0]; st->clamped = h_step->counters[1]; st->p_inject = h_step->inj[2];
+        st->weight_slow = h_step->inj[0]; st->weight_fast = h_step->inj[1]; st->total_weight = h_step->inj[4];
+    }
     if (pose3) {
         pose3[0] = (double)(float)h_step->pose[0]; pose3[1] = (double)(float)h_step->pose[1];
         pose3[2] = (double)std::atan2((float)h_step->pose[2], (float)h_step->pose[3]);      // MC:796 (fp32 atan2)

@@ -52,6 +52,7 @@ public:
     int download_ancestors(int32_t* idx);
     int download_cdf(double* cdf);
     int estimate(double* x, double* y, double* th);
+    int inj_sync_to_host();                 // the adaptive-injection state back on the host (after mcl_step)
     int ref_step(double enc_l, double enc_r, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min,
                  float range_max, int jitter_state, double* pose3, mcl_resample_stats* st);
     int get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
@@ -118,13 +119,15 @@ private:
     int ref_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
                           std::vector<HostBeam>& all, std::vector<RefBeam>& used);
     int ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync = false);
-    int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done = false, bool defer_sync = false);
+    int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done = false, bool dev_ema = false);
+    int inj_sync_to_device();
+    DevBuf<double> d_inj;                   // {weight_slow, weight_fast, p_inject, cdf_is_monotone, total}: adaptive injection on the device (mcl_step)
+    bool inj_on_device = false;             // who advanced the injection state last
     int ref_resample_front();               // normalise + CDF + guide table: needs nothing from the host
     int estimate_enqueue(double* h_sums4);
     // whole-step entry (mcl_step / mcl_step_staged): scalars the host needs travel through this pinned block
-    struct StepScalars { double total; double pose[4]; int counters[4]; };
+    struct StepScalars { double inj[5]; double pose[4]; int counters[4]; };
     StepScalars* h_step = nullptr;
-    cudaEvent_t ev_total = nullptr;
     bool guide_built = false;
     int guide_buckets = 0;
     int ref_fill_ray_lut(const std::vector<HostBeam>& all);

@@ -186,18 +186,22 @@ class ParticleFilter:
         return np.array([x.value, y.value, t.value])
 
     # -- one tick (executeParticleFilter, MC:1084-1092) as a single engine call ----------------------------------
-    def executeParticleFilter(self, enc_left, enc_right, jitter_state, scan=None, slot=None):
+    def executeParticleFilter(self, enc_left, enc_right, jitter_state, scan=None, slot=None, want_result=True):
         """predict + computeWeight + resample + estimate enqueued as one piece (mcl_step / mcl_step_staged): one wait for
-        the GPU instead of three, same results. Returns (pose, stats)."""
-        pose = (C.c_double * 3)()
+        the GPU instead of three, same results. Returns (pose, stats); with want_result=False nothing is read back and the
+        call returns as soon as the tick is queued (None)."""
+        pose = (C.c_double * 3)() if want_result else None
         st = ResampleStats()
+        stp = C.byref(st) if want_result else None
         if slot is not None:
-            self._ck(self.L.mcl_step_staged(self.h, enc_left, enc_right, slot, int(bool(jitter_state)), pose, C.byref(st)))
+            self._ck(self.L.mcl_step_staged(self.h, enc_left, enc_right, slot, int(bool(jitter_state)), pose, stp))
         else:
             r = np.ascontiguousarray(scan["ranges"], dtype=np.float32)
             self._ck(self.L.mcl_step(self.h, enc_left, enc_right, r.ctypes.data_as(_fp), len(r), C.c_float(scan["angle_min"]),
                                      C.c_float(scan["angle_inc"]), C.c_float(scan["range_min"]), C.c_float(scan["range_max"]),
-                                     int(bool(jitter_state)), pose, C.byref(st)))
+                                     int(bool(jitter_state)), pose, stp))
+        if not want_result:
+            return None
         return np.array(pose), dict(injected=st.injected, clamped=st.clamped, p_inject=st.p_inject, weight_slow=st.weight_slow,
                                     weight_fast=st.weight_fast, total_weight=st.total_weight)
 

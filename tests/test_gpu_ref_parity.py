@@ -98,6 +98,14 @@ def test_config1_kidnap_triggers_injection():
     assert injected >= 50 + 200          # the confident cap (MC:479) at step 6 and the lost cap (MC:474) at step 8 were hit
 
 
+def test_guide_table_search_with_injection():
+    """Above 4096 particles the CDF search goes through the guide table (k_ref_guide): same ancestors as std::lower_bound
+    in the oracle, with injections consuming part of the slots, over a kidnap."""
+    injected = run_loop(20_000, 12, seed=6, kidnap_at=5, jitter=[1, 1, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0],
+                        settle_injection_at={4: (6.0, 6.0), 7: (30.0, 30.0)})
+    assert injected > 0
+
+
 @pytest.mark.parametrize("n_beams", [720, 1080])
 def test_more_beams(n_beams):
     run_loop(2000, 6, seed=3, n_beams=n_beams)
@@ -307,3 +315,45 @@ def test_whole_step_call_equals_separate_calls():
         assert np.array_equal(a.downloadParticles(), b.downloadParticles()), step
         assert np.array_equal(a.ancestors(), b.ancestors()), step
     assert np.array_equal(a.injectionState(), b.injectionState())
+
+
+def test_whole_step_calls_queued_without_waiting():
+    """mcl_step with no outputs asked for returns as soon as the tick is queued (the adaptive-injection state advances on
+    the device): several ticks in flight, scans from host memory and from staged slots, then the same state as a twin
+    filter driven tick by tick through the separate calls; the two APIs can be mixed on one filter."""
+    sc = Scenario(8, n_beams=360, seed=5)
+    n = 25013
+    a = m.ParticleFilter(max_particles=n, seed=99)
+    b = m.ParticleFilter(max_particles=n, seed=99)
+    for pf in (a, b):
+        pf.setMap(sc.occ, RES)
+        pf.sampleParticles(n)
+    scans = [dict(s) for s in sc.scans]
+    scans[4]["ranges"] = np.full_like(scans[4]["ranges"], 0.05)          # weights collapse at tick 4: injections follow
+    for i, scan in enumerate(scans):
+        a.stageScan(i, scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+
+    def separate(pf, step, lost):
+        scan = scans[step]
+        pf.diffDriveModel(sc.enc_left[step], sc.enc_right[step])
+        pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        return pf.resampleParticles(lost)
+
+    for step in range(7):
+        lost = step >= 3
+        if step == 2:                                   # one tick through the separate calls in the middle of the queued ones
+            separate(a, step, lost)
+        elif step % 2 == 0:
+            a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, slot=step, want_result=False)
+        else:
+            a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, scan=scans[step], want_result=False)
+        separate(b, step, lost)
+    assert np.array_equal(a.injectionState(), b.injectionState())
+    assert np.array_equal(a.downloadParticles(), b.downloadParticles())
+    assert np.array_equal(a.ancestors(), b.ancestors())
+    # and a last tick that reads its results back
+    pose_a, st_a = a.executeParticleFilter(sc.enc_left[7], sc.enc_right[7], True, slot=7)
+    st_b = separate(b, 7, True)
+    assert st_a == st_b
+    assert np.array_equal(pose_a, b.estimateWeightedPose())
+    assert st_a["injected"] + st_b["injected"] >= 0
