@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                 const float2 dq = (k >= 0) ? S.dq[k] : make_float2(0.f, 0.f);
                 const f32x2 q02 = pk2(q0.x, q0.y), dq2 = pk2(dq.x, dq.y);
                 const f32x2 magic2 = pk2(RU_MAGICF, RU_MAGICF), nmagic2 = pk2(-RU_MAGICF, -RU_MAGICF), mone2 = pk2(-1.0f, -1.0f);
-                uint32_t codes = 0, undecided = 0;
+                uint32_t codes = 0;
 #pragma unroll
                 for (int s = 0; s < (NR ? NR : 16); s++) {                              // MC:372
                     if (!NR && s >= nr) break;
@@ -419,13 +419,12 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                     // a valid particle is inside the map and its rays end inside the border, so the index is in range;
                     // an undecided probe's code is never used (the f64 march takes over if it matters)
                     const uint32_t idx = __float_as_uint(ty) * wp_u + __float_as_uint(tx) + pad_fold;
-                    codes |= (uint32_t)occ_pad[min(idx, pad_last)] << (2 * s);
-                    if (!decided) undecided |= 3u << (2 * s);
+                    const uint32_t code = decided ? (uint32_t)occ_pad[min(idx, pad_last)] : 3u;      // 3 = undecided
+                    codes |= code << (2 * s);
                 }
-                const uint32_t events = codes | undecided;
-                const int first = events ? (__ffs((int)events) - 1) >> 1 : nrr;          // probe index of the first event
+                const int first = codes ? (__ffs((int)codes) - 1) >> 1 : nrr;            // probe index of the first event
                 double term;
-                if (__builtin_expect(first < nrr && ((undecided >> (2 * first)) & 1u), 0)) {
+                if (__builtin_expect(first < nrr && ((codes >> (2 * first)) & 3u) == 3u, 0)) {
                     const double px = S.posx[v], py = S.posy[v];
                     const double2 dir = (k >= 0) ? S.lut[k] : make_double2(0.0, 0.0);
                     double expected = P.max_range;                                       // MC:389
