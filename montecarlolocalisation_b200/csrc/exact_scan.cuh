@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(XS_THREADS) k_xs_tilesum(const float* __restri
             if (base + j < n) {
                 x[j] = __double2float_rn(ddiv((double)x[j], tot));         // MC:497,503
                 w_out[base + j] = x[j];
-                part[base + j].w = x[j];
+                // (the reference also stores it into particles(3,i); that buffer is consumed by the resampling that
+                // follows in the same call and never visible again, so the 4-byte scatter into 16-byte records is skipped)
             }
     }
     double s = 0.0;

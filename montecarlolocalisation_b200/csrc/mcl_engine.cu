@@ -241,7 +241,7 @@ int Engine::ensure_xs(int64_t count) {
 
 // The reference's sequential f64 accumulations, reproduced bit-exactly in parallel (exact_scan.cuh):
 //   normalise == false: *d_total_out = w_0 + w_1 + ... left to right over d_wraw            (MC:675)
-//   normalise == true : w_i <- (float)((double)w_i / total) into d_wn and part.w, then cdf[i]  (MC:496-505)
+//   normalise == true : w_i <- (float)((double)w_i / total) into d_wn, then cdf[i]            (MC:496-505)
 int Engine::exact_accumulate(bool normalise, double* d_total_out) {
     return exact_accumulate_on(normalise ? d_wn.p : d_wraw.p, normalise, normalise, d_total_out);
 }
