@@ -356,7 +356,7 @@ def ours(args):
     roof = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": (kernels[top]["gbs"] / peak) if kernels[top]["gbs"] else None, "traffic": traffic_for(top, n), "peak_source": peak_src,
             "share_of_step": kernels[top]["share"],
-            "note": "k_ref_update_v2 is instruction-issue bound (81% issue slots, ncu), not HBM bound: algorithmic bytes = 20 B/particle + "
+            "note": "k_ref_update_v2 is instruction-issue bound (69% of issue slots, 111M warp-instructions per launch, ncu: profiles/r1_ref_update_v2_ncu.txt), not HBM bound: algorithmic bytes = 20 B/particle + "
                     "one byte per map probe (<= 11 per scored beam); its DRAM traffic is the 16 B/particle particle stream"}
 
     ns = None
