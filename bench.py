@@ -528,7 +528,7 @@ def ns_leg(args, torch, dist, rank, world, local, cells, per_gpu, n_beams, label
                    "field": "%d KiB log-likelihood field, %s" % (field_bytes // 1024, {"smem-f32": "TMA-staged into shared memory", "global-f32": "fp32, gathered through L1/L2",
                                                                        "global-u8": "as one-byte codes (%d KiB) gathered through L1/L2 + shared-memory code table" % (field_bytes // 4096)}[steady_form]),
                    "collectives": "none (1 GPU)" if world == 1 else (
-                       "peer-memory mailboxes, no NCCL on the data path: every shard stores {payload, tag} into the other shards' mailboxes over NVLink (CUDA IPC) and polls its own; four 32-thread kernels on the filter's stream, no host round trip: all-reduce(max), all-gather(Q32 totals) fused with the resampling plan, all-reduce(pose), closing barrier; resampled particles stored into peer shards over NVLink"
+                       "peer-memory mailboxes, no NCCL on the data path: every shard stores {payload, tag} into the other shards' mailboxes over NVLink (CUDA IPC) and polls its own; three 32-thread kernels on the filter's stream, no host round trip: all-reduce(max), all-gather(Q32 totals) + all-reduce(pose) in one exchange fused with the resampling plan, closing barrier; resampled particles stored into peer shards over NVLink"
                        if shard.exchange_used() == "peer" else
                        "engine-enqueued NCCL on the filter's stream, no host round trip: all-reduce(max), all-gather(Q32 totals), all-reduce(pose), closing all-reduce as barrier; resampled particles stored into peer shards over NVLink (CUDA IPC)"),
                    "l2": "per-GPU working set %.0f MB exceeds or displaces L2 between steps" % (per_gpu * 48 / 1e6)},

@@ -208,7 +208,7 @@ int mcl_ns_first_slot(uint64_t offset_q32, uint64_t total_q32, uint64_t n_global
 int mcl_ns_shard_range(int64_t n_global, int32_t world, int32_t rank, int64_t* begin, int64_t* count, int64_t* per_rank);
 /* How mcl_ns_step does the step's collectives (all-reduce of the maximum log-likelihood, all-gather of the Q32 totals,
  * pose all-reduce, closing barrier): 1 = peer-memory mailboxes (each shard stores {payload, tag} straight into the other
- * shards' mailboxes over NVLink and polls its own; four 32-thread kernels, no NCCL on the data path; the default once
+ * shards' mailboxes over NVLink and polls its own; three 32-thread kernels, no NCCL on the data path; the default once
  * every peer's mailbox is mapped, which mcl_comm_init does), 0 = NCCL collectives on the handle's stream, -1 = default.
  * Results are identical. Environment override for the default: MCL_NS_EXCHANGE=nccl|peer.
  * mcl_ns_exchange_used: what the last sharded step used (-1: none yet). */

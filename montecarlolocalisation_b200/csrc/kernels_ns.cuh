@@ -754,8 +754,9 @@ __global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int ra
 // POSTS by storing {payload, tag} into slot [its rank] of every peer's mailbox over NVLink (payload, then a system-scope
 // release store of the tag) and COMPLETES by polling its own mailbox (system-scope acquire loads of local memory) until
 // all `world` slots carry this step's tag. One 32-thread kernel per exchange: lane r talks to shard r. What an NCCL
-// all-reduce(max) + all-gather + all-reduce(sum) + barrier cost in launches and protocol latency becomes four tiny
-// kernels, two of them fused with work the step needs anyway (the resampling plan, the pose reduction).
+// all-reduce(max) + all-gather + all-reduce(sum) + barrier cost in launches and protocol latency becomes three tiny
+// kernels and three synchronisation points: the totals and the pose sums travel in one exchange, fused with the
+// resampling plan the totals determine.
 // Value slots are double-buffered by step parity and a shard cannot start step s+1's exchange before every shard posted
 // step s's closing barrier, so a slot is never overwritten before it is read. Polls are bounded: a shard that never
 // posts makes the others give up after ~20 s and raise the mailbox status instead of hanging the GPU.
@@ -826,26 +827,12 @@ __global__ void k_ns_xchg_max(int* __restrict__ max_bits, NsPeers P, unsigned ta
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (r == 0) *max_bits = v;
 }
-// all-gather of the shards' Q32 totals fused with the resampling plan they determine
-__global__ void k_ns_plan_xchg(const uint64_t* __restrict__ local_total, NsPeers P, unsigned tag, int parity, uint64_t n_global, uint32_t u0,
-                               NsPlan* __restrict__ plan, uint64_t* __restrict__ totals_out) {
-    __shared__ uint64_t s_tot[8];
-    const int r = threadIdx.x;
-    if (r < P.world) {
-        NsMailbox* mine = P.box[P.rank];
-        unsigned long long pay = *local_total;
-        ns_mail_post<1>(&P.box[r]->total[parity][P.rank], &pay, tag);
-        uint64_t t = 0;
-        if (ns_mail_wait<false>(&mine->total[parity][r].tag, tag, &mine->status)) t = ld_relaxed_sys(&mine->total[parity][r].v[0]);
-        s_tot[r] = t;
-        totals_out[r] = t;
-    }
-    __syncwarp();
-    if (r == 0) *plan = ns_make_plan(s_tot, P.world, P.rank, n_global, u0);
-}
+// all-gather of the shards' Q32 totals fused with the resampling plan they determine, and - in the same exchange - the
 // all-reduce(sum) of the five weighted pose sums, added in rank order: the same bits on every shard.
 // pose5[5] receives the mailbox status (0 = every exchange so far completed).
-__global__ void k_ns_pose_xchg(double* __restrict__ pose5, NsPeers P, unsigned tag, int parity) {
+__global__ void k_ns_plan_xchg(const uint64_t* __restrict__ local_total, double* __restrict__ pose5, NsPeers P, unsigned tag, int parity,
+                               uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan, uint64_t* __restrict__ totals_out) {
+    __shared__ uint64_t s_tot[8];
     const int r = threadIdx.x;
     NsMailbox* mine = P.box[P.rank];
     bool ok = true;
@@ -853,11 +840,22 @@ __global__ void k_ns_pose_xchg(double* __restrict__ pose5, NsPeers P, unsigned t
         unsigned long long pay[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) pay[k] = (unsigned long long)__double_as_longlong(pose5[k]);
-        ns_mail_post<5>(&P.box[r]->pose[parity][P.rank], pay, tag);
-        ok = ns_mail_wait<false>(&mine->pose[parity][r].tag, tag, &mine->status);
+        // the pose slot carries its own tag, so the totals' tag (release) is stored last and covers both payloads
+        NsMailSlot* ps = &P.box[r]->pose[parity][P.rank];
+#pragma unroll
+        for (int k = 0; k < 5; k++) st_relaxed_sys(&ps->v[k], pay[k]);
+        unsigned long long tot = *local_total;
+        ns_mail_post<1>(&P.box[r]->total[parity][P.rank], &tot, tag);
+        uint64_t t = 0;
+        ok = ns_mail_wait<false>(&mine->total[parity][r].tag, tag, &mine->status);
+        if (ok) t = ld_relaxed_sys(&mine->total[parity][r].v[0]);
+        s_tot[r] = t;
+        totals_out[r] = t;
     }
     ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();                                                      // lane 0 reads what the other lanes' acquires made visible
     if (r == 0) {
+        *plan = ns_make_plan(s_tot, P.world, P.rank, n_global, u0);
         for (int k = 0; k < 5; k++) {
             double s = 0.0;
             for (int q = 0; q < P.world; q++) s += __longlong_as_double((long long)ld_relaxed_sys(&mine->pose[parity][q].v[k]));

@@ -51,7 +51,7 @@ int Engine::ensure_mailbox() {
     PRELOAD(k_ns_predict);
     for (int kk = 0; kk < 3; ++kk) for (int pp = 0; pp < 3; ++pp) { int rc = ns_preload_update(kk, pp); if (rc) return rc; }
     PRELOAD(k_ns_weights_sum); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_weights_scan1); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
-    PRELOAD(k_ns_pose_partials); PRELOAD(k_ns_pose_reduce); PRELOAD(k_ns_pose_xchg); PRELOAD(k_ns_xchg_barrier);
+    PRELOAD(k_ns_pose_partials); PRELOAD(k_ns_pose_reduce); PRELOAD(k_ns_xchg_barrier);
     PRELOAD(k_ns_resample_bounds); PRELOAD(k_ns_resample);
 #undef PRELOAD
     return MCL_OK;
@@ -597,11 +597,11 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
         LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
                d_partials.p);
         LAUNCH(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
-        if (mail) LAUNCH(K_NS_POSE, k_ns_pose_xchg, 1, 32, 0, d_pose.p, PX, tag, parity);
+        if (mail) {}                                                          // summed over the shards inside k_ns_plan_xchg
         else if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
     }
     const uint32_t u0 = ns_u0();
-    if (mail) LAUNCH(K_NS_PLAN, k_ns_plan_xchg, 1, 32, 0, d_u64.p, PX, tag, parity, (uint64_t)n_global, u0, (NsPlan*)d_plan.p, d_totals.p);
+    if (mail) LAUNCH(K_NS_PLAN, k_ns_plan_xchg, 1, 32, 0, d_u64.p, d_pose.p, PX, tag, parity, (uint64_t)n_global, u0, (NsPlan*)d_plan.p, d_totals.p);
     else LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
     have_weights = true;
     rc = ns_launch_resample(u0);
