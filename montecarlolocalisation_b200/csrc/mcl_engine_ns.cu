@@ -41,7 +41,7 @@ int Engine::ensure_mailbox() {
     CK(cudaMemset(d_mbox.p, 0, sizeof(NsMailbox)));
     // everything mcl_ns_step needs, allocated now: cudaMalloc waits for the device, and a shard whose stream already holds
     // an exchange kernel waiting for its peers must not be waited on by a peer living in the same process
-    CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1)); CK(d_partials.ensure(5 * 512));
+    CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1)); CK(d_partials.ensure(5 * 2048));
     const int64_t max_tiles = (n_global + NS_RS_TILE - 1) / NS_RS_TILE;
     CK(d_bounds.ensure(((size_t)max_tiles + 2) * sizeof(NsTileHead)));
     // ... and every kernel of the step loaded now: with lazy module loading the first launch of a kernel synchronises
@@ -452,8 +452,8 @@ int Engine::ns_end_step() {
 int Engine::ns_pose_partials(double* out5) {
     CK(cudaSetDevice(cfg.device));
     if (n == 0 || !out5) return fail(MCL_ERR_ARG, "pose_partials: no particles");
-    const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
-    CK(d_partials.ensure(5 * 512));
+    const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
+    CK(d_partials.ensure(5 * 2048));
     const bool from_ll = have_weights && !ns_w_in_records;
     LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, from_ll ? (const float*)d_ll.p : (const float*)nullptr, (const int*)d_maxbits.p,
            (float)cfg.ns_temper, d_partials.p);
@@ -592,8 +592,8 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     else if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
     else CK(cudaMemcpyAsync(d_totals.p, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
     {   // the weighted-mean pose (before resampling) is part of every step; it crosses to the host only when pose3 asks
-        const int blocks = (int)std::min<int64_t>(512, grid_for(n, 256));
-        CK(d_partials.ensure(5 * 512));
+        const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
+        CK(d_partials.ensure(5 * 2048));
         LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
                d_partials.p);
         LAUNCH(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);

@@ -283,12 +283,12 @@ def test_nonzero_map_origin():
     assert total_g == total_o and np.array_equal(pf.downloadParticles()[:, 3], Po[:, 3])
 
 
-def test_whole_step_call_equals_separate_calls():
+@pytest.mark.parametrize("n", [1000, 30011])
+def test_whole_step_call_equals_separate_calls(n):
     """mcl_step / mcl_step_staged (one tick enqueued as one piece, the host waiting once) against the four separate calls
     on a twin filter with the same seed: same particles, ancestors, injection state, stats and pose, over steps that
     include injections (lost mode after a weight collapse) and both scan paths."""
-    sc = Scenario(6, n_beams=360, seed=3)
-    n = 30011
+    sc = Scenario(6, n_beams=360, seed=3)          # n = 1000: below the guide-table threshold, one scan tile
     a = m.ParticleFilter(max_particles=n, seed=77)
     b = m.ParticleFilter(max_particles=n, seed=77)
     for pf in (a, b):
