@@ -759,7 +759,8 @@ __global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int ra
 // resampling plan the totals determine.
 // Value slots are double-buffered by step parity and a shard cannot start step s+1's exchange before every shard posted
 // step s's closing barrier, so a slot is never overwritten before it is read. Polls are bounded: a shard that never
-// posts makes the others give up after ~20 s and raise the mailbox status instead of hanging the GPU.
+// posts makes the others give up after 30 s (MCL_NS_EXCHANGE_TIMEOUT_S; 0 = wait for ever) and raise the mailbox status
+// instead of hanging the GPU.
 struct NsMailSlot {
     unsigned long long v[5];
     unsigned tag, pad[5];
@@ -774,6 +775,7 @@ struct NsMailbox {
 struct NsPeers {
     NsMailbox* box[8];              // box[rank] = this shard's own mailbox
     int world, rank;
+    unsigned long long timeout_ns;  // a poll gives up after this long (0: never)
 };
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -794,7 +796,6 @@ __device__ __forceinline__ unsigned long long ns_globaltimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-constexpr unsigned long long NS_MAIL_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 template <int WORDS>
 __device__ __forceinline__ void ns_mail_post(NsMailSlot* slot_on_peer, const unsigned long long* payload, unsigned tag) {
 #pragma unroll
@@ -803,12 +804,12 @@ __device__ __forceinline__ void ns_mail_post(NsMailSlot* slot_on_peer, const uns
 }
 // wait until *flag reaches `tag` (AT_LEAST: monotonic barrier tags, compared modulo 2^32; else equality)
 template <bool AT_LEAST>
-__device__ __forceinline__ bool ns_mail_wait(const unsigned* flag, unsigned tag, int* status) {
+__device__ __forceinline__ bool ns_mail_wait(const unsigned* flag, unsigned tag, int* status, unsigned long long timeout_ns) {
     const unsigned long long t0 = ns_globaltimer();
     for (unsigned spins = 0;; ++spins) {
         const unsigned seen = ld_acquire_sys(flag);
         if (AT_LEAST ? (int)(seen - tag) >= 0 : seen == tag) return true;
-        if ((spins & 1023u) == 1023u && ns_globaltimer() - t0 > NS_MAIL_TIMEOUT_NS) { atomicExch(status, 1); return false; }
+        if (timeout_ns && (spins & 1023u) == 1023u && ns_globaltimer() - t0 > timeout_ns) { atomicExch(status, 1); return false; }
         __nanosleep(32);
     }
 }
@@ -821,7 +822,7 @@ __global__ void k_ns_xchg_max(int* __restrict__ max_bits, NsPeers P, unsigned ta
         NsMailbox* mine = P.box[P.rank];
         unsigned long long pay = (unsigned long long)(unsigned)(*max_bits);
         ns_mail_post<1>(&P.box[r]->max_ll[parity][P.rank], &pay, tag);
-        if (ns_mail_wait<false>(&mine->max_ll[parity][r].tag, tag, &mine->status)) v = (int)(unsigned)ld_relaxed_sys(&mine->max_ll[parity][r].v[0]);
+        if (ns_mail_wait<false>(&mine->max_ll[parity][r].tag, tag, &mine->status, P.timeout_ns)) v = (int)(unsigned)ld_relaxed_sys(&mine->max_ll[parity][r].v[0]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -847,7 +848,7 @@ __global__ void k_ns_plan_xchg(const uint64_t* __restrict__ local_total, double*
         unsigned long long tot = *local_total;
         ns_mail_post<1>(&P.box[r]->total[parity][P.rank], &tot, tag);
         uint64_t t = 0;
-        ok = ns_mail_wait<false>(&mine->total[parity][r].tag, tag, &mine->status);
+        ok = ns_mail_wait<false>(&mine->total[parity][r].tag, tag, &mine->status, P.timeout_ns);
         if (ok) t = ld_relaxed_sys(&mine->total[parity][r].v[0]);
         s_tot[r] = t;
         totals_out[r] = t;
@@ -871,7 +872,7 @@ __global__ void k_ns_xchg_barrier(NsPeers P, unsigned tag) {
         NsMailbox* mine = P.box[P.rank];
         __threadfence_system();
         st_release_sys(&P.box[r]->barrier[P.rank], tag);
-        ns_mail_wait<true>(&mine->barrier[r], tag, &mine->status);
+        ns_mail_wait<true>(&mine->barrier[r], tag, &mine->status, P.timeout_ns);
     }
 }
 

@@ -552,6 +552,8 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (shard_world > 1 && !mail && !comm) return fail(MCL_ERR_COMM, "ns_step: sharded filter without a communicator (mcl_comm_init)");
     NsPeers PX;
     PX.world = shard_world; PX.rank = shard_rank;
+    static const double env_timeout_s = [] { const char* e = getenv("MCL_NS_EXCHANGE_TIMEOUT_S"); return e ? atof(e) : 30.0; }();
+    PX.timeout_ns = env_timeout_s > 0 ? (unsigned long long)(env_timeout_s * 1e9) : 0ull;
     for (int r = 0; r < 8; ++r) PX.box[r] = r >= shard_world ? nullptr : r == shard_rank ? (NsMailbox*)d_mbox.p : (NsMailbox*)peer_ptr[3][r];
     const unsigned tag = mail ? ++xchg_seq : 0u;
     const int parity = (int)(tag & 1u);
