@@ -26,6 +26,8 @@ int main() {
         double confident_level = pf.isLocalizationLost_densitiy_cluster(0.6);
         mcl::ParticleFilter::PoseMsg cell = mcl::ParticleFilter::poseMsg(p.x, p.y, p.theta);
         std::vector<double> poses = pf.poseArray(10);
+        mcl::RobotPosition q = pf.executeParticleFilter(0.6, 0.6, s, true);          // the whole tick as one engine call
+        if (!(q.x == q.x) || pf.lastResampleStats().total_weight < 0) return 5;
         if (poses.size() != 4 * 150 || cell.row < -1 || confident_level < 0 || confident_level > 1) return 4;
         printf("gpu ok: injected %d pose %.3f %.3f %.3f confidence %.3f best %.3f %.3f\n", injected, p.x, p.y, p.theta, confident_level, pf.x_best, pf.y_best);
         return 0;
