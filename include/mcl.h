@@ -210,7 +210,11 @@ int mcl_ns_shard_range(int64_t n_global, int32_t world, int32_t rank, int64_t* b
  * pose all-reduce, closing barrier): 1 = peer-memory mailboxes (each shard stores {payload, tag} straight into the other
  * shards' mailboxes over NVLink and polls its own; three 32-thread kernels, no NCCL on the data path; the default once
  * every peer's mailbox is mapped, which mcl_comm_init does), 0 = NCCL collectives on the handle's stream, -1 = default.
- * Results are identical. Environment override for the default: MCL_NS_EXCHANGE=nccl|peer.
+ * Results are identical. Environment override for the default: MCL_NS_EXCHANGE=nccl|peer. Mode 1 expects the shards'
+ * streams to make progress independently: one process per GPU (the intended deployment), or in one process at most as many
+ * shards as the device has hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) and scans parked with
+ * mcl_scan_stage so that enqueueing a step never waits for the device. Polls give up after MCL_NS_EXCHANGE_TIMEOUT_S
+ * seconds (30; 0 = never) with MCL_ERR_COMM.
  * mcl_ns_exchange_used: what the last sharded step used (-1: none yet). */
 int mcl_ns_set_exchange(mcl_handle* h, int32_t mode);
 int mcl_ns_exchange_used(mcl_handle* h);
