@@ -923,23 +923,45 @@ struct NsTileHead {
     int pad;
 };
 
+// first i in [lo, hi) with prefix[i] > v, else hi, by a whole warp: 32 evenly spaced probes per round (the prefix is
+// non-decreasing, so their ballot is a prefix mask and its population count selects the sub-range): log32 instead of
+// log2 dependent loads
+__device__ __forceinline__ int64_t ns_search_warp(const uint64_t* __restrict__ prefix, uint64_t v, int64_t lo, int64_t hi, int lane) {
+    int64_t len = hi - lo;
+    while (len > 0) {
+        if (len <= 32) {
+            const bool below = lane < len && !(prefix[lo + lane] > v);
+            lo += __popc(__ballot_sync(0xffffffffu, below));
+            break;
+        }
+        const int64_t step = len >> 5;
+        const int c = __popc(__ballot_sync(0xffffffffu, !(prefix[lo + (lane + 1) * step - 1] > v)));
+        lo += c * step;
+        len = c < 32 ? step - 1 : len - 32 * step;
+    }
+    return lo;
+}
 // pass 1 (merge-path partition): head[t] = threshold and ancestor of the first slot of output tile t (t = 0 .. tiles;
-// the last entry describes the last slot instead)
+// the last entry describes the last slot instead). One warp per tile head.
 __global__ void __launch_bounds__(256) k_ns_resample_bounds(const uint64_t* __restrict__ prefix, int64_t n_local, const NsPlan* __restrict__ plan,
                                                             uint64_t n_global, uint32_t u0, NsTileHead* __restrict__ head) {
     const NsPlan P = *plan;
     const int64_t tiles = (P.k_hi - P.k_lo + NS_RS_TILE - 1) / NS_RS_TILE;
     if (tiles <= 0) return;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= tiles; t += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t <= tiles; t += warps) {
         int64_t k = P.k_lo + t * NS_RS_TILE;
         if (k >= P.k_hi) k = P.k_hi - 1;
         const NsThr th = ns_thr_of((uint64_t)k, u0, P.total, n_global);
         // by the plan thr >= offset for every slot of this shard; a smaller one would select the first particle
-        int64_t i = th.q >= P.offset ? ns_search_global(prefix, th.q - P.offset, 0, n_local) : 0;
+        int64_t i = th.q >= P.offset ? ns_search_warp(prefix, th.q - P.offset, 0, n_local, lane) : 0;
         if (i >= n_local) i = n_local - 1;
-        NsTileHead h;
-        h.q = th.q; h.r = th.r; h.i_lo = (int)i; h.pad = 0;
-        head[t] = h;
+        if (lane == 0) {
+            NsTileHead h;
+            h.q = th.q; h.r = th.r; h.i_lo = (int)i; h.pad = 0;
+            head[t] = h;
+        }
     }
 }
 // pass 2: every tile of NS_RS_TILE consecutive output slots stages the prefix range its ancestors lie in (coalesced).

@@ -431,7 +431,7 @@ int Engine::ns_launch_resample(uint32_t u0) {
     CK(d_bounds.ensure(((size_t)max_tiles + 2) * sizeof(NsTileHead)));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-    const int g1 = (int)std::min<int64_t>((max_tiles + 1 + 255) / 256, (int64_t)sms * 8);
+    const int g1 = (int)std::min<int64_t>((max_tiles + 1 + 7) / 8, (int64_t)sms * 8);            // one warp per tile head, 8 per CTA
     LAUNCH(K_NS_BOUNDS, k_ns_resample_bounds, g1, 256, 0, d_prefix.p, n, (const NsPlan*)d_plan.p, (uint64_t)n_global, u0, (NsTileHead*)d_bounds.p);
     int occ = 8;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_resample, NS_RS_THREADS, 0));
