@@ -617,27 +617,44 @@ __device__ __forceinline__ float ref_wrap_theta(double t) {
 // Guide table for the CDF search: guide[b] = std::lower_bound(cdf, b / buckets) for b = 0..buckets (buckets a power of two, so
 // b / buckets and floor(r * buckets) are exact). lower_bound is monotone in its argument, hence for r in [b, b+1) / buckets
 // the answer lies in [guide[b], guide[b+1]]: each particle's search shrinks from log2(N) dependent loads to one guide load
-// plus log2(N / buckets) on a few neighbouring lines. Valid when the CDF is non-decreasing, i.e. the total weight is finite
-// and positive (the host knows it); otherwise (NaN CDF, MC:492/530) the full-range search reproduces std::lower_bound's walk.
-// One warp per bucket edge, 32-ary search (4-5 dependent loads instead of log2 N): the predicate is monotone here, so
-// the ballot of 32 evenly spaced probes is a prefix mask and its population count selects the sub-range.
+// plus log2(N / buckets) = 3 probes on neighbouring lines (the search is bound by L2 sector traffic: 32 B per 8-byte probe).
+// Valid when the CDF is non-decreasing, i.e. the total weight is finite and positive; otherwise (NaN CDF, MC:492/530) the
+// full-range search reproduces std::lower_bound's walk.
+// Built by scattering, one coalesced pass over the CDF: element i is the answer for exactly the bucket edges b / buckets in
+// (cdf[i-1], cdf[i]], i.e. b = floor(cdf[i-1] * buckets) + 1 .. floor(cdf[i] * buckets) (exact: power-of-two scaling);
+// edges beyond cdf[n-1] get n. Elements owning more than four edges (a particle holding a large share of the weight) are
+// written by their whole warp.
+__device__ __forceinline__ int ref_guide_floor(double c, double B, int buckets) {
+    const double x = c * B;
+    return !(x >= 0.0) ? -1 : (x >= B ? buckets : (int)x);           // NaN owns nothing
+}
 __global__ void __launch_bounds__(256) k_ref_guide(const double* __restrict__ cdf, int64_t n, int buckets, int* __restrict__ guide) {
-    const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (b > buckets) return;                                          // whole warps leave together
-    const double t = (double)b / (double)buckets;
-    int64_t lo = 0, len = n;                                          // the answer lies in [lo, lo + len]
-    while (len > 0) {
-        if (len <= 32) {
-            const bool below = lane < len && cdf[lo + lane] < t;
-            lo += __popc(__ballot_sync(0xffffffffu, below));
-            break;
-        }
-        const int64_t step = len >> 5;
-        const int c = __popc(__ballot_sync(0xffffffffu, cdf[lo + (lane + 1) * step - 1] < t));
-        lo += c * step;
-        len = c < 32 ? step - 1 : len - 32 * step;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const double B = (double)buckets;
+    int lo_b = 0, hi_b = -1, tail_lo = 0, tail_hi = -1;               // inclusive bucket-edge ranges
+    if (i < n) {
+        hi_b = ref_guide_floor(cdf[i], B, buckets);
+        lo_b = i == 0 ? 0 : ref_guide_floor(cdf[i - 1], B, buckets) + 1;
+        if (i == n - 1) { tail_lo = hi_b + 1; tail_hi = buckets; }
     }
-    if (lane == 0) guide[b] = (int)lo;
+    const int cnt = hi_b - lo_b + 1;
+    if (cnt > 0 && cnt <= 4)
+        for (int b = lo_b; b <= hi_b; b++) guide[b] = (int)i;
+    unsigned wide = __ballot_sync(0xffffffffu, cnt > 4);
+    while (wide) {
+        const int src = __ffs((int)wide) - 1;
+        wide &= wide - 1;
+        const int L = __shfl_sync(0xffffffffu, lo_b, src), H = __shfl_sync(0xffffffffu, hi_b, src);
+        const int v = __shfl_sync(0xffffffffu, (int)i, src);
+        for (int b = L + lane; b <= H; b += 32) guide[b] = v;
+    }
+    const unsigned has_tail = __ballot_sync(0xffffffffu, tail_hi >= tail_lo);
+    if (has_tail) {
+        const int src = __ffs((int)has_tail) - 1;
+        const int L = __shfl_sync(0xffffffffu, tail_lo, src), H = __shfl_sync(0xffffffffu, tail_hi, src);
+        for (int b = L + lane; b <= H; b += 32) guide[b] = (int)n;
+    }
 }
 
 template <bool GEN>

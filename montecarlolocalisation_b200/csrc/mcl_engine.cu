@@ -705,9 +705,9 @@ int Engine::ref_resample_front() {
     guide_built = false;
     if (n >= 4096 && !force_sequential) {
         int buckets = 1024;
-        while ((int64_t)buckets * 64 < n && buckets < (1 << 20)) buckets <<= 1;
+        while ((int64_t)buckets * 8 < n && buckets < (1 << 24)) buckets <<= 1;          // ~8 CDF entries per bucket: 3 probes
         CK(d_guide.ensure((size_t)buckets + 2));
-        LAUNCH(K_GUIDE, k_ref_guide, grid_for((int64_t)(buckets + 1) * 32, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
+        LAUNCH(K_GUIDE, k_ref_guide, grid_for(n, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
         guide_built = true; guide_buckets = buckets;
     }
     return MCL_OK;
