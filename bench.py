@@ -381,7 +381,8 @@ def ours(args):
                                                 api="four calls per tick: mcl_predict_encoders, mcl_update[_staged], mcl_resample, mcl_estimate" if args.separate_calls
                                                 else "one call per tick: mcl_step_staged (value) / mcl_step (e2e)"),
             "steps_per_s": world * K / t_res,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": scan_bytes, "d2h_bytes_per_step": 24 + 8 + 48,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": scan_bytes, "d2h_bytes_per_step": 24 + 8 + 48 if args.separate_calls else 88,      # mcl_step: the 88-byte tick report (pose sums, injection
+                    # state, counters), stored by the last kernel straight into the caller's pinned block
                     "ms_per_step": 1e3 * t_e2e / K, "wall_ms_per_step": 1e3 * wall_e2e / K},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -545,6 +545,7 @@ struct RefResampleParams {
     float new_weight;      // (float)(1.0/N) (MC:524,551)
     // sampleParticles constants (MC:396-403, 431-432, 442-443)
     double cell_meters, half_cell, init_a, init_w, yaw_a, yaw_w, init_shift;
+    uint32_t inj_rows, inj_cols;   // coarse-cell counts the injected particle's row / col draws are reduced to (MC:423-424)
 };
 
 // Production draws: the u_r / u_jitter streams come from Philox4x32-10, counter = (2i | 2i+1, stream 0x30, step):
@@ -555,12 +556,18 @@ struct RefDrawGen { uint32_t step, k0, k1; };
 __device__ __forceinline__ void ref_philox_draws(uint64_t counter, const RefDrawGen& G, uint32_t (&o)[4]) {
     Philox::gen((uint32_t)counter, (uint32_t)(counter >> 32), 0x30u, G.step, G.k0, G.k1, o);
 }
+// The named draws of an injected particle (sampleParticles(1), MC:434-446): stream 0x31 of the same generator.
+__device__ __forceinline__ void ref_philox_inject_draws(uint64_t counter, const RefDrawGen& G, uint32_t (&o)[4]) {
+    Philox::gen((uint32_t)counter, (uint32_t)(counter >> 32), 0x31u, G.step, G.k0, G.k1, o);
+}
 
 // flags[i] = (u_r[i] < p_inject); block_counts[b] = number of flags in block b.
 // Adaptive injection (MC:469-492) on the device, for mcl_step: the same IEEE operations in the same order as the host
 // form in Engine::ref_resample, so both give the same bits. inj = {weight_slow, weight_fast, p_inject, cdf_is_monotone}.
-__global__ void k_ref_ema(const double* __restrict__ total, double n, double a_slow, double a_fast, double* __restrict__ inj) {
+__global__ void k_ref_ema(const double* __restrict__ total, double n, double a_slow, double a_fast, double* __restrict__ inj,
+                          int* __restrict__ counters /* [0] injected, [1] clamped, [2] flagged, [3]: cleared for the resampling that follows */) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
     const double t = *total;
     const double avg = ddiv(t, n);
     const double slow = dadd(inj[0], dmul(a_slow, dsub(avg, inj[0])));
@@ -698,12 +705,25 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
     if (!live) return;
     float4 o;
     if (flag && rank < R.max_inject) {
-        // sampleParticles(1) with named draws (MC:434-446)
-        double orientation = dadd(dmul(inj_u_yaw[rank], R.yaw_w), R.yaw_a);
-        double x_move = dadd(dmul(inj_u_dx[rank], R.init_w), R.init_a);
-        double y_move = dadd(dmul(inj_u_dy[rank], R.init_w), R.init_a);
-        double base_x = dadd(dmul((double)inj_col[rank], R.cell_meters), R.half_cell);
-        double base_y = dadd(dmul((double)inj_row[rank], R.cell_meters), R.half_cell);
+        // sampleParticles(1) with named draws (MC:434-446). Production draws (GEN): injection slot `rank` takes Philox
+        // counters 2*rank, 2*rank+1 of stream 0x31: u_yaw = c53(A.0,A.1), u_dx = c53(A.2,A.3), u_dy = c53(B.0,B.1),
+        // row = B.2 mod rows, col = B.3 mod cols.
+        double u_yaw, u_dx, u_dy;
+        int row, col;
+        if (GEN) {
+            uint32_t a[4], b[4];
+            ref_philox_inject_draws(2 * (uint64_t)rank, G, a); ref_philox_inject_draws(2 * (uint64_t)rank + 1, G, b);
+            u_yaw = canonical53(a[0], a[1]); u_dx = canonical53(a[2], a[3]); u_dy = canonical53(b[0], b[1]);
+            row = (int)(b[2] % R.inj_rows); col = (int)(b[3] % R.inj_cols);
+        } else {
+            u_yaw = inj_u_yaw[rank]; u_dx = inj_u_dx[rank]; u_dy = inj_u_dy[rank];
+            row = inj_row[rank]; col = inj_col[rank];
+        }
+        double orientation = dadd(dmul(u_yaw, R.yaw_w), R.yaw_a);
+        double x_move = dadd(dmul(u_dx, R.init_w), R.init_a);
+        double y_move = dadd(dmul(u_dy, R.init_w), R.init_a);
+        double base_x = dadd(dmul((double)col, R.cell_meters), R.half_cell);
+        double base_y = dadd(dmul((double)row, R.cell_meters), R.half_cell);
         o.x = __double2float_rn(dadd(dadd(base_x, x_move), R.init_shift));
         o.y = __double2float_rn(dadd(dadd(base_y, y_move), R.init_shift));
         o.z = __double2float_rn(orientation);
@@ -820,9 +840,14 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n_par
 }
 // weight_sum by value (known on the host after update / resample / init, else from k_pose_wsum + k_reduce_partials). The last
 // block to finish adds the per-block partials in block order (deterministic) and leaves the four sums in out4.
+// report (mcl_step): the tick's scalar results, written by the last block straight into the caller's pinned host block
+// (zero-copy; visible to the host once the stream has drained), so a tick ends without any device-to-host copy command:
+// the four pose sums, the adaptive-injection state k_ref_ema left and the resampling counters.
+// (struct RefStepReport: mcl_engine.hpp)
 __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum_dev, double wsum_host,
                                                    double* __restrict__ partials /* [grid][4] */, unsigned* __restrict__ ticket,
-                                                   double* __restrict__ out4) {
+                                                   double* __restrict__ out4, RefStepReport* __restrict__ report /* null: none */,
+                                                   const double* __restrict__ inj5, const int* __restrict__ counters4) {
     __shared__ double ws[8][4];
     __shared__ bool last;
     const float weight_sum = __double2float_rn(wsum_dev ? *wsum_dev : wsum_host);
@@ -856,7 +881,11 @@ __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ pa
             double s = 0;
             for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 4 + o);
             s = warp_sum(s);
-            if (lane == 0) out4[o] = s;
+            if (lane == 0) { out4[o] = s; if (report) report->pose[o] = s; }
+        } else if (report) {
+            const int k = threadIdx.x - 128;
+            if (k < 5) report->inj[k] = inj5[k];
+            else if (k < 9) report->counters[k - 5] = counters4[k - 5];
         }
         if (threadIdx.x == 0) *ticket = 0;
     }

@@ -317,6 +317,7 @@ static RefResampleParams make_resample_params(const mcl_config& c, int64_t n, in
     R.init_a = -c.init_offset; R.init_w = c.init_offset - (-c.init_offset);
     R.yaw_a = -M_PI; R.yaw_w = M_PI - (-M_PI);
     R.init_shift = c.init_shift;
+    R.inj_rows = 1; R.inj_cols = 1;       // set by the caller from the map (MC:423-424)
     return R;
 }
 
@@ -722,7 +723,7 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const double a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
     double p_inject = 0.0;
     if (dev_ema) {
-        LAUNCH(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p);
+        LAUNCH(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p, d_counters.p);    // also clears the counters
     } else {
         int rc0 = inj_sync_to_host();
         if (rc0) return rc0;
@@ -734,29 +735,31 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     }
     const double* inj_dev = dev_ema ? (const double*)d_inj.p : (const double*)nullptr;
     RefResampleParams R = make_resample_params(cfg, n, jitter_state, p_inject);
+    R.inj_cols = (uint32_t)std::max(1, (int)((unsigned)map_w / (unsigned)cfg.cell_size_px));
+    R.inj_rows = (uint32_t)std::max(1, (int)((unsigned)map_h / (unsigned)cfg.cell_size_px));
     const int per = jitter_state ? 3 : 2;
     const int max_inj = R.max_inject;
-    // stage draws
-    if (d) { CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3)); }
+    // stage draws. Without injected draws nothing crosses: the kernels generate u_r / u_jitter (stream 0x30) and the named
+    // draws of injected particles (stream 0x31) from the engine's Philox generator themselves.
     CK(d_inj_f64.ensure(3 * (size_t)std::max(1, max_inj))); CK(d_inj_i32.ensure(2 * (size_t)std::max(1, max_inj)));
-    const size_t inj_f64 = 3 * (size_t)max_inj, inj_i32 = 2 * (size_t)max_inj;
-    const size_t stage_bytes = ((size_t)(d ? n : 0) * (1 + per) + inj_f64) * sizeof(double) + inj_i32 * sizeof(int);
     int rc;
-    double* hr;
-    if (dev_ema) {
-        rc = ensure_pinned_ring(std::max<size_t>(stage_bytes, 64));
-        if (rc) return rc;
-        hr = (double*)pinned_ring_next();
-    } else {
-        rc = ensure_pinned(stage_bytes);
-        if (rc) return rc;
-        hr = (double*)h_pinned;
-    }
-    double* hj = hr + (d ? n : 0);
-    double* hif = hj + (size_t)(d ? n : 0) * per;
-    int* hii = (int*)(hif + inj_f64);
-    const int n_cols = (int)((unsigned)map_w / (unsigned)cfg.cell_size_px), n_rows = (int)((unsigned)map_h / (unsigned)cfg.cell_size_px);
     if (d) {
+        CK(d_u_r.ensure((size_t)n)); CK(d_u_jit.ensure((size_t)n * 3));
+        const size_t inj_f64 = 3 * (size_t)max_inj, inj_i32 = 2 * (size_t)max_inj;
+        const size_t stage_bytes = ((size_t)n * (1 + per) + inj_f64) * sizeof(double) + inj_i32 * sizeof(int);
+        double* hr;
+        if (dev_ema) {
+            rc = ensure_pinned_ring(std::max<size_t>(stage_bytes, 64));
+            if (rc) return rc;
+            hr = (double*)pinned_ring_next();
+        } else {
+            rc = ensure_pinned(stage_bytes);
+            if (rc) return rc;
+            hr = (double*)h_pinned;
+        }
+        double* hj = hr + n;
+        double* hif = hj + (size_t)n * per;
+        int* hii = (int*)(hif + inj_f64);
         if (!d->u_r || !d->u_jitter) return fail(MCL_ERR_ARG, "resample: null draw array");
         if (d->n_jitter < (int64_t)n * per) return fail(MCL_ERR_ARG, "resample: u_jitter shorter than N*(2|3)");
         memcpy(hr, d->u_r, (size_t)n * sizeof(double));
@@ -772,34 +775,19 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
             hii[i] = ok ? d->inject.row[i] : 0;
             hii[max_inj + i] = ok ? d->inject.col[i] : 0;
         }
-    } else {
-        // u_r / u_jitter come from the device Philox stream (k_fill_resample_draws); only the <= max_inj named
-        // injection draws are made on the host
-        for (int i = 0; i < max_inj; ++i) {
-            uint32_t a[4], b[4];
-            philox_host(0x31, 2 * (uint64_t)i, a); philox_host(0x31, 2 * (uint64_t)i + 1, b);
-            hif[i] = canonical53(a[0], a[1]);
-            hif[max_inj + i] = canonical53(a[2], a[3]);
-            hif[2 * max_inj + i] = canonical53(b[0], b[1]);
-            hii[i] = (int)(b[2] % (uint32_t)std::max(1, n_rows));
-            hii[max_inj + i] = (int)(b[3] % (uint32_t)std::max(1, n_cols));
-        }
-    }
-    last_per = per;
-    if (d) {
         CK(cudaMemcpyAsync(d_u_r.p, hr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_u_jit.p, hj, (size_t)n * per * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (max_inj > 0) {
+            CK(cudaMemcpyAsync(d_inj_f64.p, hif, inj_f64 * sizeof(double), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(d_inj_i32.p, hii, inj_i32 * sizeof(int), cudaMemcpyHostToDevice, stream));
+        }
+        if (dev_ema) CK(cudaEventRecord(ring_events[ring_pos], stream));
     }
-    // no injected draws: the kernels generate the Philox streams themselves (k_fill_resample_draws materialises them on request)
+    last_per = per;
     draws_generated = d == nullptr;
     draws_step = (uint32_t)step_counter;
     const RefDrawGen G{(uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)};
-    if (max_inj > 0) {
-        CK(cudaMemcpyAsync(d_inj_f64.p, hif, inj_f64 * sizeof(double), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_inj_i32.p, hii, inj_i32 * sizeof(int), cudaMemcpyHostToDevice, stream));
-    }
-    if (dev_ema) CK(cudaEventRecord(ring_events[ring_pos], stream));
-    CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(int), stream));
+    if (!dev_ema) CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(int), stream));
     const unsigned blocks = grid_for(n, 256);
     // NaN p_inject compares false (MC:492, std::max(0.0, NaN) = 0.0); dev_ema: the kernels decide from inj_dev[2]
     const bool inject_possible = max_inj > 0 && (dev_ema || p_inject > 0.0);
@@ -861,7 +849,9 @@ int Engine::inj_sync_to_device() {
 }
 
 // ---- estimate -----------------------------------------------------------------------------------------------------
-int Engine::estimate_enqueue(double* h_sums4) {
+// h_sums4: where the four sums are copied to; step_report (mcl_step, pinned host block): the sums, the injection state and
+// the resampling counters are written there by the kernel itself instead (no copy command).
+int Engine::estimate_enqueue(double* h_sums4, RefStepReport* step_report) {
     { int rc = ns_materialise_weights(); if (rc) return rc; }
     const int blocks = (int)std::min<int64_t>(1024, grid_for(n, 256));
     CK(d_partials.ensure(4 * 1024));
@@ -871,9 +861,10 @@ int Engine::estimate_enqueue(double* h_sums4) {
         LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
         wsum_dev = d_scalars.p + 1;
     }
-    LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2);
+    LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2,
+           step_report, (const double*)d_inj.p, (const int*)d_counters.p);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (h_sums4) CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return MCL_OK;
 }
 
@@ -930,11 +921,10 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     if (rc) return rc;
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;
-    rc = estimate_enqueue(h_step->pose);                        // the estimate is part of every tick (its sums reach the pinned block)
+    // the estimate is part of every tick; its last block writes the tick's scalars straight into the pinned block
+    rc = estimate_enqueue(nullptr, h_step);
     if (rc) return rc;
     if (!pose3 && !st) return MCL_OK;                           // nothing asked for: the tick is queued, the host moves on
-    CK(cudaMemcpyAsync(h_step->counters, d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_step->inj, d_inj.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     last_total = h_step->inj[4];
     if (st) {

@@ -28,6 +28,9 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// The scalar results of one mcl_step tick, in pinned host memory; k_pose_sums' last block writes them there itself.
+struct RefStepReport { double inj[5]; double pose[4]; int counters[4]; };
+
 class Engine {
 public:
     explicit Engine(const mcl_config& cfg);
@@ -124,9 +127,9 @@ private:
     DevBuf<double> d_inj;                   // {weight_slow, weight_fast, p_inject, cdf_is_monotone, total}: adaptive injection on the device (mcl_step)
     bool inj_on_device = false;             // who advanced the injection state last
     int ref_resample_front();               // normalise + CDF + guide table: needs nothing from the host
-    int estimate_enqueue(double* h_sums4);
+    int estimate_enqueue(double* h_sums4, RefStepReport* step_report = nullptr);
     // whole-step entry (mcl_step / mcl_step_staged): scalars the host needs travel through this pinned block
-    struct StepScalars { double inj[5]; double pose[4]; int counters[4]; };
+    typedef RefStepReport StepScalars;      // {inj[5], pose[4], counters[4]}: pinned, written by k_pose_sums (zero-copy)
     StepScalars* h_step = nullptr;
     bool guide_built = false;
     int guide_buckets = 0;

@@ -2,13 +2,14 @@
 vectors. Bar (BASELINE.json north_star): resampled indices and counts bit-exact; poses and weights within 1e-5
 relative. In practice every stage below is required to be bit-identical to the oracle, except theta after
 atan2(sin,cos) and the pose estimate, which go through device libm (<= 1 fp32 ulp / 1e-5)."""
+import ctypes as C
 import os
 
 import numpy as np
 import pytest
 
 import montecarlolocalisation_b200 as m
-from oracle.pyoracle import Oracle, Scan
+from oracle.pyoracle import Oracle, Scan, oracle_lib
 from scenario import RES, Scenario, load_map
 
 pytestmark = pytest.mark.gpu
@@ -201,6 +202,53 @@ def test_philox_production_draws_run():
         P = pf.downloadParticles()
         idx = pf.ancestors()
         assert np.isfinite(P).all() and idx.min() >= -1 and idx.max() < 5000
+
+
+def _philox(c0, c2, c3, seed):
+    out = (C.c_uint32 * 4)()
+    oracle_lib().ons_philox(C.c_uint32(c0), C.c_uint32(0), C.c_uint32(c2), C.c_uint32(c3), C.c_uint32(seed & 0xffffffff), C.c_uint32(seed >> 32), out)
+    return [int(v) for v in out]
+
+
+def _c53(hi, lo):
+    return float(((hi << 32) | lo) >> 11) * 2.0 ** -53
+
+
+@pytest.mark.parametrize("whole_step", [False, True])
+def test_philox_injected_particles_are_sample_particles_of_the_named_draws(whole_step):
+    """Production draws: an injected particle is sampleParticles(1) (MC:434-446) of the named draws the resampling kernel
+    takes from Philox stream 0x31, counters 2*rank / 2*rank+1 at the tick's step number (rank = how many slots were
+    injected before this one). Checked bit for bit against the oracle's sampleParticles fed with the same words generated
+    on the CPU, through the per-function calls and through the whole-tick call."""
+    seed, n = 0x123456789, 20011
+    sc = Scenario(1, n_beams=360, seed=9)
+    o = Oracle(trig_mode=1)
+    o.set_map(sc.occ, RES)
+    n_rows, n_cols = o.cell_ranges()
+    pf = m.ParticleFilter(max_particles=n, seed=seed)
+    pf.setMap(sc.occ, RES)
+    pf.sampleParticles(n)
+    pf.setInjectionState(10.0, 0.0)               # p_inject = 1 - fast/slow well above zero on this tick
+    scan = sc.scans[0]
+    if whole_step:
+        _, st = pf.executeParticleFilter(sc.enc_left[0], sc.enc_right[0], True, scan=scan)
+    else:
+        pf.diffDriveModel(sc.enc_left[0], sc.enc_right[0])
+        pf.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        st = pf.resampleParticles(True)
+    step = 1                                      # the engine's step number: +1 per predict, +1 per resample
+    idx = pf.ancestors()
+    P = pf.downloadParticles()
+    slots = np.flatnonzero(idx == -1)
+    assert st["p_inject"] > 0.0 and st["injected"] == len(slots) == 200          # max_injection in lost mode (MC:474)
+    u_yaw, u_dx, u_dy, row, col = [], [], [], [], []
+    for rank in range(len(slots)):
+        a, b = _philox(2 * rank, 0x31, step, seed), _philox(2 * rank + 1, 0x31, step, seed)
+        u_yaw.append(_c53(a[0], a[1])); u_dx.append(_c53(a[2], a[3])); u_dy.append(_c53(b[0], b[1]))
+        row.append(b[2] % n_rows); col.append(b[3] % n_cols)
+    E = o.sample_particles(np.array(u_yaw), np.array(row, np.int32), np.array(col, np.int32), np.array(u_dx), np.array(u_dy))
+    assert np.array_equal(P[slots, :3], E[:, :3])
+    assert np.all(P[slots, 3] == np.float32(1.0 / n))
 
 
 def test_ray_parallel_update_kernel_matches_per_particle_kernel_and_oracle():
