@@ -89,8 +89,15 @@ __global__ void __launch_bounds__(256) k_ns_init(float4* __restrict__ part, int6
     part[i] = p;
 }
 
+// mcl_ns_step: the first kernel of a step also resets what the later kernels of that step accumulate into (the running
+// max log-likelihood, the scan's tile states / group sums), so the step needs no memset / copy commands in between.
+struct NsStepPrep { int* maxbits; unsigned long long* zero; int zero_words; };      // maxbits == null: nothing to prepare
 __global__ void __launch_bounds__(256) k_ns_predict(float4* __restrict__ part, int64_t n, int64_t g0, NsMotion m, uint32_t step,
-                                                    uint32_t k0, uint32_t k1) {
+                                                    uint32_t k0, uint32_t k1, NsStepPrep prep) {
+    if (prep.maxbits != nullptr && blockIdx.x == 0) {
+        if (threadIdx.x == 0) *prep.maxbits = INT32_MIN;
+        for (int j = threadIdx.x; j < prep.zero_words; j += blockDim.x) prep.zero[j] = 0ull;
+    }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t g = (uint64_t)(g0 + i);

@@ -168,15 +168,24 @@ int Engine::ns_init(int64_t count) {
 }
 
 // The clean odometry increment plus, per particle, N(0, variance) noise with the reference's variances (MC:706-710).
-int Engine::ns_predict(const Motion& m) {
+int Engine::ns_predict(const Motion& m, bool prep_step) {
     NsMotion k;
     k.rot1 = (float)m.rot_1; k.trans = (float)m.trans; k.rot2 = (float)m.rot_2;
     k.sd_rot1 = (float)std::sqrt(cfg.alpha[0] * std::fabs(m.rot_1) + cfg.alpha[1] * std::fabs(m.trans));
     k.sd_trans = (float)std::sqrt(cfg.alpha[2] * std::fabs(m.trans) + cfg.alpha[3] * (std::fabs(m.rot_1) + std::fabs(m.rot_2)));
     k.sd_rot2 = (float)std::sqrt(cfg.alpha[0] * std::fabs(m.rot_2) + cfg.alpha[1] * std::fabs(m.trans));
+    NsStepPrep prep{nullptr, nullptr, 0};
+    if (prep_step) {                     // mcl_ns_step: reset the step's accumulators here instead of by memset / copy commands
+        bool two_pass; int nt, ng;
+        ns_scan_shape(two_pass, nt, ng);
+        prep.maxbits = d_maxbits.p;
+        prep.zero = (unsigned long long*)(two_pass ? d_tile_sums.p + nt : d_tile_sums.p);
+        prep.zero_words = two_pass ? ng : nt + 1;
+    }
     LAUNCH(K_NS_PREDICT, k_ns_predict, grid_for(n, 256), 256, 0, part[cur].p, n, shard_begin, k, (uint32_t)step_counter,
-           (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+           (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), prep);
     CK(cudaGetLastError());
+    ns_maxbits_prepped = ns_scan_prepped = prep_step;
     have_weights = false; ns_have_ll = false;
     return MCL_OK;
 }
@@ -241,6 +250,7 @@ int Engine::ns_update_local_staged(int slot, float* local_max) {
 
 // The likelihood-field kernel over this shard. Returns the shard's maximum log-likelihood.
 int Engine::ns_run_update(const float2* d_pts, int n_pts, float* local_max) {
+    ns_maxbits_prepped = false;                  // phase by phase: only mcl_ns_step's own predict prepares the step
     int rc = ns_launch_update(d_pts, n_pts);
     if (rc) return rc;
     int bits = 0;
@@ -261,8 +271,11 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
     NsField F;
     F.lf = d_lf.p; F.W = map_w; F.H = map_h; F.pad = lf_pad; F.Wp = lf_wp; F.ox = (float)origin_x; F.oy = (float)origin_y;
     F.inv_res = 1.0f / res_f; F.lf_out = lf_out; F.bytes_padded = (int)lf_bytes_padded;
-    const int init_bits = INT32_MIN;
-    CK(cudaMemcpyAsync(d_maxbits.p, &init_bits, sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (!ns_maxbits_prepped) {
+        const int init_bits = INT32_MIN;
+        CK(cudaMemcpyAsync(d_maxbits.p, &init_bits, sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
+    ns_maxbits_prepped = false;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
     F.lf8 = d_lf8.p; F.codes = d_codes.p; F.n_codes = ns_n_codes;
@@ -340,6 +353,7 @@ int Engine::ns_weights_local(float global_max, uint64_t* local_total) {
     memcpy(&gbits, &global_max, 4);
     gbits = gbits >= 0 ? gbits : gbits ^ 0x7fffffff;
     CK(cudaMemcpyAsync(d_maxbits.p, &gbits, sizeof(int), cudaMemcpyHostToDevice, stream));
+    ns_scan_prepped = false;
     int rc0 = ns_launch_weights();
     if (rc0) return rc0;
     uint64_t tot = 0;
@@ -351,23 +365,30 @@ int Engine::ns_weights_local(float global_max, uint64_t* local_total) {
     return MCL_OK;
 }
 
-int Engine::ns_launch_weights() {
-    const float temper = (float)cfg.ns_temper;
-    const int nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
-    const int ng = (nt + NS_SCAN_GROUP - 1) / NS_SCAN_GROUP;
-    // One wave of tiles or less: single pass with decoupled look-back (one launch, weights computed once). More: the
-    // look-back frontier (32 tiles per L2 round trip) would cap the rate below HBM speed (measured 1.7 TB/s), so the
-    // dependency-free two-pass form takes over (tile sums, then the prefix with offsets read from the sums).
+// One wave of tiles or less: single pass with decoupled look-back (one launch, weights computed once). More: the
+// look-back frontier (32 tiles per L2 round trip) would cap the rate below HBM speed (measured 1.7 TB/s), so the
+// dependency-free two-pass form takes over (tile sums, then the prefix with offsets read from the sums).
+void Engine::ns_scan_shape(bool& two_pass, int& nt, int& ng) const {
+    nt = (int)((n + NS_SCAN_TILE - 1) / NS_SCAN_TILE);
+    ng = (nt + NS_SCAN_GROUP - 1) / NS_SCAN_GROUP;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-    const bool two_pass = force_sequential || nt > sms * (2048 / NS_SCAN_THREADS);
+    two_pass = force_sequential || nt > sms * (2048 / NS_SCAN_THREADS);
+}
+
+int Engine::ns_launch_weights() {
+    const float temper = (float)cfg.ns_temper;
+    bool two_pass; int nt, ng;
+    ns_scan_shape(two_pass, nt, ng);
+    const bool prepped = ns_scan_prepped;              // mcl_ns_step: k_ns_predict already cleared the scan's scratch
+    ns_scan_prepped = false;
     if (two_pass) {
         uint64_t* group_sums = d_tile_sums.p + nt;
-        CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
+        if (!prepped) CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
         LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
         LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
     } else {
-        CK(cudaMemsetAsync(d_tile_sums.p, 0, (size_t)(nt + 1) * sizeof(uint64_t), stream));      // tile states + ticket
+        if (!prepped) CK(cudaMemsetAsync(d_tile_sums.p, 0, (size_t)(nt + 1) * sizeof(uint64_t), stream));      // tile states + ticket
         LAUNCH(K_NS_WSCAN, k_ns_weights_scan1, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p);
     }
     CK(cudaGetLastError());
@@ -561,7 +582,7 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (n == 0) return fail(MCL_ERR_ARG, "ns_step: no particles");
     CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
     Motion m; m.rot_1 = rot1; m.trans = trans; m.rot_2 = rot2;
-    int rc = ns_predict(m);
+    int rc = ns_predict(m, true);
     if (rc) return rc;
     // sensor model (asynchronous variant of ns_run_update: the max stays on the device)
     const float2* d_pts; int n_pts;
@@ -592,7 +613,7 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (rc) return rc;
     if (mail) {}                                                              // gathered inside k_ns_plan_xchg
     else if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
-    else CK(cudaMemcpyAsync(d_totals.p, d_u64.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+    // (one shard: k_ns_plan reads the local total where the scan left it)
     {   // the weighted-mean pose (before resampling) is part of every step; it crosses to the host only when pose3 asks
         const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
         CK(d_partials.ensure(5 * 2048));
@@ -604,7 +625,7 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     }
     const uint32_t u0 = ns_u0();
     if (mail) LAUNCH(K_NS_PLAN, k_ns_plan_xchg, 1, 32, 0, d_u64.p, d_pose.p, PX, tag, parity, (uint64_t)n_global, u0, (NsPlan*)d_plan.p, d_totals.p);
-    else LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, d_totals.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
+    else LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, shard_world > 1 ? d_totals.p : d_u64.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
     have_weights = true;
     rc = ns_launch_resample(u0);
     if (rc) return rc;
