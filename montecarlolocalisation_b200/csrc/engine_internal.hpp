@@ -15,4 +15,23 @@
         ++launches;                                                     \
     } while (0)
 
+// LAUNCH_PDL: the same, with programmatic stream serialisation allowed, for kernels whose first statement is pdl_enter()
+// (mcl_device.cuh). ONLY for those: a kernel without it could run ahead of its predecessor's writes. Ordinary
+// serialisation while profiling (the events sit between the launches) or when MCL_PDL=0.
+#define LAUNCH_PDL(kid, kernel, grid, block, smem, ...)                                              \
+    do {                                                                                            \
+        prof_begin(kid);                                                                             \
+        cudaLaunchConfig_t lc__ = {};                                                               \
+        lc__.gridDim = dim3(grid); lc__.blockDim = dim3(block);                                     \
+        lc__.dynamicSmemBytes = (smem); lc__.stream = stream;                                       \
+        cudaLaunchAttribute la__[1];                                                                \
+        la__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+        la__[0].val.programmaticStreamSerializationAllowed = (use_pdl && !profiling) ? 1 : 0;       \
+        lc__.attrs = la__; lc__.numAttrs = 1;                                                       \
+        cudaError_t le__ = cudaLaunchKernelEx(&lc__, kernel, __VA_ARGS__);                          \
+        if (le__ != cudaSuccess) return cuda_fail(le__, "launch " #kernel);                         \
+        prof_end();                                                                                 \
+        ++launches;                                                                                 \
+    } while (0)
+
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }

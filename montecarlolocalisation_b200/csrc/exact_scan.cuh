@@ -94,6 +94,7 @@ template <bool NORMALISE>
 __global__ void __launch_bounds__(XS_THREADS) k_xs_tilesum(const float* __restrict__ w_in, float* __restrict__ w_out,
                                                            float4* __restrict__ part, int64_t n, const double* __restrict__ total,
                                                            double* __restrict__ tsum, double* __restrict__ toff, int* __restrict__ flag) {
+    pdl_enter();
     __shared__ double sm[8];
     __shared__ bool last;
     const int64_t base = (int64_t)blockIdx.x * XS_TILE + (int64_t)threadIdx.x * XS_ITEMS;
@@ -152,6 +153,7 @@ __device__ __forceinline__ ScanState st_shfl_up(const ScanState& s, int o) {
 template <bool APPLY>
 __global__ void __launch_bounds__(XS_THREADS) k_xs_scan(const float* __restrict__ w, int64_t n, int nt, Workspace ws,
                                                         double* __restrict__ out) {
+    pdl_enter();
     __shared__ double sm_d[8];
     __shared__ double sm_last[8];
     __shared__ ScanState sm_st[8];
@@ -304,6 +306,7 @@ __device__ __forceinline__ double seq_total_block(const float* __restrict__ w, i
 // after the apply pass).
 __global__ void __launch_bounds__(XS_CHAIN_THREADS) k_xs_chain(int nt, Workspace ws, double* __restrict__ total_out, const float* __restrict__ w,
                                                                int64_t n) {
+    pdl_enter();
     __shared__ ScanState sm_warp[XS_CHAIN_THREADS / 32];
     __shared__ ScanState sm_carry_in;          // running state entering the current chunk of tiles
     __shared__ int sm_fail;

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) k_ns_init(float4* __restrict__ part, int6
 struct NsStepPrep { int* maxbits; unsigned long long* zero; int zero_words; };      // maxbits == null: nothing to prepare
 __global__ void __launch_bounds__(256) k_ns_predict(float4* __restrict__ part, int64_t n, int64_t g0, NsMotion m, uint32_t step,
                                                     uint32_t k0, uint32_t k1, NsStepPrep prep) {
+    pdl_enter();
     if (prep.maxbits != nullptr && blockIdx.x == 0) {
         if (threadIdx.x == 0) *prep.maxbits = INT32_MIN;
         for (int j = threadIdx.x; j < prep.zero_words; j += blockDim.x) prep.zero[j] = 0ull;
@@ -412,6 +413,7 @@ template <int KIND, int PACK>
 __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
                                                                 const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
                                                                 int* __restrict__ max_bits /* ordered-int max of ll */) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ float warp_max[NS_UPD_THREADS / 32];
@@ -565,6 +567,7 @@ __device__ __forceinline__ void ns_load_weights(const float* __restrict__ ll, in
 // pass 1: tile_sums[tile], group_sums[tile / 64] += (group_sums zeroed before the launch)
 __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
                                                                    float temper, uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ group_sums) {
+    pdl_enter();
     __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float max_ll = ns_decode_max(max_bits);
@@ -587,6 +590,7 @@ __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float
                                                                     float temper, const uint64_t* __restrict__ tile_sums,
                                                                     const uint64_t* __restrict__ group_sums, int n_tiles,
                                                                     uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out) {
+    pdl_enter();
     __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32], s_offp[NS_SCAN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, group = tile / NS_SCAN_GROUP;
@@ -646,6 +650,7 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm v
 __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan1(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
                                                                      float temper, uint64_t* __restrict__ tile_state /* n_tiles + 1, zeroed */,
                                                                      int n_tiles, uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out) {
+    pdl_enter();
     __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32];
     __shared__ uint64_t s_excl;
     __shared__ int s_tile;
@@ -752,6 +757,7 @@ __device__ __forceinline__ NsPlan ns_make_plan(const uint64_t* totals, int world
     return p;
 }
 __global__ void k_ns_plan(const uint64_t* __restrict__ totals, int world, int rank, uint64_t n_global, uint32_t u0, NsPlan* __restrict__ plan) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     *plan = ns_make_plan(totals, world, rank, n_global, u0);
 }
@@ -952,6 +958,7 @@ __device__ __forceinline__ int64_t ns_search_warp(const uint64_t* __restrict__ p
 // the last entry describes the last slot instead). One warp per tile head.
 __global__ void __launch_bounds__(256) k_ns_resample_bounds(const uint64_t* __restrict__ prefix, int64_t n_local, const NsPlan* __restrict__ plan,
                                                             uint64_t n_global, uint32_t u0, NsTileHead* __restrict__ head) {
+    pdl_enter();
     const NsPlan P = *plan;
     const int64_t tiles = (P.k_hi - P.k_lo + NS_RS_TILE - 1) / NS_RS_TILE;
     if (tiles <= 0) return;
@@ -979,6 +986,7 @@ __global__ void __launch_bounds__(256) k_ns_resample_bounds(const uint64_t* __re
 __global__ void __launch_bounds__(NS_RS_THREADS) k_ns_resample(const float4* __restrict__ src, const uint64_t* __restrict__ prefix, int64_t n_local,
                                                                int64_t g0, const NsPlan* __restrict__ plan, const NsTileHead* __restrict__ head,
                                                                uint64_t n_global, double inv_n, NsDest D, float new_weight) {
+    pdl_enter();
     __shared__ uint64_t s_pre[NS_RS_CAP];
     __shared__ __align__(16) int s_anc[NS_RS_TILE];
     const NsPlan P = *plan;
@@ -1086,6 +1094,7 @@ __global__ void __launch_bounds__(512) k_gather_bench(const float* __restrict__ 
 
 // out[k] = sum over blocks of partials[b*5+k] (one warp per output, fixed order)
 __global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_blocks, double* __restrict__ out5) {
+    pdl_enter();
     const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (o >= 5) return;
     double s = 0;
@@ -1098,6 +1107,7 @@ __global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_bloc
 // W * 2^-32 recomputed from the log-likelihood (ll != null: between update and resample) or read from the particle record.
 __global__ void __launch_bounds__(256) k_ns_pose_partials(const float4* __restrict__ part, int64_t n, const float* __restrict__ ll,
                                                           const int* __restrict__ max_bits, float temper, double* __restrict__ partials) {
+    pdl_enter();
     __shared__ double ws[8][5];
     double a[5] = {0, 0, 0, 0, 0};
     const float max_ll = ll ? ns_decode_max(max_bits) : 0.f;

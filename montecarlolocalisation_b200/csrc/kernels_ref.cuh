@@ -282,6 +282,7 @@ __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_r
 template <bool ZERO_ORIGIN, bool FAST32, int NR>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
                                                            uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[RU_TILE / 32];
     RuSmem S;
@@ -506,6 +507,7 @@ __global__ void __launch_bounds__(256) k_ref_seq_total(const float* __restrict__
 // cdf[i] = cdf[i-1] + (double)w_i over already-normalised weights (MC:498,504).
 __global__ void __launch_bounds__(256) k_ref_seq_cdf(const float* __restrict__ wn_in, int64_t n, double* __restrict__ cdf,
                                                      const int* __restrict__ run_if) {
+    pdl_enter();
     if (run_if && *run_if == 0) return;
     __shared__ float wn[2][SEQ_TILE];
     __shared__ double out[2][SEQ_TILE];
@@ -566,6 +568,7 @@ __device__ __forceinline__ void ref_philox_inject_draws(uint64_t counter, const 
 // form in Engine::ref_resample, so both give the same bits. inj = {weight_slow, weight_fast, p_inject, cdf_is_monotone}.
 __global__ void k_ref_ema(const double* __restrict__ total, double n, double a_slow, double a_fast, double* __restrict__ inj,
                           int* __restrict__ counters /* [0] injected, [1] clamped, [2] flagged, [3]: cleared for the resampling that follows */) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
     const double t = *total;
@@ -583,6 +586,7 @@ __global__ void k_ref_ema(const double* __restrict__ total, double n, double a_s
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
                                                           int* __restrict__ block_counts, RefDrawGen G, const double* __restrict__ inj_dev) {
+    pdl_enter();
     if (inj_dev) { p_inject = inj_dev[2]; if (!(p_inject > 0.0)) return; }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double r = 2.0;
@@ -596,6 +600,7 @@ __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restri
 }
 // exclusive scan of block counts in place (single block, sequential chunks; n_blocks is small).
 __global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total, const double* __restrict__ inj_dev) {
+    pdl_enter();
     if (inj_dev && !(inj_dev[2] > 0.0)) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int acc = 0;
@@ -636,6 +641,7 @@ __device__ __forceinline__ int ref_guide_floor(double c, double B, int buckets) 
     return !(x >= 0.0) ? -1 : (x >= B ? buckets : (int)x);           // NaN owns nothing
 }
 __global__ void __launch_bounds__(256) k_ref_guide(const double* __restrict__ cdf, int64_t n, int buckets, int* __restrict__ guide) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const double B = (double)buckets;
@@ -676,6 +682,7 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G,
                                                       const int* __restrict__ guide /* null: full-range search */, int buckets,
                                                       const double* __restrict__ inj_dev /* mcl_step: {.., p_inject, cdf_is_monotone} on the device */) {
+    pdl_enter();
     __shared__ int warp_counts[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
@@ -807,6 +814,7 @@ __global__ void __launch_bounds__(256) k_ref_init(float4* __restrict__ part, int
 
 // ---- updateParticlePos (MC:740-755): fp32 element math -----------------------------------------------------
 __global__ void __launch_bounds__(256) k_ref_predict(float4* __restrict__ part, int64_t n, float rot1, float trans, float dtheta) {
+    pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = part[i];
@@ -848,6 +856,7 @@ __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ pa
                                                    double* __restrict__ partials /* [grid][4] */, unsigned* __restrict__ ticket,
                                                    double* __restrict__ out4, RefStepReport* __restrict__ report /* null: none */,
                                                    const double* __restrict__ inj5, const int* __restrict__ counters4) {
+    pdl_enter();
     __shared__ double ws[8][4];
     __shared__ bool last;
     const float weight_sum = __double2float_rn(wsum_dev ? *wsum_dev : wsum_host);

@@ -5,6 +5,17 @@
 
 namespace mcl {
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// The kernels of a filter tick are short and strictly dependent, so the gap between one kernel's last block and the next
+// kernel's first is a visible share of the tick. Kernels launched with LAUNCH_PDL (engine_internal.hpp) may be made
+// resident while their predecessor drains; pdl_enter() is their first statement: it waits until every earlier kernel of
+// the stream has completed and its writes are visible (a no-op under an ordinary launch), then lets the next kernel of
+// the stream be made resident in turn. Nothing may touch global memory before it.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- float trig -------------------------------------------------------------------------------------
 // The reference calls cosf/sinf (MC:644-645) and Eigen's fp32 cos/sin (MC:747-748). Neither libm's nor
 // Eigen's rounding is portable, so the engine is held to the portable definition "correctly rounded fp32":

@@ -99,6 +99,7 @@ int Engine::open() {
     CK(cudaSetDevice(cfg.device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     opened = true;
+    { const char* e_pdl = getenv("MCL_PDL"); use_pdl = !(e_pdl && e_pdl[0] == '0'); }
     // static tables
     gauss.build(cfg.sigma_hit);
     CK(d_gauss.ensure(gauss.v.size()));
@@ -254,20 +255,20 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
     ws.carry = (xs::Par*)xs_carry.p; ws.seq_base = xs_seq_base.p; ws.seq_s = xs_seq_s.p; ws.flag = xs_flag.p;
     if (!force_sequential) {
         if (normalise)
-            LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
+            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
         else
-            LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<false>, nt, xs::XS_THREADS, 0, w, (float*)nullptr, (float4*)nullptr, n, (const double*)nullptr,
+            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<false>, nt, xs::XS_THREADS, 0, w, (float*)nullptr, (float4*)nullptr, n, (const double*)nullptr,
                    xs_tsum.p, xs_toff.p, xs_flag.p);
-        LAUNCH(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
-        LAUNCH(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out, w, n);     // total: falls back in-kernel
+        LAUNCH_PDL(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
+        LAUNCH_PDL(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out, w, n);     // total: falls back in-kernel
         if (want_cdf) {
-            LAUNCH(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
-            LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)xs_flag.p);            // runs only if flagged
+            LAUNCH_PDL(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
+            LAUNCH_PDL(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)xs_flag.p);            // runs only if flagged
         }
     } else {
         if (normalise)
-            LAUNCH(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
-        if (want_cdf) LAUNCH(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)nullptr);
+            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
+        if (want_cdf) LAUNCH_PDL(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)nullptr);
         if (d_total_out) LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, w, n, d_total_out, (const int*)nullptr);
     }
     CK(cudaGetLastError());
@@ -432,7 +433,7 @@ int Engine::predict_motion(double r1, double t, double r2) {
     if (n == 0) return fail(MCL_ERR_ARG, "predict: no particles");
     if (cfg.mode == MCL_MODE_NS) { Motion m; m.rot_1 = r1; m.trans = t; m.rot_2 = r2; return ns_predict(m); }
     // Eigen narrows the f64 scalars to the array's fp32 first (MC:746-753)
-    LAUNCH(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2));
+    LAUNCH_PDL(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2));
     CK(cudaGetLastError());
     have_weights = false;
     return MCL_OK;
@@ -621,14 +622,14 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         const float tol32 = (float)(span * 4.76837158203125e-07);                  // 2^-21
         const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f && occ_pad > 0 && P.n_radii <= 16;
         if (fast32 && P.n_radii == 11) {
-            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
         } else if (fast32) {
-            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
         } else {
-            if (zero_origin) LAUNCH(K_UPDATE_V2, (k_ref_update_v2<true, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH(K_UPDATE_V2, (k_ref_update_v2<false, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+            else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
         }
     } else {
         LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
@@ -708,7 +709,7 @@ int Engine::ref_resample_front() {
         int buckets = 1024;
         while ((int64_t)buckets * 8 < n && buckets < (1 << 24)) buckets <<= 1;          // ~8 CDF entries per bucket: 3 probes
         CK(d_guide.ensure((size_t)buckets + 2));
-        LAUNCH(K_GUIDE, k_ref_guide, grid_for(n, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
+        LAUNCH_PDL(K_GUIDE, k_ref_guide, grid_for(n, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
         guide_built = true; guide_buckets = buckets;
     }
     return MCL_OK;
@@ -723,7 +724,7 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const double a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
     double p_inject = 0.0;
     if (dev_ema) {
-        LAUNCH(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p, d_counters.p);    // also clears the counters
+        LAUNCH_PDL(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p, d_counters.p);    // also clears the counters
     } else {
         int rc0 = inj_sync_to_host();
         if (rc0) return rc0;
@@ -793,9 +794,9 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const bool inject_possible = max_inj > 0 && (dev_ema || p_inject > 0.0);
     if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
-        if (d) LAUNCH(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G, inj_dev);
-        else LAUNCH(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G, inj_dev);
-        LAUNCH(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2, inj_dev);
+        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G, inj_dev);
+        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G, inj_dev);
+        LAUNCH_PDL(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2, inj_dev);
         CK(cudaGetLastError());
     }
     if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
@@ -804,11 +805,11 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const int* guide = use_guide ? d_guide.p : nullptr;
     const int buckets = use_guide ? guide_buckets : 0;
     if (d)
-        LAUNCH(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
+        LAUNCH_PDL(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
                d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
                inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev);
     else
-        LAUNCH(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
+        LAUNCH_PDL(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
                d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
                inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev);
     CK(cudaGetLastError());
@@ -861,7 +862,7 @@ int Engine::estimate_enqueue(double* h_sums4, RefStepReport* step_report) {
         LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
         wsum_dev = d_scalars.p + 1;
     }
-    LAUNCH(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2,
+    LAUNCH_PDL(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2,
            step_report, (const double*)d_inj.p, (const int*)d_counters.p);
     CK(cudaGetLastError());
     if (h_sums4) CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));

@@ -182,7 +182,7 @@ int Engine::ns_predict(const Motion& m, bool prep_step) {
         prep.zero = (unsigned long long*)(two_pass ? d_tile_sums.p + nt : d_tile_sums.p);
         prep.zero_words = two_pass ? ng : nt + 1;
     }
-    LAUNCH(K_NS_PREDICT, k_ns_predict, grid_for(n, 256), 256, 0, part[cur].p, n, shard_begin, k, (uint32_t)step_counter,
+    LAUNCH_PDL(K_NS_PREDICT, k_ns_predict, grid_for(n, 256), 256, 0, part[cur].p, n, shard_begin, k, (uint32_t)step_counter,
            (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), prep);
     CK(cudaGetLastError());
     ns_maxbits_prepped = ns_scan_prepped = prep_step;
@@ -329,7 +329,7 @@ int Engine::ns_launch_update(const float2* d_pts, int n_pts) {
         const int grid = (int)std::min<int64_t>((int64_t)sms * std::max(1, occ), ctas_needed);     // persistent: resident CTAs only
         const bool measure = tuning && !ns_tune_pending && ns_beams_n > 0;
         if (measure) CK(cudaEventRecord(ns_tune_ev[0], stream));
-        LAUNCH(K_NS_UPDATE, kernel, std::max(1, grid), threads, smem, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
+        LAUNCH_PDL(K_NS_UPDATE, kernel, std::max(1, grid), threads, smem, part[cur].p, n, F, d_pts, ns_beams_n, d_ll.p, d_maxbits.p);
         if (measure) { CK(cudaEventRecord(ns_tune_ev[1], stream)); ns_tune_pending = true; ns_tune_kind = kind; ns_tune_beams = ns_beams_n; }
         return MCL_OK;
     };
@@ -385,11 +385,11 @@ int Engine::ns_launch_weights() {
     if (two_pass) {
         uint64_t* group_sums = d_tile_sums.p + nt;
         if (!prepped) CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
-        LAUNCH(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
-        LAUNCH(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
+        LAUNCH_PDL(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
+        LAUNCH_PDL(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
     } else {
         if (!prepped) CK(cudaMemsetAsync(d_tile_sums.p, 0, (size_t)(nt + 1) * sizeof(uint64_t), stream));      // tile states + ticket
-        LAUNCH(K_NS_WSCAN, k_ns_weights_scan1, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p);
+        LAUNCH_PDL(K_NS_WSCAN, k_ns_weights_scan1, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p);
     }
     CK(cudaGetLastError());
     ns_w_in_records = false;
@@ -453,11 +453,11 @@ int Engine::ns_launch_resample(uint32_t u0) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
     const int g1 = (int)std::min<int64_t>((max_tiles + 1 + 7) / 8, (int64_t)sms * 8);            // one warp per tile head, 8 per CTA
-    LAUNCH(K_NS_BOUNDS, k_ns_resample_bounds, g1, 256, 0, d_prefix.p, n, (const NsPlan*)d_plan.p, (uint64_t)n_global, u0, (NsTileHead*)d_bounds.p);
+    LAUNCH_PDL(K_NS_BOUNDS, k_ns_resample_bounds, g1, 256, 0, d_prefix.p, n, (const NsPlan*)d_plan.p, (uint64_t)n_global, u0, (NsTileHead*)d_bounds.p);
     int occ = 8;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ns_resample, NS_RS_THREADS, 0));
     const int g2 = (int)std::min<int64_t>(max_tiles, (int64_t)sms * std::max(1, occ));      // resident CTAs only: tiles are taken grid-stride
-    LAUNCH(K_NS_RESAMPLE, k_ns_resample, g2, NS_RS_THREADS, 0, part[cur].p, d_prefix.p, n, shard_begin, (const NsPlan*)d_plan.p,
+    LAUNCH_PDL(K_NS_RESAMPLE, k_ns_resample, g2, NS_RS_THREADS, 0, part[cur].p, d_prefix.p, n, shard_begin, (const NsPlan*)d_plan.p,
            (const NsTileHead*)d_bounds.p, (uint64_t)n_global, 1.0 / (double)n_global, D, (float)(1.0 / (double)n_global));
     CK(cudaGetLastError());
     return MCL_OK;
@@ -476,7 +476,7 @@ int Engine::ns_pose_partials(double* out5) {
     const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
     CK(d_partials.ensure(5 * 2048));
     const bool from_ll = have_weights && !ns_w_in_records;
-    LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, from_ll ? (const float*)d_ll.p : (const float*)nullptr, (const int*)d_maxbits.p,
+    LAUNCH_PDL(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, from_ll ? (const float*)d_ll.p : (const float*)nullptr, (const int*)d_maxbits.p,
            (float)cfg.ns_temper, d_partials.p);
     CK(cudaGetLastError());
     std::vector<double> h((size_t)blocks * 5);
@@ -617,15 +617,15 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     {   // the weighted-mean pose (before resampling) is part of every step; it crosses to the host only when pose3 asks
         const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
         CK(d_partials.ensure(5 * 2048));
-        LAUNCH(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
+        LAUNCH_PDL(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
                d_partials.p);
-        LAUNCH(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
+        LAUNCH_PDL(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
         if (mail) {}                                                          // summed over the shards inside k_ns_plan_xchg
         else if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
     }
     const uint32_t u0 = ns_u0();
     if (mail) LAUNCH(K_NS_PLAN, k_ns_plan_xchg, 1, 32, 0, d_u64.p, d_pose.p, PX, tag, parity, (uint64_t)n_global, u0, (NsPlan*)d_plan.p, d_totals.p);
-    else LAUNCH(K_NS_PLAN, k_ns_plan, 1, 32, 0, shard_world > 1 ? d_totals.p : d_u64.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
+    else LAUNCH_PDL(K_NS_PLAN, k_ns_plan, 1, 32, 0, shard_world > 1 ? d_totals.p : d_u64.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
     have_weights = true;
     rc = ns_launch_resample(u0);
     if (rc) return rc;
