@@ -413,7 +413,6 @@ template <int KIND, int PACK>
 __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* __restrict__ part, int64_t n, NsField F,
                                                                 const float2* __restrict__ beams, int n_beams, float* __restrict__ ll_out,
                                                                 int* __restrict__ max_bits /* ordered-int max of ll */) {
-    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ float warp_max[NS_UPD_THREADS / 32];
@@ -446,6 +445,10 @@ __global__ void __launch_bounds__(NS_UPD_THREADS, 1) k_ns_update(const float4* _
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const int64_t n_batches = (n + 31) / 32;
     float best = -3.0e38f;
+    // The staging above read only the field, the code table and the beams (written by host copies / map set-up, never by a
+    // kernel of the step), so under a programmatic launch it overlaps the predecessor's tail; particles, ll_out and
+    // max_bits belong to the step.
+    pdl_enter();
     for (int64_t batch = (int64_t)blockIdx.x * warps_per_block + warp; batch < n_batches; batch += (int64_t)gridDim.x * warps_per_block) {
         const int64_t i = batch * 32 + lane;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1093,14 +1096,16 @@ __global__ void __launch_bounds__(512) k_gather_bench(const float* __restrict__ 
 }
 
 // out[k] = sum over blocks of partials[b*5+k] (one warp per output, fixed order)
-__global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_blocks, double* __restrict__ out5) {
+// host5 (single-shard mcl_ns_step): the sums also go straight into the caller's pinned host block (zero-copy), so the
+// step ends without a device-to-host copy command.
+__global__ void k_ns_pose_reduce(const double* __restrict__ partials, int n_blocks, double* __restrict__ out5, double* __restrict__ host5) {
     pdl_enter();
     const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (o >= 5) return;
     double s = 0;
     for (int b = lane; b < n_blocks; b += 32) s += partials[(size_t)b * 5 + o];
     s = warp_sum(s);
-    if (lane == 0) out5[o] = s;
+    if (lane == 0) { out5[o] = s; if (host5) host5[o] = s; }
 }
 
 // Weighted pose sums {sum w, sum w x, sum w y, sum w sin, sum w cos} per block, w = the unnormalised fp32 weight

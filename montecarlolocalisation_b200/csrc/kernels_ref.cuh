@@ -282,7 +282,6 @@ __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_r
 template <bool ZERO_ORIGIN, bool FAST32, int NR>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
                                                            uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32) {
-    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[RU_TILE / 32];
     RuSmem S;
@@ -337,6 +336,10 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     const int nb = P.n_beams, nr = P.n_radii, stride = nb + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_tiles = (n + RU_TILE - 1) / RU_TILE;
+    // Everything above read only tables that no kernel of a tick writes (map, ray directions, beams, Gaussian table: set by
+    // host copies, which serialise the stream), so under a programmatic launch it overlaps the predecessor's tail; the
+    // particles are the predecessor's output.
+    pdl_enter();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- phase A -------------------------------------------------------------------------------------------------
         const int64_t j = tile * RU_TILE + threadIdx.x;

@@ -23,6 +23,7 @@ Engine::~Engine() {
     for (int w = 0; w < 4; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
     if (h_step) cudaFreeHost(h_step);
+    if (h_ns_pose) cudaFreeHost(h_ns_pose);
     d_inj.release();
     if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
     ns_comm_destroy(); ancestors.release(); d_occ.release(); d_occ_pad.release(); d_gauss.release();
@@ -897,9 +898,11 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     if (!h_step) CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars)));
     int rc = inj_sync_to_device();
     if (rc) return rc;
-    rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
-    if (rc) return rc;
-    if (ranges || slot < 0) {
+    // The scan goes to the device first: the copy command then sits at the head of the tick and the kernels follow one
+    // another without a copy in between (programmatic launches overlap only kernel with kernel).
+    const bool host_scan = ranges || slot < 0;
+    int n_used = 0;
+    if (host_scan) {
         if (n_beams < 0 || (n_beams > 0 && !ranges)) return fail(MCL_ERR_ARG, "step: bad scan");
         std::vector<RefBeam> used;
         rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, beams_all, used);
@@ -914,11 +917,12 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
             CK(cudaMemcpyAsync(d_beams.p, hp, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
             CK(cudaEventRecord(ring_events[ring_pos], stream));
         }
-        rc = ref_run_update(d_beams.p, (int)used.size(), beams_all, nullptr, true);
-    } else {
-        if ((size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "step: empty scan slot");
-        rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true);
-    }
+        n_used = (int)used.size();
+    } else if ((size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "step: empty scan slot");
+    rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
+    if (rc) return rc;
+    if (host_scan) rc = ref_run_update(d_beams.p, n_used, beams_all, nullptr, true);
+    else rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true);
     if (rc) return rc;
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;

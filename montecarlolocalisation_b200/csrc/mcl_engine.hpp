@@ -210,6 +210,7 @@ private:
     int ns_predict(const Motion& clean, bool prep_step = false);      // prep_step: also reset the step's accumulators (mcl_ns_step)
     void ns_scan_shape(bool& two_pass, int& nt, int& ng) const;
     bool ns_maxbits_prepped = false, ns_scan_prepped = false;
+    double* h_ns_pose = nullptr;            // pinned: the single-shard step's five pose sums, written by k_ns_pose_reduce
     void ns_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
                           std::vector<float2>& pts) const;
     int ns_run_update(const float2* d_pts, int n_pts, float* local_max);

@@ -582,9 +582,9 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (n == 0) return fail(MCL_ERR_ARG, "ns_step: no particles");
     CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
     Motion m; m.rot_1 = rot1; m.trans = trans; m.rot_2 = rot2;
-    int rc = ns_predict(m, true);
-    if (rc) return rc;
-    // sensor model (asynchronous variant of ns_run_update: the max stays on the device)
+    int rc;
+    // the scan goes to the device first, so that no copy command sits between the step's kernels (programmatic launches
+    // overlap only kernel with kernel)
     const float2* d_pts; int n_pts;
     if (ranges) {
         std::vector<float2> pts;
@@ -604,6 +604,9 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
         if (slot < 0 || (size_t)slot >= ns_staged.size() || !ns_staged[slot].valid) return fail(MCL_ERR_ARG, "ns_step: empty scan slot");
         d_pts = ns_staged[slot].d_pts.p; n_pts = ns_staged[slot].n;
     }
+    rc = ns_predict(m, true);
+    if (rc) return rc;
+    // sensor model (asynchronous variant of ns_run_update: the max stays on the device)
     rc = ns_launch_update(d_pts, n_pts);
     if (rc) return rc;
     auto& N = nccl_api();
@@ -619,7 +622,8 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
         CK(d_partials.ensure(5 * 2048));
         LAUNCH_PDL(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
                d_partials.p);
-        LAUNCH_PDL(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p);
+        if (shard_world == 1 && !h_ns_pose) CK(cudaMallocHost((void**)&h_ns_pose, 8 * sizeof(double)));
+        LAUNCH_PDL(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p, shard_world == 1 ? h_ns_pose : (double*)nullptr);
         if (mail) {}                                                          // summed over the shards inside k_ns_plan_xchg
         else if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
     }
@@ -636,8 +640,13 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     ++step_counter;
     if (pose3) {
         double h[6] = {0, 0, 0, 0, 0, 0};
-        CK(cudaMemcpyAsync(h, d_pose.p, (mail ? 6 : 5) * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+        if (shard_world == 1) {                      // the sums are already on their way to the pinned block
+            CK(cudaStreamSynchronize(stream));
+            memcpy(h, h_ns_pose, 5 * sizeof(double));
+        } else {
+            CK(cudaMemcpyAsync(h, d_pose.p, (mail ? 6 : 5) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
         if (mail && h[5] != 0.0) return fail(MCL_ERR_COMM, "ns_step: a peer-memory exchange timed out (a shard never posted)");
         pose3[0] = h[1] / h[0]; pose3[1] = h[2] / h[0]; pose3[2] = std::atan2(h[3], h[4]);
     }
