@@ -174,7 +174,16 @@ int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
  * NULL the call returns as soon as the tick is queued (the estimate is still computed; several ticks may be in flight;
  * any call that returns data synchronises); otherwise it waits for the GPU once, at the end, instead of three times. MCL_MODE_REF only (NS filters:
  * mcl_ns_step). pose3 = {x, y, theta} of the resampled particles; stats as mcl_resample. The per-function calls and
- * mcl_step can be mixed on one handle. mcl_step_staged takes a scan parked by mcl_scan_stage. */
+ * mcl_step can be mixed on one handle. mcl_step_staged takes a scan parked by mcl_scan_stage.
+ * What crosses the bus per tick: the scored beams in (24 B each, one copy command at the head of the tick; nothing with a
+ * staged scan) and an 88-byte report out (pose sums, injection state, counters), which the tick's last kernel stores
+ * straight into the engine's pinned host block. No other copy or memset command is enqueued, and the tick's kernels follow
+ * one another by programmatic dependent launch (MCL_PDL=0 in the environment: ordinary stream order).
+ * The engine's own draw streams (draws == NULL / mcl_step), all Philox4x32-10 keyed by mcl_config.seed with counter
+ * (index lo, index hi, stream, tick number): stream 0x30 = u_r and the jitter draws of slot i (indices 2i, 2i+1; readable
+ * through mcl_debug_download_resample_draws), stream 0x31 = the named draws of the rank-th injected particle (indices
+ * 2*rank, 2*rank+1: u_yaw, u_dx, u_dy as 53-bit fractions, row and col as words mod the coarse grid), generated inside the
+ * resampling kernel; stream 0x20 = the three odometry normals (host); stream 0x10 = mcl_init without draws. */
 int mcl_step(mcl_handle* h, double enc_left, double enc_right, const float* ranges, int32_t n_beams, float angle_min,
              float angle_increment, float range_min, float range_max, int32_t jitter_state, double* pose3, mcl_resample_stats* stats);
 int mcl_step_staged(mcl_handle* h, double enc_left, double enc_right, int32_t slot, int32_t jitter_state, double* pose3,
