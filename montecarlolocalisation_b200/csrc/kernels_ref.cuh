@@ -256,7 +256,7 @@ __device__ __forceinline__ int cell_fast32(float q, float tol, bool& ok) {
 }
 
 struct RuSmem {
-    double2* lut;
+    const double2* lut;   // f64 ray directions: shared memory, or (fp32 march) the global table itself, read by the ~1e-3 undecided rays only
     RefBeam* beams;
     double* radii;
     double* posx;
@@ -272,8 +272,10 @@ struct RuSmem {
     double* gterm;        // [beam][hit index 0..n_radii]: w_hit * GaussianLookup(|obs - expected|), last = no hit (max range)
 };
 // map_bytes = plain + bordered table bytes when they are staged in shared memory, else 0
-__host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes, size_t pad_bytes) {
-    return (size_t)n_keys * 16 + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
+// lut_in_smem: false for the fp32 march, which leaves the f64 direction table (16 B per key, 38 KB for the reference's
+// 2401 keys) in global memory: 60 -> 22 KB per block, four resident blocks per SM instead of three.
+__host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes, size_t pad_bytes, bool lut_in_smem) {
+    return (lut_in_smem ? (size_t)n_keys * 16 : 0) + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
            RU_TILE * 4 + (((size_t)n_radii * 4 + 15) & ~(size_t)15) + ((map_bytes + 15) & ~(size_t)15) + ((pad_bytes + 15) & ~(size_t)15) +
            (size_t)n_keys * 8 + RU_TILE * 8 + (size_t)n_beams * (n_radii + 1) * 8;
 }
@@ -285,8 +287,9 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[RU_TILE / 32];
     RuSmem S;
-    S.lut = reinterpret_cast<double2*>(smem_raw);
-    S.beams = reinterpret_cast<RefBeam*>(S.lut + P.n_keys);
+    double2* s_lut = reinterpret_cast<double2*>(smem_raw);
+    S.lut = FAST32 ? P.lut : s_lut;
+    S.beams = reinterpret_cast<RefBeam*>(s_lut + (FAST32 ? 0 : P.n_keys));
     S.radii = reinterpret_cast<double*>(S.beams + P.n_beams);
     S.posx = S.radii + P.n_radii;
     S.posy = S.posx + RU_TILE;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     S.q0 = S.dq + P.n_keys;
     S.gterm = reinterpret_cast<double*>(S.q0 + RU_TILE);
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii_f[i] = __double2float_rn(P.radii[i]);
-    for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) S.lut[i] = P.lut[i];
+    if (!FAST32) for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) s_lut[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = P.beams[i];
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii[i] = P.radii[i];
     if (P.map_in_smem) {
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
         // per key: the direction in fp32 cell units; per (beam, step at which the ray ended): the beam's score term. A ray
         // ends at one of n_radii + 1 distances, so GaussianLookup::get (MC:154-168) is evaluated here once per pair.
         for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE)
-            S.dq[i] = make_float2(__double2float_rn(dmul(S.lut[i].x, P.inv_res)), __double2float_rn(dmul(S.lut[i].y, P.inv_res)));
+            { const double2 d = P.lut[i]; S.dq[i] = make_float2(__double2float_rn(dmul(d.x, P.inv_res)), __double2float_rn(dmul(d.y, P.inv_res))); }
         const int per = P.n_radii + 1;
         for (int i = threadIdx.x; i < P.n_beams * per; i += RU_TILE) {
             const int b = i / per, k = i - b * per;

@@ -598,7 +598,11 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         int rc = ref_fill_ray_lut(all);
         if (rc) return rc;
     }
-    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0);
+    // fp32 pre-filter tolerance: 4x the bound 2^-23*(cells + 2*max_range/res + 2) on the fp32 cell coordinate's error
+    const double span = (double)std::max(map_w, map_h) + 2.0 * cfg.max_laser_range / (double)res_f + 2.0;
+    const float tol32 = (float)(span * 4.76837158203125e-07);                  // 2^-21
+    const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f && occ_pad > 0 && P.n_radii <= 16;
+    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0, !fast32);
     const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
     if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024 && bounded_ok) {
         if (!attr_set2) {
@@ -612,16 +616,13 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         }
         int occ_blocks = 1, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<false, true, 0>), RU_TILE, smem2));
+        if (fast32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<false, true, 0>), RU_TILE, smem2));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<false, false, 0>), RU_TILE, smem2));
         // the bounded fast path needs every probe quotient below 2^31: particle inside the map, ray at most max_range long
         const bool zero_origin = origin_x == 0.0 && origin_y == 0.0;
         const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
         const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));
         const uint32_t div_magic = (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
-        // fp32 pre-filter tolerance: 4x the bound 2^-23*(cells + 2*max_range/res + 2) on the fp32 cell coordinate's error
-        const double span = (double)std::max(map_w, map_h) + 2.0 * cfg.max_laser_range / (double)res_f + 2.0;
-        const float tol32 = (float)(span * 4.76837158203125e-07);                  // 2^-21
-        const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f && occ_pad > 0 && P.n_radii <= 16;
         if (fast32 && P.n_radii == 11) {
             if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
             else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
