@@ -17,7 +17,9 @@
 
 // LAUNCH_PDL: the same, with programmatic stream serialisation allowed, for kernels whose first statement is pdl_enter()
 // (mcl_device.cuh). ONLY for those: a kernel without it could run ahead of its predecessor's writes. Ordinary
-// serialisation while profiling (the events sit between the launches) or when MCL_PDL=0.
+// serialisation while profiling (the events sit between the launches), when MCL_PDL=0, and for the first kernel after an
+// exchange (pdl_hold): a kernel that polls other shards must not have its successor's blocks parked on the SMs meanwhile,
+// or shards that share one GPU (in-process tests) could keep each other's kernels from being scheduled.
 #define LAUNCH_PDL(kid, kernel, grid, block, smem, ...)                                              \
     do {                                                                                            \
         prof_begin(kid);                                                                             \
@@ -26,7 +28,8 @@
         lc__.dynamicSmemBytes = (smem); lc__.stream = stream;                                       \
         cudaLaunchAttribute la__[1];                                                                \
         la__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
-        la__[0].val.programmaticStreamSerializationAllowed = (use_pdl && !profiling) ? 1 : 0;       \
+        la__[0].val.programmaticStreamSerializationAllowed = (use_pdl && !profiling && !pdl_hold) ? 1 : 0; \
+        pdl_hold = false;                                                                           \
         lc__.attrs = la__; lc__.numAttrs = 1;                                                       \
         cudaError_t le__ = cudaLaunchKernelEx(&lc__, kernel, __VA_ARGS__);                          \
         if (le__ != cudaSuccess) return cuda_fail(le__, "launch " #kernel);                         \

@@ -140,6 +140,7 @@ private:
     bool attr_set = false, attr_set2 = false;
     bool profiling = false;
     bool use_pdl = true;                    // programmatic dependent launch between the kernels of a tick (MCL_PDL=0: off)
+    bool pdl_hold = false;                  // the next LAUNCH_PDL is an ordinary launch (set after a kernel that waits for other shards)
     struct ProfEvent { int id; cudaEvent_t a, b; };
     std::vector<ProfEvent> prof_events;
     double prof_ms[K_COUNT] = {0};

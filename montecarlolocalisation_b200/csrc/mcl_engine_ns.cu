@@ -612,10 +612,11 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     auto& N = nccl_api();
     if (mail) LAUNCH(K_NS_PLAN, k_ns_xchg_max, 1, 32, 0, d_maxbits.p, PX, tag, parity);
     else if (shard_world > 1) NCK(N.AllReduce(d_maxbits.p, d_maxbits.p, 1, ncclInt32, ncclMax, (ncclComm_t)comm, stream));
+    if (shard_world > 1) pdl_hold = true;        // the exchange polls other shards: its successor is launched in stream order
     rc = ns_launch_weights();
     if (rc) return rc;
     if (mail) {}                                                              // gathered inside k_ns_plan_xchg
-    else if (shard_world > 1) NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream));
+    else if (shard_world > 1) { NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream)); pdl_hold = true; }
     // (one shard: k_ns_plan reads the local total where the scan left it)
     {   // the weighted-mean pose (before resampling) is part of every step; it crosses to the host only when pose3 asks
         const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
@@ -625,16 +626,18 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
         if (shard_world == 1 && !h_ns_pose) CK(cudaMallocHost((void**)&h_ns_pose, 8 * sizeof(double)));
         LAUNCH_PDL(K_NS_POSE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p, shard_world == 1 ? h_ns_pose : (double*)nullptr);
         if (mail) {}                                                          // summed over the shards inside k_ns_plan_xchg
-        else if (shard_world > 1) NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream));
+        else if (shard_world > 1) { NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream)); pdl_hold = true; }
     }
     const uint32_t u0 = ns_u0();
     if (mail) LAUNCH(K_NS_PLAN, k_ns_plan_xchg, 1, 32, 0, d_u64.p, d_pose.p, PX, tag, parity, (uint64_t)n_global, u0, (NsPlan*)d_plan.p, d_totals.p);
     else LAUNCH_PDL(K_NS_PLAN, k_ns_plan, 1, 32, 0, shard_world > 1 ? d_totals.p : d_u64.p, shard_world, shard_rank, (uint64_t)n_global, u0, (NsPlan*)d_plan.p);
     have_weights = true;
+    if (shard_world > 1) pdl_hold = true;
     rc = ns_launch_resample(u0);
     if (rc) return rc;
     if (mail) LAUNCH(K_NS_PLAN, k_ns_xchg_barrier, 1, 32, 0, PX, tag);                                            // closing barrier
     else if (shard_world > 1) NCK(N.AllReduce(d_bar.p, d_bar.p, 1, ncclInt32, ncclSum, (ncclComm_t)comm, stream));
+    if (shard_world > 1) pdl_hold = true;        // next step's first kernel follows the closing barrier in stream order
     cur ^= 1;
     have_weights = false; ns_have_ll = false;
     ++step_counter;
