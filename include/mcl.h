@@ -153,7 +153,9 @@ int mcl_update(mcl_handle* h, const float* ranges, int32_t n_beams, float angle_
                float range_min, float range_max, double* total_weight);
 
 /* The same with the scan pre-processed and parked in device memory (slot in [0,4096)): replaying recorded scans,
- * and benchmarks that want the inputs resident in HBM before the timed region. */
+ * and benchmarks that want the inputs resident in HBM before the timed region. Slot lifetime: a slot may be re-staged at
+ * any time; mcl_scan_stage first waits for every tick already queued on the handle (mcl_step_staged / mcl_ns_step_staged
+ * return before their ticks ran), so a queued tick always reads the scan that was in its slot when it was queued. */
 int mcl_scan_stage(mcl_handle* h, int32_t slot, const float* ranges, int32_t n_beams, float angle_min, float angle_increment,
                    float range_min, float range_max);
 int mcl_update_staged(mcl_handle* h, int32_t slot, double* total_weight);
@@ -163,7 +165,11 @@ int mcl_resample(mcl_handle* h, int32_t jitter_state, const mcl_resample_draws* 
 int mcl_download_ancestors(mcl_handle* h, int32_t* idx);   /* ancestor index per output slot, -1 = injected */
 int mcl_download_cdf(mcl_handle* h, double* cdf);          /* REF: the f64 CDF of MC:496-505 */
 
-/* ---- estimate: estimateWeightedPose(particles) (MC:782-800) ------------------------------------------- */
+/* ---- estimate: estimateWeightedPose(particles) (MC:782-800) -------------------------------------------
+ * Tolerance-graded, not bit-exact: the reference reduces in fp32 through Eigen packets (vendored without Eigen/Core, so
+ * its summation order cannot be pinned); the engine does the fp32 element math (w/weight_sum, w*x, w*sin, w*cos) and
+ * accumulates in f64 in a fixed order, with weight_sum taken from the known f64 total. Agreement with the reference is
+ * 1e-5 relative, the bound north_star states for poses; the value feeds nothing downstream on the path. */
 int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
 
 /* ---- one tick of the node's loop: executeParticleFilter (MC:1084-1092) = diffDriveModel + updateParticlePos,
@@ -281,27 +287,7 @@ int mcl_get_injection_state(mcl_handle* h, double* weight_slow, double* weight_f
 int mcl_set_injection_state(mcl_handle* h, double weight_slow, double weight_fast);
 int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
 
-/* ---- instrumentation ------------------------------------------------------------------------------------ */
-/* The u_r / u_jitter streams the last mcl_resample consumed (injected, or generated by the device Philox stream),
- * so a checker can replay the same step. u_jitter holds N*(3 if jitter_state else 2) values. */
-int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter);
-/* The engine's bit-exact sequential f64 accumulation s_i = s_{i-1} + (double)w[i] on an arbitrary fp32 vector:
- * cdf[n] and/or total; *fell_back != 0 when the parallel path handed over to the single-chain kernel. */
-int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back);
-/* Cross-check switches (slow paths): bit 0 = single-chain sequential accumulation kernels instead of the parallel exact
- * scan; bit 1 = the one-thread-per-particle computeWeight kernel instead of the ray-parallel one; bit 2 = ray-parallel
- * kernel without its fp32 pre-filter; bit 3 = NS sensor model reads the one-byte coded field, bit 4 = the fp32 field
- * through global memory (each regardless of the field's size; all three forms give identical values); bit 5 = NS sensor
- * model in scalar FFMA form on every path. */
-int mcl_debug_force_sequential(mcl_handle* h, int32_t on);
-/* Random 4-byte gather micro-benchmark: the roofline denominator of the sensor-model kernel.
- * tier 0 = table in shared memory (<= 200 KiB), tier 1 = table in global memory (L2- or HBM-resident by its size). */
-int mcl_bench_gather(mcl_handle* h, int32_t tier, int64_t table_bytes, int32_t iters, double* reads_per_s);
-/* Per-kernel CUDA-event timing on the handle's stream; off by default (it serialises launches). */
-int mcl_profile_enable(mcl_handle* h, int32_t on);
-int mcl_profile_kernel_count(void);
-const char* mcl_profile_kernel_name(int32_t id);
-int mcl_profile_read(mcl_handle* h, int32_t id, double* total_ms, int64_t* count);
+/* ---- handle plumbing (cross-check switches, micro-benchmarks and per-kernel timers live in mcl_debug.h) ---- */
 void* mcl_stream(mcl_handle* h);                  /* the cudaStream_t all kernels of this handle run on */
 int mcl_synchronize(mcl_handle* h);
 int64_t mcl_kernel_launches(mcl_handle* h);       /* kernels launched by this handle so far */

@@ -57,7 +57,7 @@ class KmeansResult(C.Structure):
                 ("best_cluster", C.c_int32), ("passes", C.c_int32), ("reinit_used", C.c_int32), ("exact", C.c_int32)]
 
 
-# every symbol include/mcl.h declares: (name, restype, argtypes)
+# every symbol include/mcl.h and include/mcl_debug.h declare: (name, restype, argtypes)
 _vp, _i32, _i64, _d, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_float
 _dp, _fp, _ip, _bp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int8)
 SYMBOLS = [
@@ -136,7 +136,7 @@ _lib = None
 
 def build(verbose=False):
     """Compile libmcl_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=not verbose, text=True)
+    r = subprocess.run(["make", "-j4", "-C", os.path.join(HERE, "csrc")], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libmcl_b200.so failed:\n%s\n%s" % (r.stdout, r.stderr))
 

@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
         const int n_rays = nv * nb;
         const int nrr = NR ? NR : nr;
         for (int r = threadIdx.x; r < n_rays; r += RU_TILE) {
-            const int v = (int)__umulhi((unsigned)r, div_magic);
+            // r / nb by multiplication with ceil(2^32 / nb) (exact for r < 2^32 / nb); ceil(2^32 / 1) does not fit 32 bits,
+            // so one scored beam (a scan with 1..beam_stride filtered readings inside the FOV) is its own case
+            const int v = nb == 1 ? r : (int)__umulhi((unsigned)r, div_magic);
             const int b = r - v * nb;
             const int k = ref_key_index(P, S.yawd[v], S.beams[b].off_deg);
             if (FAST32) {

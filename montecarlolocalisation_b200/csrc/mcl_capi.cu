@@ -1,9 +1,11 @@
-// mcl_capi.cu — the extern "C" boundary declared in include/mcl.h. Nothing throws across it.
+// mcl_capi.cu — the extern "C" boundary declared in include/mcl.h (+ the instrumentation of include/mcl_debug.h). Nothing
+// throws across it.
 #include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
 
+#include "../../include/mcl_debug.h"
 #include "mcl_engine.hpp"
 #include "ns_plan.hpp"
 

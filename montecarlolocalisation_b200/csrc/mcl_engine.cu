@@ -219,6 +219,7 @@ int Engine::ensure_particles(int64_t count) {
     CK(part[0].ensure(count)); CK(part[1].ensure(count));
     CK(ancestors.ensure(count));
     if (cfg.mode == MCL_MODE_NS) {
+        if (shard_world == 1 && count >= (1ll << 28)) return fail(MCL_ERR_ARG, "NS filters hold fewer than 2^28 particles (Q32 totals stay below 2^60)");
         CK(d_ll.ensure(count)); CK(d_prefix.ensure(count));
         CK(d_tile_sums.ensure((size_t)(count + 4095) / 4096 + (size_t)(count + 4095) / 4096 / 64 + 4)); CK(d_u64.ensure(4)); CK(d_maxbits.ensure(1));
         if (shard_world == 1) { n_global = count; shard_begin = 0; per_rank = count; }
@@ -506,8 +507,14 @@ int Engine::stage_scan(int slot, const float* ranges, int n_beams, float angle_m
     std::vector<RefBeam> used;
     int rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, s.all, used);
     if (rc) return rc;
+    // Ticks queued by mcl_step_staged may still be reading this slot (or the buffer ensure() is about to free): the engine's
+    // stream is non-blocking, so a plain cudaMemcpy would not be ordered behind them. Drain the stream, then copy on it.
+    CK(cudaStreamSynchronize(stream));
     CK(s.d_used.ensure(std::max<size_t>(1, used.size())));
-    if (!used.empty()) CK(cudaMemcpy(s.d_used.p, used.data(), used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice));
+    if (!used.empty()) {
+        CK(cudaMemcpyAsync(s.d_used.p, used.data(), used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
     s.n_used = (int)used.size();
     s.valid = true;
     return MCL_OK;
@@ -622,7 +629,8 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         const bool zero_origin = origin_x == 0.0 && origin_y == 0.0;
         const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
         const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));
-        const uint32_t div_magic = (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
+        // ceil(2^32 / n_used); n_used == 1 would need 2^32 itself: the kernel divides by one without it
+        const uint32_t div_magic = n_used == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
         if (fast32 && P.n_radii == 11) {
             if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
             else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);

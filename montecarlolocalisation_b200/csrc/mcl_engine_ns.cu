@@ -15,6 +15,9 @@ namespace mcl {
 int Engine::ns_set_shard(int rank, int world, int64_t ng) {
     if (cfg.mode != MCL_MODE_NS) return fail(MCL_ERR_STATE, "set_shard: NS mode only (REF resampling needs the global f64 CDF on one GPU)");
     if (world < 1 || world > 8 || rank < 0 || rank >= world || ng <= 0) return fail(MCL_ERR_ARG, "set_shard: bad rank/world/count");
+    // the Q32 resampling arithmetic keeps totals below 2^60 (N * 2^32), thresholds' remainders below 2^31 + 2^9 * 2^31 and
+    // stores ancestors as int: all of that assumes fewer than 2^28 particles in the whole filter
+    if (ng >= (1ll << 28)) return fail(MCL_ERR_ARG, "set_shard: n_global must be below 2^28 (Q32 totals stay below 2^60, ancestors are 32-bit)");
     shard_rank = rank; shard_world = world; n_global = ng;
     int64_t cnt;
     ns::shard_range(ng, world, rank, &shard_begin, &cnt, &per_rank);
@@ -234,8 +237,13 @@ int Engine::ns_stage_scan(int slot, const float* ranges, int n_beams, float angl
     std::vector<float2> pts;
     ns_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, pts);
     NsStagedScan& s = ns_staged[slot];
+    // steps queued by mcl_ns_step_staged may still read this slot: drain the (non-blocking) stream, then copy on it
+    CK(cudaStreamSynchronize(stream));
     CK(s.d_pts.ensure(std::max<size_t>(1, pts.size())));
-    if (!pts.empty()) CK(cudaMemcpy(s.d_pts.p, pts.data(), pts.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (!pts.empty()) {
+        CK(cudaMemcpyAsync(s.d_pts.p, pts.data(), pts.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
     s.n = (int)pts.size();
     s.valid = true;
     return MCL_OK;
@@ -576,10 +584,13 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     static const double env_timeout_s = [] { const char* e = getenv("MCL_NS_EXCHANGE_TIMEOUT_S"); return e ? atof(e) : 30.0; }();
     PX.timeout_ns = env_timeout_s > 0 ? (unsigned long long)(env_timeout_s * 1e9) : 0ull;
     for (int r = 0; r < 8; ++r) PX.box[r] = r >= shard_world ? nullptr : r == shard_rank ? (NsMailbox*)d_mbox.p : (NsMailbox*)peer_ptr[3][r];
-    const unsigned tag = mail ? ++xchg_seq : 0u;
-    const int parity = (int)(tag & 1u);
-    if (shard_world > 1) ns_exchange_used = mail ? 1 : 0;
+    // every argument check comes before the exchange tag advances: a shard that returned an error with its tag already
+    // incremented would never again match its peers' tags
     if (n == 0) return fail(MCL_ERR_ARG, "ns_step: no particles");
+    if (!map_ready) return fail(MCL_ERR_ARG, "ns_step: no map");
+    if (ranges ? (n_beams < 0) : (slot < 0 || (size_t)slot >= ns_staged.size() || !ns_staged[slot].valid))
+        return fail(MCL_ERR_ARG, ranges ? "ns_step: bad scan" : "ns_step: empty scan slot");
+    if (shard_world > 1) ns_exchange_used = mail ? 1 : 0;
     CK(d_totals.ensure(8)); CK(d_plan.ensure(sizeof(NsPlan))); CK(d_pose.ensure(8)); CK(d_bar.ensure(1));
     Motion m; m.rot_1 = rot1; m.trans = trans; m.rot_2 = rot2;
     int rc;
@@ -601,7 +612,6 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
         }
         d_pts = d_ns_beams.p; n_pts = (int)pts.size();
     } else {
-        if (slot < 0 || (size_t)slot >= ns_staged.size() || !ns_staged[slot].valid) return fail(MCL_ERR_ARG, "ns_step: empty scan slot");
         d_pts = ns_staged[slot].d_pts.p; n_pts = ns_staged[slot].n;
     }
     rc = ns_predict(m, true);
@@ -610,6 +620,8 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     rc = ns_launch_update(d_pts, n_pts);
     if (rc) return rc;
     auto& N = nccl_api();
+    const unsigned tag = mail ? ++xchg_seq : 0u;       // advanced only now, immediately before the first exchange kernel is enqueued
+    const int parity = (int)(tag & 1u);
     if (mail) LAUNCH(K_NS_PLAN, k_ns_xchg_max, 1, 32, 0, d_maxbits.p, PX, tag, parity);
     else if (shard_world > 1) NCK(N.AllReduce(d_maxbits.p, d_maxbits.p, 1, ncclInt32, ncclMax, (ncclComm_t)comm, stream));
     if (shard_world > 1) pdl_hold = true;        // the exchange polls other shards: its successor is launched in stream order

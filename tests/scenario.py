@@ -1,18 +1,20 @@
 """Shared test scenario = BASELINE.json config 1 in miniature: pink_fundamentals/map.txt, a 360-beam synthetic scan
-per step from a ground-truth pose, a wheel-encoder trace. Inputs only; no oracle, no engine."""
+per step from a ground-truth pose, a wheel-encoder trace. Inputs only: no oracle, no engine, and the product library is
+never loaded from here (the reference arm of bench.py builds its workload with this module). The occupancy grid is the
+committed rasterisation of tests/golden/map.txt (tests/golden/map_occ_49x49.npy, SHA-256 9d700e0d...; tests/test_abi.py
+checks that the engine's and the oracle's rasterisers both reproduce it)."""
 import os
 
 import numpy as np
 
-from montecarlolocalisation_b200 import rasterise_map_txt, synth
+from montecarlolocalisation_b200 import synth      # numpy-only workload generators; importing it does not dlopen anything
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RES = np.float32(0.1)
 
 
 def load_map():
-    with open(os.path.join(ROOT, "tests", "golden", "map.txt")) as f:
-        return rasterise_map_txt(f.read())
+    return np.load(os.path.join(ROOT, "tests", "golden", "map_occ_49x49.npy"))
 
 
 class Scenario:

@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/mcl.h declares; host-only entry points work;
+"""The C-ABI library loads and exports every symbol include/mcl.h and include/mcl_debug.h declare; host-only entry points work;
 without a GPU the engine refuses to start instead of falling back."""
 import ctypes as C
 import hashlib
@@ -24,10 +24,20 @@ def gpu_present():
         return False
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "mcl.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mcl_[a-z0-9_]+)\s*\(", text)))
+def declared_symbols(headers=("mcl.h", "mcl_debug.h")):
+    names = set()
+    for hname in headers:
+        text = open(os.path.join(ROOT, "include", hname)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(mcl_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_debug_entry_points_are_not_in_the_boundary_header():
+    """Cross-check switches, the gather micro-benchmark and the per-kernel timers live in include/mcl_debug.h."""
+    boundary = declared_symbols(("mcl.h",))
+    assert not [n for n in boundary if n.startswith(("mcl_debug_", "mcl_bench_", "mcl_profile_"))]
+    assert "mcl_debug_exact_scan" in declared_symbols(("mcl_debug.h",))
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -55,6 +65,8 @@ def test_host_rasteriser_matches_kat_and_oracle(map_txt):
     from oracle.pyoracle import Oracle
     occ = m.rasterise_map_txt(map_txt)
     assert hashlib.sha256(occ.tobytes()).hexdigest() == "9d700e0d21c8b669621222f4c2514d9d80a7e502fc476f77120c348c4849c275"
+    from scenario import load_map
+    assert np.array_equal(load_map(), occ) and np.array_equal(Oracle.rasterise_map_txt(map_txt), occ)      # the committed fixture
     for txt in ("[[[T,L],[T,R]],[[L,B]]]", "[[[T,L,B,R]]]", "[[[],[B]],[[R],[L,T]],[[B],[B,R]]]"):
         assert np.array_equal(m.rasterise_map_txt(txt), Oracle.rasterise_map_txt(txt))
     with pytest.raises(m.MclError):
