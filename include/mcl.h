@@ -38,6 +38,15 @@ typedef struct mcl_handle mcl_handle;
 
 enum { MCL_MODE_REF = 0, MCL_MODE_NS = 1 };
 
+/* How MCL_MODE_REF evaluates the reference's fp32 cos/sin.
+ *   MCL_TRIG_LIBM (default)        bit for bit what the reference BINARY computes on this host: glibc's sinf/cosf (2.28 and
+ *                                  later, x86-64), whose FMA and SSE2 builds differ at 34 of the 2^32 arguments; mcl_create
+ *                                  probes the host's libm at those arguments and the kernels run that build's operation
+ *                                  sequence in f64 (csrc/glibc_trigf.cuh). mcl_create fails if the host's libm is neither.
+ *   MCL_TRIG_CORRECTLY_ROUNDED     (float)cos((double)x): the portable definition, independent of any libm; differs from
+ *                                  glibc's result for 0.26 % / 0.55 % of arguments by one fp32 ulp. */
+enum { MCL_TRIG_LIBM = 0, MCL_TRIG_CORRECTLY_ROUNDED = 1 };
+
 enum {
     MCL_OK = 0,
     MCL_ERR_ARG = -1,      /* bad argument / call order (e.g. update before set_map) */
@@ -89,6 +98,9 @@ typedef struct mcl_config {
     double ns_temper;            /* weight = exp(ns_temper * (loglik - max loglik)); 1 = plain product of beam likelihoods */
     /* confidence estimate, MC:889-890, 933 */
     double kmeans_radius;        /* 0.4: density radius around the best cluster (countParticlesNearCluster) */
+    /* float trig of the path: cosf/sinf at MC:644-645 (laser origin) and Eigen's fp32 cos/sin at MC:747-748 (predict) */
+    int32_t trig_mode;           /* MCL_TRIG_LIBM | MCL_TRIG_CORRECTLY_ROUNDED */
+    int32_t _pad2;
 } mcl_config;
 
 /* Named draws for sampleParticles (MC:427-440): per particle yaw~U[0,1) canonical, row, col, dx, dy canonical. */

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcl_b200.so")
 
 MODE_REF, MODE_NS = 0, 1
+TRIG_LIBM, TRIG_CORRECTLY_ROUNDED = 0, 1
 
 
 class MclError(RuntimeError):
@@ -32,7 +33,7 @@ class Config(C.Structure):
         ("jitter_xy_lost", C.c_double), ("jitter_theta_lost", C.c_double), ("jitter_xy_conf", C.c_double),
         ("seed", C.c_uint64), ("ns_sigma_hit", C.c_double), ("ns_z_hit", C.c_double), ("ns_z_rand", C.c_double),
         ("ns_max_range", C.c_double), ("ns_beam_stride", C.c_int32), ("ns_use_fov", C.c_int32), ("ns_temper", C.c_double),
-        ("kmeans_radius", C.c_double),
+        ("kmeans_radius", C.c_double), ("trig_mode", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -97,6 +98,7 @@ SYMBOLS = [
     ("mcl_debug_download_resample_draws", _i32, [_vp, _dp, _dp]),
     ("mcl_debug_exact_scan", _i32, [_vp, _fp, _i64, _dp, _dp, _ip]),
     ("mcl_debug_force_sequential", _i32, [_vp, _i32]),
+    ("mcl_debug_trigf", _i32, [_vp, _fp, _i64, _fp, _fp, _ip]),
     ("mcl_bench_gather", _i32, [_vp, _i32, _i64, _i32, _dp]),
     ("mcl_profile_enable", _i32, [_vp, _i32]),
     ("mcl_profile_kernel_count", _i32, []),

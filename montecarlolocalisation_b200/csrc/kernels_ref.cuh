@@ -45,6 +45,7 @@ struct RefParams {
     // beams
     const RefBeam* beams;
     int n_beams;
+    int trig;                  // TRIG_*: how cosf/sinf of MC:644-645 are evaluated (mcl_device.cuh)
 };
 
 // ---- map probes ---------------------------------------------------------------------------------------
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(256) k_ref_update(float4* __restrict__ part, f
     float4 p = part[j];
     double prob = 0.0;
     if (ref_is_valid(m, P, (double)p.x, (double)p.y)) {                                   // MC:648
-        double posx = dadd((double)p.x, dmul(P.laser_offset, (double)cr_cosf(p.z)));      // MC:644
-        double posy = dadd((double)p.y, dmul(P.laser_offset, (double)cr_sinf(p.z)));      // MC:645
+        double posx = dadd((double)p.x, dmul(P.laser_offset, (double)ref_cosf(p.z, P.trig)));   // MC:644
+        double posy = dadd((double)p.y, dmul(P.laser_offset, (double)ref_sinf(p.z, P.trig)));   // MC:645
         double yaw_deg = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);         // MC:351-352
         for (int b = 0; b < P.n_beams; b++) {
             RefBeam bm = S.beams[b];
@@ -376,10 +377,14 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                 valid = !hit;
             }
             if (valid) {
-                double sn, cs;
-                sincos((double)p.z, &sn, &cs);
-                posx = dadd(x, dmul(P.laser_offset, (double)__double2float_rn(cs)));        // MC:644 (correctly rounded cosf)
-                posy = dadd(y, dmul(P.laser_offset, (double)__double2float_rn(sn)));        // MC:645
+                float snf, csf;
+                if (P.trig == TRIG_CR) {
+                    double sn, cs;
+                    sincos((double)p.z, &sn, &cs);
+                    snf = __double2float_rn(sn); csf = __double2float_rn(cs);             // correctly rounded sinf / cosf
+                } else { snf = ref_sinf(p.z, P.trig); csf = ref_cosf(p.z, P.trig); }        // the host libm's sinf / cosf
+                posx = dadd(x, dmul(P.laser_offset, (double)csf));                        // MC:644
+                posy = dadd(y, dmul(P.laser_offset, (double)snf));                        // MC:645
                 yawd = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);            // MC:351-352
             }
         }
@@ -821,16 +826,25 @@ __global__ void __launch_bounds__(256) k_ref_init(float4* __restrict__ part, int
 }
 
 // ---- updateParticlePos (MC:740-755): fp32 element math -----------------------------------------------------
-__global__ void __launch_bounds__(256) k_ref_predict(float4* __restrict__ part, int64_t n, float rot1, float trans, float dtheta) {
+__global__ void __launch_bounds__(256) k_ref_predict(float4* __restrict__ part, int64_t n, float rot1, float trans, float dtheta, int trig) {
     pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = part[i];
     float h = __fadd_rn(p.z, rot1);
-    p.x = __fadd_rn(p.x, __fmul_rn(trans, cr_cosf(h)));
-    p.y = __fadd_rn(p.y, __fmul_rn(trans, cr_sinf(h)));
+    p.x = __fadd_rn(p.x, __fmul_rn(trans, ref_cosf(h, trig)));      // MC:747
+    p.y = __fadd_rn(p.y, __fmul_rn(trans, ref_sinf(h, trig)));      // MC:748
     p.z = __fadd_rn(p.z, dtheta);
     part[i] = p;
+}
+
+// the kernels' float trig on an array (mcl_debug_trigf): what a checker compares with the host libm
+__global__ void __launch_bounds__(256) k_debug_trigf(const float* __restrict__ x, int64_t n, int trig, float* __restrict__ s_out, float* __restrict__ c_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    s_out[i] = ref_sinf(v, trig);
+    c_out[i] = ref_cosf(v, trig);
 }
 
 // ---- estimateWeightedPose (MC:782-800) ---------------------------------------------------------------------

@@ -44,12 +44,14 @@ void mcl_config_default(mcl_config* c) {
     c->ns_sigma_hit = 0.1; c->ns_z_hit = 0.8; c->ns_z_rand = 0.2; c->ns_max_range = 5.6;
     c->ns_beam_stride = 1; c->ns_use_fov = 0; c->ns_temper = 0.05;
     c->kmeans_radius = 0.4;                                                                         // MC:933
+    c->trig_mode = MCL_TRIG_LIBM;                                                                   // what the reference binary executes
 }
 
 int mcl_create(const mcl_config* cfg, mcl_handle** out) {
     if (!cfg || !out) { g_create_error = "mcl_create: null argument"; return MCL_ERR_ARG; }
     *out = nullptr;
     if (cfg->mode != MCL_MODE_REF && cfg->mode != MCL_MODE_NS) { g_create_error = "mcl_create: unknown mode"; return MCL_ERR_ARG; }
+    if (cfg->trig_mode != MCL_TRIG_LIBM && cfg->trig_mode != MCL_TRIG_CORRECTLY_ROUNDED) { g_create_error = "mcl_create: unknown trig_mode"; return MCL_ERR_ARG; }
     mcl_handle* h = new (std::nothrow) mcl_handle(*cfg);
     if (!h) { g_create_error = "mcl_create: out of host memory"; return MCL_ERR_ARG; }
     int rc;
@@ -124,6 +126,7 @@ int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitt
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back) { GUARD(h); TRY(h->engine.debug_exact_scan(w, n, cdf, total, fell_back)) }
 int mcl_debug_force_sequential(mcl_handle* h, int32_t on) { GUARD(h); h->engine.force_sequential = (on & 1) != 0; h->engine.force_v1_update = (on & 2) != 0; h->engine.force_f64_probe = (on & 4) != 0;
     h->engine.ns_force_field = (on & 8) ? 2 : (on & 16) ? 1 : -1; h->engine.ns_force_scalar = (on & 32) != 0; return MCL_OK; }
+int mcl_debug_trigf(mcl_handle* h, const float* x, int64_t n, float* s, float* c, int32_t* kind) { GUARD(h); TRY(h->engine.debug_trigf(x, n, s, c, kind)) }
 int mcl_profile_enable(mcl_handle* h, int32_t on) { GUARD(h); h->engine.profile_enable(on != 0); return MCL_OK; }
 int mcl_profile_kernel_count(void) { return mcl::Engine::K_COUNT; }
 const char* mcl_profile_kernel_name(int32_t id) { return mcl::Engine::kernel_name(id); }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "glibc_trigf.cuh"
+
 namespace mcl {
 
 // ---- programmatic dependent launch ---------------------------------------------------------------------------------
@@ -17,12 +19,22 @@ __device__ __forceinline__ void pdl_enter() {
 }
 
 // ---- float trig -------------------------------------------------------------------------------------
-// The reference calls cosf/sinf (MC:644-645) and Eigen's fp32 cos/sin (MC:747-748). Neither libm's nor
-// Eigen's rounding is portable, so the engine is held to the portable definition "correctly rounded fp32":
-// evaluate in f64 (error ~1e-16) and round once. Differs from a correctly rounded result only when the f64
-// value falls within ~1e-16 of an fp32 rounding boundary (probability ~1e-9 per call). See DESIGN.md.
+// The reference calls cosf/sinf (MC:644-645) and Eigen's fp32 cos/sin (MC:747-748, which oracle/shim maps to the same libm
+// calls). `trig` selects what the kernels evaluate (mcl_config.trig_mode resolved by Engine::open):
+//   TRIG_GLIBC_FMA / TRIG_GLIBC_SSE2   glibc's sinf/cosf operation for operation in f64 (glibc_trigf.cuh): bit-identical to
+//                                      the reference binary on a host whose libm selected that build;
+//   TRIG_CR                            "correctly rounded fp32": evaluate in f64 (error ~1e-16) and round once. Differs from
+//                                      a correctly rounded result only when the f64 value falls within ~1e-16 of an fp32
+//                                      rounding boundary (probability ~1e-9 per call).
+constexpr int TRIG_GLIBC_FMA = 0, TRIG_GLIBC_SSE2 = 1, TRIG_CR = 2;
 __device__ __forceinline__ float cr_cosf(float t) { return __double2float_rn(cos((double)t)); }
 __device__ __forceinline__ float cr_sinf(float t) { return __double2float_rn(sin((double)t)); }
+__device__ __forceinline__ float ref_cosf(float t, int trig) {
+    return trig == TRIG_GLIBC_FMA ? glibc_trig::cosf_as_glibc<true>(t) : trig == TRIG_GLIBC_SSE2 ? glibc_trig::cosf_as_glibc<false>(t) : cr_cosf(t);
+}
+__device__ __forceinline__ float ref_sinf(float t, int trig) {
+    return trig == TRIG_GLIBC_FMA ? glibc_trig::sinf_as_glibc<true>(t) : trig == TRIG_GLIBC_SSE2 ? glibc_trig::sinf_as_glibc<false>(t) : cr_sinf(t);
+}
 
 // ---- exact f64 building blocks (never contracted into FMA) -----------------------------------------------
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }

@@ -101,6 +101,10 @@ int Engine::open() {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     opened = true;
     { const char* e_pdl = getenv("MCL_PDL"); use_pdl = !(e_pdl && e_pdl[0] == '0'); }
+    {   // which float trig the kernels evaluate (include/mcl.h, MCL_TRIG_*)
+        int rc = resolve_trig();
+        if (rc) return rc;
+    }
     // static tables
     gauss.build(cfg.sigma_hit);
     CK(d_gauss.ensure(gauss.v.size()));
@@ -123,6 +127,35 @@ int Engine::open() {
     CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4] = ticket of k_pose_sums (resets itself)
     CK(d_partials.ensure(4 * 1024));
     CK(cudaStreamSynchronize(stream));
+    return MCL_OK;
+}
+
+// MCL_TRIG_LIBM: find out which build of glibc's sinf/cosf this host's libm selected (ifunc: FMA + AVX2 CPUs get the fused
+// build). The two builds differ at 17 magnitudes (34 floats) of the 2^32 arguments; the host libm is probed there and on a
+// spread of ordinary arguments, and must agree with one restatement everywhere.
+int Engine::resolve_trig() {
+    if (cfg.trig_mode == MCL_TRIG_CORRECTLY_ROUNDED) { trig_kind = TRIG_CR; return MCL_OK; }
+    static const uint32_t differ[] = {0x4255b0a9u, 0x42a35c07u, 0x42a35d44u, 0x42a97360u, 0x42cf5854u, 0x42e87a55u,            // sinf
+                                      0x418a3adbu, 0x418a3adcu, 0x418a3addu, 0x418a3adeu, 0x41bc76d9u, 0x4202eb4bu, 0x42687a55u,
+                                      0x4280ce28u, 0x42870e40u, 0x42c55faau, 0x42d8d23eu};                                    // cosf
+    bool ok[2] = {true, true};
+    auto probe = [&](uint32_t bits) {
+        float y;
+        memcpy(&y, &bits, 4);
+        volatile float vy = y;
+        const float hs = sinf(vy), hc = cosf(vy);
+        const float s1 = glibc_trig::sinf_as_glibc<true>(y), c1 = glibc_trig::cosf_as_glibc<true>(y);
+        const float s0 = glibc_trig::sinf_as_glibc<false>(y), c0 = glibc_trig::cosf_as_glibc<false>(y);
+        if (memcmp(&hs, &s1, 4) || memcmp(&hc, &c1, 4)) ok[1] = false;
+        if (memcmp(&hs, &s0, 4) || memcmp(&hc, &c0, 4)) ok[0] = false;
+    };
+    for (uint32_t b : differ) { probe(b); probe(b | 0x80000000u); }
+    for (uint32_t k = 0; k < 4096; ++k) probe(0x30000000u + k * 0x0004F1A3u);      // 2^-31 .. 2^33: every path of the function
+    if (ok[1] == ok[0])
+        return fail(MCL_ERR_STATE, ok[1] ? "trig_mode MCL_TRIG_LIBM: the host libm's sinf/cosf could not be told apart (unexpected)"
+                                         : "trig_mode MCL_TRIG_LIBM: the host libm's sinf/cosf is not glibc's (>= 2.28, x86-64) FMA or SSE2 build; "
+                                           "use MCL_TRIG_CORRECTLY_ROUNDED");
+    trig_kind = ok[1] ? TRIG_GLIBC_FMA : TRIG_GLIBC_SSE2;
     return MCL_OK;
 }
 
@@ -300,6 +333,22 @@ int Engine::debug_exact_scan(const float* w, int64_t count, double* cdf_out, dou
     return MCL_OK;
 }
 
+int Engine::debug_trigf(const float* x, int64_t count, float* s_out, float* c_out, int* kind_out) {
+    CK(cudaSetDevice(cfg.device));
+    if (!x || !s_out || !c_out || count <= 0) return fail(MCL_ERR_ARG, "debug_trigf: bad argument");
+    DevBuf<float> d;
+    CK(d.ensure(3 * (size_t)count));
+    CK(cudaMemcpyAsync(d.p, x, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, stream));
+    LAUNCH(K_PREDICT, k_debug_trigf, grid_for(count, 256), 256, 0, d.p, count, trig_kind, d.p + count, d.p + 2 * count);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s_out, d.p + count, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(c_out, d.p + 2 * count, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    d.release();
+    if (kind_out) *kind_out = trig_kind;
+    return MCL_OK;
+}
+
 void Engine::philox_host(uint32_t stream_id, uint64_t index, uint32_t out[4]) const {
     uint32_t o[4];
     Philox::gen((uint32_t)index, (uint32_t)(index >> 32), stream_id, (uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), o);
@@ -435,7 +484,7 @@ int Engine::predict_motion(double r1, double t, double r2) {
     if (n == 0) return fail(MCL_ERR_ARG, "predict: no particles");
     if (cfg.mode == MCL_MODE_NS) { Motion m; m.rot_1 = r1; m.trans = t; m.rot_2 = r2; return ns_predict(m); }
     // Eigen narrows the f64 scalars to the array's fp32 first (MC:746-753)
-    LAUNCH_PDL(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2));
+    LAUNCH_PDL(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2), trig_kind);
     CK(cudaGetLastError());
     have_weights = false;
     return MCL_OK;
@@ -574,6 +623,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
     P.gauss = d_gauss.p; P.gauss_size = (int)gauss.v.size(); P.gauss_res = gauss.step; P.gauss_min = gauss.lo; P.gauss_max = gauss.hi;
     P.lut = d_lut.p; P.lut_filled = d_lut_filled.p; P.key_min = key_min; P.n_keys = n_keys;
     P.beams = d_used; P.n_beams = n_used;
+    P.trig = trig_kind;
     const size_t smem = ref_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0);
     if (smem > 200 * 1024) return fail(MCL_ERR_ARG, "update: too many beams for the shared-memory staging area");
     if (!attr_set) {

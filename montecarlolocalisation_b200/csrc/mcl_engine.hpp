@@ -94,6 +94,7 @@ public:
     int64_t n_global = 0, shard_begin = 0, per_rank = 0;
     int download_resample_draws(double* u_r, double* u_jit);
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
+    int debug_trigf(const float* x, int64_t count, float* s_out, float* c_out, int* kind_out);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
                     K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
@@ -117,6 +118,8 @@ public:
 
 private:
     int fail(int code, const std::string& what);
+    int resolve_trig();                     // cfg.trig_mode -> trig_kind (probes the host libm for MCL_TRIG_LIBM)
+    int trig_kind = 2;                      // TRIG_GLIBC_FMA / TRIG_GLIBC_SSE2 / TRIG_CR (mcl_device.cuh)
     int cuda_fail(cudaError_t e, const char* where);
     int ensure_particles(int64_t count);
     int ref_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,

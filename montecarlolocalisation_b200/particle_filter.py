@@ -262,6 +262,13 @@ class ParticleFilter:
         self._ck(self.L.mcl_debug_exact_scan(self.h, w.ctypes.data_as(_fp), len(w), cdf.ctypes.data_as(_dp), C.byref(total), C.byref(fb)))
         return cdf, total.value, fb.value
 
+    def trigf(self, x):
+        """(sin, cos, kind) of the float trig the REF kernels evaluate, on the device (mcl_debug_trigf)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        s = np.empty_like(x); c = np.empty_like(x); kind = C.c_int32()
+        self._ck(self.L.mcl_debug_trigf(self.h, x.ctypes.data_as(_fp), x.size, s.ctypes.data_as(_fp), c.ctypes.data_as(_fp), C.byref(kind)))
+        return s, c, kind.value
+
     def forceSequential(self, on):
         """bit 0: single-chain accumulation kernels; bit 1: per-particle computeWeight kernel (cross-checks)."""
         self._ck(self.L.mcl_debug_force_sequential(self.h, int(on)))

@@ -270,6 +270,11 @@ extern "C" {
 void* orc_create() { return new Ctx(); }
 void orc_destroy(void* h) { delete (Ctx*)h; }
 void orc_set_trig_mode(void* h, int m) { ((Ctx*)h)->trig_mode = m; }
+// this process's libm sinf / cosf (what the reference binary calls at MC:644-645 and, through Eigen, MC:747-748) over an
+// array: the checker of the engine's device restatement of them (csrc/glibc_trigf.cuh)
+void orc_libm_trigf(const float* x, long long n, float* s_out, float* c_out) {
+    for (long long i = 0; i < n; ++i) { volatile float v = x[i]; s_out[i] = sinf(v); c_out[i] = cosf(v); }
+}
 long long orc_clamp_count(void* h) { return ((Ctx*)h)->clamp_count; }
 
 // ---- map.txt -> wall lists -> occupancy grid (publish_map.py:8-16, Cell.msg:2-5, RV:272-276,306-437)

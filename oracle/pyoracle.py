@@ -77,6 +77,15 @@ def oracle_lib():
     return _oracle_lib
 
 
+def libm_trigf(x):
+    """(sinf(x), cosf(x)) of this process's libm for a float32 array."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s = np.empty_like(x); c = np.empty_like(x)
+    oracle_lib().orc_libm_trigf(x.ctypes.data_as(C.POINTER(C.c_float)), C.c_longlong(x.size), s.ctypes.data_as(C.POINTER(C.c_float)),
+                                c.ctypes.data_as(C.POINTER(C.c_float)))
+    return s, c
+
+
 class Oracle:
     """One reference-process worth of global state (map, LUTs, motion model, injection EMA)."""
 

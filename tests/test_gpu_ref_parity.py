@@ -1,7 +1,11 @@
 """GPU parity, MCL_MODE_REF: the CUDA engine (through the C-ABI) against the CPU oracle and the reference's golden
 vectors. Bar (BASELINE.json north_star): resampled indices and counts bit-exact; poses and weights within 1e-5
 relative. In practice every stage below is required to be bit-identical to the oracle, except theta after
-atan2(sin,cos) and the pose estimate, which go through device libm (<= 1 fp32 ulp / 1e-5)."""
+atan2(sin,cos) and the pose estimate, which go through device libm (<= 1 fp32 ulp / 1e-5).
+Float trig (MC:644-645, 747-748) comes in two definitions on both sides: "libm" = what the reference binary computes
+(engine MCL_TRIG_LIBM, the default, against oracle trig_mode 0 = this host's sinf/cosf) and "cr" = correctly rounded
+(engine MCL_TRIG_CORRECTLY_ROUNDED against oracle trig_mode 1). With "libm" the engine is also bit-identical to the golden
+vectors recorded from the compiled reference itself."""
 import ctypes as C
 import os
 
@@ -27,19 +31,19 @@ def ulp_diff(a, b):
     return np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32))
 
 
-def make_pair(occ):
-    o = Oracle(trig_mode=1)
+def make_pair(occ, trig="libm"):
+    o = Oracle(trig_mode=0 if trig == "libm" else 1)
     o.set_map(occ, RES)
     o.precompute_ray_directions(-120.0, 120.0, 0.1)
-    pf = m.ParticleFilter()
+    pf = m.ParticleFilter(trig_mode=m.TRIG_LIBM if trig == "libm" else m.TRIG_CORRECTLY_ROUNDED)
     pf.setMap(occ, RES)
     return o, pf
 
 
-def run_loop(n, steps, seed, kidnap_at=None, jitter=None, n_beams=360, settle_injection_at=None):
+def run_loop(n, steps, seed, kidnap_at=None, jitter=None, n_beams=360, settle_injection_at=None, trig="libm"):
     """Free-running predict/update/resample/estimate on both sides with identical injected draws."""
     sc = Scenario(steps, n_beams=n_beams, kidnap_at=kidnap_at)
-    o, pf = make_pair(sc.occ)
+    o, pf = make_pair(sc.occ, trig)
     rng = np.random.default_rng(seed)
     n_rows, n_cols = o.cell_ranges()
     init = dict(u_yaw=rng.random(n), row=rng.integers(0, n_rows, n).astype(np.int32), col=rng.integers(0, n_cols, n).astype(np.int32),
@@ -88,9 +92,10 @@ def run_loop(n, steps, seed, kidnap_at=None, jitter=None, n_beams=360, settle_in
     return injected
 
 
-def test_config1_loop_1000_particles():
+@pytest.mark.parametrize("trig", ["libm", "cr"])
+def test_config1_loop_1000_particles(trig):
     """BASELINE.json config 1: map.txt, 1000 particles, 360-beam scan + odometry trace."""
-    run_loop(1000, 40, seed=1)
+    run_loop(1000, 40, seed=1, trig=trig)
 
 
 def test_config1_kidnap_triggers_injection():
@@ -117,26 +122,26 @@ def test_ragged_sizes():
         run_loop(n, 3, seed=100 + n)
 
 
-def test_config2_one_million_particles():
+@pytest.mark.parametrize("trig", ["libm", "cr"])
+def test_config2_one_million_particles(trig):
     """BASELINE.json config 2 at full size: 1M particles; indices bit-exact against the oracle."""
-    run_loop(1_000_000, 2, seed=4)
+    run_loop(1_000_000, 2, seed=4, trig=trig)
 
 
 def test_stagewise_against_reference_golden():
-    """Stage by stage from the golden inputs recorded from the compiled reference (libm float trig): the engine's
-    correctly-rounded float trig may move a predicted coordinate by one fp32 ulp; everything else must agree."""
+    """Stage by stage from the golden inputs recorded from the COMPILED REFERENCE (tests/golden/make_golden.py): with the
+    default float trig (MCL_TRIG_LIBM = the reference binary's sinf/cosf) the engine reproduces it bit for bit: predicted
+    particles, injected count, resampled particles and the adaptive-injection state."""
     g = np.load(G)
     pf = m.ParticleFilter()
     pf.setMap(g["occ"], RES)
-    n = int(g["n"])
     P = g["P0"].copy()
     for s in range(int(g["steps"])):
         pf.uploadParticles(P)
         mo = g["motion%d" % s]
         pf.updateParticlePos(mo[0], mo[1], mo[2])
         pred = pf.downloadParticles()
-        assert ulp_diff(pred[:, :3], g["pred%d" % s][:, :3]).max() <= 1.0
-        pf.uploadParticles(g["pred%d" % s])
+        assert np.array_equal(pred[:, :3], g["pred%d" % s][:, :3]), "predict step %d" % s
         pf.computeWeight(g["scan%d_ranges" % s], g["scan%d_angle_min" % s], g["scan%d_angle_inc" % s], g["scan%d_range_min" % s],
                          g["scan%d_range_max" % s])
         a = g["inj%d" % s]
@@ -145,12 +150,29 @@ def test_stagewise_against_reference_golden():
         assert st["injected"] == int(g["injected%d" % s])
         new = pf.downloadParticles()
         gold_new = g["new%d" % s]
-        mism = (new[:, :2] != gold_new[:, :2]).any(axis=1)
-        assert mism.mean() <= 0.002, "step %d: %d particles differ from the reference" % (s, mism.sum())
-        ok = ~mism
-        assert ulp_diff(new[ok, 2], gold_new[ok, 2]).max() <= 1.0
-        assert np.array_equal(pf.injectionState(), g["inj_state%d" % s]) or mism.any()
+        mism = (new[:, :3] != gold_new[:, :3]).any(axis=1)
+        assert mism.sum() == 0, "step %d: %d particles differ from the reference" % (s, mism.sum())
+        assert np.array_equal(pf.injectionState(), g["inj_state%d" % s])
         P = gold_new
+
+
+def test_golden_with_correctly_rounded_trig_differs_only_by_rounding():
+    """The portable float trig against the same golden vectors: a predicted coordinate may move by one fp32 ulp (glibc's
+    sinf/cosf are not correctly rounded for 0.26 % / 0.55 % of arguments); nothing else may change."""
+    g = np.load(G)
+    pf = m.ParticleFilter(trig_mode=m.TRIG_CORRECTLY_ROUNDED)
+    pf.setMap(g["occ"], RES)
+    P = g["P0"].copy()
+    moved = 0
+    for s in range(int(g["steps"])):
+        pf.uploadParticles(P)
+        mo = g["motion%d" % s]
+        pf.updateParticlePos(mo[0], mo[1], mo[2])
+        pred = pf.downloadParticles()
+        assert ulp_diff(pred[:, :3], g["pred%d" % s][:, :3]).max() <= 1.0
+        moved += int((pred[:, :3] != g["pred%d" % s][:, :3]).sum())
+        P = g["new%d" % s]
+    assert moved > 0
 
 
 def test_edge_total_weight_zero_and_empty_scan():
@@ -222,7 +244,7 @@ def test_philox_injected_particles_are_sample_particles_of_the_named_draws(whole
     on the CPU, through the per-function calls and through the whole-tick call."""
     seed, n = 0x123456789, 20011
     sc = Scenario(1, n_beams=360, seed=9)
-    o = Oracle(trig_mode=1)
+    o = Oracle(trig_mode=0)
     o.set_map(sc.occ, RES)
     n_rows, n_cols = o.cell_ranges()
     pf = m.ParticleFilter(max_particles=n, seed=seed)
@@ -300,7 +322,7 @@ def test_large_map_not_in_shared_memory():
     P = np.zeros((n, 4), np.float32)
     P[:, 0] = rng.uniform(0, 102.5, n); P[:, 1] = rng.uniform(0, 102.5, n); P[:, 2] = rng.uniform(-3.2, 3.2, n); P[:, 3] = 1
     scan = synth.make_scan(occ, 0.1, (30.45, 40.45, 0.3), 360, 5)
-    o = Oracle(trig_mode=1); o.set_map(occ, RES); o.precompute_ray_directions()
+    o = Oracle(trig_mode=0); o.set_map(occ, RES); o.precompute_ray_directions()
     pf = m.ParticleFilter(); pf.setMap(occ, RES)
     Po = P.copy()
     total_o = o.compute_weight(Po, Scan(**scan))
@@ -322,7 +344,7 @@ def test_nonzero_map_origin():
     P[:, 3] = 1
     scan = Scenario(1).scans[0]
     o = Oracle(trig_mode=1); o.set_map(occ, RES, ox, oy); o.precompute_ray_directions()
-    pf = m.ParticleFilter(); pf.setMap(occ, RES, ox, oy)
+    pf = m.ParticleFilter(trig_mode=m.TRIG_CORRECTLY_ROUNDED); pf.setMap(occ, RES, ox, oy)
     Po = P.copy()
     total_o = o.compute_weight(Po, Scan(**scan))
     pf.uploadParticles(P)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def make_pair(occ):
-    o = Oracle(trig_mode=1)
+    o = Oracle(trig_mode=0)          # the host libm's sinf/cosf, like the engine's default MCL_TRIG_LIBM
     o.set_map(occ, RES)
     o.precompute_ray_directions(-120.0, 120.0, 0.1)
     pf = m.ParticleFilter()
