@@ -80,12 +80,14 @@ def raycast_true(occ, res, x, y, angles, max_range):
 
 
 def make_scan(occ, res, pose, n_beams, seed, range_min=0.02, range_max=5.6, noise_sigma=0.01, p_nan=0.05,
-              laser_offset=0.1):
-    """A full-circle scan (angle_min=-pi, inc=2pi/B as float32) seen from `pose`. The sensor sits laser_offset
-    ahead of the robot and its beam angles are mirrored, matching how the reference projects them (MC:644,653)."""
+              laser_offset=0.1, angle_min=None, angle_inc=None):
+    """A scan seen from `pose`: full circle by default (angle_min=-pi, inc=2pi/B as float32), or the given float32
+    angle_min / angle_inc (e.g. the robot's own 683 beams at 0.352 degrees from -120 degrees, comment MC:638-640). The sensor
+    sits laser_offset ahead of the robot and its beam angles are mirrored, matching how the reference projects them
+    (MC:644,653)."""
     rng = SplitMix64(seed)
-    angle_min = np.float32(-np.pi)
-    angle_inc = np.float32(2 * np.pi / n_beams)
+    angle_min = np.float32(-np.pi) if angle_min is None else np.float32(angle_min)
+    angle_inc = np.float32(2 * np.pi / n_beams) if angle_inc is None else np.float32(angle_inc)
     beam = np.float64(angle_min) + np.arange(n_beams) * np.float64(angle_inc)
     x, y, th = pose
     lx, ly = x + laser_offset * np.cos(th), y + laser_offset * np.sin(th)

