@@ -37,7 +37,9 @@ struct Par {
 };
 constexpr uint64_t SAT = 1ull << 60;      // saturating cap: a composite this large means the binade prediction was wrong
 
-XS_HD uint64_t sat_add(uint64_t a, uint64_t b) { uint64_t s = a + b; return (s >= SAT || a >= SAT || b >= SAT) ? SAT : s; }
+// Every Par component is <= SAT by construction (par_of_weight clamps, par_compose saturates, the identity is 0), so a + b
+// cannot wrap and "either operand saturated" implies s >= SAT: the cap is decided on the high word of the sum alone.
+XS_HD uint64_t sat_add(uint64_t a, uint64_t b) { uint64_t s = a + b; return (uint32_t)(s >> 32) >= (uint32_t)(SAT >> 32) ? SAT : s; }
 
 XS_HD Par par_identity() { return Par{0, 0}; }
 // apply a first, then b

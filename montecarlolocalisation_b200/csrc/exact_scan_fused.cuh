@@ -1,0 +1,563 @@
+// exact_scan_fused.cuh — the bit-exact sequential f64 accumulation (exact_scan_core.cuh) as ONE kernel per accumulation.
+//
+// exact_scan.cuh runs an accumulation as three to five dependent launches (tile sums, classification scan, chain, apply scan,
+// fallback), each re-reading the weights; at 1M particles the launches cost more than the arithmetic. Here a tile of 2048
+// weights stays in the registers of its block through all four stages and the stages of DIFFERENT tiles are ordered by
+// per-tile flags instead of kernel boundaries:
+//
+//   1. tile sum -> pub1[t]                                                (publish)
+//      wait for pub1 of every lower tile; P~ at the tile's two edges = F(t), F(t + 1), a FIXED-association sum of
+//      tsum[0 .. t) that every block evaluates identically (so neighbouring tiles agree on the value at their shared edge)
+//   2. classify by THREAD (16 consecutive weights): a thread whose first item's predecessor and whose last item lie safely
+//      inside one binade E holds only PAR items of that binade (the sums are non-decreasing): their increments of the integer
+//      significand are RN(w / 2^(E-52)), a pair (even, odd) only for exact ties - a handful of independent f64 operations
+//      per item. A thread that straddles a binade edge or the start of the sum, or holds a negative, NaN, Inf or huge weight,
+//      becomes one SEQ block: its 16 weights go through the hardware adder in order (~20 such threads per million weights).
+//      Segmented parity-monoid scan of the thread aggregates -> SEQ blocks + tile summary pub2[2t..]
+//      wait for pub2 of every lower tile; segmented scan of their summaries -> the composite carried into this tile and
+//      the SEQ blocks below it, in order
+//   3. one thread walks the SEQ blocks of the lower tiles and of this tile with the hardware adder (every block does this
+//      redundantly, and no block waits for another block's walk)
+//   4. apply: exact s_i for the tile's own elements from the registers -> CDF (or just the total). What a PAR thread writes
+//      is VERIFIED, not predicted: the value entering it must lie in binade E and its last value below 2^(E+1).
+//
+// Tiles are taken in ticket order, so a block only ever waits for tiles that are already running: no co-residency
+// requirement, any number of tiles, safe next to other kernels. What a tile publishes is self-validating 64-bit words (data
+// and "ready" in one load, no fence on the polling path), which the last block to finish leaves empty for the next launch. The last block to finish runs the single-chain fallback if any prediction could not be trusted, so
+// correctness never rests on the margin analysis, and (optionally) advances the adaptive-injection state from the total
+// (what k_ref_ema did as a launch of its own).
+#pragma once
+#include "exact_scan.cuh"
+
+namespace mcl {
+namespace xs {
+
+constexpr int XSF_ITEMS = 16;                // per thread: 4 x float4 (a 1M-weight accumulation is 245 tiles: one wave at 3 CTAs per SM, and
+                                             // one round of the block-wide scan over the lower tiles' summaries)
+constexpr int XSF_TILE = XS_THREADS * XSF_ITEMS;
+constexpr int XSF_WALK = 96;                 // SEQ blocks below a tile that its block can walk (more: fallback)
+constexpr int XSF_BLOCKS = 48;               // SEQ blocks per tile (more: fallback); the summary words carry the count in 8 bits
+constexpr int XSF_BSTRIDE = 64;              // blocks reserved per tile in global memory
+constexpr int XSF_PSTRIDE = 16;              // u64 words between published records: one 128-byte line each, so that the polls of
+                                             // all tiles (every tile reads every lower tile's words) spread over the L2 slices
+constexpr int XSF_MAX_TILES = 1 << 13;       // beyond (16M weights) the multi-launch form takes over
+
+struct FusedWs {
+    unsigned long long* pub;     // [16 nt]  one line per tile: word 0 the tile sum, words 2-3 the tile summary (self-validating)
+    struct SeqBlock* blocks;     // [nt * 16]  SEQ blocks of every tile, written before the tile's summary words
+    unsigned* counters;          // [0] tile ticket, [1] finished blocks (both left at 0 by the last block), [2] == epoch: fall back
+    unsigned long long* trace;   // null, or [nt][8] %globaltimer stamps at the stage boundaries of every tile (mcl_debug_exact_scan_trace)
+};
+// adaptive injection (MC:469-492) advanced by the accumulation that produces the total (mcl_step); inj == null: not asked
+struct FusedEma {
+    double* inj;             // {weight_slow, weight_fast, p_inject, cdf_is_monotone, total}
+    int* counters;           // resampling counters [0..3], cleared for the resampling that follows
+    double n, a_slow, a_fast;
+};
+
+__device__ __forceinline__ unsigned long long xsf_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define XSF_STAMP(k) do { if (ws.trace != nullptr && tid == 0) ws.trace[(size_t)t * 16 + (k)] = xsf_now(); } while (0)
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__device__ __forceinline__ void load_items12(const float* __restrict__ w, int64_t base, int64_t n, float (&x)[XSF_ITEMS]) {
+    if (base + XSF_ITEMS <= n) {
+        const float4* p = reinterpret_cast<const float4*>(w + base);          // base is a multiple of 16 floats
+#pragma unroll
+        for (int q = 0; q < XSF_ITEMS / 4; q++) { const float4 a = __ldg(p + q); x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < XSF_ITEMS; j++) x[j] = (base + j < n) ? w[base + j] : 0.f;
+    }
+}
+
+// Deterministic block-wide sum of one double per thread: warp trees (fixed shuffle pattern), then the warp totals in order.
+__device__ __forceinline__ double block_sum_fixed(double v, double* smem8) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_down_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem8[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < XS_THREADS / 32; k++) s = dadd(s, smem8[k]);
+    return s;
+}
+
+// The single-chain fallback inside the fused kernel: s_i = s_{i-1} + (double)w_i left to right by one thread while the rest
+// of the block stages the next 1024 terms (normalised on the fly when the accumulation is the CDF's).
+template <bool CDF>
+__device__ __forceinline__ void fused_sequential(const float* __restrict__ w, int64_t n, double divisor, double* __restrict__ cdf,
+                                                 double* __restrict__ total_out, float (*tile)[XS_SEQ_TILE], double (*outb)[XS_SEQ_TILE]) {
+    double acc = 0.0;
+    const int64_t n_tiles = (n + XS_SEQ_TILE - 1) / XS_SEQ_TILE;
+    auto term = [&](int64_t g) -> float {
+        if (g >= n) return 0.f;
+        const float x = w[g];
+        return CDF ? __double2float_rn(ddiv((double)x, divisor)) : x;
+    };
+    for (int i = threadIdx.x; i < XS_SEQ_TILE; i += blockDim.x) tile[0][i] = term(i);
+    __syncthreads();
+    for (int64_t t = 0; t < n_tiles; t++) {
+        const int cur = t & 1;
+        if (threadIdx.x == 0) {
+            const int64_t cnt = min((int64_t)XS_SEQ_TILE, n - t * XS_SEQ_TILE);
+            for (int i = 0; i < cnt; i++) { acc = dadd(acc, (double)tile[cur][i]); if (CDF) outb[cur][i] = acc; }
+        } else {
+            if (CDF && t > 0) {
+                const int64_t base = (t - 1) * XS_SEQ_TILE;
+                for (int i = threadIdx.x - 1; i < XS_SEQ_TILE; i += blockDim.x - 1) { const int64_t g = base + i; if (g < n) cdf[g] = outb[cur ^ 1][i]; }
+            }
+            if (t + 1 < n_tiles) {
+                const int64_t base = (t + 1) * XS_SEQ_TILE;
+                for (int i = threadIdx.x - 1; i < XS_SEQ_TILE; i += blockDim.x - 1) tile[cur ^ 1][i] = term(base + i);
+            }
+        }
+        __syncthreads();
+    }
+    if (CDF) {
+        const int64_t base = (n_tiles - 1) * XS_SEQ_TILE;
+        const int cur = (n_tiles - 1) & 1;
+        for (int i = threadIdx.x; i < XS_SEQ_TILE; i += blockDim.x) { const int64_t g = base + i; if (g < n) cdf[g] = outb[cur][i]; }
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = acc;
+}
+
+// A thread's 16 weights that go through the hardware adder in order, with the composite of the PAR items between the previous
+// SEQ block of the tile (or the tile's start) and the block, and the predicted binade of the value that composite applies to.
+struct SeqBlock {
+    uint32_t idx0;
+    int n_items;
+    Par pre;
+    int first_in_tile, E_prev;
+    float w[XSF_ITEMS];
+};
+constexpr int XSF_BPIECES = (int)sizeof(SeqBlock) / 16;
+static_assert(sizeof(SeqBlock) == 32 + 4 * XSF_ITEMS && sizeof(SeqBlock) % 16 == 0, "published as 16-byte words");
+__device__ __forceinline__ SeqBlock ld_seq_block(const SeqBlock* p) {          // what another CTA published: from L2, never a stale L1 line
+    SeqBlock b;
+    const int4* q = reinterpret_cast<const int4*>(p);
+    int4* d = reinterpret_cast<int4*>(&b);
+#pragma unroll
+    for (int k = 0; k < XSF_BPIECES; k++) d[k] = __ldcg(q + k);
+    return b;
+}
+
+// published words, one 128-byte line per tile: pub[16 t] = the bits of tile t's f64 sum (never the EMPTY NaN pattern);
+// pub[16 t + 2], pub[16 t + 3] = the tile summary, word = composite component (clamped to 2^58: anything that large means a
+// wrong prediction and fails verification) | four bits of the SEQ block count << 59 | valid << 63. The last block of every
+// launch leaves all of them EMPTY, so a word is data and "ready" flag in one: polling needs no second load and no fence.
+constexpr unsigned long long XSF_EMPTY1 = ~0ull;
+constexpr unsigned long long XSF_VALID = 1ull << 63;
+constexpr unsigned long long XSF_VMASK = (1ull << 59) - 1, XSF_VCLAMP = 1ull << 58;
+__device__ __forceinline__ unsigned long long xsf_pack(unsigned long long v, unsigned cnt4) {
+    return (v < XSF_VCLAMP ? v : XSF_VCLAMP) | ((unsigned long long)(cnt4 & 15u) << 59) | XSF_VALID;
+}
+__device__ __forceinline__ void ld_relaxed_u64x2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// CDF == false: *total_out = w_0 + w_1 + ... left to right                                  (MC:675)
+// CDF == true : x_i = (float)((double)w_i / *divisor), cdf[i] = x_0 + ... + x_i              (MC:496-505)
+template <bool CDF>
+__global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restrict__ w, int64_t n, int nt, unsigned epoch, FusedWs ws,
+                                                            const double* __restrict__ divisor, double* __restrict__ cdf_out,
+                                                            double* __restrict__ total_out, FusedEma ema) {
+    pdl_enter();
+    __shared__ double sm_d[8];
+    __shared__ double sm_last[8];
+    __shared__ unsigned long long sm_u[8];
+    __shared__ ScanState sm_st[8];
+    __shared__ ScanState sm_carry_in, sm_tile_state;
+    __shared__ int sm_tile, sm_fail, sm_is_last;
+    __shared__ double sm_start;                                        // exact value after the last SEQ block below this tile
+    __shared__ int sm_start_valid;                                     // 0: no SEQ block below this tile (the sum so far is exactly 0)
+    // one raw block, two lives: [SEQ blocks below this tile | this tile's own | exact values after every item of the own blocks]
+    // while the tile is processed, the single-chain fallback's staging buffers in the last block to finish
+    constexpr int WALK_BYTES = XSF_WALK * (int)sizeof(SeqBlock), OWN_BYTES = XSF_BLOCKS * (int)sizeof(SeqBlock), OWNS_BYTES = XSF_BLOCKS * XSF_ITEMS * (int)sizeof(double);
+    constexpr int FB_BYTES = 2 * XS_SEQ_TILE * (int)sizeof(float) + 2 * XS_SEQ_TILE * (int)sizeof(double);
+    constexpr int RAW_BYTES = WALK_BYTES + OWN_BYTES + OWNS_BYTES > FB_BYTES ? WALK_BYTES + OWN_BYTES + OWNS_BYTES : FB_BYTES;
+    __shared__ __align__(16) unsigned char sm_raw[RAW_BYTES];
+    SeqBlock* const sm_walk = reinterpret_cast<SeqBlock*>(sm_raw);
+    SeqBlock* const sm_own = reinterpret_cast<SeqBlock*>(sm_raw + WALK_BYTES);
+    double* const sm_own_s = reinterpret_cast<double*>(sm_raw + WALK_BYTES + OWN_BYTES);      // [block][item]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        sm_tile = (int)atomicAdd(ws.counters + 0, 1u);
+        sm_fail = 0;
+        sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0;
+    }
+    __syncthreads();
+    const int t = sm_tile;
+    XSF_STAMP(0);
+    const int64_t base = (int64_t)t * XSF_TILE + (int64_t)tid * XSF_ITEMS;
+    float x[XSF_ITEMS];
+    load_items12(w, base, n, x);
+    if (CDF) {
+        // x = (float)((double)w / total) (MC:497,503) without a division per element: r = w * (1 / total) is within 1.5 ulp of
+        // the quotient, so the quotient and its correctly rounded double both lie in [r (1 - 2^-50), r (1 + 2^-50)]; when the two
+        // ends round to the same float that float is the answer, otherwise (~1e-8 of the elements, and NaN) the division decides
+        const double tot = *divisor;
+        const double inv = ddiv(1.0, tot);
+#pragma unroll
+        for (int j = 0; j < XSF_ITEMS; j++) {
+            const double r = dmul((double)x[j], inv);
+            const float lo = __double2float_rn(dmul(r, 1.0 - 0x1p-50)), hi = __double2float_rn(dmul(r, 1.0 + 0x1p-50));
+            x[j] = (base + j < n) ? (lo == hi ? lo : __double2float_rn(ddiv((double)x[j], tot))) : 0.f;
+        }
+    }
+    // ---- stage 1: tile sum, then P~ at the tile's edges from the lower tiles' sums --------------------------------------------
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < XSF_ITEMS; j++) s = dadd(s, (double)x[j]);
+    const double incl = block_scan_incl(s, sm_d);
+    double excl_thr = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 31) sm_last[warp] = incl;
+    __syncthreads();
+    if (lane == 0) excl_thr = warp ? sm_last[warp - 1] : 0.0;
+    const double tile_sum = sm_last[XS_THREADS / 32 - 1];
+    if (tid == 0) {
+        unsigned long long b = (unsigned long long)__double_as_longlong(tile_sum);
+        if (tile_sum != tile_sum) b = 0x7ff8000000000000ull;          // any NaN: the canonical one (never the EMPTY pattern)
+        st_relaxed_u64(ws.pub + (size_t)t * XSF_PSTRIDE, b);
+    }
+    XSF_STAMP(1);
+    double part = 0.0;
+    for (int k0 = tid; k0 < t; k0 += 2 * XS_THREADS) {                  // two lower tiles per round trip
+        const int k1 = k0 + XS_THREADS;
+        const unsigned long long* p0 = ws.pub + (size_t)k0 * XSF_PSTRIDE;
+        const unsigned long long* p1 = ws.pub + (size_t)k1 * XSF_PSTRIDE;
+        unsigned long long v0 = ld_relaxed_u64(p0), v1 = k1 < t ? ld_relaxed_u64(p1) : 0ull;
+        while (v0 == XSF_EMPTY1) v0 = ld_relaxed_u64(p0);              // (plain spinning: __nanosleep oversleeps by microseconds here)
+        while (v1 == XSF_EMPTY1) v1 = ld_relaxed_u64(p1);
+        part = dadd(part, __longlong_as_double((long long)v0));
+        if (k1 < t) part = dadd(part, __longlong_as_double((long long)v1));
+    }
+    const double toff = block_sum_fixed(part, sm_d);                                        // F(t)
+    if (tid == (t % XS_THREADS)) part = dadd(part, tile_sum);
+    const double toff_next = block_sum_fixed(part, sm_d);                                   // F(t + 1): the same value tile t + 1 computes as its F
+    XSF_STAMP(2);
+    const int64_t tile_end = min(n, (int64_t)(t + 1) * XSF_TILE);       // one past the last valid element of this tile
+    // P~ after this thread's last item, and after the previous thread's (tile edges are shared values)
+    double my_last = dadd(toff, dadd(excl_thr, s));
+    if (base + XSF_ITEMS - 1 >= tile_end - 1 && base <= tile_end - 1) my_last = toff_next;
+    double prev_last = __shfl_up_sync(0xffffffffu, my_last, 1);
+    __syncthreads();
+    if (lane == 31) sm_last[warp] = my_last;
+    __syncthreads();
+    if (lane == 0) prev_last = warp ? sm_last[warp - 1] : toff;
+    const uint64_t depth = 2ull * (uint64_t)((nt + 31) / 32) + 64;
+    // ---- stage 2: thread kinds, increments, segmented parity-monoid scan ---------------------------------------------------------
+    const int n_mine = (int)max((int64_t)0, min((int64_t)XSF_ITEMS, n - base));              // valid items of this thread
+    const uint64_t thr_margin = margin_for((uint64_t)min(n, base + XSF_ITEMS), depth);
+    const Pred q0 = predict(prev_last, thr_margin), q1 = predict(my_last, thr_margin);
+    // P~ exactly zero after the thread and its own weights all (+-)0: every weight so far is zero, so are the sums. (Earlier
+    // weights that cancel, +1 then -1, sit in a SEQ block - a negative weight is never PAR - and the apply stage checks
+    // that no block precedes a zero thread.)
+    bool own_zero = true;
+#pragma unroll
+    for (int j = 0; j < XSF_ITEMS; j++) own_zero &= (x[j] == 0.f);
+    const bool zero = n_mine == 0 || (my_last == 0.0 && own_zero);
+    const int thr_E = q0.E;
+    bool easy = !zero && q0.ok && q1.ok && q0.E == q1.E && thr_E >= -900 && thr_E <= 900;
+    const double fscale = __longlong_as_double((long long)(1023 + 52 - (easy ? thr_E : 0)) << 52);          // 2^(52 - E)
+    // increment of the significand by weight xj in binade E: even = for an even significand, odd = for an odd one (they differ
+    // by one for an exact tie, MC's round-to-nearest-even); invalid: negative, NaN, Inf or too large for the binade
+    auto increment = [&](float xj, unsigned long long& odd, bool& invalid) -> unsigned long long {
+        const double y = dmul((double)xj, fscale);
+        const double z = dadd(y, 0x1p52);                                      // RN-even(y) in the low significand bits
+        const double r = dsub(y, dsub(z, 0x1p52));                             // y - RN(y), exact
+        invalid = !(y >= 0.0) || !(y < 0x1p52);
+        const unsigned long long even = (unsigned long long)__double_as_longlong(z) & ((1ull << 52) - 1);
+        odd = r == 0.5 ? even + 1 : (r == -0.5 ? even - 1 : even);
+        return even;
+    };
+    unsigned long long excl_d = 0, thr_d = 0;
+    bool has_tie = false;
+    Par thr_par = par_identity();
+    if (easy) {
+        bool any_invalid = false;
+#pragma unroll
+        for (int j = 0; j < XSF_ITEMS; j++) {
+            unsigned long long o; bool inv;
+            const unsigned long long e = increment(x[j], o, inv);              // (items past n are +0: nothing)
+            any_invalid |= inv; has_tie |= (o != e);
+            thr_d += e;
+        }
+        easy = !any_invalid;
+        if (easy && has_tie) {                                                 // rare: the thread's composite depends on the parity
+#pragma unroll 1
+            for (int j = 0; j < XSF_ITEMS; j++) {
+                float xj = x[0];
+#pragma unroll
+                for (int q = 1; q < XSF_ITEMS; q++) xj = (q == j) ? x[q] : xj;   // (x stays in registers)
+                unsigned long long o; bool inv;
+                Par f;
+                f.e = increment(xj, o, inv); f.o = o;
+                thr_par = par_compose(thr_par, f);
+            }
+        }
+    }
+    const bool is_block = !zero && !easy;
+    const bool fast = !__syncthreads_or(!easy || has_tie);          // every thread easy and tie-free: the tile is one u64 prefix sum
+    ScanState pre;
+    pre.v = par_identity(); pre.reset = 0; pre.cnt = 0;
+    ScanState agg;
+    agg.v = par_identity(); agg.reset = 0; agg.cnt = 0;
+    if (fast) {
+        unsigned long long incl_d = thr_d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl_d, o);
+            if (lane >= o) incl_d += up;
+        }
+        if (lane == 31) sm_u[warp] = incl_d;
+        __syncthreads();
+        unsigned long long woff = 0, whole = 0;
+#pragma unroll
+        for (int k = 0; k < XS_THREADS / 32; k++) { if (k < warp) woff += sm_u[k]; whole += sm_u[k]; }
+        excl_d = woff + incl_d - thr_d;
+        if (tid == XS_THREADS - 1) {
+            const unsigned long long D = whole < SAT ? whole : SAT;
+            sm_tile_state.v.e = D; sm_tile_state.v.o = D; sm_tile_state.reset = 0; sm_tile_state.cnt = 0;
+            st_relaxed_u64(ws.pub + (size_t)t * XSF_PSTRIDE + 2, xsf_pack(D, 0));
+            st_relaxed_u64(ws.pub + (size_t)t * XSF_PSTRIDE + 3, xsf_pack(D, 0));
+        }
+    } else {
+        if (easy) agg.v = has_tie ? thr_par : Par{thr_d < SAT ? thr_d : SAT, thr_d < SAT ? thr_d : SAT};
+        else if (is_block) { agg.reset = 1; agg.cnt = 1; }
+        // block-wide exclusive scan of the thread aggregates
+        ScanState inc = agg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            ScanState up = st_shfl_up(inc, o);
+            if (lane >= o) inc = st_combine(up, inc);
+        }
+        if (lane == 31) sm_st[warp] = inc;
+        __syncthreads();
+        for (int k = 0; k < warp; k++) pre = st_combine(pre, sm_st[k]);
+        {
+            ScanState lane_excl = st_shfl_up(inc, 1);
+            if (lane > 0) pre = st_combine(pre, lane_excl);
+        }
+        // SEQ blocks out: rank = blocks before this thread; composite = the PAR items since the previous block / the tile's start
+        if (is_block) {
+            if (pre.cnt < XSF_BLOCKS) {
+                SeqBlock b;
+                b.idx0 = (uint32_t)base; b.n_items = n_mine; b.pre = pre.v; b.first_in_tile = pre.reset ? 0 : 1; b.E_prev = q0.E;
+#pragma unroll
+                for (int j = 0; j < XSF_ITEMS; j++) b.w[j] = x[j];
+                sm_own[pre.cnt] = b;
+                int4* g = reinterpret_cast<int4*>(ws.blocks + (size_t)t * XSF_BSTRIDE + pre.cnt);
+                const int4* sb4 = reinterpret_cast<const int4*>(&b);
+#pragma unroll
+                for (int k = 0; k < XSF_BPIECES; k++) g[k] = sb4[k];
+                __threadfence();                               // the block before the summary words
+            } else sm_fail = 1;
+        }
+        __syncthreads();
+        // state of the whole tile = the last thread's inclusive state; publish it
+        if (tid == XS_THREADS - 1) {
+            const ScanState whole = st_combine(pre, agg);
+            sm_tile_state = whole;
+            const unsigned cnt = (unsigned)min(whole.cnt, XSF_BLOCKS);
+            if (whole.cnt > XSF_BLOCKS) sm_fail = 1;
+            st_relaxed_u64(ws.pub + (size_t)t * XSF_PSTRIDE + 2, xsf_pack(whole.v.e, cnt & 15u));
+            st_relaxed_u64(ws.pub + (size_t)t * XSF_PSTRIDE + 3, xsf_pack(whole.v.o, cnt >> 4));
+        }
+    }
+    XSF_STAMP(3);
+    // ---- stage 3: the composite carried into this tile, and the SEQ blocks below it ---------------------------------------------------
+    __shared__ int sm_src[XSF_WALK];                  // walk position -> tile * XSF_BSTRIDE + block
+    __shared__ Par sm_cin[XSF_WALK];                  // walk position -> composite carried into that block's tile
+    for (int c0 = 0; c0 < t; c0 += XS_THREADS) {
+        const int k = c0 + tid;
+        ScanState mine;
+        mine.v = par_identity(); mine.reset = 0; mine.cnt = 0;
+        if (k < t) {
+            const unsigned long long* pk = ws.pub + (size_t)k * XSF_PSTRIDE + 2;
+            unsigned long long a, b;
+            ld_relaxed_u64x2(pk, a, b);
+            while (!(a & b & XSF_VALID)) ld_relaxed_u64x2(pk, a, b);
+            mine.v.e = a & XSF_VMASK; mine.v.o = b & XSF_VMASK;
+            if (mine.v.e >= XSF_VCLAMP) mine.v.e = SAT;
+            if (mine.v.o >= XSF_VCLAMP) mine.v.o = SAT;
+            mine.cnt = (int)(((a >> 59) & 15ull) | (((b >> 59) & 15ull) << 4));
+            mine.reset = mine.cnt ? 1 : 0;
+        }
+        XSF_STAMP(7);
+        ScanState in2 = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            ScanState up = st_shfl_up(in2, o);
+            if (lane >= o) in2 = st_combine(up, in2);
+        }
+        __syncthreads();                          // sm_st / sm_carry_in of the previous chunk consumed
+        if (lane == 31) sm_st[warp] = in2;
+        __syncthreads();
+        ScanState p2 = sm_carry_in;
+        for (int q = 0; q < warp; q++) p2 = st_combine(p2, sm_st[q]);
+        {
+            ScanState lane_excl = st_shfl_up(in2, 1);
+            if (lane > 0) p2 = st_combine(p2, lane_excl);            // state entering tile k: p2.cnt = SEQ blocks below it
+        }
+        for (int q = 0; q < mine.cnt; q++) {      // where tile k's blocks go in walk order, and what is carried into tile k
+            const int pos = p2.cnt + q;
+            if (pos >= XSF_WALK) { sm_fail = 1; break; }
+            sm_src[pos] = k * XSF_BSTRIDE + q;
+            sm_cin[pos] = p2.v;
+        }
+        __syncthreads();
+        if (tid == XS_THREADS - 1) sm_carry_in = st_combine(p2, mine);       // state leaving the chunk
+        __syncthreads();
+    }
+    {
+        // all threads fetch the blocks below this tile, 16 bytes each (their tiles' summary words were seen, and a fence
+        // follows: the blocks written before those words are visible); then the first block of every tile takes in what is
+        // carried into its tile
+        const int n_below = sm_fail ? 0 : min(sm_carry_in.cnt, XSF_WALK);
+        XSF_STAMP(8);
+        __threadfence();
+        XSF_STAMP(9);
+        for (int q = tid; q < n_below * XSF_BPIECES; q += XS_THREADS) {
+            const int f = q / XSF_BPIECES, piece = q - f * XSF_BPIECES;
+            reinterpret_cast<int4*>(sm_walk + f)[piece] = __ldcg(reinterpret_cast<const int4*>(ws.blocks + sm_src[f]) + piece);
+        }
+        __syncthreads();
+        for (int f = tid; f < n_below; f += XS_THREADS)
+            if (sm_walk[f].first_in_tile) { sm_walk[f].pre = par_compose(sm_cin[f], sm_walk[f].pre); sm_walk[f].first_in_tile = 0; }
+        __syncthreads();
+    }
+    XSF_STAMP(4);
+    const ScanState carry = sm_carry_in;             // state entering this tile
+    const ScanState tstate = sm_tile_state;
+    if (tid == 0) {
+        bool ok = sm_fail == 0;
+        double sv = 0.0;
+        if (ok) {
+            const int n_below = min(carry.cnt, XSF_WALK);
+            for (int q = 0; q < n_below; q++) {
+                const SeqBlock* b = sm_walk + q;
+                sv = par_apply(sv, b->pre, b->E_prev, ok);
+                const int m = b->n_items;
+                for (int k = 0; k < m; k++) sv = dadd(sv, (double)b->w[k]);      // the hardware adder: exactly the reference's rounding
+            }
+            sm_start = sv; sm_start_valid = carry.cnt > 0;
+            const int own = min(tstate.cnt, XSF_BLOCKS);
+            for (int q = 0; q < own; q++) {
+                const SeqBlock* b = sm_own + q;
+                const Par comp = b->first_in_tile ? par_compose(carry.v, b->pre) : b->pre;
+                sv = par_apply(sv, comp, b->E_prev, ok);
+                for (int k = 0; k < XSF_ITEMS; k++) { sv = dadd(sv, k < b->n_items ? (double)b->w[k] : 0.0); sm_own_s[q * XSF_ITEMS + k] = sv; }
+            }
+        }
+        if (!ok) sm_fail = 1;
+    }
+    __syncthreads();
+    XSF_STAMP(5);
+    // ---- stage 4: apply ----------------------------------------------------------------------------------------------------------
+    bool okflag = sm_fail == 0;
+    const double start0 = sm_start_valid ? sm_start : 0.0;
+    if (okflag && (fast || easy)) {
+        // value after the last SEQ block before this thread, and the composite of the PAR items since then
+        double thr_start = start0;
+        Par thr_comp = carry.v;
+        bool have_start = sm_start_valid != 0;
+        if (!fast) {
+            if (pre.reset) { thr_start = sm_own_s[min(pre.cnt - 1, XSF_BLOCKS - 1) * XSF_ITEMS + XSF_ITEMS - 1]; thr_comp = pre.v; have_start = true; }
+            else thr_comp = par_compose(carry.v, pre.v);
+        }
+        // integer significand entering the thread; every item adds its increment
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(thr_start);
+        const int be = (int)((sb >> 52) & 0x7ff);
+        const unsigned long long A_start = (sb & ((1ull << 52) - 1)) | (1ull << 52);
+        const unsigned long long csel = (A_start & 1) ? thr_comp.o : thr_comp.e;
+        okflag = have_start && !(sb >> 63) && be - 1023 == thr_E && csel < SAT;
+        unsigned long long A = A_start + csel + excl_d;
+        const unsigned long long hi_bits = (unsigned long long)be << 52;
+#pragma unroll
+        for (int j = 0; j < XSF_ITEMS; j++) {
+            const int64_t i = base + j;
+            if (i >= n) break;
+            unsigned long long o; bool inv;
+            const unsigned long long e = increment(x[j], o, inv);
+            A += (A & 1) ? o : e;
+            const double v = __longlong_as_double((long long)(hi_bits | (A & ((1ull << 52) - 1))));
+            if (CDF) cdf_out[i] = v;
+            if (i == n - 1 && total_out) *total_out = v;
+        }
+        if (A >= (1ull << 53)) okflag = false;           // the thread's last value left the binade: the prediction was wrong
+    } else if (okflag && is_block) {
+#pragma unroll
+        for (int j = 0; j < XSF_ITEMS; j++) {
+            const int64_t i = base + j;
+            if (i >= n) break;
+            const double v = sm_own_s[min(pre.cnt, XSF_BLOCKS - 1) * XSF_ITEMS + j];
+            if (CDF) cdf_out[i] = v;
+            if (i == n - 1 && total_out) *total_out = v;
+        }
+    } else if (okflag) {
+        // every weight up to and including this thread's is zero: so are the sums
+        if (n_mine > 0 && (carry.cnt != 0 || pre.cnt != 0)) okflag = false;       // (cannot happen: a SEQ block means a non-zero P~ before here)
+#pragma unroll
+        for (int j = 0; j < XSF_ITEMS; j++) {
+            const int64_t i = base + j;
+            if (i >= n) break;
+            if (CDF) cdf_out[i] = 0.0;
+            if (i == n - 1 && total_out) *total_out = 0.0;
+        }
+    }
+    if (!okflag) atomicExch(ws.counters + 2, epoch);
+    XSF_STAMP(6);
+    // ---- the last block to finish: clean-up, fallback if anybody asked for it, then the adaptive-injection state ---------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sm_is_last = atomicAdd(ws.counters + 1, 1u) == (unsigned)nt - 1u;
+    __syncthreads();
+    if (!sm_is_last) return;
+    __threadfence();
+    for (int k = tid; k < nt; k += XS_THREADS) {
+        unsigned long long* pk = ws.pub + (size_t)k * XSF_PSTRIDE;
+        pk[0] = XSF_EMPTY1; pk[2] = 0ull; pk[3] = 0ull;
+    }
+    if (tid == 0) { ws.counters[0] = 0; ws.counters[1] = 0; }
+    if (*(volatile unsigned*)(ws.counters + 2) == epoch) {
+        __syncthreads();                          // every thread is done with what lived in sm_raw
+        fused_sequential<CDF>(w, n, CDF ? *divisor : 1.0, cdf_out, total_out, reinterpret_cast<float(*)[XS_SEQ_TILE]>(sm_raw),
+                              reinterpret_cast<double(*)[XS_SEQ_TILE]>(sm_raw + 2 * XS_SEQ_TILE * sizeof(float)));
+        __syncthreads();
+    }
+    if (ema.inj != nullptr && tid == 0) {
+        // adaptive injection (MC:469-492): the same IEEE operations in the same order as the host form in Engine::ref_resample
+        ema.counters[0] = 0; ema.counters[1] = 0; ema.counters[2] = 0; ema.counters[3] = 0;
+        const double tv = *(volatile double*)total_out;
+        const double avg = ddiv(tv, ema.n);
+        const double slow = dadd(ema.inj[0], dmul(ema.a_slow, dsub(avg, ema.inj[0])));
+        const double fast_w = dadd(ema.inj[1], dmul(ema.a_fast, dsub(avg, ema.inj[1])));
+        const double p = dsub(1.0, ddiv(fast_w, slow));
+        ema.inj[0] = slow; ema.inj[1] = fast_w;
+        ema.inj[2] = (0.0 < p) ? p : 0.0;                                   // std::max(0.0, p): NaN gives 0.0 (MC:492)
+        ema.inj[3] = (tv > 0.0 && tv < 1.0e300) ? 1.0 : 0.0;                // finite positive total: the CDF is non-decreasing
+        ema.inj[4] = tv;
+    }
+}
+
+}  // namespace xs
+}  // namespace mcl

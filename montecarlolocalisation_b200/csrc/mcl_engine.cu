@@ -9,6 +9,7 @@
 
 #include "engine_internal.hpp"
 #include "exact_scan.cuh"
+#include "exact_scan_fused.cuh"
 #include "kernels_ref.cuh"
 
 namespace mcl {
@@ -18,7 +19,7 @@ Engine::Engine(const mcl_config& c) : cfg(c) {}
 Engine::~Engine() {
     if (!opened) return;
     cudaSetDevice(cfg.device);
-    part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); for (auto& e : ns_tune_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    part[0].release(); part[1].release(); cdf.release(); d_wraw.release(); d_wn.release(); xs_pub.release(); xs_blocks.release(); xs_counters.release(); xs_trace.release(); xs_tsum.release(); xs_toff.release(); xs_seq_s.release(); xs_tiles.release(); xs_entries.release(); xs_carry.release(); xs_seq_base.release(); xs_flag.release(); for (auto& e : ns_tune_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     d_guide.release(); d_mbox.release(); d_lf.release(); d_lf8.release(); d_codes.release(); d_code_of_d2.release(); d_lf_table.release(); d_ll.release(); d_d2.release(); d_g.release(); d_ns_beams.release(); d_prefix.release(); d_tile_sums.release(); d_u64.release(); d_maxbits.release();
     for (int w = 0; w < 4; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
@@ -37,7 +38,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
-                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
@@ -124,6 +125,7 @@ int Engine::open() {
     CK(cudaMemcpyAsync(d_lut.p, h_lut.data(), n_keys * sizeof(double2), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
     CK(d_counters.ensure(8)); CK(d_scalars.ensure(8));
+    { const double one = 1.0; CK(cudaMemcpyAsync(d_scalars.p + 7, &one, sizeof(double), cudaMemcpyHostToDevice, stream)); }      // divisor of an un-normalised CDF
     CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4] = ticket of k_pose_sums (resets itself)
     CK(d_partials.ensure(4 * 1024));
     CK(cudaStreamSynchronize(stream));
@@ -271,6 +273,16 @@ int Engine::ensure_xs(int64_t count) {
     CK(xs_tsum.ensure(nt)); CK(xs_toff.ensure(nt + 1)); CK(xs_seq_s.ensure((size_t)nt * xs::XS_SEQ_CAP));
     CK(xs_tiles.ensure((size_t)nt * sizeof(xs::TileSummary))); CK(xs_entries.ensure((size_t)nt * xs::XS_SEQ_CAP * sizeof(xs::SeqEntry)));
     CK(xs_carry.ensure((size_t)(nt + 1) * sizeof(xs::Par))); CK(xs_seq_base.ensure(nt + 1));
+    // the one-kernel form's published words: EMPTY once; every launch's last block leaves them EMPTY again
+    CK(xs_pub.ensure((size_t)nt * xs::XSF_PSTRIDE)); CK(xs_counters.ensure(4)); CK(xs_blocks.ensure((size_t)nt * xs::XSF_BSTRIDE * sizeof(xs::SeqBlock)));
+    {   // word 0 of every line EMPTY (all ones), the summary words 0
+        std::vector<unsigned long long> init((size_t)nt * xs::XSF_PSTRIDE, 0ull);
+        for (int k = 0; k < nt; ++k) init[(size_t)k * xs::XSF_PSTRIDE] = ~0ull;
+        CK(cudaMemcpyAsync(xs_pub.p, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    CK(cudaMemsetAsync(xs_counters.p, 0, 4 * sizeof(unsigned), stream));
+    xs_epoch = 0;
     xs_tiles_cap = nt;
     return MCL_OK;
 }
@@ -278,33 +290,55 @@ int Engine::ensure_xs(int64_t count) {
 // The reference's sequential f64 accumulations, reproduced bit-exactly in parallel (exact_scan.cuh):
 //   normalise == false: *d_total_out = w_0 + w_1 + ... left to right over d_wraw            (MC:675)
 //   normalise == true : w_i <- (float)((double)w_i / total) into d_wn, then cdf[i]            (MC:496-505)
-int Engine::exact_accumulate(bool normalise, double* d_total_out) {
-    return exact_accumulate_on(normalise ? d_wn.p : d_wraw.p, normalise, normalise, d_total_out);
+int Engine::exact_accumulate(bool normalise, double* d_total_out, const EmaArgs* ema) {
+    return exact_accumulate_on(d_wraw.p, normalise, normalise, d_total_out, ema);
 }
 
-// w: the dense fp32 terms to accumulate (d_wraw, or d_wn which normalise==true fills from d_wraw first).
-int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out) {
+// w: the dense fp32 terms. normalise: they are divided by the total in d_scalars[0] first (the quotients are what is
+// accumulated; the multi-launch form also leaves them in d_wn). ema (mcl_step, with the total): the accumulation's last block
+// also advances the adaptive-injection state on the device; ema_in_total tells the caller whether that happened.
+int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out, const EmaArgs* ema) {
     const int nt = (int)((n + xs::XS_TILE - 1) / xs::XS_TILE);
+    const int ntf = (int)((n + xs::XSF_TILE - 1) / xs::XSF_TILE);          // the one-kernel form's tiles (never more than nt)
+    ema_in_total = false;
+    if (!force_sequential && !force_multilaunch_scan && ntf <= xs::XSF_MAX_TILES) {
+        xs::FusedWs fw;
+        fw.pub = xs_pub.p; fw.blocks = (xs::SeqBlock*)xs_blocks.p; fw.counters = xs_counters.p;
+        fw.trace = nullptr;
+        if (xs_trace_on) { CK(xs_trace.ensure((size_t)nt * 16)); CK(cudaMemsetAsync(xs_trace.p, 0, (size_t)nt * 16 * sizeof(unsigned long long), stream)); fw.trace = xs_trace.p; }      // (nt >= ntf)
+        xs::FusedEma fe;
+        fe.inj = nullptr; fe.counters = nullptr; fe.n = (double)n; fe.a_slow = 0; fe.a_fast = 0;
+        if (ema && !want_cdf) { fe.inj = d_inj.p; fe.counters = d_counters.p; fe.a_slow = ema->a_slow; fe.a_fast = ema->a_fast; ema_in_total = true; }
+        ++xs_epoch;
+        if (want_cdf)      // divisor: the total (normalise) or the constant 1.0 parked in d_scalars[7]
+            LAUNCH_PDL(K_XS_CDF, xs::k_xs_fused<true>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)(normalise ? d_scalars.p : d_scalars.p + 7), cdf.p,
+                       d_total_out, fe);
+        else
+            LAUNCH_PDL(K_XS_TOTAL, xs::k_xs_fused<false>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)nullptr, (double*)nullptr, d_total_out, fe);
+        CK(cudaGetLastError());
+        return MCL_OK;
+    }
     xs::Workspace ws;
     ws.tsum = xs_tsum.p; ws.toff = xs_toff.p; ws.tiles = (xs::TileSummary*)xs_tiles.p; ws.entries = (xs::SeqEntry*)xs_entries.p;
     ws.carry = (xs::Par*)xs_carry.p; ws.seq_base = xs_seq_base.p; ws.seq_s = xs_seq_s.p; ws.flag = xs_flag.p;
+    const float* wa = normalise ? d_wn.p : w;                  // what the multi-launch form accumulates
     if (!force_sequential) {
         if (normalise)
-            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
+            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, w, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
         else
             LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<false>, nt, xs::XS_THREADS, 0, w, (float*)nullptr, (float4*)nullptr, n, (const double*)nullptr,
                    xs_tsum.p, xs_toff.p, xs_flag.p);
-        LAUNCH_PDL(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, w, n, nt, ws, (double*)nullptr);
-        LAUNCH_PDL(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out, w, n);     // total: falls back in-kernel
+        LAUNCH_PDL(K_XS_SCAN, xs::k_xs_scan<false>, nt, xs::XS_THREADS, 0, wa, n, nt, ws, (double*)nullptr);
+        LAUNCH_PDL(K_XS_CHAIN, xs::k_xs_chain, 1, xs::XS_CHAIN_THREADS, 0, nt, ws, d_total_out, wa, n);     // total: falls back in-kernel
         if (want_cdf) {
-            LAUNCH_PDL(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, w, n, nt, ws, cdf.p);
-            LAUNCH_PDL(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)xs_flag.p);            // runs only if flagged
+            LAUNCH_PDL(K_XS_APPLY, xs::k_xs_scan<true>, nt, xs::XS_THREADS, 0, wa, n, nt, ws, cdf.p);
+            LAUNCH_PDL(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, wa, n, cdf.p, (const int*)xs_flag.p);            // runs only if flagged
         }
     } else {
         if (normalise)
-            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, d_wraw.p, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
-        if (want_cdf) LAUNCH_PDL(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, w, n, cdf.p, (const int*)nullptr);
-        if (d_total_out) LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, w, n, d_total_out, (const int*)nullptr);
+            LAUNCH_PDL(K_XS_TILESUM, xs::k_xs_tilesum<true>, nt, xs::XS_THREADS, 0, w, d_wn.p, part[cur].p, n, d_scalars.p, xs_tsum.p, xs_toff.p, xs_flag.p);
+        if (want_cdf) LAUNCH_PDL(K_SEQ_CDF, k_ref_seq_cdf, 1, 256, 0, wa, n, cdf.p, (const int*)nullptr);
+        if (d_total_out) LAUNCH(K_SEQ_TOTAL, k_ref_seq_total, 1, 256, 0, wa, n, d_total_out, (const int*)nullptr);
     }
     CK(cudaGetLastError());
     return MCL_OK;
@@ -323,13 +357,32 @@ int Engine::debug_exact_scan(const float* w, int64_t count, double* cdf_out, dou
     rc = exact_accumulate_on(d_wn.p, false, true, d_scalars.p + 6);
     if (rc) { n = saved_n; return rc; }
     int flag = 0;
+    unsigned fused_flag = 0;
     if (cdf_out) CK(cudaMemcpyAsync(cdf_out, cdf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (total_out) CK(cudaMemcpyAsync(total_out, d_scalars.p + 6, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(&flag, xs_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&fused_flag, xs_counters.p + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    const bool fused = !force_sequential && !force_multilaunch_scan && (count + xs::XSF_TILE - 1) / xs::XSF_TILE <= xs::XSF_MAX_TILES;
+    if (fused) flag = (xs_epoch != 0 && fused_flag == xs_epoch) ? 1 : 0;
     if (fell_back) *fell_back = force_sequential ? 1 : flag;
     n = saved_n;
     have_weights = false;
+    return MCL_OK;
+}
+
+// Stage time stamps (%globaltimer, ns) of every tile of the one-kernel exact scan, for the NEXT mcl_debug_exact_scan calls
+// (out == null: switch tracing on) or of the last one (out != null: [n_tiles][8], stamps 0..6 used).
+int Engine::debug_exact_scan_trace(unsigned long long* out, int64_t cap_tiles, int* n_tiles) {
+    CK(cudaSetDevice(cfg.device));
+    if (!out) { xs_trace_on = cap_tiles != 0; return MCL_OK; }
+    const int64_t have = (int64_t)(xs_trace.n / 16);
+    const int64_t cnt = std::min(cap_tiles, have);
+    if (n_tiles) *n_tiles = (int)have;
+    if (cnt > 0) {
+        CK(cudaMemcpyAsync(out, xs_trace.p, (size_t)cnt * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
     return MCL_OK;
 }
 
@@ -608,7 +661,7 @@ int Engine::ref_prepare_beams(const float* ranges, int n_beams, float angle_min,
     return MCL_OK;
 }
 
-int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync) {
+int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync, const EmaArgs* ema) {
     RefParams P;
     P.occ = d_occ.p; P.width = map_w; P.height = map_h;
     P.occ_pad = d_occ_pad.p; P.pad = occ_pad; P.wp = occ_wp;
@@ -696,7 +749,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
     }
     CK(cudaGetLastError());
     {
-        int rc = exact_accumulate(false, d_scalars.p);
+        int rc = exact_accumulate(false, d_scalars.p, ema);
         if (rc) return rc;
     }
     if (defer_sync) {            // mcl_step: the total stays on the device (k_ref_ema reads it there)
@@ -784,7 +837,8 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const double a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
     double p_inject = 0.0;
     if (dev_ema) {
-        LAUNCH_PDL(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p, d_counters.p);    // also clears the counters
+        // (the one-kernel accumulation of the total has already advanced the state and cleared the counters: ema_in_total)
+        if (!ema_in_total) LAUNCH_PDL(K_INJECT_SCAN, k_ref_ema, 1, 1, 0, d_scalars.p, (double)n, a_slow, a_fast, d_inj.p, d_counters.p);    // also clears the counters
     } else {
         int rc0 = inj_sync_to_host();
         if (rc0) return rc0;
@@ -980,8 +1034,11 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     } else if ((size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "step: empty scan slot");
     rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
     if (rc) return rc;
-    if (host_scan) rc = ref_run_update(d_beams.p, n_used, beams_all, nullptr, true);
-    else rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true);
+    EmaArgs ema;
+    ema.a_slow = jitter_state ? cfg.inject_alpha_slow_lost : cfg.inject_alpha_slow_conf;
+    ema.a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
+    if (host_scan) rc = ref_run_update(d_beams.p, n_used, beams_all, nullptr, true, &ema);
+    else rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true, &ema);
     if (rc) return rc;
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;

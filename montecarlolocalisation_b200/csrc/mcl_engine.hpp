@@ -95,9 +95,10 @@ public:
     int download_resample_draws(double* u_r, double* u_jit);
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     int debug_trigf(const float* x, int64_t count, float* s_out, float* c_out, int* kind_out);
+    int debug_exact_scan_trace(unsigned long long* out, int64_t cap_tiles, int* n_tiles);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_XS_TOTAL, K_XS_CDF, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
@@ -111,12 +112,14 @@ public:
     int ns_force_field = -1;            // tests: NS_FIELD_* to use regardless of size (-1 = by size)
     bool ns_force_scalar = false;       // tests: scalar FFMA form of the sensor model on every path
     bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
+    bool force_multilaunch_scan = false; // tests / A-B: the multi-launch exact scan (exact_scan.cuh) instead of the one-kernel form
     cudaStream_t stream = nullptr;
     int64_t n = 0;
     int64_t launches = 0;
     double inj_slow = 0, inj_fast = 0;      // adaptiveInjection (MC:191)
 
 private:
+    struct EmaArgs { double a_slow, a_fast; };     // mcl_step: the total's accumulation also advances the injection state
     int fail(int code, const std::string& what);
     int resolve_trig();                     // cfg.trig_mode -> trig_kind (probes the host libm for MCL_TRIG_LIBM)
     int trig_kind = 2;                      // TRIG_GLIBC_FMA / TRIG_GLIBC_SSE2 / TRIG_CR (mcl_device.cuh)
@@ -124,7 +127,8 @@ private:
     int ensure_particles(int64_t count);
     int ref_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
                           std::vector<HostBeam>& all, std::vector<RefBeam>& used);
-    int ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync = false);
+    int ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync = false,
+                       const EmaArgs* ema = nullptr);
     int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done = false, bool dev_ema = false);
     int inj_sync_to_device();
     DevBuf<double> d_inj;                   // {weight_slow, weight_fast, p_inject, cdf_is_monotone, total}: adaptive injection on the device (mcl_step)
@@ -162,9 +166,17 @@ private:
     DevBuf<unsigned char> xs_tiles, xs_entries, xs_carry;
     DevBuf<int> xs_seq_base, xs_flag;
     int xs_tiles_cap = 0;
+    // one-kernel form (exact_scan_fused.cuh): per-tile flags stamped with the launch's epoch, ticket / finished / fall-back words
+    DevBuf<unsigned long long> xs_pub;                           // one 128-byte line of published words per tile
+    DevBuf<unsigned char> xs_blocks;                             // SEQ blocks of the one-kernel form: 64 x 80 bytes per tile
+    DevBuf<unsigned> xs_counters;
+    DevBuf<unsigned long long> xs_trace;                         // stage time stamps of the last debug_exact_scan (mcl_debug_exact_scan_trace)
+    bool xs_trace_on = false;
+    unsigned xs_epoch = 0;
+    bool ema_in_total = false;                                   // ... and did so for the tick being enqueued
     int ensure_xs(int64_t count);
-    int exact_accumulate(bool normalise, double* d_total_out);   // total of d_wraw, or normalise + CDF
-    int exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out);
+    int exact_accumulate(bool normalise, double* d_total_out, const EmaArgs* ema = nullptr);   // total of d_wraw, or normalise + CDF
+    int exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out, const EmaArgs* ema = nullptr);
     DevBuf<int> ancestors;
     // map
     bool map_ready = false;

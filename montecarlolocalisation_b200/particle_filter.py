@@ -262,6 +262,17 @@ class ParticleFilter:
         self._ck(self.L.mcl_debug_exact_scan(self.h, w.ctypes.data_as(_fp), len(w), cdf.ctypes.data_as(_dp), C.byref(total), C.byref(fb)))
         return cdf, total.value, fb.value
 
+    def exactScanTrace(self, w):
+        """Stage time stamps [tiles, 16] (ns) of the one-kernel exact scan over fp32 w (mcl_debug_exact_scan_trace)."""
+        self._ck(self.L.mcl_debug_exact_scan_trace(self.h, None, 1, None))
+        self.exactScan(w)
+        nt = C.c_int32()
+        tiles = (len(w) + 4095) // 4096          # XSF_TILE
+        out = np.zeros((tiles, 16), np.uint64)
+        self._ck(self.L.mcl_debug_exact_scan_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), tiles, C.byref(nt)))
+        self._ck(self.L.mcl_debug_exact_scan_trace(self.h, None, 0, None))
+        return out
+
     def trigf(self, x):
         """(sin, cos, kind) of the float trig the REF kernels evaluate, on the device (mcl_debug_trigf)."""
         x = np.ascontiguousarray(x, dtype=np.float32)

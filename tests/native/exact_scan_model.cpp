@@ -16,7 +16,7 @@ static const int TILE = 2048;
 static const int SEQ_CAP = 16;
 
 struct SeqEntry { uint32_t idx; float w; Par pre; int first_in_tile; int E_prev; };
-struct Stats { long seq = 0, fallback = 0, cases = 0; };
+struct Stats { long seq = 0, fallback = 0, cases = 0, uniform_tiles = 0; };
 
 // returns false => the algorithm asked for the sequential fallback
 static bool exact_scan(const std::vector<float>& w, std::vector<double>& out, int order, Stats& st) {
@@ -24,7 +24,7 @@ static bool exact_scan(const std::vector<float>& w, std::vector<double>& out, in
     const size_t nt = (n + TILE - 1) / TILE;
     out.assign(n, 0.0);
     // pass 1+2: tile sums in some non-sequential association, then offsets
-    std::vector<double> toff(nt + 1, 0.0);
+    std::vector<double> toff(nt + 1, 0.0), tsum_of(nt, 0.0);
     std::vector<double> ptilde(n);
     for (size_t t = 0; t < nt; t++) {
         size_t a = t * TILE, b = std::min(n, a + (size_t)TILE);
@@ -37,6 +37,17 @@ static bool exact_scan(const std::vector<float>& w, std::vector<double>& out, in
             s = part.empty() ? 0 : part[0];
         }
         toff[t + 1] = toff[t] + s;
+        tsum_of[t] = s;
+    }
+    if (order == 2) {
+        // the one-kernel form (exact_scan_fused.cuh): the value at every tile edge is F(t) = a fixed-association sum of the lower
+        // tile sums (256 lane-strided partials in ascending order, then a tree), evaluated independently for every t
+        for (size_t t = 0; t <= nt; t++) {
+            double part[256] = {0};
+            for (size_t k = 0; k < t; k++) part[k % 256] += tsum_of[k];
+            for (int stride = 128; stride > 0; stride >>= 1) for (int l = 0; l < stride; l++) part[l] += part[l + stride];
+            toff[t] = part[0];
+        }
     }
     for (size_t t = 0; t < nt; t++) {
         size_t a = t * TILE, b = std::min(n, a + (size_t)TILE);
@@ -55,9 +66,15 @@ static bool exact_scan(const std::vector<float>& w, std::vector<double>& out, in
     for (size_t t = 0; t < nt; t++) {
         size_t a = t * TILE, b = std::min(n, a + (size_t)TILE);
         Par v = par_identity();
+        // one-kernel form: a tile whose two edge values lie safely inside one binade is uniform - every element is PAR in that
+        // binade and the per-element predictions are skipped
+        const Pred e0 = predict(toff[t], margin_for(b, depth)), e1 = predict(toff[t + 1], margin_for(b, depth));
+        const bool uniform = order == 2 && t > 0 && e0.ok && e1.ok && e0.E == e1.E;
+        if (uniform) st.uniform_tiles++;
         for (size_t i = a; i < b; i++) {
             Pred cur = predict(ptilde[i], margin_for(i, depth));
             Pred prev = predict(i ? ptilde[i - 1] : 0.0, margin_for(i ? i - 1 : 0, depth));
+            if (uniform) { cur.ok = prev.ok = true; cur.zero = false; cur.E = prev.E = e0.E; }
             Par f;
             bool par;
             if (cur.zero) { par = true; f = par_identity(); }
@@ -146,7 +163,7 @@ int main(int argc, char** argv) {
             std::vector<double> ref(n);
             double s = 0;
             for (size_t i = 0; i < n; i++) { s = s + (double)w[i]; ref[i] = s; }
-            for (int order = 0; order < 2; order++) {
+            for (int order = 0; order < 3; order++) {
                 std::vector<double> out;
                 st.cases++;
                 if (!exact_scan(w, out, order, st)) { st.fallback++; continue; }
@@ -159,6 +176,6 @@ int main(int argc, char** argv) {
             }
         }
     }
-    printf("cases %ld fallbacks %ld seq-elements %ld mismatching-cases %ld\n", st.cases, st.fallback, st.seq, mismatches);
+    printf("cases %ld fallbacks %ld seq-elements %ld uniform-tiles %ld mismatching-cases %ld\n", st.cases, st.fallback, st.seq, st.uniform_tiles, mismatches);
     return mismatches ? 1 : 0;
 }
