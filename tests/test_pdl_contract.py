@@ -39,7 +39,7 @@ def pdl_launched_kernels():
 
 
 def kernel_body(name):
-    for f in ("kernels_ref.cuh", "kernels_ns.cuh", "kernels_next.cuh", "exact_scan.cuh"):
+    for f in ("kernels_ref.cuh", "kernels_ns.cuh", "kernels_next.cuh", "exact_scan.cuh", "exact_scan_fused.cuh"):
         src = _strip_comments(_read(f))
         m_ = re.search(r"__global__\s+void\s+(?:__launch_bounds__\([^{;]*?\)\s+)?" + name + r"\s*\(", src)
         if not m_:
