@@ -88,6 +88,21 @@ __device__ __forceinline__ double ref_yaw(float theta) {
     return atan2(wz, m00);
 }
 
+// tf::getYaw(tf::createQuaternionMsgFromYaw(theta)) in degrees, the cheap way. Mathematically the round trip returns theta
+// wrapped to [-pi, pi]; numerically it lands within ~1e-15 rad of it. The only consumer is (int)round(yaw_deg + off_deg), so
+// z = theta - k 2 pi (two-term 2 pi, fused) is used wherever the wrap is unambiguous, and the caller redoes the round trip for
+// the rays whose sum lies within 1e-9 of a rounding boundary. exact = true: the full round trip was evaluated here (near
+// +-pi, where atan2 may return either sign, for huge |theta|, NaN and Inf).
+__device__ __forceinline__ double ref_yaw_deg_fast(float theta, bool& exact) {
+    const double PI = 3.14159265358979323846;
+    const double t = (double)theta;
+    const double k = rint(dmul(t, 0.15915494309189535));
+    const double z = fma(-k, 2.4492935982947064e-16, fma(-k, 6.283185307179586, t));
+    exact = !(fabs(t) < 1.0e5 && fabs(fabs(z) - PI) > 1e-9);
+    if (exact) return ddiv(dmul(ref_yaw(theta), 180.0), PI);
+    return dmul(z, 57.295779513082323);
+}
+
 // GaussianLookup::get (MC:154-168)
 __device__ __forceinline__ double ref_gauss(const RefParams& P, double diff) {
     if (diff < P.gauss_min || diff > P.gauss_max) return 0.0;
@@ -271,6 +286,8 @@ struct RuSmem {
     float2* dq;           // per ray-table key: fp32 direction in cells per metre (dir / res)
     float2* q0;           // per valid particle: fp32 laser origin in cell units, minus 0.5
     double* gterm;        // [beam][hit index 0..n_radii]: w_hit * GaussianLookup(|obs - expected|), last = no hit (max range)
+    float* yawf;          // per valid particle: (float)yaw_deg, for the fp32 pre-decision of the ray-table key
+    float* offf;          // per beam: (float)off_deg
 };
 // map_bytes = plain + bordered table bytes when they are staged in shared memory, else 0
 // lut_in_smem: false for the fp32 march, which leaves the f64 direction table (16 B per key, 38 KB for the reference's
@@ -278,11 +295,13 @@ struct RuSmem {
 __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes, size_t pad_bytes, bool lut_in_smem) {
     return (lut_in_smem ? (size_t)n_keys * 16 : 0) + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
            RU_TILE * 4 + (((size_t)n_radii * 4 + 15) & ~(size_t)15) + ((map_bytes + 15) & ~(size_t)15) + ((pad_bytes + 15) & ~(size_t)15) +
-           (size_t)n_keys * 8 + RU_TILE * 8 + (size_t)n_beams * (n_radii + 1) * 8;
+           (size_t)n_keys * 8 + RU_TILE * 8 + (size_t)n_beams * (n_radii + 1) * 8 + RU_TILE * 4 + (((size_t)n_beams * 4 + 15) & ~(size_t)15);
 }
 
 // NR: number of ray steps known at compile time (11 for the reference's 1.0 m / 0.1 m), 0 = run-time count (<= 16)
-template <bool ZERO_ORIGIN, bool FAST32, int NR>
+// MAP_SMEM: the bordered ray-march table is in shared memory (maps up to ~30 KB): probes are addressed with 32-bit shared
+// addresses (IMAD + IADD + LDS.U8) instead of through a generic 64-bit pointer.
+template <bool ZERO_ORIGIN, bool FAST32, int NR, bool MAP_SMEM>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
                                                            uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -303,6 +322,9 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     S.dq = reinterpret_cast<float2*>(S.occ_pad + ((P.map_in_smem ? (size_t)P.wp * (P.height + 2 * P.pad) + 15 : 0) & ~(size_t)15));
     S.q0 = S.dq + P.n_keys;
     S.gterm = reinterpret_cast<double*>(S.q0 + RU_TILE);
+    S.yawf = reinterpret_cast<float*>(S.gterm + (size_t)P.n_beams * (P.n_radii + 1));
+    S.offf = S.yawf + RU_TILE;
+    for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.offf[i] = __double2float_rn(P.beams[i].off_deg);
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii_f[i] = __double2float_rn(P.radii[i]);
     if (!FAST32) for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) s_lut[i] = P.lut[i];
     for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = P.beams[i];
@@ -334,6 +356,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     const uint32_t wp_u = (uint32_t)P.wp;
     const float lim32 = 0.5f - tol32;
     const uint32_t pad_last = (uint32_t)P.wp * (uint32_t)(P.height + 2 * P.pad) - 1u;
+    const uint32_t pad_saddr = (uint32_t)__cvta_generic_to_shared(S.occ_pad) + pad_fold;      // MAP_SMEM: shared byte address of cell (0,0) + folded constants
     // constants in registers
     const double res = P.res, inv_res = P.inv_res, ox = P.ox, oy = P.oy;
     const int W = P.width, H = P.height;
@@ -347,7 +370,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- phase A -------------------------------------------------------------------------------------------------
         const int64_t j = tile * RU_TILE + threadIdx.x;
-        bool valid = false;
+        bool valid = false, yaw_exact = false;
         double posx = 0, posy = 0, yawd = 0;
         if (j < n) {
             const float4 p = part[j];
@@ -385,7 +408,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                 } else { snf = ref_sinf(p.z, P.trig); csf = ref_cosf(p.z, P.trig); }        // the host libm's sinf / cosf
                 posx = dadd(x, dmul(P.laser_offset, (double)csf));                        // MC:644
                 posy = dadd(y, dmul(P.laser_offset, (double)snf));                        // MC:645
-                yawd = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);            // MC:351-352
+                yawd = ref_yaw_deg_fast(p.z, yaw_exact);                                   // MC:351-352 (see ref_yaw_deg_fast)
             }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -394,7 +417,8 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
         int slot = __popc(bal & ((1u << lane) - 1u)), nv = 0;
         for (int w = 0; w < RU_TILE / 32; w++) { if (w < warp) slot += warp_cnt[w]; nv += warp_cnt[w]; }
         if (valid) {
-            S.vlist[slot] = threadIdx.x; S.posx[slot] = posx; S.posy[slot] = posy; S.yawd[slot] = yawd;
+            S.vlist[slot] = threadIdx.x | (yaw_exact ? 0x10000 : 0); S.posx[slot] = posx; S.posy[slot] = posy; S.yawd[slot] = yawd;
+            S.yawf[slot] = __double2float_rn(yawd);
             if (FAST32) S.q0[slot] = make_float2(__double2float_rn(dsub(dmul(dsub(posx, ox), inv_res), 0.5)), __double2float_rn(dsub(dmul(dsub(posy, oy), inv_res), 0.5)));
         }
         __syncthreads();
@@ -406,7 +430,29 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
             // so one scored beam (a scan with 1..beam_stride filtered readings inside the FOV) is its own case
             const int v = nb == 1 ? r : (int)__umulhi((unsigned)r, div_magic);
             const int b = r - v * nb;
-            const int k = ref_key_index(P, S.yawd[v], S.beams[b].off_deg);
+            // angle_key = (int)round(yaw_deg + off_deg) (MC:352-355): decided in fp32 unless the sum lies within 1e-3 of a
+            // rounding boundary (the fp32 sum is within 4e-5 of the f64 one), then in f64 from the fast yaw unless within 1e-9
+            // (the fast yaw is within 1e-12 of the tf round trip), then - once per ~1e9 rays - through the round trip itself
+            int k;
+            {
+                const float a32 = __fadd_rn(S.yawf[v], S.offf[b]);
+                const float tk = __fadd_rn(a32, RU_MAGICF);
+                const float ek = __fadd_rn(a32, -__fadd_rn(tk, -RU_MAGICF));
+                if (__builtin_expect(fabsf(ek) < 0.499f, 1)) {
+                    const int kk = (__float_as_int(tk) - RU_MAGICF_BITS) - P.key_min;
+                    k = (kk < 0 || kk >= P.n_keys) ? -1 : kk;
+                } else {
+                    const double off = S.beams[b].off_deg;
+                    double a = dadd(S.yawd[v], off);
+                    const double fr = fabs(dsub(a, trunc(a)));
+                    if (!(S.vlist[v] & 0x10000) && !(fabs(fr - 0.5) > 1e-9)) {
+                        const float th = part[tile * RU_TILE + (S.vlist[v] & 0xffff)].z;
+                        a = dadd(ddiv(dmul(ref_yaw(th), 180.0), 3.14159265358979323846), off);
+                    }
+                    const int kk = trunc_x86(round(a)) - P.key_min;
+                    k = (kk < 0 || kk >= P.n_keys) ? -1 : kk;
+                }
+            }
             if (FAST32) {
                 // All probes of the ray at once, branch-free, in fp32: q' = cell coordinate - 0.5, so that round-to-nearest
                 // (magic add) gives floor(q) and e = q' - RN(q') = frac(q) - 0.5. A probe whose q lies within tol of a cell
@@ -432,9 +478,18 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                     const bool decided = (fabsf(ex) < lim32) & (fabsf(ey) < lim32);      // NaN fails
                     // a valid particle is inside the map and its rays end inside the border, so the index is in range;
                     // an undecided probe's code is never used (the f64 march takes over if it matters)
-                    const uint32_t idx = __float_as_uint(ty) * wp_u + __float_as_uint(tx) + pad_fold;
-                    const uint32_t code = decided ? (uint32_t)occ_pad[min(idx, pad_last)] : 3u;      // 3 = undecided
-                    codes |= code << (2 * s);
+                    uint32_t code = 3u;                                                  // 3 = undecided
+                    if (MAP_SMEM) {
+                        // a decided probe of a valid particle (inside the map, ray inside the border) is always in range
+                        if (decided)
+                            asm("{\n.reg .u32 a;\nmad.lo.u32 a, %1, %2, %3;\nadd.u32 a, a, %4;\nld.shared.u8 %0, [a];\n}"
+                                : "=r"(code)
+                                : "r"(__float_as_uint(ty)), "r"(wp_u), "r"(__float_as_uint(tx)), "r"(pad_saddr));
+                    } else {
+                        const uint32_t idx = __float_as_uint(ty) * wp_u + __float_as_uint(tx) + pad_fold;
+                        if (decided) code = (uint32_t)occ_pad[min(idx, pad_last)];
+                    }
+                    codes += code << (2 * s);
                 }
                 const int first = codes ? (__ffs((int)codes) - 1) >> 1 : nrr;            // probe index of the first event
                 double term;
@@ -480,7 +535,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                 prob = dadd(prob, S.beams[b].rand_term);                                 // MC:669
             }
             const float wf = __double2float_rn(prob);                                    // MC:673
-            const int64_t jj = tile * RU_TILE + S.vlist[threadIdx.x];
+            const int64_t jj = tile * RU_TILE + (S.vlist[threadIdx.x] & 0xffff);
             part[jj].w = wf;
             w_dense[jj] = wf;
         }

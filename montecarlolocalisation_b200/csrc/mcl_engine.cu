@@ -715,35 +715,35 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
     const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0, !fast32);
     const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
     if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024 && bounded_ok) {
+        const bool ms = P.map_in_smem != 0;
+        // instantiation = (zero origin, fp32 march, compile-time ray steps, map in shared memory)
+#define RU_FOR_ALL(X) X(true, true, 11, true) X(false, true, 11, true) X(true, true, 0, true) X(false, true, 0, true) X(true, false, 0, true) X(false, false, 0, true) \
+                      X(true, true, 11, false) X(false, true, 11, false) X(true, true, 0, false) X(false, true, 0, false) X(true, false, 0, false) X(false, false, 0, false)
         if (!attr_set2) {
-            CK(cudaFuncSetAttribute((k_ref_update_v2<true, true, 11>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute((k_ref_update_v2<false, true, 11>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute((k_ref_update_v2<true, true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute((k_ref_update_v2<false, true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute((k_ref_update_v2<true, false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CK(cudaFuncSetAttribute((k_ref_update_v2<false, false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define X(Z, F, N, M) CK(cudaFuncSetAttribute((k_ref_update_v2<Z, F, N, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RU_FOR_ALL(X)
+#undef X
             attr_set2 = true;
         }
         int occ_blocks = 1, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
-        if (fast32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<false, true, 0>), RU_TILE, smem2));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<false, false, 0>), RU_TILE, smem2));
         // the bounded fast path needs every probe quotient below 2^31: particle inside the map, ray at most max_range long
         const bool zero_origin = origin_x == 0.0 && origin_y == 0.0;
+        const int nr_ct = (fast32 && P.n_radii == 11) ? 11 : 0;
         const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
-        const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));
         // ceil(2^32 / n_used); n_used == 1 would need 2^32 itself: the kernel divides by one without it
         const uint32_t div_magic = n_used == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
-        if (fast32 && P.n_radii == 11) {
-            if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, true, 11>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-        } else if (fast32) {
-            if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, true, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-        } else {
-            if (zero_origin) LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<true, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
-            else LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<false, false, 0>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32);
+        bool launched = false;
+#define X(Z, F, N, M)                                                                                                                    \
+        if (!launched && zero_origin == Z && fast32 == F && nr_ct == N && ms == M) {                                                     \
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<Z, F, N, M>), RU_TILE, smem2));               \
+            const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));                                      \
+            LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<Z, F, N, M>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32); \
+            launched = true;                                                                                                             \
         }
+        RU_FOR_ALL(X)
+#undef X
+#undef RU_FOR_ALL
     } else {
         LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
     }
