@@ -724,9 +724,17 @@ def ns_leg(c, args, cells, n_global, n_beams, label, K, W, key, map_seed=4, scal
     evals_res = sum(n_global * valid_beams[i % n_scans] for i in range(W, W + K))
     evals_e2e = sum(n_global * valid_beams[i % n_scans] for i in range(2 * W + K, 2 * (W + K)))
     nb = valid_beams[0]
-    algo = {"k_ns_update": n_mine * (20 + 4 * nb), "k_ns_predict": n_mine * 32, "k_ns_weights_sum": n_mine * 4,
+    algo = {"k_ns_update": n_mine * (20 + 4 * nb), "k_ns_predict": n_mine * 32, "k_ns_weights_sum": n_mine * 20,
             "k_ns_weights_scan": n_mine * 12, "k_ns_weights_pose": n_mine * 32, "k_ns_resample": n_mine * 44, "k_ns_pose_partials": n_mine * 20}
     kernels = kernel_table(prof, lambda name: algo.get(name))
+    per_rank = None
+    if world > 1:
+        # every shard's own kernel times (the table above is rank 0's): the sensor-model kernel's spread over the shards is the
+        # skew that the step's exchanges wait for
+        mine_t = {name: 1e3 * v[0] / v[1] for name, v in prof.items() if name in ("k_ns_update", "k_ns_resample", "k_ns_predict", "k_ns_plan")}
+        allt = [None] * world
+        c.dist.all_gather_object(allt, mine_t)
+        per_rank = {name: [round(t.get(name, 0.0), 1) for t in allt] for name in mine_t}
     field_bytes = occ.size * 4
     out = {
         "label": label, "value": evals_res / t_res, "unit": UNIT, "ms_per_step": 1e3 * t_res / K, "steps_per_s": K / t_res,
@@ -749,6 +757,11 @@ def ns_leg(c, args, cells, n_global, n_beams, label, K, W, key, map_seed=4, scal
         "roofline": roofline_record(kernels, key, per_gpu),
         "kernels": kernels,
     }
+    if per_rank:
+        out["kernel_us_per_rank"] = per_rank
+        u = per_rank.get("k_ns_update")
+        if u and min(u) > 0:
+            out["update_skew"] = {"max_over_min": max(u) / min(u), "max_over_mean": max(u) / (sum(u) / len(u))}
     if uni:
         out["uniform_particles"] = uni
     if gather:

@@ -38,7 +38,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
-                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_ns_pose_reduce", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
