@@ -724,7 +724,7 @@ def ns_leg(c, args, cells, n_global, n_beams, label, K, W, key, map_seed=4, scal
     evals_res = sum(n_global * valid_beams[i % n_scans] for i in range(W, W + K))
     evals_e2e = sum(n_global * valid_beams[i % n_scans] for i in range(2 * W + K, 2 * (W + K)))
     nb = valid_beams[0]
-    algo = {"k_ns_update": n_mine * (20 + 4 * nb), "k_ns_predict": n_mine * 32, "k_ns_weights_sum": n_mine * 20,
+    algo = {"k_ns_update": n_mine * (20 + 4 * nb), "k_ns_predict": n_mine * 32, "k_ns_weights_sum": n_mine * 4,
             "k_ns_weights_scan": n_mine * 12, "k_ns_weights_pose": n_mine * 32, "k_ns_resample": n_mine * 44, "k_ns_pose_partials": n_mine * 20}
     kernels = kernel_table(prof, lambda name: algo.get(name))
     per_rank = None

@@ -567,48 +567,11 @@ __device__ __forceinline__ void ns_load_weights(const float* __restrict__ ll, in
         for (int e = 0; e < 4; e++) { w[j][e] = (i + e < n) ? ns_weight(v[e], max_ll, temper) : 0ull; s[j] += w[j][e]; }
     }
 }
-// The five weighted pose sums {sum w, sum w x, sum w y, sum w sin, sum w cos} of the 16 particles whose Q32 weights a thread
-// holds (layout of ns_load_weights), w = the unnormalised fp32 weight W * 2^-32: the pose estimate rides on the pass that
-// computes the weights anyway (NS-8 is a reduction over the same particles; a pass of its own re-reads ll and recomputes exp).
-__device__ __forceinline__ void ns_pose_accumulate(const float4* __restrict__ part, int64_t n, int64_t base, const uint64_t (&w)[4][4], double (&a)[5]) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int64_t i = base + j * 128;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            if (i + e < n) {
-                const float4 p = part[i + e];
-                float s, c;
-                ns::det_sincosf32(p.z, s, c);
-                const double wd = (double)(float)((double)w[j][e] * 2.3283064365386963e-10);
-                a[0] += wd; a[1] += wd * (double)p.x; a[2] += wd * (double)p.y; a[3] += wd * (double)s; a[4] += wd * (double)c;
-            }
-        }
-    }
-}
-// block sums of the five -> partials[block * 5 + k] (fixed order: deterministic)
-__device__ __forceinline__ void ns_pose_block_store(double (&a)[5], double (*ws)[5], double* __restrict__ partials, int block) {
-#pragma unroll
-    for (int k = 0; k < 5; k++) a[k] = warp_sum(a[k]);
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < 5; k++) ws[threadIdx.x >> 5][k] = a[k];
-    __syncthreads();
-    if (threadIdx.x < 5) {
-        double t = 0;
-        for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += ws[q][threadIdx.x];
-        partials[(size_t)block * 5 + threadIdx.x] = t;
-    }
-}
-
 // pass 1: tile_sums[tile], group_sums[tile / 64] += (group_sums zeroed before the launch)
-// POSE: also the tile's five weighted pose sums -> pose_partials[tile * 5 ..] (mcl_ns_step)
-template <bool POSE>
 __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
-                                                                   float temper, uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ group_sums,
-                                                                   const float4* __restrict__ part, double* __restrict__ pose_partials) {
+                                                                   float temper, uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ group_sums) {
     pdl_enter();
     __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32];
-    __shared__ double s_pose[NS_SCAN_THREADS / 32][5];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float max_ll = ns_decode_max(max_bits);
     const int64_t base = (int64_t)blockIdx.x * NS_SCAN_TILE + (int64_t)warp * NS_SCAN_WARP_ITEMS + lane * 4;
@@ -623,11 +586,6 @@ __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_sum(const float*
         for (int k = 0; k < NS_SCAN_THREADS / 32; k++) t += s_warp[k];
         tile_sums[blockIdx.x] = t;
         atomicAdd((unsigned long long*)(group_sums + blockIdx.x / NS_SCAN_GROUP), (unsigned long long)t);
-    }
-    if (POSE) {
-        double a[5] = {0, 0, 0, 0, 0};
-        ns_pose_accumulate(part, n, base, w, a);
-        ns_pose_block_store(a, s_pose, pose_partials, blockIdx.x);
     }
 }
 // pass 2: inclusive prefix per particle (local to this shard); block 0 also writes the shard total
@@ -692,14 +650,11 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
     return v;
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-template <bool POSE>
 __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan1(const float* __restrict__ ll, int64_t n, const int* __restrict__ max_bits,
                                                                      float temper, uint64_t* __restrict__ tile_state /* n_tiles + 1, zeroed */,
-                                                                     int n_tiles, uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out,
-                                                                     const float4* __restrict__ part, double* __restrict__ pose_partials) {
+                                                                     int n_tiles, uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out) {
     pdl_enter();
     __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32];
-    __shared__ double s_pose[NS_SCAN_THREADS / 32][5];
     __shared__ uint64_t s_excl;
     __shared__ int s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -754,11 +709,6 @@ __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan1(const floa
         for (int e = 0; e < 4; e++) { run += w[j][e]; o[e] = run; }
         if (i + 3 < n) st_v4_u64(prefix + i, o[0], o[1], o[2], o[3]);
         else { for (int e = 0; e < 4; e++) if (i + e < n) prefix[i + e] = o[e]; }
-    }
-    if (POSE) {
-        double a[5] = {0, 0, 0, 0, 0};
-        ns_pose_accumulate(part, n, base, w, a);
-        ns_pose_block_store(a, s_pose, pose_partials, tile);
     }
 }
 // The unnormalised weight W * 2^-32 (max particle = 1) into the particle records: only when somebody asks for the

@@ -231,7 +231,7 @@ private:
                           std::vector<float2>& pts) const;
     int ns_run_update(const float2* d_pts, int n_pts, float* local_max);
     int ns_launch_update(const float2* d_pts, int n_pts);
-    int ns_launch_weights(bool with_pose = false, int* pose_blocks = nullptr);
+    int ns_launch_weights();
     int ns_materialise_weights();
     int ns_launch_resample(uint32_t u0);
     bool ns_w_in_records = false;

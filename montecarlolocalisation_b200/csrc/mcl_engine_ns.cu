@@ -53,7 +53,7 @@ int Engine::ensure_mailbox() {
 #define PRELOAD(k) CK(cudaFuncGetAttributes(&fa, k))
     PRELOAD(k_ns_predict);
     for (int kk = 0; kk < 3; ++kk) for (int pp = 0; pp < 3; ++pp) { int rc = ns_preload_update(kk, pp); if (rc) return rc; }
-    PRELOAD(k_ns_weights_sum<false>); PRELOAD(k_ns_weights_sum<true>); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_weights_scan1<false>); PRELOAD(k_ns_weights_scan1<true>); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
+    PRELOAD(k_ns_weights_sum); PRELOAD(k_ns_weights_scan); PRELOAD(k_ns_weights_scan1); PRELOAD(k_ns_plan); PRELOAD(k_ns_plan_xchg); PRELOAD(k_ns_xchg_max);
     PRELOAD(k_ns_pose_partials); PRELOAD(k_ns_pose_reduce); PRELOAD(k_ns_xchg_barrier);
     PRELOAD(k_ns_resample_bounds); PRELOAD(k_ns_resample);
 #undef PRELOAD
@@ -384,9 +384,7 @@ void Engine::ns_scan_shape(bool& two_pass, int& nt, int& ng) const {
     two_pass = force_sequential || nt > sms * (2048 / NS_SCAN_THREADS);
 }
 
-// with_pose (mcl_ns_step): the pass that computes the weights also leaves the five weighted pose sums of every tile in
-// d_partials[tile * 5 ..]; *pose_blocks = how many tiles
-int Engine::ns_launch_weights(bool with_pose, int* pose_blocks) {
+int Engine::ns_launch_weights() {
     const float temper = (float)cfg.ns_temper;
     bool two_pass; int nt, ng;
     ns_scan_shape(two_pass, nt, ng);
@@ -395,17 +393,14 @@ int Engine::ns_launch_weights(bool with_pose, int* pose_blocks) {
     if (two_pass) {
         uint64_t* group_sums = d_tile_sums.p + nt;
         if (!prepped) CK(cudaMemsetAsync(group_sums, 0, (size_t)ng * sizeof(uint64_t), stream));
-        if (with_pose) LAUNCH_PDL(K_NS_WSUM, k_ns_weights_sum<true>, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, (const float4*)part[cur].p, d_partials.p);
-        else LAUNCH_PDL(K_NS_WSUM, k_ns_weights_sum<false>, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, (const float4*)nullptr, (double*)nullptr);
+        LAUNCH_PDL(K_NS_WSUM, k_ns_weights_sum, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums);
         LAUNCH_PDL(K_NS_WSCAN, k_ns_weights_scan, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, group_sums, nt, d_prefix.p, d_u64.p);
     } else {
         if (!prepped) CK(cudaMemsetAsync(d_tile_sums.p, 0, (size_t)(nt + 1) * sizeof(uint64_t), stream));      // tile states + ticket
-        if (with_pose) LAUNCH_PDL(K_NS_WSCAN, k_ns_weights_scan1<true>, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p, (const float4*)part[cur].p, d_partials.p);
-        else LAUNCH_PDL(K_NS_WSCAN, k_ns_weights_scan1<false>, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p, (const float4*)nullptr, (double*)nullptr);
+        LAUNCH_PDL(K_NS_WSCAN, k_ns_weights_scan1, nt, NS_SCAN_THREADS, 0, d_ll.p, n, d_maxbits.p, temper, d_tile_sums.p, nt, d_prefix.p, d_u64.p);
     }
     CK(cudaGetLastError());
     ns_w_in_records = false;
-    if (pose_blocks) *pose_blocks = nt;
     return MCL_OK;
 }
 
@@ -630,21 +625,18 @@ int Engine::ns_step(double rot1, double trans, double rot2, int slot, const floa
     if (mail) LAUNCH(K_NS_PLAN, k_ns_xchg_max, 1, 32, 0, d_maxbits.p, PX, tag, parity);
     else if (shard_world > 1) NCK(N.AllReduce(d_maxbits.p, d_maxbits.p, 1, ncclInt32, ncclMax, (ncclComm_t)comm, stream));
     if (shard_world > 1) pdl_hold = true;        // the exchange polls other shards: its successor is launched in stream order
-    int pose_blocks = 0;
-    {
-        bool two_pass; int nt_w, ng_w;
-        ns_scan_shape(two_pass, nt_w, ng_w);
-        CK(d_partials.ensure(5 * (size_t)std::max(2048, nt_w)));              // one record of five sums per weight tile
-    }
-    rc = ns_launch_weights(true, &pose_blocks);
+    rc = ns_launch_weights();
     if (rc) return rc;
     if (mail) {}                                                              // gathered inside k_ns_plan_xchg
     else if (shard_world > 1) { NCK(N.AllGather(d_u64.p, d_totals.p, 1, ncclUint64, (ncclComm_t)comm, stream)); pdl_hold = true; }
     // (one shard: k_ns_plan reads the local total where the scan left it)
     {   // the weighted-mean pose (before resampling) is part of every step; it crosses to the host only when pose3 asks
-        // (its per-tile partial sums came out of the weights pass; only their reduction is left)
+        const int blocks = (int)std::min<int64_t>(148 * 8, grid_for(n, 256));      // one wave of resident CTAs, grid-stride
+        CK(d_partials.ensure(5 * 2048));
+        LAUNCH_PDL(K_NS_POSE, k_ns_pose_partials, blocks, 256, 0, part[cur].p, n, (const float*)d_ll.p, (const int*)d_maxbits.p, (float)cfg.ns_temper,
+               d_partials.p);
         if (shard_world == 1 && !h_ns_pose) CK(cudaMallocHost((void**)&h_ns_pose, 8 * sizeof(double)));
-        LAUNCH_PDL(K_NS_POSE_REDUCE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, pose_blocks, d_pose.p, shard_world == 1 ? h_ns_pose : (double*)nullptr);
+        LAUNCH_PDL(K_NS_POSE_REDUCE, k_ns_pose_reduce, 1, 160, 0, d_partials.p, blocks, d_pose.p, shard_world == 1 ? h_ns_pose : (double*)nullptr);
         if (mail) {}                                                          // summed over the shards inside k_ns_plan_xchg
         else if (shard_world > 1) { NCK(N.AllReduce(d_pose.p, d_pose.p, 5, ncclFloat64, ncclSum, (ncclComm_t)comm, stream)); pdl_hold = true; }
     }
