@@ -732,9 +732,14 @@ def ns_leg(c, args, cells, n_global, n_beams, label, K, W, key, map_seed=4, scal
         # every shard's own kernel times (the table above is rank 0's): the sensor-model kernel's spread over the shards is the
         # skew that the step's exchanges wait for
         mine_t = {name: 1e3 * v[0] / v[1] for name, v in prof.items() if name in ("k_ns_update", "k_ns_resample", "k_ns_predict", "k_ns_plan")}
+        # the rebalance: which of the slots this shard resolved in its last step live on another shard (stored over NVLink)
+        k_lo, k_hi, own_b, own_n = shard.last_plan()
+        local = max(0, min(k_hi, own_b + own_n) - max(k_lo, own_b))
+        mine_t["remote_fraction"] = (1.0 - local / (k_hi - k_lo)) if k_hi > k_lo else 0.0
+        mine_t["remote_mb"] = (k_hi - k_lo - local) * 20 / 1e6                # float4 + ancestor index per survivor
         allt = [None] * world
         c.dist.all_gather_object(allt, mine_t)
-        per_rank = {name: [round(t.get(name, 0.0), 1) for t in allt] for name in mine_t}
+        per_rank = {name: [round(t.get(name, 0.0), 3 if name == "remote_fraction" else 1) for t in allt] for name in mine_t}
     field_bytes = occ.size * 4
     out = {
         "label": label, "value": evals_res / t_res, "unit": UNIT, "ms_per_step": 1e3 * t_res / K, "steps_per_s": K / t_res,

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("mcl_debug_exact_scan", _i32, [_vp, _fp, _i64, _dp, _dp, _ip]),
     ("mcl_debug_force_sequential", _i32, [_vp, _i32]),
     ("mcl_debug_exact_scan_trace", _i32, [_vp, C.POINTER(C.c_uint64), _i64, _ip]),
+    ("mcl_debug_ns_last_plan", _i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     ("mcl_debug_trigf", _i32, [_vp, _fp, _i64, _fp, _fp, _ip]),
     ("mcl_bench_gather", _i32, [_vp, _i32, _i64, _i32, _dp]),
     ("mcl_profile_enable", _i32, [_vp, _i32]),

@@ -78,6 +78,7 @@ public:
     int ns_download_field(float* lf, uint16_t* d2);
     int ns_download_loglik(float* ll);
     int ns_download_prefix(uint64_t* prefix);
+    int ns_last_plan(int64_t* k_lo, int64_t* k_hi, int64_t* own_begin, int64_t* own_count);
     // rows either side of the hot path
     int kmeans_confidence(const int32_t* init_idx, const int32_t* reinit_idx, int n_reinit, double ratio_threshold, mcl_kmeans_result* out);
     int download_assignments(int32_t* a);

@@ -509,6 +509,19 @@ int Engine::ns_download_prefix(uint64_t* prefix) {
     return MCL_OK;
 }
 
+int Engine::ns_last_plan(int64_t* k_lo, int64_t* k_hi, int64_t* own_begin, int64_t* own_count) {
+    CK(cudaSetDevice(cfg.device));
+    if (cfg.mode != MCL_MODE_NS || !d_plan.p) return fail(MCL_ERR_STATE, "ns_last_plan: no NS step yet");
+    NsPlan P;
+    CK(cudaMemcpyAsync(&P, d_plan.p, sizeof(P), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (k_lo) *k_lo = P.k_lo;
+    if (k_hi) *k_hi = P.k_hi;
+    if (own_begin) *own_begin = shard_begin;
+    if (own_count) *own_count = n;
+    return MCL_OK;
+}
+
 // ---- engine-native collectives: NCCL on the engine's stream ------------------------------------------------------------------
 #define NCK(call)                                                                                          \
     do {                                                                                                   \

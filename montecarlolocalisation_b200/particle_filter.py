@@ -402,6 +402,12 @@ class NsShard:
                                            C.c_float(scan["angle_inc"]), C.c_float(scan["range_min"]), C.c_float(scan["range_max"]), pose))
         return np.array(pose) if want_pose else None
 
+    def last_plan(self):
+        """(k_lo, k_hi, own_begin, own_count) of the last step: the output slots this shard resolved and the ones it holds."""
+        v = [C.c_int64() for _ in range(4)]
+        self.pf._ck(self.L.mcl_debug_ns_last_plan(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
     def device_buffer(self, which):
         return self.L.mcl_device_buffer(self.h, which)
 
