@@ -594,29 +594,27 @@ __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float
                                                                     const uint64_t* __restrict__ group_sums, int n_tiles,
                                                                     uint64_t* __restrict__ prefix, uint64_t* __restrict__ total_out) {
     pdl_enter();
-    __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32], s_offp[NS_SCAN_THREADS / 32];
+    __shared__ uint64_t s_warp[NS_SCAN_THREADS / 32], s_offp[NS_SCAN_THREADS / 32], s_tot[NS_SCAN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, group = tile / NS_SCAN_GROUP;
+    // the tile's own weights first: the loads are in flight while the tile's offset is summed from the (L2-resident) sums
+    const float max_ll = ns_decode_max(max_bits);
+    const int64_t base = (int64_t)tile * NS_SCAN_TILE + (int64_t)warp * NS_SCAN_WARP_ITEMS + lane * 4;
+    uint64_t w[4][4], s[4], incl[4];
+    ns_load_weights(ll, n, base, max_ll, temper, w, s);
     // this tile's offset: whole groups before it + the tiles of its own group before it
     uint64_t part = 0;
     for (int g = tid; g < group; g += NS_SCAN_THREADS) part += group_sums[g];
     if (tid < tile - group * NS_SCAN_GROUP) part += tile_sums[group * NS_SCAN_GROUP + tid];
     part = warp_sum_u64(part);
     if (lane == 0) s_offp[warp] = part;
+    uint64_t t = 0;
     if (tile == 0) {                                                 // shard total = all group sums
         const int n_groups = (n_tiles + NS_SCAN_GROUP - 1) / NS_SCAN_GROUP;
-        uint64_t t = 0;
         for (int g = tid; g < n_groups; g += NS_SCAN_THREADS) t += group_sums[g];
         t = warp_sum_u64(t);
-        if (lane == 0) s_warp[warp] = t;
-        __syncthreads();
-        if (tid == 0) { uint64_t a = 0; for (int k = 0; k < NS_SCAN_THREADS / 32; k++) a += s_warp[k]; *total_out = a; }
-        __syncthreads();
+        if (lane == 0) s_tot[warp] = t;
     }
-    const float max_ll = ns_decode_max(max_bits);
-    const int64_t base = (int64_t)tile * NS_SCAN_TILE + (int64_t)warp * NS_SCAN_WARP_ITEMS + lane * 4;
-    uint64_t w[4][4], s[4], incl[4];
-    ns_load_weights(ll, n, base, max_ll, temper, w, s);
     uint64_t carry = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -625,6 +623,7 @@ __global__ void __launch_bounds__(NS_SCAN_THREADS) k_ns_weights_scan(const float
     }
     if (lane == 31) s_warp[warp] = carry;                            // warp total
     __syncthreads();
+    if (tile == 0 && tid == 0) { uint64_t a = 0; for (int k = 0; k < NS_SCAN_THREADS / 32; k++) a += s_tot[k]; *total_out = a; }
     uint64_t off = 0;
 #pragma unroll
     for (int k = 0; k < NS_SCAN_THREADS / 32; k++) { off += s_offp[k]; if (k < warp) off += s_warp[k]; }

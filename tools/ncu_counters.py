@@ -40,7 +40,7 @@ def val(name):
 
 resources = {
     "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "fmaheavy": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+    "fmaheavy": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "fp64": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "alu": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "lsu": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
