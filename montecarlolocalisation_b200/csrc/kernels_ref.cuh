@@ -46,6 +46,10 @@ struct RefParams {
     const RefBeam* beams;
     int n_beams;
     int trig;                  // TRIG_*: how cosf/sinf of MC:644-645 are evaluated (mcl_device.cuh)
+    // mcl_step: updateParticlePos (MC:740-755) applied to every particle as it is loaded, so the tick has no predict pass of
+    // its own (k_ref_update_v2 only; the particle is written back whole, with its weight)
+    int do_predict;
+    float rot1, trans, dtheta;
 };
 
 // ---- map probes ---------------------------------------------------------------------------------------
@@ -288,6 +292,7 @@ struct RuSmem {
     double* gterm;        // [beam][hit index 0..n_radii]: w_hit * GaussianLookup(|obs - expected|), last = no hit (max range)
     float* yawf;          // per valid particle: (float)yaw_deg, for the fp32 pre-decision of the ray-table key
     float* offf;          // per beam: (float)off_deg
+    float* wout;          // per particle of the tile: its weight, handed from the slot's thread back to the particle's thread
 };
 // map_bytes = plain + bordered table bytes when they are staged in shared memory, else 0
 // lut_in_smem: false for the fp32 march, which leaves the f64 direction table (16 B per key, 38 KB for the reference's
@@ -295,7 +300,7 @@ struct RuSmem {
 __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes, size_t pad_bytes, bool lut_in_smem) {
     return (lut_in_smem ? (size_t)n_keys * 16 : 0) + (size_t)n_beams * 24 + (size_t)n_radii * 8 + 3 * RU_TILE * 8 + (size_t)RU_TILE * (n_beams + 1) * 8 +
            RU_TILE * 4 + (((size_t)n_radii * 4 + 15) & ~(size_t)15) + ((map_bytes + 15) & ~(size_t)15) + ((pad_bytes + 15) & ~(size_t)15) +
-           (size_t)n_keys * 8 + RU_TILE * 8 + (size_t)n_beams * (n_radii + 1) * 8 + RU_TILE * 4 + (((size_t)n_beams * 4 + 15) & ~(size_t)15);
+           (size_t)n_keys * 8 + RU_TILE * 8 + (size_t)n_beams * (n_radii + 1) * 8 + RU_TILE * 4 + (((size_t)n_beams * 4 + 15) & ~(size_t)15) + RU_TILE * 4;
 }
 
 // NR: number of ray steps known at compile time (11 for the reference's 1.0 m / 0.1 m), 0 = run-time count (<= 16)
@@ -324,6 +329,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     S.gterm = reinterpret_cast<double*>(S.q0 + RU_TILE);
     S.yawf = reinterpret_cast<float*>(S.gterm + (size_t)P.n_beams * (P.n_radii + 1));
     S.offf = S.yawf + RU_TILE;
+    S.wout = S.offf + ((P.n_beams + 3) & ~3);
     for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.offf[i] = __double2float_rn(P.beams[i].off_deg);
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii_f[i] = __double2float_rn(P.radii[i]);
     if (!FAST32) for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) s_lut[i] = P.lut[i];
@@ -372,8 +378,15 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
         const int64_t j = tile * RU_TILE + threadIdx.x;
         bool valid = false, yaw_exact = false;
         double posx = 0, posy = 0, yawd = 0;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < n) {
-            const float4 p = part[j];
+            p = part[j];
+            if (P.do_predict) {                                                          // updateParticlePos, MC:746-753 (fp32 element math)
+                const float h = __fadd_rn(p.z, P.rot1);
+                p.x = __fadd_rn(p.x, __fmul_rn(P.trans, ref_cosf(h, P.trig)));           // MC:747
+                p.y = __fadd_rn(p.y, __fmul_rn(P.trans, ref_sinf(h, P.trig)));           // MC:748
+                p.z = __fadd_rn(p.z, P.dtheta);                                          // MC:753
+            }
             const double x = (double)p.x, y = (double)p.y;
             if ((x >= ox && x < P.max_x) && (y >= oy && y < P.max_y)) {                  // isInsideMap, MC:685-692
                 const double o = P.validity_offset;
@@ -526,7 +539,6 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
         }
         __syncthreads();
         // ---- phase C -------------------------------------------------------------------------------------------------
-        if (j < n && !valid) { part[j].w = 0.f; w_dense[j] = 0.f; }
         if ((int)threadIdx.x < nv) {
             double prob = 0.0;
             const double* t = S.terms + threadIdx.x * stride;
@@ -534,10 +546,13 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                 prob = dadd(prob, t[b]);                                                 // MC:665
                 prob = dadd(prob, S.beams[b].rand_term);                                 // MC:669
             }
-            const float wf = __double2float_rn(prob);                                    // MC:673
-            const int64_t jj = tile * RU_TILE + (S.vlist[threadIdx.x] & 0xffff);
-            part[jj].w = wf;
-            w_dense[jj] = wf;
+            S.wout[S.vlist[threadIdx.x] & 0xffff] = __double2float_rn(prob);             // MC:673
+        }
+        __syncthreads();
+        if (j < n) {                                                                     // the particle's own thread writes it back whole
+            p.w = valid ? S.wout[threadIdx.x] : 0.f;
+            part[j] = p;
+            w_dense[j] = p.w;
         }
         __syncthreads();
     }

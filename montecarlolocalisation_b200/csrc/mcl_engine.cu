@@ -537,9 +537,24 @@ int Engine::predict_motion(double r1, double t, double r2) {
     if (n == 0) return fail(MCL_ERR_ARG, "predict: no particles");
     if (cfg.mode == MCL_MODE_NS) { Motion m; m.rot_1 = r1; m.trans = t; m.rot_2 = r2; return ns_predict(m); }
     // Eigen narrows the f64 scalars to the array's fp32 first (MC:746-753)
+    if (pending_motion.valid) { int rc = flush_pending_motion(); if (rc) return rc; }
+    if (defer_predict) {           // mcl_step: the computeWeight kernel that follows applies it while it loads the particles
+        pending_motion.valid = true; pending_motion.rot1 = (float)r1; pending_motion.trans = (float)t; pending_motion.dtheta = (float)(r1 + r2);
+        have_weights = false;
+        return MCL_OK;
+    }
     LAUNCH_PDL(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, (float)r1, (float)t, (float)(r1 + r2), trig_kind);
     CK(cudaGetLastError());
     have_weights = false;
+    return MCL_OK;
+}
+
+// A motion that no computeWeight kernel took along (first-touch pre-pass needed, per-particle kernel, ...): its own pass.
+int Engine::flush_pending_motion() {
+    if (!pending_motion.valid) return MCL_OK;
+    pending_motion.valid = false;
+    LAUNCH_PDL(K_PREDICT, k_ref_predict, grid_for(n, 256), 256, 0, part[cur].p, n, pending_motion.rot1, pending_motion.trans, pending_motion.dtheta, trig_kind);
+    CK(cudaGetLastError());
     return MCL_OK;
 }
 
@@ -677,6 +692,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
     P.lut = d_lut.p; P.lut_filled = d_lut_filled.p; P.key_min = key_min; P.n_keys = n_keys;
     P.beams = d_used; P.n_beams = n_used;
     P.trig = trig_kind;
+    P.do_predict = 0; P.rot1 = P.trans = P.dtheta = 0.f;
     const size_t smem = ref_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0);
     if (smem > 200 * 1024) return fail(MCL_ERR_ARG, "update: too many beams for the shared-memory staging area");
     if (!attr_set) {
@@ -700,6 +716,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         for (int k = k_lo; k <= k_hi && !need_prepass; ++k) need_prepass = !h_lut_filled[k];
     }
     if (need_prepass) {
+        { int rc = flush_pending_motion(); if (rc) return rc; }           // the pre-pass looks at the predicted particles
         CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream));
         LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
         CK(cudaGetLastError());
@@ -715,6 +732,10 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
     const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0, !fast32);
     const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
     if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024 && bounded_ok) {
+        if (pending_motion.valid) {
+            P.do_predict = 1; P.rot1 = pending_motion.rot1; P.trans = pending_motion.trans; P.dtheta = pending_motion.dtheta;
+            pending_motion.valid = false;
+        }
         const bool ms = P.map_in_smem != 0;
         // instantiation = (zero origin, fp32 march, compile-time ray steps, map in shared memory)
 #define RU_FOR_ALL(X) X(true, true, 11, true) X(false, true, 11, true) X(true, true, 0, true) X(false, true, 0, true) X(true, false, 0, true) X(false, false, 0, true) \
@@ -745,6 +766,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
 #undef X
 #undef RU_FOR_ALL
     } else {
+        { int rc = flush_pending_motion(); if (rc) return rc; }
         LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
     }
     CK(cudaGetLastError());
@@ -1032,14 +1054,16 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
         }
         n_used = (int)used.size();
     } else if ((size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "step: empty scan slot");
+    defer_predict = true;
     rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
+    defer_predict = false;
     if (rc) return rc;
     EmaArgs ema;
     ema.a_slow = jitter_state ? cfg.inject_alpha_slow_lost : cfg.inject_alpha_slow_conf;
     ema.a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
     if (host_scan) rc = ref_run_update(d_beams.p, n_used, beams_all, nullptr, true, &ema);
     else rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true, &ema);
-    if (rc) return rc;
+    if (rc) { flush_pending_motion(); return rc; }        // (a tick that failed before its computeWeight kernel still moves the particles)
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;
     // the estimate is part of every tick; its last block writes the tick's scalars straight into the pinned block

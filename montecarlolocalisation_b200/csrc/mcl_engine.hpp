@@ -47,6 +47,10 @@ public:
     int download(float* p);
     int predict_encoders(double enc_l, double enc_r, const double* z3, double* motion_out);
     int predict_motion(double r1, double t, double r2);
+    // mcl_step: the motion of the tick being enqueued, applied by the computeWeight kernel as it loads the particles
+    struct PendingMotion { bool valid = false; float rot1 = 0, trans = 0, dtheta = 0; } pending_motion;
+    bool defer_predict = false;
+    int flush_pending_motion();
     int update(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max, double* total);
     // scans pre-staged in HBM (bench: inputs resident before the timed region)
     int stage_scan(int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max);
