@@ -384,6 +384,13 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         }
     }
     XSF_STAMP(3);
+    // The total alone needs no per-element values: only the tile that holds the last element walks and applies. The walk is
+    // where the result is verified: every composite between two SEQ blocks is applied to a value that must lie in its binade
+    // and must leave the result there, and the threads of such a run all use that one binade (each takes it from the value
+    // its predecessor handed on), so with non-decreasing sums every add in between happened in that binade.
+    const bool need_rest = CDF || t == nt - 1;
+    if (!need_rest && sm_fail) atomicExch(ws.counters + 2, epoch);
+    if (need_rest) {
     // ---- stage 3: the composite carried into this tile, and the SEQ blocks below it ---------------------------------------------------
     __shared__ int sm_src[XSF_WALK];                  // walk position -> tile * XSF_BSTRIDE + block
     __shared__ Par sm_cin[XSF_WALK];                  // walk position -> composite carried into that block's tile
@@ -525,6 +532,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         }
     }
     if (!okflag) atomicExch(ws.counters + 2, epoch);
+    }   // need_rest
     XSF_STAMP(6);
     // ---- the last block to finish: clean-up, fallback if anybody asked for it, then the adaptive-injection state ---------------------
     __threadfence();
