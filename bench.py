@@ -507,13 +507,17 @@ def timed_e2e(c, stream, fn, first, K, W, flush):
 
 
 def kernel_table(prof, algo_of):
+    """Per kernel: live CUDA-event duration per launch (events around every launch: serialised, tiny kernels read ~4 us
+    high), share of the step, algorithmic bytes and what they make against the measured HBM peak."""
     total_ms = sum(v[0] for v in prof.values()) or 1.0
+    peak, _ = peaks()
     kernels = {}
     for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per = ms / cnt
         a = algo_of(name)
-        kernels[name] = {"ms_per_launch": per, "launches": cnt, "share": ms / total_ms, "algo_bytes": a,
-                         "gbs": (a / (per * 1e-3) / 1e9) if a else None}
+        gbs = (a / (per * 1e-3) / 1e9) if a else None
+        kernels[name] = {"ms_per_launch": per, "launches": cnt, "share": ms / total_ms, "algo_bytes": a, "gbs": gbs,
+                         "hbm_frac": (gbs / peak) if gbs else None}
     return kernels
 
 

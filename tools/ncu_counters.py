@@ -1,7 +1,7 @@
 """Which resource binds a kernel, from an `ncu --set full` capture: writes/updates profiles/r2_counters.json, which bench.py
 reads for its `roofline` record.
 
-    python tools/ncu_counters.py <report.ncu-rep> <kernel-name substring> <key> [particles] [note]
+    python tools/ncu_counters.py <report.ncu-rep> <kernel-name substring> <key> [particles] [note] [index among the matching launches]
 
 key: "<kernel>" or "<kernel>@<bench leg>" (e.g. k_ns_update@grid4096). The binding resource is the busiest of: instruction
 issue (smsp__issue_active), the FMA-heavy pipe, the FP64 pipe, the LSU pipe (shared-memory wavefronts) and DRAM; `frac` is that
@@ -16,14 +16,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kern, key = sys.argv[1:4]
 particles = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else None
-note = sys.argv[5] if len(sys.argv) > 5 else None
+note = sys.argv[5] if len(sys.argv) > 5 and sys.argv[5] else None
+which = int(sys.argv[6]) if len(sys.argv) > 6 else -1          # which of the matching launches (default: the last)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 cands = [r for r in rows[2:] if kern in r[hdr.index("Kernel Name")]]
 if not cands:
     raise SystemExit("no kernel matching %r in %s" % (kern, rep))
-d = cands[-1]
+d = cands[which]
 
 
 def val(name):
