@@ -55,6 +55,28 @@ struct FusedEma {
     double n, a_slow, a_fast;
 };
 
+// guide table of the CDF search (kernels_ref.cuh: k_ref_guide, which this replaces when the CDF comes from the one-kernel form):
+// table[b] = first i with cdf[i] >= b / buckets for b = 0..buckets, n beyond the last CDF value; table == null: not asked
+struct FusedGuide {
+    int* table;
+    int buckets, log2_buckets;   // a power of two
+    int force_fallback;          // tests: take the single-chain fallback (which also rebuilds the table) whatever the predictions say
+};
+constexpr int XSF_GQ = 64;       // bucket-edge ranges too long for one thread, per tile, that the whole block writes (more: the thread loops)
+__device__ __forceinline__ int xsf_guide_floor(double c, double B, int buckets) {          // = ref_guide_floor
+    const double x = c * B;
+    return !(x >= 0.0) ? -1 : (x >= B ? buckets : (int)x);           // NaN owns nothing
+}
+
+// edges lo..hi answer `val`; ranges too long for one thread go to the block-wide queue (gq: [XSF_GQ][3], *gq_n entries asked for)
+__device__ __noinline__ void xsf_guide_range(int* __restrict__ table, int lo, int hi, int val, int* gq, int* gq_n) {
+    if (hi - lo + 1 > 8) {                                 // a particle holding a large share of the weight
+        const int slot = atomicAdd(gq_n, 1);
+        if (slot < XSF_GQ) { gq[3 * slot] = lo; gq[3 * slot + 1] = hi; gq[3 * slot + 2] = val; return; }
+    }
+    for (int b = lo; b <= hi; b++) table[b] = val;
+}
+
 __device__ __forceinline__ unsigned long long xsf_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -179,7 +201,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 template <bool CDF>
 __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restrict__ w, int64_t n, int nt, unsigned epoch, FusedWs ws,
                                                             const double* __restrict__ divisor, double* __restrict__ cdf_out,
-                                                            double* __restrict__ total_out, FusedEma ema) {
+                                                            double* __restrict__ total_out, FusedEma ema, FusedGuide guide) {
     pdl_enter();
     __shared__ double sm_d[8];
     __shared__ double sm_last[8];
@@ -187,6 +209,9 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     __shared__ ScanState sm_st[8];
     __shared__ ScanState sm_carry_in, sm_tile_state;
     __shared__ int sm_tile, sm_fail, sm_is_last;
+    __shared__ int sm_gq[XSF_GQ * 3];                                  // (first edge, last edge, element) ranges for the whole block
+    __shared__ int sm_gq_n;
+    __shared__ double sm_own_pre[XSF_BLOCKS];                           // exact value entering every SEQ block of this tile
     __shared__ double sm_start;                                        // exact value after the last SEQ block below this tile
     __shared__ int sm_start_valid;                                     // 0: no SEQ block below this tile (the sum so far is exactly 0)
     // one raw block, two lives: [SEQ blocks below this tile | this tile's own | exact values after every item of the own blocks]
@@ -201,12 +226,25 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         sm_tile = (int)atomicAdd(ws.counters + 0, 1u);
-        sm_fail = 0;
+        sm_fail = 0; sm_gq_n = 0;
         sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0;
     }
     __syncthreads();
     const int t = sm_tile;
     XSF_STAMP(0);
+    if (guide.force_fallback && t == 0 && tid == 0) atomicExch(ws.counters + 2, epoch);
+    // guide table: element i answers the bucket edges in (cdf[i-1], cdf[i]] (k_ref_guide's rule); `pf` carries floor(cdf[i-1] * buckets)
+    const bool want_guide = CDF && guide.table != nullptr;
+    const double GB = (double)guide.buckets;
+    auto guide_emit = [&](int lo, int hi, int val) {
+        if (hi == lo) guide.table[hi] = val;
+        else if (hi > lo) xsf_guide_range(guide.table, lo, hi, val, sm_gq, &sm_gq_n);
+    };
+    auto guide_item = [&](int64_t i, double v, int& pf) {          // (the SEQ-block and all-zero threads; PAR threads shift integers)
+        const int hi = xsf_guide_floor(v, GB, guide.buckets);
+        guide_emit(pf + 1, hi, (int)i);
+        pf = hi;
+    };
     const int64_t base = (int64_t)t * XSF_TILE + (int64_t)tid * XSF_ITEMS;
     float x[XSF_ITEMS];
     load_items12(w, base, n, x);
@@ -341,6 +379,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
             st_relaxed_u64(ws.pub + (size_t)t * XSF_PSTRIDE + 3, xsf_pack(D, 0));
         }
     } else {
+        XSF_STAMP(10);
         if (easy) agg.v = has_tie ? thr_par : Par{thr_d < SAT ? thr_d : SAT, thr_d < SAT ? thr_d : SAT};
         else if (is_block) { agg.reset = 1; agg.cnt = 1; }
         // block-wide exclusive scan of the thread aggregates
@@ -358,6 +397,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
             if (lane > 0) pre = st_combine(pre, lane_excl);
         }
         // SEQ blocks out: rank = blocks before this thread; composite = the PAR items since the previous block / the tile's start
+        XSF_STAMP(11);
         if (is_block) {
             if (pre.cnt < XSF_BLOCKS) {
                 SeqBlock b;
@@ -369,7 +409,9 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
                 const int4* sb4 = reinterpret_cast<const int4*>(&b);
 #pragma unroll
                 for (int k = 0; k < XSF_BPIECES; k++) g[k] = sb4[k];
+                if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 12] = xsf_now();
                 __threadfence();                               // the block before the summary words
+                if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 13] = xsf_now();
             } else sm_fail = 1;
         }
         __syncthreads();
@@ -472,6 +514,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
                 const SeqBlock* b = sm_own + q;
                 const Par comp = b->first_in_tile ? par_compose(carry.v, b->pre) : b->pre;
                 sv = par_apply(sv, comp, b->E_prev, ok);
+                sm_own_pre[q] = sv;
                 for (int k = 0; k < XSF_ITEMS; k++) { sv = dadd(sv, k < b->n_items ? (double)b->w[k] : 0.0); sm_own_s[q * XSF_ITEMS + k] = sv; }
             }
         }
@@ -499,6 +542,10 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         okflag = have_start && !(sb >> 63) && be - 1023 == thr_E && csel < SAT;
         unsigned long long A = A_start + csel + excl_d;
         const unsigned long long hi_bits = (unsigned long long)be << 52;
+        // floor(v * buckets) of a value v = A 2^(be - 1075) of this thread's binade is a shift of its integer significand
+        const int gsh = min(63, max(0, 1075 - be - guide.log2_buckets));
+        int pf = -1;
+        if (want_guide && base > 0) pf = (int)min(A >> gsh, (unsigned long long)guide.buckets);
 #pragma unroll
         for (int j = 0; j < XSF_ITEMS; j++) {
             const int64_t i = base + j;
@@ -508,30 +555,50 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
             A += (A & 1) ? o : e;
             const double v = __longlong_as_double((long long)(hi_bits | (A & ((1ull << 52) - 1))));
             if (CDF) cdf_out[i] = v;
+            if (want_guide) {
+                const int hi = (int)min(A >> gsh, (unsigned long long)guide.buckets);
+                if (hi != pf) { guide_emit(pf + 1, hi, (int)i); pf = hi; }
+            }
             if (i == n - 1 && total_out) *total_out = v;
         }
+        if (want_guide && n_mine > 0 && base + n_mine == n) guide_emit(pf + 1, guide.buckets, (int)n);      // edges beyond the last CDF value
         if (A >= (1ull << 53)) okflag = false;           // the thread's last value left the binade: the prediction was wrong
     } else if (okflag && is_block) {
+        int pf = -1;
+        if (want_guide && base > 0) pf = xsf_guide_floor(sm_own_pre[min(pre.cnt, XSF_BLOCKS - 1)], GB, guide.buckets);
 #pragma unroll
         for (int j = 0; j < XSF_ITEMS; j++) {
             const int64_t i = base + j;
             if (i >= n) break;
             const double v = sm_own_s[min(pre.cnt, XSF_BLOCKS - 1) * XSF_ITEMS + j];
             if (CDF) cdf_out[i] = v;
+            if (want_guide) guide_item(i, v, pf);
             if (i == n - 1 && total_out) *total_out = v;
         }
+        if (want_guide && n_mine > 0 && base + n_mine == n) guide_emit(pf + 1, guide.buckets, (int)n);
     } else if (okflag) {
         // every weight up to and including this thread's is zero: so are the sums
         if (n_mine > 0 && (carry.cnt != 0 || pre.cnt != 0)) okflag = false;       // (cannot happen: a SEQ block means a non-zero P~ before here)
+        int pf = base > 0 ? 0 : -1;
 #pragma unroll
         for (int j = 0; j < XSF_ITEMS; j++) {
             const int64_t i = base + j;
             if (i >= n) break;
             if (CDF) cdf_out[i] = 0.0;
+            if (want_guide) guide_item(i, 0.0, pf);
             if (i == n - 1 && total_out) *total_out = 0.0;
         }
+        if (want_guide && n_mine > 0 && base + n_mine == n) guide_emit(pf + 1, guide.buckets, (int)n);
     }
     if (!okflag) atomicExch(ws.counters + 2, epoch);
+    if (want_guide) {
+        __syncthreads();
+        const int nq = min(sm_gq_n, XSF_GQ);
+        for (int q = 0; q < nq; q++) {
+            const int hi = sm_gq[3 * q + 1], val = sm_gq[3 * q + 2];
+            for (int b = sm_gq[3 * q] + tid; b <= hi; b += XS_THREADS) guide.table[b] = val;
+        }
+    }
     }   // need_rest
     XSF_STAMP(6);
     // ---- the last block to finish: clean-up, fallback if anybody asked for it, then the adaptive-injection state ---------------------
@@ -551,6 +618,14 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         fused_sequential<CDF>(w, n, CDF ? *divisor : 1.0, cdf_out, total_out, reinterpret_cast<float(*)[XS_SEQ_TILE]>(sm_raw),
                               reinterpret_cast<double(*)[XS_SEQ_TILE]>(sm_raw + 2 * XS_SEQ_TILE * sizeof(float)));
         __syncthreads();
+        if (want_guide) {                         // whatever the tiles scattered came from values that were not trusted: all of it again
+            for (int64_t i = tid; i < n; i += XS_THREADS) {
+                const int hi = xsf_guide_floor(cdf_out[i], GB, guide.buckets);
+                const int lo = i == 0 ? 0 : xsf_guide_floor(cdf_out[i - 1], GB, guide.buckets) + 1;
+                for (int b = lo; b <= hi; b++) guide.table[b] = (int)i;
+                if (i == n - 1) for (int b = hi + 1; b <= guide.buckets; b++) guide.table[b] = (int)n;
+            }
+        }
     }
     if (ema.inj != nullptr && tid == 0) {
         // adaptive injection (MC:469-492): the same IEEE operations in the same order as the host form in Engine::ref_resample

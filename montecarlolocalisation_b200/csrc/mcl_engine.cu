@@ -290,17 +290,18 @@ int Engine::ensure_xs(int64_t count) {
 // The reference's sequential f64 accumulations, reproduced bit-exactly in parallel (exact_scan.cuh):
 //   normalise == false: *d_total_out = w_0 + w_1 + ... left to right over d_wraw            (MC:675)
 //   normalise == true : w_i <- (float)((double)w_i / total) into d_wn, then cdf[i]            (MC:496-505)
-int Engine::exact_accumulate(bool normalise, double* d_total_out, const EmaArgs* ema) {
-    return exact_accumulate_on(d_wraw.p, normalise, normalise, d_total_out, ema);
+int Engine::exact_accumulate(bool normalise, double* d_total_out, const EmaArgs* ema, int guide_buckets_wanted) {
+    return exact_accumulate_on(d_wraw.p, normalise, normalise, d_total_out, ema, guide_buckets_wanted);
 }
 
 // w: the dense fp32 terms. normalise: they are divided by the total in d_scalars[0] first (the quotients are what is
 // accumulated; the multi-launch form also leaves them in d_wn). ema (mcl_step, with the total): the accumulation's last block
 // also advances the adaptive-injection state on the device; ema_in_total tells the caller whether that happened.
-int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out, const EmaArgs* ema) {
+int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out, const EmaArgs* ema, int guide_buckets_wanted) {
     const int nt = (int)((n + xs::XS_TILE - 1) / xs::XS_TILE);
     const int ntf = (int)((n + xs::XSF_TILE - 1) / xs::XSF_TILE);          // the one-kernel form's tiles (never more than nt)
     ema_in_total = false;
+    guide_in_cdf = false;
     if (!force_sequential && !force_multilaunch_scan && ntf <= xs::XSF_MAX_TILES) {
         xs::FusedWs fw;
         fw.pub = xs_pub.p; fw.blocks = (xs::SeqBlock*)xs_blocks.p; fw.counters = xs_counters.p;
@@ -309,12 +310,15 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
         xs::FusedEma fe;
         fe.inj = nullptr; fe.counters = nullptr; fe.n = (double)n; fe.a_slow = 0; fe.a_fast = 0;
         if (ema && !want_cdf) { fe.inj = d_inj.p; fe.counters = d_counters.p; fe.a_slow = ema->a_slow; fe.a_fast = ema->a_fast; ema_in_total = true; }
+        xs::FusedGuide fg;
+        fg.table = nullptr; fg.buckets = 0; fg.log2_buckets = 0; fg.force_fallback = force_scan_fallback ? 1 : 0;
+        if (want_cdf && guide_buckets_wanted > 0) { fg.table = d_guide.p; fg.buckets = guide_buckets_wanted; fg.log2_buckets = __builtin_ctz((unsigned)guide_buckets_wanted); guide_in_cdf = true; }      // (d_guide sized by the caller)
         ++xs_epoch;
         if (want_cdf)      // divisor: the total (normalise) or the constant 1.0 parked in d_scalars[7]
             LAUNCH_PDL(K_XS_CDF, xs::k_xs_fused<true>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)(normalise ? d_scalars.p : d_scalars.p + 7), cdf.p,
-                       d_total_out, fe);
+                       d_total_out, fe, fg);
         else
-            LAUNCH_PDL(K_XS_TOTAL, xs::k_xs_fused<false>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)nullptr, (double*)nullptr, d_total_out, fe);
+            LAUNCH_PDL(K_XS_TOTAL, xs::k_xs_fused<false>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)nullptr, (double*)nullptr, d_total_out, fe, fg);
         CK(cudaGetLastError());
         return MCL_OK;
     }
@@ -837,14 +841,17 @@ int Engine::resample(int jitter_state, const mcl_resample_draws* d, mcl_resample
 // normalise + sequential CDF (MC:496-505) and the guide table of the CDF search: everything resampling needs that does not
 // depend on a host decision, so mcl_step can enqueue it before it waits for the weight total.
 int Engine::ref_resample_front() {
-    int rc = exact_accumulate(true, nullptr);
-    if (rc) return rc;
     guide_built = false;
+    int buckets = 0;
     if (n >= 4096 && !force_sequential) {
-        int buckets = 1024;
+        buckets = 1024;
         while ((int64_t)buckets * 8 < n && buckets < (1 << 24)) buckets <<= 1;          // ~8 CDF entries per bucket: 3 probes
         CK(d_guide.ensure((size_t)buckets + 2));
-        LAUNCH_PDL(K_GUIDE, k_ref_guide, grid_for(n, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
+    }
+    int rc = exact_accumulate(true, nullptr, nullptr, buckets);          // the one-kernel form scatters the guide table as it writes the CDF
+    if (rc) return rc;
+    if (buckets) {
+        if (!guide_in_cdf) LAUNCH_PDL(K_GUIDE, k_ref_guide, grid_for(n, 256), 256, 0, cdf.p, n, buckets, d_guide.p);
         guide_built = true; guide_buckets = buckets;
     }
     return MCL_OK;

@@ -117,6 +117,8 @@ public:
     int ns_force_field = -1;            // tests: NS_FIELD_* to use regardless of size (-1 = by size)
     bool ns_force_scalar = false;       // tests: scalar FFMA form of the sensor model on every path
     bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
+    bool force_scan_fallback = false;    // tests: the one-kernel exact scan takes its in-kernel single-chain fallback every time
+    bool guide_in_cdf = false;           // the last CDF accumulation also scattered the guide table
     bool force_multilaunch_scan = false; // tests / A-B: the multi-launch exact scan (exact_scan.cuh) instead of the one-kernel form
     cudaStream_t stream = nullptr;
     int64_t n = 0;
@@ -180,8 +182,8 @@ private:
     unsigned xs_epoch = 0;
     bool ema_in_total = false;                                   // ... and did so for the tick being enqueued
     int ensure_xs(int64_t count);
-    int exact_accumulate(bool normalise, double* d_total_out, const EmaArgs* ema = nullptr);   // total of d_wraw, or normalise + CDF
-    int exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out, const EmaArgs* ema = nullptr);
+    int exact_accumulate(bool normalise, double* d_total_out, const EmaArgs* ema = nullptr, int guide_buckets_wanted = 0);   // total of d_wraw, or normalise + CDF
+    int exact_accumulate_on(const float* w, bool normalise, bool want_cdf, double* d_total_out, const EmaArgs* ema = nullptr, int guide_buckets_wanted = 0);
     DevBuf<int> ancestors;
     // map
     bool map_ready = false;

@@ -112,6 +112,50 @@ def test_guide_table_search_with_injection():
     assert injected > 0
 
 
+@pytest.mark.parametrize("layout", ["few-heavy", "one-tile-crowded", "spread"])
+def test_guide_table_forms_agree_and_match_oracle(layout):
+    """The guide table of the CDF search is scattered by the one-kernel CDF accumulation (exact_scan_fused.cuh); its three other
+    builders - the separate k_ref_guide launch behind the multi-launch scan (force bit 6), the rebuild after the in-kernel
+    single-chain fallback (bit 7) and no table at all (bit 0: full-range search) - must pick the same ancestors, and all of
+    them the oracle's std::lower_bound. Layouts: a handful of particles own hundreds of bucket edges each; more wide ranges
+    in one tile than the block-wide queue holds; ordinary."""
+    occ = load_map()
+    rng = np.random.default_rng(31)
+    n = 20000
+    P = np.zeros((n, 4), np.float32)
+    P[:, 0] = -50.0; P[:, 1] = -50.0; P[:, 3] = 1                       # off the map: weight 0
+    def valid(k):
+        q = np.zeros((k, 4), np.float32)
+        q[:, 0] = rng.uniform(2.2, 2.6, k); q[:, 1] = rng.uniform(2.2, 2.6, k); q[:, 2] = rng.uniform(-3.1, 3.1, k); q[:, 3] = 1
+        return q
+    if layout == "few-heavy":
+        where = np.sort(rng.choice(n, 10, replace=False))
+    elif layout == "one-tile-crowded":
+        where = 8192 + np.sort(rng.choice(4096, 200, replace=False))
+    else:
+        where = np.arange(n)
+    P[where] = valid(len(where))
+    scan = Scenario(1).scans[0]
+    args = (scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+    n_rows, n_cols = 49, 49
+    u_r, u_jit, inj = draws_for(rng, n, n_rows, n_cols)
+    o = Oracle(trig_mode=0); o.set_map(occ, RES); o.precompute_ray_directions(-120.0, 120.0, 0.1)
+    Pnew, idx, cdf, st = o.resample(P.copy(), 1, Scan(**scan), u_r, u_jit, inj)
+    for bits in (0, 64, 128, 1):
+        pf = m.ParticleFilter(); pf.setMap(occ, RES)
+        pf.forceSequential(bits)
+        pf.uploadParticles(P)
+        pf.computeWeight(*args)
+        pf.resampleParticles(1, u_r, u_jit, inj)
+        assert np.array_equal(pf.cdf(), cdf), "cdf, force bits %d" % bits
+        assert np.array_equal(pf.ancestors(), idx), "ancestors, force bits %d" % bits
+    # the one-kernel form built the table itself: no k_ref_guide launch
+    pf = m.ParticleFilter(); pf.setMap(occ, RES)
+    pf.uploadParticles(P); pf.profileEnable(True)
+    pf.computeWeight(*args); pf.resampleParticles(1, u_r, u_jit, inj)
+    names = pf.profileRead()
+    assert "k_xs_cdf" in names and "k_ref_guide" not in names, sorted(names)
+
 @pytest.mark.parametrize("n_beams", [720, 1080])
 def test_more_beams(n_beams):
     run_loop(2000, 6, seed=3, n_beams=n_beams)

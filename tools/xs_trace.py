@@ -1,4 +1,5 @@
-"""Where the one-kernel exact scan spends its time: per-tile stage stamps. python tools/xs_trace.py [n]"""
+"""Where the one-kernel exact scan spends its time: per-tile stage stamps. python tools/xs_trace.py [n] [real]
+real: the weights of a configs[1] filter after 12 ticks (bench.py's workload) instead of random ones."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,7 +9,22 @@ import montecarlolocalisation_b200 as m
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 rng = np.random.default_rng(1)
 w = (40.0 * rng.random(n)).astype(np.float32)
-pf = m.ParticleFilter()
+pf = m.ParticleFilter(max_particles=n)
+if len(sys.argv) > 2 and sys.argv[2] == "real":
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    from scenario import RES
+    sc = bench.workload(16)
+    pf.setMap(sc.occ, RES)
+    pf.sampleParticles(n)
+    for s_ in range(12):
+        sca = sc.scans[s_]
+        pf.executeParticleFilter(sc.enc_left[s_], sc.enc_right[s_], 1, scan=sca)
+    sca = sc.scans[12]
+    pf.diffDriveModel(sc.enc_left[12], sc.enc_right[12])
+    pf.computeWeight(sca["ranges"], sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
+    w = np.ascontiguousarray(pf.downloadParticles()[:, 3])
+    print("real weights: min %g max %g sum %g" % (w.min(), w.max(), w.astype(np.float64).sum()))
 for rep in range(3):
     tr = pf.exactScanTrace(w).astype(np.int64)
 t0 = tr[:, 0].min()
@@ -33,4 +49,8 @@ for k in range(min(8, len(rel))):
 print("  inside stage 3 (summary published, own poll done, scan done, fence done, blocks fetched), tiles every 24th:")
 for k in range(0, len(tr), 24):
     a = (tr[k, [3, 7, 8, 9, 4]] - t0) / 1e3
+    print("   tile %4d: " % k + " ".join("%6.1f" % v for v in a))
+print("  inside stage 2 of the slow tiles (edges known, non-fast branch entered, aggregates scanned, block written, fence done, summary published):")
+for k in sorted(slow):
+    a = (tr[k, [2, 10, 11, 12, 13, 3]] - t0) / 1e3
     print("   tile %4d: " % k + " ".join("%6.1f" % v for v in a))
