@@ -1,31 +1,39 @@
 // exact_scan_fused.cuh — the bit-exact sequential f64 accumulation (exact_scan_core.cuh) as ONE kernel per accumulation.
 //
 // exact_scan.cuh runs an accumulation as three to five dependent launches (tile sums, classification scan, chain, apply scan,
-// fallback), each re-reading the weights; at 1M particles the launches cost more than the arithmetic. Here a tile of 2048
-// weights stays in the registers of its block through all four stages and the stages of DIFFERENT tiles are ordered by
-// per-tile flags instead of kernel boundaries:
+// fallback), each re-reading the weights; at 1M particles the launches cost more than the arithmetic. Here a tile of 4096
+// weights (16 per thread) stays in the registers of its block through all four stages and the stages of DIFFERENT tiles are
+// ordered by per-tile published words instead of kernel boundaries:
 //
-//   1. tile sum -> pub1[t]                                                (publish)
-//      wait for pub1 of every lower tile; P~ at the tile's two edges = F(t), F(t + 1), a FIXED-association sum of
+//   1. tile sum -> published
+//      wait for the sums of every lower tile; P~ at the tile's two edges = F(t), F(t + 1), a FIXED-association sum of
 //      tsum[0 .. t) that every block evaluates identically (so neighbouring tiles agree on the value at their shared edge)
 //   2. classify by THREAD (16 consecutive weights): a thread whose first item's predecessor and whose last item lie safely
 //      inside one binade E holds only PAR items of that binade (the sums are non-decreasing): their increments of the integer
 //      significand are RN(w / 2^(E-52)), a pair (even, odd) only for exact ties - a handful of independent f64 operations
 //      per item. A thread that straddles a binade edge or the start of the sum, or holds a negative, NaN, Inf or huge weight,
 //      becomes one SEQ block: its 16 weights go through the hardware adder in order (~20 such threads per million weights).
-//      Segmented parity-monoid scan of the thread aggregates -> SEQ blocks + tile summary pub2[2t..]
-//      wait for pub2 of every lower tile; segmented scan of their summaries -> the composite carried into this tile and
+//      Segmented parity-monoid scan of the thread aggregates -> SEQ blocks + tile summary, published
+//      wait for the summaries of every lower tile; segmented scan of them -> the composite carried into this tile and
 //      the SEQ blocks below it, in order
 //   3. one thread walks the SEQ blocks of the lower tiles and of this tile with the hardware adder (every block does this
 //      redundantly, and no block waits for another block's walk)
-//   4. apply: exact s_i for the tile's own elements from the registers -> CDF (or just the total). What a PAR thread writes
-//      is VERIFIED, not predicted: the value entering it must lie in binade E and its last value below 2^(E+1).
+//   4. apply: exact s_i for the tile's own elements from the registers -> CDF (or just the total), and - for the CDF that
+//      resampling searches - the guide table of that search, scattered as the values are written (what k_ref_guide did as a
+//      launch of its own, re-reading the CDF). What a PAR thread writes is VERIFIED, not predicted: the value entering it must
+//      lie in binade E and its last value below 2^(E+1).
 //
-// Tiles are taken in ticket order, so a block only ever waits for tiles that are already running: no co-residency
-// requirement, any number of tiles, safe next to other kernels. What a tile publishes is self-validating 64-bit words (data
-// and "ready" in one load, no fence on the polling path), which the last block to finish leaves empty for the next launch. The last block to finish runs the single-chain fallback if any prediction could not be trusted, so
-// correctness never rests on the margin analysis, and (optionally) advances the adaptive-injection state from the total
-// (what k_ref_ema did as a launch of its own).
+// A block only ever waits for lower tiles. When the whole grid fits on the device at once (the host checks: 444 tiles = 1.8M
+// weights on a B200) a tile is simply its block index; otherwise tiles are taken in ticket order, so that a block only waits
+// for tiles that are already running: any number of tiles, no co-residency requirement. What a tile publishes is
+// self-validating 64-bit words (data and "ready" in one load, no fence on the polling path), which the last block to finish
+// leaves empty for the next launch. The last block to finish also runs the single-chain fallback if any prediction could not
+// be trusted, so correctness never rests on the margin analysis, and (optionally) advances the adaptive-injection state from
+// the total (what k_ref_ema did as a launch of its own).
+//
+// Where the time goes (profiles/r2_xs_trace.txt, 1M weights, 245 tiles, ~22 us): every stage is a latency, not a throughput:
+// load + tile sum 2.8 us, first exchange 1.2, classification 1.5 (3 for the handful of tiles that hold a SEQ block or a tie,
+// and every higher tile waits for those), second exchange + scan of 244 summaries ~4, block fetch 1.4, walk 3.7, apply 3.
 #pragma once
 #include "exact_scan.cuh"
 
@@ -46,7 +54,9 @@ struct FusedWs {
     unsigned long long* pub;     // [16 nt]  one line per tile: word 0 the tile sum, words 2-3 the tile summary (self-validating)
     struct SeqBlock* blocks;     // [nt * 16]  SEQ blocks of every tile, written before the tile's summary words
     unsigned* counters;          // [0] tile ticket, [1] finished blocks (both left at 0 by the last block), [2] == epoch: fall back
-    unsigned long long* trace;   // null, or [nt][8] %globaltimer stamps at the stage boundaries of every tile (mcl_debug_exact_scan_trace)
+    unsigned long long* trace;   // null, or [nt][16] %globaltimer stamps at the stage boundaries of every tile (mcl_debug_exact_scan_trace)
+    int by_index;                // 1: tile = blockIdx.x (the host checked that the whole grid fits on the device at once, so every
+                                 // block a block waits for is running or done); 0: tiles are taken in ticket order
 };
 // adaptive injection (MC:469-492) advanced by the accumulation that produces the total (mcl_step); inj == null: not asked
 struct FusedEma {
@@ -83,13 +93,6 @@ __device__ __forceinline__ unsigned long long xsf_now() {
     return t;
 }
 #define XSF_STAMP(k) do { if (ws.trace != nullptr && tid == 0) ws.trace[(size_t)t * 16 + (k)] = xsf_now(); } while (0)
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ void load_items12(const float* __restrict__ w, int64_t base, int64_t n, float (&x)[XSF_ITEMS]) {
     if (base + XSF_ITEMS <= n) {
@@ -165,14 +168,6 @@ struct SeqBlock {
 };
 constexpr int XSF_BPIECES = (int)sizeof(SeqBlock) / 16;
 static_assert(sizeof(SeqBlock) == 32 + 4 * XSF_ITEMS && sizeof(SeqBlock) % 16 == 0, "published as 16-byte words");
-__device__ __forceinline__ SeqBlock ld_seq_block(const SeqBlock* p) {          // what another CTA published: from L2, never a stale L1 line
-    SeqBlock b;
-    const int4* q = reinterpret_cast<const int4*>(p);
-    int4* d = reinterpret_cast<int4*>(&b);
-#pragma unroll
-    for (int k = 0; k < XSF_BPIECES; k++) d[k] = __ldcg(q + k);
-    return b;
-}
 
 // published words, one 128-byte line per tile: pub[16 t] = the bits of tile t's f64 sum (never the EMPTY NaN pattern);
 // pub[16 t + 2], pub[16 t + 3] = the tile summary, word = composite component (clamped to 2^58: anything that large means a
@@ -184,6 +179,8 @@ constexpr unsigned long long XSF_VMASK = (1ull << 59) - 1, XSF_VCLAMP = 1ull << 
 __device__ __forceinline__ unsigned long long xsf_pack(unsigned long long v, unsigned cnt4) {
     return (v < XSF_VCLAMP ? v : XSF_VCLAMP) | ((unsigned long long)(cnt4 & 15u) << 59) | XSF_VALID;
 }
+// (publishing with red.and/red.or instead of plain stores, and polling with ld.volatile or ld.relaxed.sys instead of
+// ld.relaxed.gpu, were measured: no difference; a summary is seen by every poller ~0.5 us after it is stored)
 __device__ __forceinline__ void ld_relaxed_u64x2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
@@ -225,12 +222,12 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     double* const sm_own_s = reinterpret_cast<double*>(sm_raw + WALK_BYTES + OWN_BYTES);      // [block][item]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        sm_tile = (int)atomicAdd(ws.counters + 0, 1u);
+        if (!ws.by_index) sm_tile = (int)atomicAdd(ws.counters + 0, 1u);
         sm_fail = 0; sm_gq_n = 0;
         sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0;
     }
-    __syncthreads();
-    const int t = sm_tile;
+    if (!ws.by_index) __syncthreads();          // (by index: the block-wide scans below synchronise long before those are read)
+    const int t = ws.by_index ? (int)blockIdx.x : sm_tile;
     XSF_STAMP(0);
     if (guide.force_fallback && t == 0 && tid == 0) atomicExch(ws.counters + 2, epoch);
     // guide table: element i answers the bucket edges in (cdf[i-1], cdf[i]] (k_ref_guide's rule); `pf` carries floor(cdf[i-1] * buckets)
@@ -340,15 +337,18 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
             thr_d += e;
         }
         easy = !any_invalid;
-        if (easy && has_tie) {                                                 // rare: the thread's composite depends on the parity
+        if (easy && has_tie) {                                                 // the thread's composite depends on the parity it starts from
+            // (rare, but a tile with a tie anywhere publishes its summary only after this and every higher tile waits for it: the
+            // weights go through a local array, touched in this branch only, instead of a register select per item. Folding the
+            // ties into the pass above was measured: the extra branch there slows every tile by more than this costs one)
+            float xl[XSF_ITEMS];
+#pragma unroll
+            for (int j = 0; j < XSF_ITEMS; j++) xl[j] = x[j];
 #pragma unroll 1
             for (int j = 0; j < XSF_ITEMS; j++) {
-                float xj = x[0];
-#pragma unroll
-                for (int q = 1; q < XSF_ITEMS; q++) xj = (q == j) ? x[q] : xj;   // (x stays in registers)
                 unsigned long long o; bool inv;
                 Par f;
-                f.e = increment(xj, o, inv); f.o = o;
+                f.e = increment(xl[j], o, inv); f.o = o;
                 thr_par = par_compose(thr_par, f);
             }
         }
@@ -400,13 +400,12 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         XSF_STAMP(11);
         if (is_block) {
             if (pre.cnt < XSF_BLOCKS) {
-                SeqBlock b;
-                b.idx0 = (uint32_t)base; b.n_items = n_mine; b.pre = pre.v; b.first_in_tile = pre.reset ? 0 : 1; b.E_prev = q0.E;
+                SeqBlock* const d = sm_own + pre.cnt;              // built in shared memory, copied out by the same thread as 16-byte words
+                d->idx0 = (uint32_t)base; d->n_items = n_mine; d->pre = pre.v; d->first_in_tile = pre.reset ? 0 : 1; d->E_prev = q0.E;
 #pragma unroll
-                for (int j = 0; j < XSF_ITEMS; j++) b.w[j] = x[j];
-                sm_own[pre.cnt] = b;
+                for (int j = 0; j < XSF_ITEMS / 4; j++) reinterpret_cast<float4*>(d->w)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
                 int4* g = reinterpret_cast<int4*>(ws.blocks + (size_t)t * XSF_BSTRIDE + pre.cnt);
-                const int4* sb4 = reinterpret_cast<const int4*>(&b);
+                const int4* sb4 = reinterpret_cast<const int4*>(d);
 #pragma unroll
                 for (int k = 0; k < XSF_BPIECES; k++) g[k] = sb4[k];
                 if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 12] = xsf_now();
@@ -452,6 +451,15 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
             mine.reset = mine.cnt ? 1 : 0;
         }
         XSF_STAMP(7);
+        if (ws.trace != nullptr) {                // which lower tile's summary this block saw last, and when
+            __shared__ unsigned long long sm_tmax;
+            const unsigned long long tp = k < t ? xsf_now() : 0ull;       // when this thread's own poll succeeded
+            if (tid == 0) sm_tmax = 0;
+            __syncthreads();
+            atomicMax(&sm_tmax, tp);
+            __syncthreads();
+            if (tp == sm_tmax) { ws.trace[(size_t)t * 16 + 14] = tp; ws.trace[(size_t)t * 16 + 15] = (unsigned long long)k; }
+        }
         ScanState in2 = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -502,11 +510,27 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         double sv = 0.0;
         if (ok) {
             const int n_below = min(carry.cnt, XSF_WALK);
+            // one dependent chain of hardware additions (exactly the reference's roundings); the next block's weights are fetched
+            // while the current block's sixteen additions run. Items past a block's count are +0: adding them changes nothing.
+            float4 nx[XSF_ITEMS / 4];
+            if (n_below > 0) {
+#pragma unroll
+                for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_walk[0].w)[k];
+            }
             for (int q = 0; q < n_below; q++) {
                 const SeqBlock* b = sm_walk + q;
+                float4 cur[XSF_ITEMS / 4];
+#pragma unroll
+                for (int k = 0; k < XSF_ITEMS / 4; k++) cur[k] = nx[k];
+                if (q + 1 < n_below) {
+#pragma unroll
+                    for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_walk[q + 1].w)[k];
+                }
                 sv = par_apply(sv, b->pre, b->E_prev, ok);
-                const int m = b->n_items;
-                for (int k = 0; k < m; k++) sv = dadd(sv, (double)b->w[k]);      // the hardware adder: exactly the reference's rounding
+#pragma unroll
+                for (int k = 0; k < XSF_ITEMS / 4; k++) {
+                    sv = dadd(sv, (double)cur[k].x); sv = dadd(sv, (double)cur[k].y); sv = dadd(sv, (double)cur[k].z); sv = dadd(sv, (double)cur[k].w);
+                }
             }
             sm_start = sv; sm_start_valid = carry.cnt > 0;
             const int own = min(tstate.cnt, XSF_BLOCKS);

@@ -306,13 +306,21 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
         xs::FusedWs fw;
         fw.pub = xs_pub.p; fw.blocks = (xs::SeqBlock*)xs_blocks.p; fw.counters = xs_counters.p;
         fw.trace = nullptr;
+        if (xs_resident_tiles < 0) {           // how many tiles the device holds at once: up to there a tile can be its block index
+            int per_sm_a = 0, per_sm_b = 0, sms = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, xs::k_xs_fused<true>, xs::XS_THREADS, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, xs::k_xs_fused<false>, xs::XS_THREADS, 0));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device));
+            xs_resident_tiles = std::min(per_sm_a, per_sm_b) * sms;
+        }
+        fw.by_index = (ntf <= xs_resident_tiles && !force_scan_tickets) ? 1 : 0;
         if (xs_trace_on) { CK(xs_trace.ensure((size_t)nt * 16)); CK(cudaMemsetAsync(xs_trace.p, 0, (size_t)nt * 16 * sizeof(unsigned long long), stream)); fw.trace = xs_trace.p; }      // (nt >= ntf)
         xs::FusedEma fe;
         fe.inj = nullptr; fe.counters = nullptr; fe.n = (double)n; fe.a_slow = 0; fe.a_fast = 0;
         if (ema && !want_cdf) { fe.inj = d_inj.p; fe.counters = d_counters.p; fe.a_slow = ema->a_slow; fe.a_fast = ema->a_fast; ema_in_total = true; }
         xs::FusedGuide fg;
         fg.table = nullptr; fg.buckets = 0; fg.log2_buckets = 0; fg.force_fallback = force_scan_fallback ? 1 : 0;
-        if (want_cdf && guide_buckets_wanted > 0) { fg.table = d_guide.p; fg.buckets = guide_buckets_wanted; fg.log2_buckets = __builtin_ctz((unsigned)guide_buckets_wanted); guide_in_cdf = true; }      // (d_guide sized by the caller)
+        if (want_cdf && guide_buckets_wanted > 0 && !force_separate_guide) { fg.table = d_guide.p; fg.buckets = guide_buckets_wanted; fg.log2_buckets = __builtin_ctz((unsigned)guide_buckets_wanted); guide_in_cdf = true; }      // (d_guide sized by the caller)
         ++xs_epoch;
         if (want_cdf)      // divisor: the total (normalise) or the constant 1.0 parked in d_scalars[7]
             LAUNCH_PDL(K_XS_CDF, xs::k_xs_fused<true>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)(normalise ? d_scalars.p : d_scalars.p + 7), cdf.p,

@@ -117,6 +117,9 @@ public:
     int ns_force_field = -1;            // tests: NS_FIELD_* to use regardless of size (-1 = by size)
     bool ns_force_scalar = false;       // tests: scalar FFMA form of the sensor model on every path
     bool force_sequential = false;      // tests: use the single-chain kernels instead of the exact parallel scan
+    int xs_resident_tiles = -1;          // blocks of the one-kernel exact scan the device holds at once (queried on first use)
+    bool force_scan_tickets = false;     // tests: ticket order even when the grid is co-resident
+    bool force_separate_guide = false;   // tests / A-B: the guide table by its own launch (k_ref_guide) behind the one-kernel CDF
     bool force_scan_fallback = false;    // tests: the one-kernel exact scan takes its in-kernel single-chain fallback every time
     bool guide_in_cdf = false;           // the last CDF accumulation also scattered the guide table
     bool force_multilaunch_scan = false; // tests / A-B: the multi-launch exact scan (exact_scan.cuh) instead of the one-kernel form

@@ -54,3 +54,7 @@ print("  inside stage 2 of the slow tiles (edges known, non-fast branch entered,
 for k in sorted(slow):
     a = (tr[k, [2, 10, 11, 12, 13, 3]] - t0) / 1e3
     print("   tile %4d: " % k + " ".join("%6.1f" % v for v in a))
+print("  the summary each tile saw last (tile: its scan done at; last summary seen at, of tile, which published at):")
+for k in range(8, len(tr), 16):
+    src = int(tr[k, 15])
+    print("   tile %4d: scan done %6.1f; last seen %6.1f of tile %4d published %6.1f" % (k, (tr[k, 8] - t0) / 1e3, (tr[k, 14] - t0) / 1e3, src, (tr[src, 3] - t0) / 1e3))
