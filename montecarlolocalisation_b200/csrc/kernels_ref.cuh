@@ -15,6 +15,8 @@ struct RefBeam {
     double rand_term;  // w_rand * (|obs - max_range| < 0.01 ? 1.0 : 0.0)     (MC:669)
 };
 
+constexpr int RU_INLINE_BEAMS = 40;        // (the reference scores 12 beams of its 360-beam scan, 35 of its 683-beam one)
+
 struct RefParams {
     // occupancy: 1 byte per cell, 1 = value > 50 (MC:327,377)
     const uint8_t* occ;
@@ -50,7 +52,11 @@ struct RefParams {
     // its own (k_ref_update_v2 only; the particle is written back whole, with its weight)
     int do_predict;
     float rot1, trans, dtheta;
+    // beams == null: the scored beams ride in the launch parameters (k_ref_update_v2 only), so a tick whose scan arrives from the
+    // host needs no copy command ahead of its first kernel
+    RefBeam inline_beams[RU_INLINE_BEAMS];
 };
+__device__ __forceinline__ RefBeam ref_beam_of(const RefParams& P, int i) { return P.beams ? P.beams[i] : P.inline_beams[i]; }
 
 // ---- map probes ---------------------------------------------------------------------------------------
 struct MapView {
@@ -330,10 +336,10 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     S.yawf = reinterpret_cast<float*>(S.gterm + (size_t)P.n_beams * (P.n_radii + 1));
     S.offf = S.yawf + RU_TILE;
     S.wout = S.offf + ((P.n_beams + 3) & ~3);
-    for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.offf[i] = __double2float_rn(P.beams[i].off_deg);
+    for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.offf[i] = __double2float_rn(ref_beam_of(P, i).off_deg);
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii_f[i] = __double2float_rn(P.radii[i]);
     if (!FAST32) for (int i = threadIdx.x; i < P.n_keys; i += RU_TILE) s_lut[i] = P.lut[i];
-    for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = P.beams[i];
+    for (int i = threadIdx.x; i < P.n_beams; i += RU_TILE) S.beams[i] = ref_beam_of(P, i);
     for (int i = threadIdx.x; i < P.n_radii; i += RU_TILE) S.radii[i] = P.radii[i];
     if (P.map_in_smem) {
         const int cells = P.width * P.height;
@@ -947,7 +953,7 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n_par
 __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum_dev, double wsum_host,
                                                    double* __restrict__ partials /* [grid][4] */, unsigned* __restrict__ ticket,
                                                    double* __restrict__ out4, RefStepReport* __restrict__ report /* null: none */,
-                                                   const double* __restrict__ inj5, const int* __restrict__ counters4) {
+                                                   const double* __restrict__ inj5, const int* __restrict__ counters4, unsigned long long seq) {
     pdl_enter();
     __shared__ double ws[8][4];
     __shared__ bool last;
@@ -989,6 +995,10 @@ __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ pa
             else if (k < 9) report->counters[k - 5] = counters4[k - 5];
         }
         if (threadIdx.x == 0) *ticket = 0;
+        if (report) {                             // the report is complete: the host may be spinning on its sequence number
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence_system(); *(volatile unsigned long long*)&report->seq = seq; }
+        }
     }
 }
 

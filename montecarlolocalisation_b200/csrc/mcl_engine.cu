@@ -616,14 +616,7 @@ int Engine::update(const float* ranges, int n_beams, float angle_min, float angl
     std::vector<RefBeam> used;
     int rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, beams_all, used);
     if (rc) return rc;
-    CK(d_beams.ensure(std::max<size_t>(1, used.size())));
-    if (!used.empty()) {
-        rc = ensure_pinned(used.size() * sizeof(RefBeam));
-        if (rc) return rc;
-        memcpy(h_pinned, used.data(), used.size() * sizeof(RefBeam));
-        CK(cudaMemcpyAsync(d_beams.p, h_pinned, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
-    }
-    return ref_run_update(d_beams.p, (int)used.size(), beams_all, total);
+    return ref_run_update(nullptr, used.data(), (int)used.size(), beams_all, total);
 }
 
 int Engine::stage_scan(int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max) {
@@ -665,7 +658,7 @@ int Engine::update_staged(int slot, double* total) {
         return MCL_OK;
     }
     if (slot < 0 || (size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "update_staged: empty slot");
-    return ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, total);
+    return ref_run_update(staged[slot].d_used.p, nullptr, staged[slot].n_used, staged[slot].all, total);
 }
 
 static size_t ref_smem_bytes(int n_keys, int n_beams, int n_radii, size_t map_bytes) {
@@ -688,8 +681,29 @@ int Engine::ref_prepare_beams(const float* ranges, int n_beams, float angle_min,
     return MCL_OK;
 }
 
-int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync, const EmaArgs* ema) {
+// d_used: the scored beams in device memory (a staged scan), or null with h_used: the beams of a scan that has just arrived
+// from the host. Those ride in k_ref_update_v2's launch parameters when they fit (RU_INLINE_BEAMS); the kernels that read
+// them through a pointer (first-touch pre-pass, the per-particle kernel) and longer lists get a copy through the pinned ring.
+int Engine::ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync, const EmaArgs* ema) {
     RefParams P;
+    auto beams_on_device = [&]() -> int {
+        if (d_used || n_used == 0) return MCL_OK;
+        CK(d_beams.ensure((size_t)n_used));
+        // a ring of pinned slots: earlier ticks may still be in flight, their scans must not be overwritten
+        int rc = ensure_pinned_ring((size_t)n_used * sizeof(RefBeam));
+        if (rc) return rc;
+        void* hp = pinned_ring_next();
+        memcpy(hp, h_used, (size_t)n_used * sizeof(RefBeam));
+        CK(cudaMemcpyAsync(d_beams.p, hp, (size_t)n_used * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(ring_events[ring_pos], stream));
+        d_used = d_beams.p;
+        P.beams = d_used;
+        return MCL_OK;
+    };
+    if (!d_used && n_used > 0 && !h_used) return fail(MCL_ERR_ARG, "update: no beams");
+    if (!d_used && n_used > RU_INLINE_BEAMS) { int rc = beams_on_device(); if (rc) return rc; }
+    if (!d_used)
+        for (int i = 0; i < n_used; i++) P.inline_beams[i] = h_used[i];
     P.occ = d_occ.p; P.width = map_w; P.height = map_h;
     P.occ_pad = d_occ_pad.p; P.pad = occ_pad; P.wp = occ_wp;
     const size_t map_bytes = (size_t)map_w * map_h;
@@ -728,6 +742,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
         for (int k = k_lo; k <= k_hi && !need_prepass; ++k) need_prepass = !h_lut_filled[k];
     }
     if (need_prepass) {
+        { int rc = beams_on_device(); if (rc) return rc; }
         { int rc = flush_pending_motion(); if (rc) return rc; }           // the pre-pass looks at the predicted particles
         CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream));
         LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
@@ -778,6 +793,7 @@ int Engine::ref_run_update(const RefBeam* d_used, int n_used, const std::vector<
 #undef X
 #undef RU_FOR_ALL
     } else {
+        { int rc = beams_on_device(); if (rc) return rc; }
         { int rc = flush_pending_motion(); if (rc) return rc; }
         LAUNCH(K_UPDATE, k_ref_update, grid_for(n, 256), 256, smem, part[cur].p, d_wraw.p, n, P);
     }
@@ -1014,7 +1030,7 @@ int Engine::estimate_enqueue(double* h_sums4, RefStepReport* step_report) {
         wsum_dev = d_scalars.p + 1;
     }
     LAUNCH_PDL(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2,
-           step_report, (const double*)d_inj.p, (const int*)d_counters.p);
+           step_report, (const double*)d_inj.p, (const int*)d_counters.p, step_report ? ++step_seq : 0ull);
     CK(cudaGetLastError());
     if (h_sums4) CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return MCL_OK;
@@ -1045,11 +1061,11 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "step: MCL_MODE_REF only (NS filters use mcl_ns_step)");
     if (!map_ready) return fail(MCL_ERR_ARG, "step: no map");
     if (n == 0) return fail(MCL_ERR_ARG, "step: no particles");
-    if (!h_step) CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars)));
+    if (!h_step) { CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars))); memset(h_step, 0, sizeof(StepScalars)); }
     int rc = inj_sync_to_device();
     if (rc) return rc;
-    // The scan goes to the device first: the copy command then sits at the head of the tick and the kernels follow one
-    // another without a copy in between (programmatic launches overlap only kernel with kernel).
+    // A scan from the host: its scored beams ride in the computeWeight kernel's launch parameters (ref_run_update), so the
+    // tick is kernels only (programmatic launches overlap only kernel with kernel).
     const bool host_scan = ranges || slot < 0;
     int n_used = 0;
     if (host_scan) {
@@ -1057,17 +1073,8 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
         std::vector<RefBeam> used;
         rc = ref_prepare_beams(ranges, n_beams, angle_min, angle_inc, range_min, range_max, beams_all, used);
         if (rc) return rc;
-        CK(d_beams.ensure(std::max<size_t>(1, used.size())));
-        if (!used.empty()) {
-            // a ring of pinned slots: earlier steps may still be in flight, their scans must not be overwritten
-            rc = ensure_pinned_ring(used.size() * sizeof(RefBeam));
-            if (rc) return rc;
-            void* hp = pinned_ring_next();
-            memcpy(hp, used.data(), used.size() * sizeof(RefBeam));
-            CK(cudaMemcpyAsync(d_beams.p, hp, used.size() * sizeof(RefBeam), cudaMemcpyHostToDevice, stream));
-            CK(cudaEventRecord(ring_events[ring_pos], stream));
-        }
-        n_used = (int)used.size();
+        step_used.swap(used);
+        n_used = (int)step_used.size();
     } else if ((size_t)slot >= staged.size() || !staged[slot].valid) return fail(MCL_ERR_ARG, "step: empty scan slot");
     defer_predict = true;
     rc = predict_encoders(enc_l, enc_r, nullptr, nullptr);
@@ -1076,8 +1083,8 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     EmaArgs ema;
     ema.a_slow = jitter_state ? cfg.inject_alpha_slow_lost : cfg.inject_alpha_slow_conf;
     ema.a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
-    if (host_scan) rc = ref_run_update(d_beams.p, n_used, beams_all, nullptr, true, &ema);
-    else rc = ref_run_update(staged[slot].d_used.p, staged[slot].n_used, staged[slot].all, nullptr, true, &ema);
+    if (host_scan) rc = ref_run_update(nullptr, step_used.data(), n_used, beams_all, nullptr, true, &ema);
+    else rc = ref_run_update(staged[slot].d_used.p, nullptr, staged[slot].n_used, staged[slot].all, nullptr, true, &ema);
     if (rc) { flush_pending_motion(); return rc; }        // (a tick that failed before its computeWeight kernel still moves the particles)
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;
@@ -1085,7 +1092,20 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     rc = estimate_enqueue(nullptr, h_step);
     if (rc) return rc;
     if (!pose3 && !st) return MCL_OK;                           // nothing asked for: the tick is queued, the host moves on
-    CK(cudaStreamSynchronize(stream));
+    // The report lands in pinned memory, its sequence number last: the host watches for that instead of waiting for the
+    // stream to be reported idle (a few microseconds later). Every few thousand looks it asks the runtime as well, so that a
+    // failed launch ends the wait with its error.
+    {
+        const volatile unsigned long long* seq = &h_step->seq;
+        const unsigned long long want = step_seq;
+        for (unsigned spins = 1; *seq != want; ++spins) {
+            if ((spins & 0xfff) == 0 && cudaStreamQuery(stream) != cudaErrorNotReady) { CK(cudaStreamSynchronize(stream)); break; }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (*seq != want) return fail(MCL_ERR_CUDA, "step: the tick finished without writing its report");
+    }
     last_total = h_step->inj[4];
     if (st) {
         st->injected = h_step->counters[0]; st->clamped = h_step->counters[1]; st->p_inject = h_step->inj[2];

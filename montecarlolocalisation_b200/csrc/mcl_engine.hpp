@@ -29,7 +29,7 @@ struct DevBuf {
 };
 
 // The scalar results of one mcl_step tick, in pinned host memory; k_pose_sums' last block writes them there itself.
-struct RefStepReport { double inj[5]; double pose[4]; int counters[4]; };
+struct RefStepReport { double inj[5]; double pose[4]; int counters[4]; unsigned long long seq; };      // seq: written last, the tick's number
 
 class Engine {
 public:
@@ -137,7 +137,7 @@ private:
     int ensure_particles(int64_t count);
     int ref_prepare_beams(const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min, float range_max,
                           std::vector<HostBeam>& all, std::vector<RefBeam>& used);
-    int ref_run_update(const RefBeam* d_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync = false,
+    int ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_used, const std::vector<HostBeam>& all, double* total, bool defer_sync = false,
                        const EmaArgs* ema = nullptr);
     int ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resample_stats* st, bool front_done = false, bool dev_ema = false);
     int inj_sync_to_device();
@@ -148,6 +148,8 @@ private:
     // whole-step entry (mcl_step / mcl_step_staged): scalars the host needs travel through this pinned block
     typedef RefStepReport StepScalars;      // {inj[5], pose[4], counters[4]}: pinned, written by k_pose_sums (zero-copy)
     StepScalars* h_step = nullptr;
+    std::vector<RefBeam> step_used;          // scored beams of the tick being enqueued (host scan)
+    unsigned long long step_seq = 0;         // ticks enqueued with a report; the report carries the number of the tick that wrote it
     bool guide_built = false;
     int guide_buckets = 0;
     int ref_fill_ray_lut(const std::vector<HostBeam>& all);

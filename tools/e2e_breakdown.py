@@ -21,15 +21,21 @@ from scenario import RES  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 W = 5
-sc = bench.workload(3 * (K + W))
-pf = m.ParticleFilter(device=0, max_particles=n, seed=0x1234)
-pf.setMap(sc.occ, RES)
-pf.sampleParticles(n)
-stream = torch.cuda.ExternalStream(pf.stream(), device=0)
-for s in range(3 * (K + W)):
-    sca = sc.scans[s]
-    pf.stageScan(s, sca["ranges"], sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
-pinned = [torch.from_numpy(np.ascontiguousarray(sc.scans[s]["ranges"])).pin_memory() for s in range(3 * (K + W))]
+sc = bench.workload(K + W)
+pinned = [torch.from_numpy(np.ascontiguousarray(sc.scans[s]["ranges"])).pin_memory() for s in range(K + W)]
+
+
+def fresh():
+    """The same filter for every mode: same seed, same ticks."""
+    global pf, stream
+    pf = m.ParticleFilter(device=0, max_particles=n, seed=0x1234)
+    pf.setMap(sc.occ, RES)
+    pf.sampleParticles(n)
+    stream = torch.cuda.ExternalStream(pf.stream(), device=0)
+    for s in range(K + W):
+        sca = sc.scans[s]
+        pf.stageScan(s, sca["ranges"], sca["angle_min"], sca["angle_inc"], sca["range_min"], sca["range_max"])
+
 
 
 def a(s):
@@ -57,15 +63,18 @@ def wall(fn, first):
     return np.array(out) * 1e6
 
 
+fresh()
 wa = wall(a, 0)
-wb = wall(b, K + W)
-for s in range(2 * (K + W), 2 * (K + W) + W):
+fresh()
+wb = wall(b, 0)
+fresh()
+for s in range(W):
     cq(s)
 stream.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 with torch.cuda.stream(stream):
     e0.record()
-    for s in range(2 * (K + W) + W, 3 * (K + W)):
+    for s in range(W, K + W):
         cq(s)
     e1.record()
 stream.synchronize()
