@@ -672,9 +672,12 @@ __global__ void k_ref_ema(const double* __restrict__ total, double n, double a_s
 }
 
 // inj_dev (mcl_step): p_inject lives in device memory (inj_dev[2]); nothing to do when it is zero
+// The last block to finish turns the per-block counts into exclusive offsets in place (the n-th flagged particle of the whole
+// population takes the n-th injection draw, MC:508-523) and leaves their total in *total; `ticket` resets itself.
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
-                                                          int* __restrict__ block_counts, RefDrawGen G, const double* __restrict__ inj_dev) {
+                                                          int* __restrict__ block_counts, RefDrawGen G, const double* __restrict__ inj_dev,
+                                                          int* __restrict__ total, unsigned* __restrict__ ticket) {
     pdl_enter();
     if (inj_dev) { p_inject = inj_dev[2]; if (!(p_inject > 0.0)) return; }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -685,17 +688,34 @@ __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restri
     }
     int f = (r < p_inject) ? 1 : 0;
     int c = __syncthreads_count(f);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
-}
-// exclusive scan of block counts in place (single block, sequential chunks; n_blocks is small).
-__global__ void k_ref_inject_scan(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total, const double* __restrict__ inj_dev) {
-    pdl_enter();
-    if (inj_dev && !(inj_dev[2] > 0.0)) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < n_blocks; b++) { int c = block_counts[b]; block_counts[b] = acc; acc += c; }
-        *total = acc;
+    __shared__ bool last;
+    __shared__ int warp_tot[8];
+    if (threadIdx.x == 0) {
+        block_counts[blockIdx.x] = c;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nb = (int)gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int carry = 0;
+    for (int base = 0; base < nb; base += 256) {
+        const int idx = base + (int)threadIdx.x;
+        const int v = idx < nb ? __ldcg(block_counts + idx) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        int woff = 0, chunk = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { if (k < warp) woff += warp_tot[k]; chunk += warp_tot[k]; }
+        if (idx < nb) block_counts[idx] = carry + woff + inc - v;
+        carry += chunk;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *total = carry; *ticket = 0u; }
 }
 
 // (float)atan2(sin(t), cos(t)) (MC:550). For |t| < 3 pi the mathematical value is t, t - 2 pi or t + 2 pi; libm's composed

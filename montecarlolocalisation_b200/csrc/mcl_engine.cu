@@ -37,7 +37,7 @@ Engine::~Engine() {
 
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
-                                         "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_inject_scan",
+                                         "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_ema",
                                          "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_ns_pose_reduce", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
@@ -126,7 +126,7 @@ int Engine::open() {
     CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
     CK(d_counters.ensure(8)); CK(d_scalars.ensure(8));
     { const double one = 1.0; CK(cudaMemcpyAsync(d_scalars.p + 7, &one, sizeof(double), cudaMemcpyHostToDevice, stream)); }      // divisor of an un-normalised CDF
-    CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4] = ticket of k_pose_sums (resets itself)
+    CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4], [5] = tickets of k_pose_sums and k_ref_inject_count (they reset themselves)
     CK(d_partials.ensure(4 * 1024));
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
@@ -961,9 +961,9 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const bool inject_possible = max_inj > 0 && (dev_ema || p_inject > 0.0);
     if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
-        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G, inj_dev);
-        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G, inj_dev);
-        LAUNCH_PDL(K_INJECT_SCAN, k_ref_inject_scan, 1, 32, 0, d_block_counts.p, (int)blocks, d_counters.p + 2, inj_dev);
+        // (counts per block, then - by the last block to finish - their exclusive offsets and total: [5] = that kernel's ticket)
+        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
+        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
         CK(cudaGetLastError());
     }
     if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
