@@ -674,36 +674,47 @@ __global__ void k_ref_ema(const double* __restrict__ total, double n, double a_s
 // inj_dev (mcl_step): p_inject lives in device memory (inj_dev[2]); nothing to do when it is zero
 // The last block to finish turns the per-block counts into exclusive offsets in place (the n-th flagged particle of the whole
 // population takes the n-th injection draw, MC:508-523) and leaves their total in *total; `ticket` resets itself.
+// n_counts = ceil(n / 256) counts (one per 256 slots: k_ref_resample's blocks); a block of this kernel produces RIC_SEGS of them,
+// so that the whole population is one wave of blocks with one fence and one ticket each.
+constexpr int RIC_SEGS = 4;
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
-                                                          int* __restrict__ block_counts, RefDrawGen G, const double* __restrict__ inj_dev,
+                                                          int* __restrict__ block_counts, int n_counts, RefDrawGen G, const double* __restrict__ inj_dev,
                                                           int* __restrict__ total, unsigned* __restrict__ ticket) {
     pdl_enter();
     if (inj_dev) { p_inject = inj_dev[2]; if (!(p_inject > 0.0)) return; }
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double r = 2.0;
-    if (i < n) {
-        if (GEN) { uint32_t a[4]; ref_philox_draws(2 * (uint64_t)i, G, a); r = canonical53(a[0], a[1]); }
-        else r = u_r[i];
-    }
-    int f = (r < p_inject) ? 1 : 0;
-    int c = __syncthreads_count(f);
     __shared__ bool last;
     __shared__ int warp_tot[8];
+#pragma unroll
+    for (int sgm = 0; sgm < RIC_SEGS; sgm++) {
+        const int cb = (int)blockIdx.x * RIC_SEGS + sgm;                 // the count this segment produces
+        if (cb >= n_counts) break;
+        const int64_t i = (int64_t)cb * 256 + threadIdx.x;
+        double r = 2.0;
+        if (i < n) {
+            if (GEN) { uint32_t a[4]; ref_philox_draws(2 * (uint64_t)i, G, a); r = canonical53(a[0], a[1]); }
+            else r = u_r[i];
+        }
+        const int c = __syncthreads_count((r < p_inject) ? 1 : 0);
+        if (threadIdx.x == 0) block_counts[cb] = c;
+    }
     if (threadIdx.x == 0) {
-        block_counts[blockIdx.x] = c;
         __threadfence();
         last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!last) return;
     __threadfence();
-    const int nb = (int)gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = n_counts, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int carry = 0;
-    for (int base = 0; base < nb; base += 256) {
-        const int idx = base + (int)threadIdx.x;
-        const int v = idx < nb ? __ldcg(block_counts + idx) : 0;
-        int inc = v;
+    for (int base = 0; base < nb; base += 256 * 16) {               // 16 consecutive counts per thread, all loads in flight at once
+        int v[16], sum = 0;
+        const int first = base + (int)threadIdx.x * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = first + k < nb ? __ldcg(block_counts + first + k) : 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) sum += v[k];
+        int inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
         if (lane == 31) warp_tot[warp] = inc;
@@ -711,7 +722,9 @@ __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restri
         int woff = 0, chunk = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) { if (k < warp) woff += warp_tot[k]; chunk += warp_tot[k]; }
-        if (idx < nb) block_counts[idx] = carry + woff + inc - v;
+        int run = carry + woff + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { if (first + k < nb) block_counts[first + k] = run; run += v[k]; }
         carry += chunk;
         __syncthreads();
     }

@@ -962,8 +962,8 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
         // (counts per block, then - by the last block to finish - their exclusive offsets and total: [5] = that kernel's ticket)
-        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, blocks, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
-        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, blocks, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
+        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
+        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
         CK(cudaGetLastError());
     }
     if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
