@@ -459,12 +459,15 @@ def l2_flusher(c, stream):
     return flush
 
 
-def timed_resident(c, stream, fn, first, K, W, flush):
+def timed_resident(c, stream, fn, first, K, W, flush, after_warmup=None):
     """W warm-up + K timed steps; each timed step bracketed by CUDA events on the engine's stream (`flush` runs between
-    steps, outside the events). Returns (per-step ms list, host wall seconds of the whole loop)."""
+    steps, outside the events). Returns (per-step ms list, host wall seconds of the whole loop). after_warmup(): called
+    once between the warm-up and the timed steps (the launch counter is read there)."""
     torch = c.torch
     for s in range(first, first + W):
         fn(s)
+    if after_warmup:
+        after_warmup()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     gc.collect()
     gc.disable()                 # a collection inside a 0.3 ms step would be charged to the step
@@ -564,9 +567,9 @@ def ref_leg(c, args, n, K, W, replicas_note=False, want_kernels=True):
         sca["ranges"] = pinned[s].numpy()
         return pf.executeParticleFilter(sc.enc_left[s], sc.enc_right[s], 1, scan=sca)[0]
 
-    launches0 = pf.kernelLaunches()
-    ms_res, wall_res = timed_resident(c, stream, step_resident, 0, K, W, flush)
-    launches = pf.kernelLaunches() - launches0
+    mark = {}
+    ms_res, wall_res = timed_resident(c, stream, step_resident, 0, K, W, flush, after_warmup=lambda: mark.update(l0=pf.kernelLaunches()))
+    launches = pf.kernelLaunches() - mark["l0"]          # kernels of the K timed ticks only
     s_e2e = timed_e2e(c, stream, step_e2e, W + K, K, W, flush)
     kernels = None
     if want_kernels:
@@ -698,9 +701,9 @@ def ns_leg(c, args, cells, n_global, n_beams, label, K, W, key, map_seed=4, scal
         sca["ranges"] = pinned[i % n_scans].numpy()
         return shard.step(motion, scan=sca, want_pose=True)
 
-    l0 = shard.pf.kernelLaunches()
-    ms_res, wall_res = timed_resident(c, stream, step_resident, 0, K, W, flush)
-    launches = shard.pf.kernelLaunches() - l0
+    mark = {}
+    ms_res, wall_res = timed_resident(c, stream, step_resident, 0, K, W, flush, after_warmup=lambda: mark.update(l0=shard.pf.kernelLaunches()))
+    launches = shard.pf.kernelLaunches() - mark["l0"]    # kernels of the K timed steps only
     s_e2e = timed_e2e(c, stream, step_e2e, W + K, K, W, flush)
     shard.pf.profileEnable(True)
     for k in range(K):

@@ -133,6 +133,7 @@ SYMBOLS = [
     ("mcl_stream", _vp, [_vp]),
     ("mcl_synchronize", _i32, [_vp]),
     ("mcl_kernel_launches", _i64, [_vp]),
+    ("mcl_debug_optimistic_redos", _i64, [_vp]),
 ]
 
 _lib = None

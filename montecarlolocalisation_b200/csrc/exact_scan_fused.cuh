@@ -55,6 +55,7 @@ struct FusedWs {
     struct SeqBlock* blocks;     // [nt * 16]  SEQ blocks of every tile, written before the tile's summary words
     unsigned* counters;          // [0] tile ticket, [1] finished blocks (both left at 0 by the last block), [2] == epoch: fall back
     unsigned long long* trace;   // null, or [nt][16] %globaltimer stamps at the stage boundaries of every tile (mcl_debug_exact_scan_trace)
+    const int* abort;            // optimistic tick (kernels_ref.cuh: RefParams::abort): non-null and set = return at once
     int by_index;                // 1: tile = blockIdx.x (the host checked that the whole grid fits on the device at once, so every
                                  // block a block waits for is running or done); 0: tiles are taken in ticket order
 };
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
                                                             const double* __restrict__ divisor, double* __restrict__ cdf_out,
                                                             double* __restrict__ total_out, FusedEma ema, FusedGuide guide) {
     pdl_enter();
+    if (ws.abort != nullptr && *ws.abort != 0) return;
     __shared__ double sm_d[8];
     __shared__ double sm_last[8];
     __shared__ unsigned long long sm_u[8];

@@ -55,6 +55,9 @@ struct RefParams {
     // beams == null: the scored beams ride in the launch parameters (k_ref_update_v2 only), so a tick whose scan arrives from the
     // host needs no copy command ahead of its first kernel
     RefBeam inline_beams[RU_INLINE_BEAMS];
+    // optimistic tick (mcl_step): non-null and *abort != 0 = the first-touch pre-pass of this tick found ray directions that the
+    // host has to evaluate first; every kernel of the tick returns at once and the host runs the tick again
+    const int* abort;
 };
 __device__ __forceinline__ RefBeam ref_beam_of(const RefParams& P, int i) { return P.beams ? P.beams[i] : P.inline_beams[i]; }
 
@@ -139,7 +142,7 @@ __device__ __forceinline__ RefSmem ref_stage_smem(const RefParams& P, unsigned c
     s.radii = reinterpret_cast<double*>(s.beams + P.n_beams);
     s.occ = reinterpret_cast<uint8_t*>(s.radii + P.n_radii);
     for (int i = threadIdx.x; i < P.n_keys; i += blockDim.x) s.lut[i] = P.lut[i];
-    for (int i = threadIdx.x; i < P.n_beams; i += blockDim.x) s.beams[i] = P.beams[i];
+    for (int i = threadIdx.x; i < P.n_beams; i += blockDim.x) s.beams[i] = ref_beam_of(P, i);
     for (int i = threadIdx.x; i < P.n_radii; i += blockDim.x) s.radii[i] = P.radii[i];
     if (stage_map) {
         int cells = P.width * P.height;
@@ -167,6 +170,12 @@ __global__ void __launch_bounds__(256) k_ref_first_touch(const float4* __restric
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     float4 p = part[j];
+    if (P.do_predict) {                  // the motion the computeWeight kernel will apply (MC:746-753), here without writing it back
+        const float h = __fadd_rn(p.z, P.rot1);
+        p.x = __fadd_rn(p.x, __fmul_rn(P.trans, ref_cosf(h, P.trig)));
+        p.y = __fadd_rn(p.y, __fmul_rn(P.trans, ref_sinf(h, P.trig)));
+        p.z = __fadd_rn(p.z, P.dtheta);
+    }
     if (!ref_is_valid(m, P, (double)p.x, (double)p.y)) return;
     double yaw_deg = ddiv(dmul(ref_yaw(p.z), 180.0), 3.14159265358979323846);
     for (int b = 0; b < P.n_beams; b++) {
@@ -183,6 +192,33 @@ __global__ void k_ref_touch_theta(const float4* __restrict__ part, const unsigne
     if (k >= n_keys) return;
     unsigned long long t = touch[k];
     theta_out[k] = (t == ~0ull) ? 0.f : part[t >> 32].z;
+}
+// The same for an optimistic tick (one block): first touchers and their theta (after the tick's motion) go straight into the
+// caller's pinned host block, the touch table is left empty for the next pre-pass, and *abort tells the kernels that follow
+// whether any key was found (then they return at once: the host evaluates those directions and runs the tick again).
+struct RefTouchReport { unsigned long long seq; int n_new; int pad; };      // followed by touch[n_keys] (u64) and theta[n_keys] (f32)
+__global__ void __launch_bounds__(1024) k_ref_touch_report(const float4* __restrict__ part, unsigned long long* __restrict__ touch, int n_keys,
+                                                           int do_predict, float dtheta, RefTouchReport* __restrict__ report,
+                                                           unsigned long long* __restrict__ h_touch, float* __restrict__ h_theta,
+                                                           unsigned long long seq, int* __restrict__ abort) {
+    int mine = 0;
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) {
+        const unsigned long long t = touch[k];
+        if (t != ~0ull) {
+            float th = part[t >> 32].z;
+            if (do_predict) th = __fadd_rn(th, dtheta);
+            h_touch[k] = t; h_theta[k] = th;
+            touch[k] = ~0ull;
+            mine++;
+        } else h_touch[k] = ~0ull;
+    }
+    const int total = __syncthreads_count(mine != 0);            // threads that found something: zero = nothing new
+    if (threadIdx.x == 0) {
+        *abort = total != 0 ? 1 : 0;
+        report->n_new = total;
+        __threadfence_system();
+        *(volatile unsigned long long*)&report->seq = seq;
+    }
 }
 
 // ---- computeWeight (MC:623-682): one thread per particle ---------------------------------------------------
@@ -379,6 +415,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     // host copies, which serialise the stream), so under a programmatic launch it overlaps the predecessor's tail; the
     // particles are the predecessor's output.
     pdl_enter();
+    if (P.abort != nullptr && *P.abort != 0) return;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- phase A -------------------------------------------------------------------------------------------------
         const int64_t j = tile * RU_TILE + threadIdx.x;
@@ -680,8 +717,9 @@ constexpr int RIC_SEGS = 4;
 template <bool GEN>
 __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restrict__ u_r, int64_t n, double p_inject,
                                                           int* __restrict__ block_counts, int n_counts, RefDrawGen G, const double* __restrict__ inj_dev,
-                                                          int* __restrict__ total, unsigned* __restrict__ ticket) {
+                                                          int* __restrict__ total, unsigned* __restrict__ ticket, const int* __restrict__ abort) {
     pdl_enter();
+    if (abort != nullptr && *abort != 0) return;
     if (inj_dev) { p_inject = inj_dev[2]; if (!(p_inject > 0.0)) return; }
     __shared__ bool last;
     __shared__ int warp_tot[8];
@@ -803,8 +841,10 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       RefResampleParams R, int* __restrict__ ancestors,
                                                       int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G,
                                                       const int* __restrict__ guide /* null: full-range search */, int buckets,
-                                                      const double* __restrict__ inj_dev /* mcl_step: {.., p_inject, cdf_is_monotone} on the device */) {
+                                                      const double* __restrict__ inj_dev /* mcl_step: {.., p_inject, cdf_is_monotone} on the device */,
+                                                      const int* __restrict__ abort /* optimistic tick: see RefParams */) {
     pdl_enter();
+    if (abort != nullptr && *abort != 0) return;
     __shared__ int warp_counts[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
@@ -986,8 +1026,17 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n_par
 __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum_dev, double wsum_host,
                                                    double* __restrict__ partials /* [grid][4] */, unsigned* __restrict__ ticket,
                                                    double* __restrict__ out4, RefStepReport* __restrict__ report /* null: none */,
-                                                   const double* __restrict__ inj5, const int* __restrict__ counters4, unsigned long long seq) {
+                                                   const double* __restrict__ inj5, const int* __restrict__ counters4, unsigned long long seq,
+                                                   const int* __restrict__ abort /* optimistic tick: see RefParams */) {
     pdl_enter();
+    if (abort != nullptr && *abort != 0) {         // nothing ran: tell the host, which is watching the report
+        if (blockIdx.x == 0 && threadIdx.x == 0 && report) {
+            report->aborted = 1;
+            __threadfence_system();
+            *(volatile unsigned long long*)&report->seq = seq;
+        }
+        return;
+    }
     __shared__ double ws[8][4];
     __shared__ bool last;
     const float weight_sum = __double2float_rn(wsum_dev ? *wsum_dev : wsum_host);
@@ -1030,7 +1079,7 @@ __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ pa
         if (threadIdx.x == 0) *ticket = 0;
         if (report) {                             // the report is complete: the host may be spinning on its sequence number
             __syncthreads();
-            if (threadIdx.x == 0) { __threadfence_system(); *(volatile unsigned long long*)&report->seq = seq; }
+            if (threadIdx.x == 0) { report->aborted = 0; __threadfence_system(); *(volatile unsigned long long*)&report->seq = seq; }
         }
     }
 }

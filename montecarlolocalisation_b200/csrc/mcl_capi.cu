@@ -212,5 +212,6 @@ int mcl_ns_field_form(mcl_handle* h) { return h ? h->engine.ns_field_kind : -1; 
 void* mcl_stream(mcl_handle* h) { return h ? (void*)h->engine.stream : nullptr; }
 int mcl_synchronize(mcl_handle* h) { GUARD(h); TRY(h->engine.synchronize()) }
 int64_t mcl_kernel_launches(mcl_handle* h) { return h ? h->engine.launches : 0; }
+int64_t mcl_debug_optimistic_redos(mcl_handle* h) { return h ? h->engine.optimistic_redos : 0; }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ Engine::~Engine() {
     for (int w = 0; w < 4; w++) for (int r = 0; r < 8; r++) if (peer_ipc[w][r] && peer_ptr[w][r]) cudaIpcCloseMemHandle(peer_ptr[w][r]);
     d_assign.release(); d_km_reinit.release(); d_km.release(); d_posearr.release(); d_bounds.release(); d_totals.release(); d_plan.release(); d_pose.release(); d_bar.release();
     if (h_step) cudaFreeHost(h_step);
+    if (h_touch_report) cudaFreeHost(h_touch_report);
     if (h_ns_pose) cudaFreeHost(h_ns_pose);
     d_inj.release();
     if (ring_base) { cudaFreeHost(ring_base); for (auto& e : ring_events) cudaEventDestroy(e); }
@@ -126,7 +127,7 @@ int Engine::open() {
     CK(cudaMemcpyAsync(d_lut_filled.p, h_lut_filled.data(), n_keys, cudaMemcpyHostToDevice, stream));
     CK(d_counters.ensure(8)); CK(d_scalars.ensure(8));
     { const double one = 1.0; CK(cudaMemcpyAsync(d_scalars.p + 7, &one, sizeof(double), cudaMemcpyHostToDevice, stream)); }      // divisor of an un-normalised CDF
-    CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4], [5] = tickets of k_pose_sums and k_ref_inject_count (they reset themselves)
+    CK(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(int), stream));      // [4], [5] = tickets of k_pose_sums and k_ref_inject_count (they reset themselves); [6] = abort flag of an optimistic tick
     CK(d_partials.ensure(4 * 1024));
     CK(cudaStreamSynchronize(stream));
     return MCL_OK;
@@ -306,6 +307,7 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
         xs::FusedWs fw;
         fw.pub = xs_pub.p; fw.blocks = (xs::SeqBlock*)xs_blocks.p; fw.counters = xs_counters.p;
         fw.trace = nullptr;
+        fw.abort = tick_abort;
         if (xs_resident_tiles < 0) {           // how many tiles the device holds at once: up to there a tile can be its block index
             int per_sm_a = 0, per_sm_b = 0, sms = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, xs::k_xs_fused<true>, xs::XS_THREADS, 0));
@@ -741,10 +743,36 @@ int Engine::ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_u
         const int k_hi = std::min(n_keys - 1, (int)std::round(180.000001 + off_hi) - key_min);
         for (int k = k_lo; k <= k_hi && !need_prepass; ++k) need_prepass = !h_lut_filled[k];
     }
-    if (need_prepass) {
+    // fp32 pre-filter tolerance: 4x the bound 2^-23*(cells + 2*max_range/res + 2) on the fp32 cell coordinate's error
+    const double span = (double)std::max(map_w, map_h) + 2.0 * cfg.max_laser_range / (double)res_f + 2.0;
+    const float tol32 = (float)(span * 4.76837158203125e-07);                  // 2^-21
+    const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f && occ_pad > 0 && P.n_radii <= 16;
+    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0, !fast32);
+    const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
+    const bool use_v2 = !force_v1_update && n_used > 0 && smem2 <= 200 * 1024 && bounded_ok;
+    P.abort = tick_abort;                      // (null outside an optimistic mcl_step tick)
+    tick_optimistic = false;
+    if (need_prepass && tick_abort != nullptr && use_v2 && scans_are_fused()) {
+        // Optimistic tick: with a few thousand particles the table never fills (only the keys some particle's heading reaches
+        // are ever touched), so EVERY tick would pay the pre-pass and its round trip through the host, although after the
+        // first ticks it almost never finds a key. Here the pre-pass only reports (zero-copy, into pinned memory) and raises
+        // *abort if it found something; the tick's kernels are enqueued behind it at once and return immediately if the flag
+        // is up, in which case ref_step evaluates the directions and runs the tick again. Nothing of the tick is written
+        // before that decision: the pre-pass applies the pending motion to the particles it looks at without storing it.
+        if (pending_motion.valid) { P.do_predict = 1; P.rot1 = pending_motion.rot1; P.trans = pending_motion.trans; P.dtheta = pending_motion.dtheta; }
+        { int rc = ensure_touch_block(); if (rc) return rc; }
+        if (!touch_clean) { CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream)); touch_clean = true; }
+        LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
+        CK(cudaGetLastError());
+        LAUNCH(K_TOUCH_THETA, k_ref_touch_report, 1, 1024, 0, part[cur].p, d_touch.p, n_keys, P.do_predict, P.dtheta, h_touch_report, h_touch_keys, h_touch_theta,
+               ++touch_seq, d_counters.p + 6);
+        CK(cudaGetLastError());
+        tick_optimistic = true;
+    } else if (need_prepass) {
         { int rc = beams_on_device(); if (rc) return rc; }
         { int rc = flush_pending_motion(); if (rc) return rc; }           // the pre-pass looks at the predicted particles
         CK(cudaMemsetAsync(d_touch.p, 0xFF, n_keys * sizeof(unsigned long long), stream));
+        touch_clean = false;
         LAUNCH(K_FIRST_TOUCH, k_ref_first_touch, grid_for(n, 256), 256, smem, part[cur].p, n, P, d_touch.p);
         CK(cudaGetLastError());
         LAUNCH(K_TOUCH_THETA, k_ref_touch_theta, grid_for(n_keys, 256), 256, 0, part[cur].p, d_touch.p, n_keys, d_touch_theta.p);
@@ -752,13 +780,7 @@ int Engine::ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_u
         int rc = ref_fill_ray_lut(all);
         if (rc) return rc;
     }
-    // fp32 pre-filter tolerance: 4x the bound 2^-23*(cells + 2*max_range/res + 2) on the fp32 cell coordinate's error
-    const double span = (double)std::max(map_w, map_h) + 2.0 * cfg.max_laser_range / (double)res_f + 2.0;
-    const float tol32 = (float)(span * 4.76837158203125e-07);                  // 2^-21
-    const bool fast32 = !force_f64_probe && span < 2.0e6 && tol32 < 0.05f && occ_pad > 0 && P.n_radii <= 16;
-    const size_t smem2 = ru_smem_bytes(n_keys, n_used, P.n_radii, P.map_in_smem ? map_bytes : 0, P.map_in_smem ? pad_bytes : 0, !fast32);
-    const bool bounded_ok = ((double)std::max(map_w, map_h) + cfg.max_laser_range / (double)res_f + 16.0) < 1.0e9;
-    if (!force_v1_update && n_used > 0 && smem2 <= 100 * 1024 && bounded_ok) {
+    if (use_v2) {
         if (pending_motion.valid) {
             P.do_predict = 1; P.rot1 = pending_motion.rot1; P.trans = pending_motion.trans; P.dtheta = pending_motion.dtheta;
             pending_motion.valid = false;
@@ -768,7 +790,7 @@ int Engine::ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_u
 #define RU_FOR_ALL(X) X(true, true, 11, true) X(false, true, 11, true) X(true, true, 0, true) X(false, true, 0, true) X(true, false, 0, true) X(false, false, 0, true) \
                       X(true, true, 11, false) X(false, true, 11, false) X(true, true, 0, false) X(false, true, 0, false) X(true, false, 0, false) X(false, false, 0, false)
         if (!attr_set2) {
-#define X(Z, F, N, M) CK(cudaFuncSetAttribute((k_ref_update_v2<Z, F, N, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define X(Z, F, N, M) CK(cudaFuncSetAttribute((k_ref_update_v2<Z, F, N, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             RU_FOR_ALL(X)
 #undef X
             attr_set2 = true;
@@ -822,6 +844,31 @@ int Engine::ref_fill_ray_lut(const std::vector<HostBeam>& all) {
     CK(cudaMemcpyAsync(touch.data(), d_touch.p, n_keys * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(theta.data(), d_touch_theta.p, n_keys * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    return ref_fill_ray_lut_from(all, touch.data(), theta.data());
+}
+
+// pinned block of an optimistic tick's pre-pass: {RefTouchReport, touch[n_keys], theta[n_keys]}
+int Engine::ensure_touch_block() {
+    if (h_touch_report && h_touch_cap >= n_keys) return MCL_OK;
+    if (h_touch_report) cudaFreeHost(h_touch_report);
+    h_touch_report = nullptr; h_touch_cap = 0;
+    const size_t bytes = sizeof(RefTouchReport) + (size_t)n_keys * (sizeof(unsigned long long) + sizeof(float));
+    void* p = nullptr;
+    CK(cudaMallocHost(&p, bytes));
+    memset(p, 0, bytes);
+    h_touch_report = (RefTouchReport*)p;
+    h_touch_keys = (unsigned long long*)(h_touch_report + 1);
+    h_touch_theta = (float*)(h_touch_keys + n_keys);
+    h_touch_cap = n_keys;
+    return MCL_OK;
+}
+
+bool Engine::scans_are_fused() const {
+    return !force_sequential && !force_multilaunch_scan && (n + xs::XSF_TILE - 1) / xs::XSF_TILE <= xs::XSF_MAX_TILES;
+}
+
+// first touchers (touch[k] = particle << 32 | beam, ~0 = none) and their theta -> directions evaluated with the host's libm
+int Engine::ref_fill_ray_lut_from(const std::vector<HostBeam>& all, const unsigned long long* touch, const float* theta) {
     bool changed = false;
     const int stride = std::max(1, cfg.beam_stride);
     for (int k = 0; k < n_keys; ++k) {
@@ -962,8 +1009,8 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
         // (counts per block, then - by the last block to finish - their exclusive offsets and total: [5] = that kernel's ticket)
-        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
-        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5));
+        if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5), tick_abort);
+        else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5), tick_abort);
         CK(cudaGetLastError());
     }
     if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
@@ -974,11 +1021,11 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     if (d)
         LAUNCH_PDL(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
                d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort);
     else
         LAUNCH_PDL(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
                d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort);
     CK(cudaGetLastError());
     int counters[4] = {0, 0, 0, 0};
     if (!dev_ema) {
@@ -1030,7 +1077,7 @@ int Engine::estimate_enqueue(double* h_sums4, RefStepReport* step_report) {
         wsum_dev = d_scalars.p + 1;
     }
     LAUNCH_PDL(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2,
-           step_report, (const double*)d_inj.p, (const int*)d_counters.p, step_report ? ++step_seq : 0ull);
+           step_report, (const double*)d_inj.p, (const int*)d_counters.p, step_report ? ++step_seq : 0ull, step_report ? tick_abort : (const int*)nullptr);
     CK(cudaGetLastError());
     if (h_sums4) CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return MCL_OK;
@@ -1056,7 +1103,7 @@ int Engine::estimate(double* x, double* y, double* th) {
 // counters and the pose. Same kernels, same results as mcl_predict_encoders + mcl_update + mcl_resample + mcl_estimate,
 // which wait for the GPU three times. Draws come from the engine's Philox streams (parity runs inject theirs per call).
 int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min,
-                     float range_max, int jitter_state, double* pose3, mcl_resample_stats* st) {
+                     float range_max, int jitter_state, double* pose3, mcl_resample_stats* st, bool allow_optimistic) {
     CK(cudaSetDevice(cfg.device));
     if (cfg.mode != MCL_MODE_REF) return fail(MCL_ERR_STATE, "step: MCL_MODE_REF only (NS filters use mcl_ns_step)");
     if (!map_ready) return fail(MCL_ERR_ARG, "step: no map");
@@ -1064,6 +1111,13 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     if (!h_step) { CK(cudaMallocHost((void**)&h_step, sizeof(StepScalars))); memset(h_step, 0, sizeof(StepScalars)); }
     int rc = inj_sync_to_device();
     if (rc) return rc;
+    // An optimistic tick (ref_run_update) needs a caller that waits for the report, and everything the host side of a tick
+    // changes is kept so that the tick can be run again
+    tick_abort = (allow_optimistic && (pose3 || st)) ? d_counters.p + 6 : nullptr;
+    struct Saved { decltype(odo) odo; decltype(step_counter) step_counter; int cur; PendingMotion pending; bool have_weights, wsum_known; double known_wsum;
+                   int last_per; bool draws_generated; uint32_t draws_step; double last_total; } saved{odo, step_counter, cur, pending_motion, have_weights,
+                   wsum_known, known_wsum, last_per, draws_generated, draws_step, last_total};
+    struct Reset { const int*& p; ~Reset() { p = nullptr; } } reset_abort{tick_abort};
     // A scan from the host: its scored beams ride in the computeWeight kernel's launch parameters (ref_run_update), so the
     // tick is kernels only (programmatic launches overlap only kernel with kernel).
     const bool host_scan = ranges || slot < 0;
@@ -1105,6 +1159,20 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
 #endif
         }
         if (*seq != want) return fail(MCL_ERR_CUDA, "step: the tick finished without writing its report");
+    }
+    if (tick_optimistic && h_step->aborted) {
+        // the pre-pass found ray directions that must be evaluated first: no kernel of the tick ran. Evaluate them (host libm),
+        // put the host side back and run the tick again, this time with the pre-pass waited for.
+        const std::vector<HostBeam>& all = host_scan ? beams_all : staged[slot].all;
+        if (h_touch_report->seq != touch_seq) return fail(MCL_ERR_CUDA, "step: aborted tick without a pre-pass report");
+        rc = ref_fill_ray_lut_from(all, h_touch_keys, h_touch_theta);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(d_counters.p + 6, 0, sizeof(int), stream));
+        odo = saved.odo; step_counter = saved.step_counter; cur = saved.cur; pending_motion = saved.pending; have_weights = saved.have_weights;
+        wsum_known = saved.wsum_known; known_wsum = saved.known_wsum; last_per = saved.last_per; draws_generated = saved.draws_generated;
+        draws_step = saved.draws_step; last_total = saved.last_total;
+        ++optimistic_redos;
+        return ref_step(enc_l, enc_r, slot, ranges, n_beams, angle_min, angle_inc, range_min, range_max, jitter_state, pose3, st, false);
     }
     last_total = h_step->inj[4];
     if (st) {

@@ -29,7 +29,7 @@ struct DevBuf {
 };
 
 // The scalar results of one mcl_step tick, in pinned host memory; k_pose_sums' last block writes them there itself.
-struct RefStepReport { double inj[5]; double pose[4]; int counters[4]; unsigned long long seq; };      // seq: written last, the tick's number
+struct RefStepReport { double inj[5]; double pose[4]; int counters[4]; unsigned long long seq; int aborted; int pad; };      // seq: written last, the tick's number; aborted: optimistic tick that did not run
 
 class Engine {
 public:
@@ -61,7 +61,7 @@ public:
     int estimate(double* x, double* y, double* th);
     int inj_sync_to_host();                 // the adaptive-injection state back on the host (after mcl_step)
     int ref_step(double enc_l, double enc_r, int slot, const float* ranges, int n_beams, float angle_min, float angle_inc, float range_min,
-                 float range_max, int jitter_state, double* pose3, mcl_resample_stats* st);
+                 float range_max, int jitter_state, double* pose3, mcl_resample_stats* st, bool allow_optimistic = true);
     int get_ray_lut(int32_t* keys, double* dx, double* dy, int32_t cap, int32_t* count);
     int synchronize();
     // NS mode (north-star formulation); the *_local phases are what a multi-GPU driver sequences around its collectives
@@ -126,6 +126,7 @@ public:
     cudaStream_t stream = nullptr;
     int64_t n = 0;
     int64_t launches = 0;
+    int64_t optimistic_redos = 0;       // mcl_step ticks that were run again because their pre-pass found new ray directions
     double inj_slow = 0, inj_fast = 0;      // adaptiveInjection (MC:191)
 
 private:
@@ -148,6 +149,18 @@ private:
     // whole-step entry (mcl_step / mcl_step_staged): scalars the host needs travel through this pinned block
     typedef RefStepReport StepScalars;      // {inj[5], pose[4], counters[4]}: pinned, written by k_pose_sums (zero-copy)
     StepScalars* h_step = nullptr;
+    // optimistic tick (ref_run_update): the pre-pass reports into this pinned block, the tick's kernels watch d_counters[6]
+    const int* tick_abort = nullptr;         // non-null while an mcl_step tick whose caller waits for the report is being enqueued
+    bool tick_optimistic = false;            // the tick being enqueued has an unwaited pre-pass in front of it
+    bool touch_clean = false;                // d_touch holds no first touchers (k_ref_touch_report leaves it that way)
+    struct RefTouchReport* h_touch_report = nullptr;
+    unsigned long long* h_touch_keys = nullptr;
+    float* h_touch_theta = nullptr;
+    int h_touch_cap = 0;
+    unsigned long long touch_seq = 0;
+    int ensure_touch_block();
+    bool scans_are_fused() const;
+    int ref_fill_ray_lut_from(const std::vector<HostBeam>& all, const unsigned long long* touch, const float* theta);
     std::vector<RefBeam> step_used;          // scored beams of the tick being enqueued (host scan)
     unsigned long long step_seq = 0;         // ticks enqueued with a report; the report carries the number of the tick that wrote it
     bool guide_built = false;

@@ -312,6 +312,10 @@ class ParticleFilter:
     def kernelLaunches(self):
         return self.L.mcl_kernel_launches(self.h)
 
+    def optimisticRedos(self):
+        """Whole-tick calls that ran twice because their first-touch pre-pass found new ray directions (mcl_debug_optimistic_redos)."""
+        return self.L.mcl_debug_optimistic_redos(self.h)
+
 
 class NsShard:
     """One shard (= one GPU handle) of an MCL_MODE_NS filter, phase by phase (include/mcl.h "NS mode across GPUs")."""

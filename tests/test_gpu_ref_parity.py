@@ -429,6 +429,56 @@ def test_whole_step_call_equals_separate_calls(n):
     assert np.array_equal(a.injectionState(), b.injectionState())
 
 
+def test_optimistic_tick_equals_separate_calls_on_the_robot_scan():
+    """A small cloud with a narrow spread of headings on the robot's 683-beam / 0.352-degree scan (35 scored beams): most
+    ray-direction keys are never touched, so the table stays incomplete and EVERY tick needs the first-touch pre-pass.
+    mcl_step enqueues the tick behind the pre-pass without waiting for it and runs it again only when the pre-pass found a
+    new key (DESIGN.md section 3 "Tick plumbing"): same particles, ancestors, pose, injection state and ray table as the
+    separate calls (which wait for the pre-pass every tick) over 40 ticks; some ticks ran twice, most ran once behind an
+    unwaited pre-pass (8 launches: pre-pass 2 + tick 6)."""
+    from montecarlolocalisation_b200 import synth
+    n, ticks = 300, 40
+    sc = Scenario(ticks, n_beams=360, seed=9)
+    scans = [synth.make_scan(sc.occ, 0.1, sc.truth[s], 683, 700 + s, angle_min=np.float32(-120.0 * np.pi / 180.0),
+                             angle_inc=np.float32(0.352 * np.pi / 180.0)) for s in range(ticks)]
+    rng = np.random.default_rng(5)
+    P = np.zeros((n, 4), np.float32)
+    P[:, 0] = sc.truth[0][0] + rng.uniform(-0.1, 0.1, n); P[:, 1] = sc.truth[0][1] + rng.uniform(-0.1, 0.1, n)
+    P[:, 2] = sc.truth[0][2] + rng.uniform(-0.05, 0.05, n); P[:, 3] = 1
+    a = m.ParticleFilter(max_particles=n, seed=31)
+    b = m.ParticleFilter(max_particles=n, seed=31)
+    for pf in (a, b):
+        pf.setMap(sc.occ, RES)
+        pf.uploadParticles(P)
+    for i in range(0, ticks, 3):
+        a.stageScan(i, scans[i]["ranges"], scans[i]["angle_min"], scans[i]["angle_inc"], scans[i]["range_min"], scans[i]["range_max"])
+    unwaited = 0
+    for step in range(ticks):
+        scan = scans[step]
+        lost = step % 7 < 2
+        l0, r0 = a.kernelLaunches(), a.optimisticRedos()
+        if step % 3 == 0:
+            pose_a, st_a = a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, slot=step)
+        else:
+            pose_a, st_a = a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, scan=scan)
+        if a.optimisticRedos() == r0 and a.kernelLaunches() - l0 == 8:
+            unwaited += 1
+        b.diffDriveModel(sc.enc_left[step], sc.enc_right[step])
+        total = b.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
+        st_b = b.resampleParticles(lost)
+        pose_b = b.estimateWeightedPose()
+        assert st_a == st_b and st_a["total_weight"] == total, (step, st_a, st_b)
+        assert np.array_equal(pose_a, pose_b), (step, pose_a, pose_b)
+        assert np.array_equal(a.downloadParticles(), b.downloadParticles()), step
+        assert np.array_equal(a.ancestors(), b.ancestors()), step
+        for x, y in zip(a.rayLut(), b.rayLut()):
+            assert np.array_equal(x, y), step
+    assert np.array_equal(a.injectionState(), b.injectionState())
+    redos = a.optimisticRedos()
+    assert redos >= 1 and unwaited >= 10, (redos, unwaited)
+    assert b.optimisticRedos() == 0
+
+
 def test_whole_step_calls_queued_without_waiting():
     """mcl_step with no outputs asked for returns as soon as the tick is queued (the adaptive-injection state advances on
     the device): several ticks in flight, scans from host memory and from staged slots, then the same state as a twin
