@@ -599,8 +599,9 @@ def ref_leg(c, args, n, K, W, replicas_note=False, want_kernels=True):
         "ms_per_step_rank0": {"min": min(ms_res), "median": statistics.median(ms_res), "max": max(ms_res)},
         "steps_per_s": c.world * K / t_res,
         "e2e": {"value": c.world * ev_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": scan_bytes,
-                "d2h_bytes_per_step": 24 + 8 + 48 if args.separate_calls else 88,     # mcl_step: the 88-byte tick report (pose sums, injection state,
-                # counters), stored by the last kernel straight into the engine's pinned block
+                "d2h_bytes_per_step": 24 + 8 + 48 if args.separate_calls else 104,    # mcl_step: the 104-byte tick report (pose sums, injection state,
+                # counters, sequence number), stored by the last kernel straight into the engine's pinned block. h2d: the scan as
+                # the caller hands it over (host buffer); of that, the scored beams (24 B each) reach the GPU in the launch parameters
                 "ms_per_step": 1e3 * t_e2e / K, "clock": "host wall clock around each mcl_step call (returns with the pose); L2 flush + device "
                 "synchronisation between calls, outside the timed intervals", "ms_per_step_rank0": {"min": 1e3 * min(s_e2e), "median": 1e3 * statistics.median(s_e2e), "max": 1e3 * max(s_e2e)}},
         "gpu_launches": launches, "launches_per_step": launches / K,

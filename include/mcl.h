@@ -193,10 +193,14 @@ int mcl_estimate(mcl_handle* h, double* x, double* y, double* theta);
  * any call that returns data synchronises); otherwise it waits for the GPU once, at the end, instead of three times. MCL_MODE_REF only (NS filters:
  * mcl_ns_step). pose3 = {x, y, theta} of the resampled particles; stats as mcl_resample. The per-function calls and
  * mcl_step can be mixed on one handle. mcl_step_staged takes a scan parked by mcl_scan_stage.
- * What crosses the bus per tick: the scored beams in (24 B each, one copy command at the head of the tick; nothing with a
- * staged scan) and an 88-byte report out (pose sums, injection state, counters), which the tick's last kernel stores
- * straight into the engine's pinned host block. No other copy or memset command is enqueued, and the tick's kernels follow
- * one another by programmatic dependent launch (MCL_PDL=0 in the environment: ordinary stream order).
+ * What crosses the bus per tick: the scored beams in (24 B each: up to 40 of them ride in the computeWeight kernel's launch
+ * parameters, longer lists take one copy command at the head of the tick; nothing with a staged scan) and a 104-byte report
+ * out (pose sums, injection state, counters, the tick's sequence number), which the tick's last kernel stores straight into
+ * the engine's pinned host block; a call that returns data returns when that sequence number lands. No other copy or memset
+ * command is enqueued, and the tick's kernels follow one another by programmatic dependent launch (MCL_PDL=0 in the
+ * environment: ordinary stream order). While the ray-direction table is incomplete (first tick; clouds with a narrow spread
+ * of headings) a call that returns data enqueues the tick behind the first-touch pre-pass without waiting for it, and runs
+ * the tick a second time only when the pre-pass found a direction the host has to evaluate (same results either way).
  * The engine's own draw streams (draws == NULL / mcl_step), all Philox4x32-10 keyed by mcl_config.seed with counter
  * (index lo, index hi, stream, tick number): stream 0x30 = u_r and the jitter draws of slot i (indices 2i, 2i+1; readable
  * through mcl_debug_download_resample_draws), stream 0x31 = the named draws of the rank-th injected particle (indices
