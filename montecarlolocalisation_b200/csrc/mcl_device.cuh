@@ -64,12 +64,10 @@ __device__ __forceinline__ int cell_of(double a, double res, double inv_res) {
 struct Philox {
     static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#ifdef __CUDA_ARCH__
-        uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
-#else
-        uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c[2]) >> 32);
-#endif
-        uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+        // one widening multiply per product (IMAD.WIDE.U32 on the device) instead of a high and a low one
+        const uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), hi1 = (uint32_t)(p1 >> 32);
+        const uint32_t lo0 = (uint32_t)p0, lo1 = (uint32_t)p1;
         uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
         c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
     }
