@@ -84,7 +84,7 @@ SYMBOLS = [
     ("mcl_download_ancestors", _i32, [_vp, _ip]),
     ("mcl_download_cdf", _i32, [_vp, _dp]),
     ("mcl_estimate", _i32, [_vp, _dp, _dp, _dp]),
-    ("mcl_step", _i32, [_vp, _d, _d, _fp, _i32, _f, _f, _f, _f, _i32, _dp, _vp]),
+    ("mcl_step", _i32, [_vp, _d, _d, _vp, _i32, _f, _f, _f, _f, _i32, _dp, _vp]),       # ranges as an address: the hot call skips the pointer object
     ("mcl_step_staged", _i32, [_vp, _d, _d, _i32, _i32, _dp, _vp]),
     ("mcl_kmeans_confidence", _i32, [_vp, _ip, _ip, _i32, _d, C.POINTER(KmeansResult)]),
     ("mcl_download_assignments", _i32, [_vp, _ip]),
