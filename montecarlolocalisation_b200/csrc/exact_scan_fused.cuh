@@ -194,14 +194,19 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// CDF == false: *total_out = w_0 + w_1 + ... left to right                                  (MC:675)
-// CDF == true : x_i = (float)((double)w_i / *divisor), cdf[i] = x_0 + ... + x_i              (MC:496-505)
+// one raw block of shared memory, two lives: [SEQ blocks below this tile | this tile's own | exact values after every item of the
+// own blocks] while the tile is processed, the single-chain fallback's staging buffers in the last block to finish
+constexpr int XSF_WALK_BYTES = XSF_WALK * (int)sizeof(SeqBlock), XSF_OWN_BYTES = XSF_BLOCKS * (int)sizeof(SeqBlock),
+              XSF_OWNS_BYTES = XSF_BLOCKS * XSF_ITEMS * (int)sizeof(double);
+constexpr int XSF_FB_BYTES = 2 * XS_SEQ_TILE * (int)sizeof(float) + 2 * XS_SEQ_TILE * (int)sizeof(double);
+constexpr int XSF_RAW_BYTES = XSF_WALK_BYTES + XSF_OWN_BYTES + XSF_OWNS_BYTES > XSF_FB_BYTES ? XSF_WALK_BYTES + XSF_OWN_BYTES + XSF_OWNS_BYTES : XSF_FB_BYTES;
+
+// The body of the kernels below. single: the accumulation is ONE tile handled by this block alone (no ticket, nobody to wait
+// for, the block is its own "last block to finish"), which lets k_xs_both run the total and the CDF back to back in one launch.
 template <bool CDF>
-__global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restrict__ w, int64_t n, int nt, unsigned epoch, FusedWs ws,
-                                                            const double* __restrict__ divisor, double* __restrict__ cdf_out,
-                                                            double* __restrict__ total_out, FusedEma ema, FusedGuide guide) {
-    pdl_enter();
-    if (ws.abort != nullptr && *ws.abort != 0) return;
+__device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, const bool single, const float* __restrict__ w, const int64_t n, const int nt,
+                                        const unsigned epoch, const FusedWs& ws, const double* __restrict__ divisor, double* __restrict__ cdf_out,
+                                        double* __restrict__ total_out, const FusedEma& ema, const FusedGuide& guide) {
     __shared__ double sm_d[8];
     __shared__ double sm_last[8];
     __shared__ unsigned long long sm_u[8];
@@ -213,23 +218,18 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     __shared__ double sm_own_pre[XSF_BLOCKS];                           // exact value entering every SEQ block of this tile
     __shared__ double sm_start;                                        // exact value after the last SEQ block below this tile
     __shared__ int sm_start_valid;                                     // 0: no SEQ block below this tile (the sum so far is exactly 0)
-    // one raw block, two lives: [SEQ blocks below this tile | this tile's own | exact values after every item of the own blocks]
-    // while the tile is processed, the single-chain fallback's staging buffers in the last block to finish
-    constexpr int WALK_BYTES = XSF_WALK * (int)sizeof(SeqBlock), OWN_BYTES = XSF_BLOCKS * (int)sizeof(SeqBlock), OWNS_BYTES = XSF_BLOCKS * XSF_ITEMS * (int)sizeof(double);
-    constexpr int FB_BYTES = 2 * XS_SEQ_TILE * (int)sizeof(float) + 2 * XS_SEQ_TILE * (int)sizeof(double);
-    constexpr int RAW_BYTES = WALK_BYTES + OWN_BYTES + OWNS_BYTES > FB_BYTES ? WALK_BYTES + OWN_BYTES + OWNS_BYTES : FB_BYTES;
-    __shared__ __align__(16) unsigned char sm_raw[RAW_BYTES];
     SeqBlock* const sm_walk = reinterpret_cast<SeqBlock*>(sm_raw);
-    SeqBlock* const sm_own = reinterpret_cast<SeqBlock*>(sm_raw + WALK_BYTES);
-    double* const sm_own_s = reinterpret_cast<double*>(sm_raw + WALK_BYTES + OWN_BYTES);      // [block][item]
+    SeqBlock* const sm_own = reinterpret_cast<SeqBlock*>(sm_raw + XSF_WALK_BYTES);
+    double* const sm_own_s = reinterpret_cast<double*>(sm_raw + XSF_WALK_BYTES + XSF_OWN_BYTES);      // [block][item]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool by_index = single || ws.by_index != 0;
     if (tid == 0) {
-        if (!ws.by_index) sm_tile = (int)atomicAdd(ws.counters + 0, 1u);
+        if (!by_index) sm_tile = (int)atomicAdd(ws.counters + 0, 1u);
         sm_fail = 0; sm_gq_n = 0;
         sm_carry_in.v = par_identity(); sm_carry_in.reset = 0; sm_carry_in.cnt = 0;
     }
-    if (!ws.by_index) __syncthreads();          // (by index: the block-wide scans below synchronise long before those are read)
-    const int t = ws.by_index ? (int)blockIdx.x : sm_tile;
+    if (!by_index) __syncthreads();             // (by index: the block-wide scans below synchronise long before those are read)
+    const int t = single ? 0 : (ws.by_index ? (int)blockIdx.x : sm_tile);
     XSF_STAMP(0);
     if (guide.force_fallback && t == 0 && tid == 0) atomicExch(ws.counters + 2, epoch);
     // guide table: element i answers the bucket edges in (cdf[i-1], cdf[i]] (k_ref_guide's rule); `pf` carries floor(cdf[i-1] * buckets)
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         // x = (float)((double)w / total) (MC:497,503) without a division per element: r = w * (1 / total) is within 1.5 ulp of
         // the quotient, so the quotient and its correctly rounded double both lie in [r (1 - 2^-50), r (1 + 2^-50)]; when the two
         // ends round to the same float that float is the answer, otherwise (~1e-8 of the elements, and NaN) the division decides
-        const double tot = *divisor;
+        const double tot = single ? __ldcg(divisor) : *divisor;      // (single: written a moment ago by this very block)
         const double inv = ddiv(1.0, tot);
 #pragma unroll
         for (int j = 0; j < XSF_ITEMS; j++) {
@@ -630,18 +630,20 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     // ---- the last block to finish: clean-up, fallback if anybody asked for it, then the adaptive-injection state ---------------------
     __threadfence();
     __syncthreads();
-    if (tid == 0) sm_is_last = atomicAdd(ws.counters + 1, 1u) == (unsigned)nt - 1u;
-    __syncthreads();
-    if (!sm_is_last) return;
-    __threadfence();
+    if (!single) {
+        if (tid == 0) sm_is_last = atomicAdd(ws.counters + 1, 1u) == (unsigned)nt - 1u;
+        __syncthreads();
+        if (!sm_is_last) return;
+        __threadfence();
+    }
     for (int k = tid; k < nt; k += XS_THREADS) {
         unsigned long long* pk = ws.pub + (size_t)k * XSF_PSTRIDE;
         pk[0] = XSF_EMPTY1; pk[2] = 0ull; pk[3] = 0ull;
     }
-    if (tid == 0) { ws.counters[0] = 0; ws.counters[1] = 0; }
+    if (tid == 0 && !single) { ws.counters[0] = 0; ws.counters[1] = 0; }
     if (*(volatile unsigned*)(ws.counters + 2) == epoch) {
         __syncthreads();                          // every thread is done with what lived in sm_raw
-        fused_sequential<CDF>(w, n, CDF ? *divisor : 1.0, cdf_out, total_out, reinterpret_cast<float(*)[XS_SEQ_TILE]>(sm_raw),
+        fused_sequential<CDF>(w, n, CDF ? (single ? __ldcg(divisor) : *divisor) : 1.0, cdf_out, total_out, reinterpret_cast<float(*)[XS_SEQ_TILE]>(sm_raw),
                               reinterpret_cast<double(*)[XS_SEQ_TILE]>(sm_raw + 2 * XS_SEQ_TILE * sizeof(float)));
         __syncthreads();
         if (want_guide) {                         // whatever the tiles scattered came from values that were not trusted: all of it again
@@ -666,6 +668,36 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
         ema.inj[3] = (tv > 0.0 && tv < 1.0e300) ? 1.0 : 0.0;                // finite positive total: the CDF is non-decreasing
         ema.inj[4] = tv;
     }
+}
+
+// CDF == false: *total_out = w_0 + w_1 + ... left to right                                  (MC:675)
+// CDF == true : x_i = (float)((double)w_i / *divisor), cdf[i] = x_0 + ... + x_i              (MC:496-505)
+template <bool CDF>
+__global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restrict__ w, int64_t n, int nt, unsigned epoch, FusedWs ws,
+                                                            const double* __restrict__ divisor, double* __restrict__ cdf_out,
+                                                            double* __restrict__ total_out, FusedEma ema, FusedGuide guide) {
+    pdl_enter();
+    if (ws.abort != nullptr && *ws.abort != 0) return;
+    __shared__ __align__(16) unsigned char sm_raw[XSF_RAW_BYTES];
+    xsf_run<CDF>(sm_raw, false, w, n, nt, epoch, ws, divisor, cdf_out, total_out, ema, guide);
+}
+
+// Up to one tile of weights (the reference's own few thousand particles), where a tick is bound by the number of dependent
+// launches: the total (+ adaptive-injection state) and then the normalised CDF by the same block in ONE launch. Uses epochs
+// `epoch` and `epoch + 1`. (No guide table: below 4096 particles the CDF search is the plain lower_bound.)
+__global__ void __launch_bounds__(XS_THREADS, 3) k_xs_both(const float* __restrict__ w, int64_t n, unsigned epoch, FusedWs ws, double* __restrict__ cdf_out,
+                                                           double* __restrict__ total_out, FusedEma ema, int force_fallback) {
+    pdl_enter();
+    if (ws.abort != nullptr && *ws.abort != 0) return;
+    __shared__ __align__(16) unsigned char sm_raw[XSF_RAW_BYTES];
+    FusedGuide no_guide;
+    no_guide.table = nullptr; no_guide.buckets = 0; no_guide.log2_buckets = 0; no_guide.force_fallback = force_fallback;
+    FusedEma no_ema;
+    no_ema.inj = nullptr; no_ema.counters = nullptr; no_ema.n = 0; no_ema.a_slow = 0; no_ema.a_fast = 0;
+    xsf_run<false>(sm_raw, true, w, n, 1, epoch, ws, nullptr, nullptr, total_out, ema, no_guide);
+    __threadfence();
+    __syncthreads();
+    xsf_run<true>(sm_raw, true, w, n, 1, epoch + 1u, ws, total_out, cdf_out, nullptr, no_ema, no_guide);
 }
 
 }  // namespace xs

@@ -39,7 +39,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_ema",
-                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_ns_pose_reduce", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials"};
+                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_ns_pose_reduce", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials", "k_xs_both"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
@@ -323,6 +323,16 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
         xs::FusedGuide fg;
         fg.table = nullptr; fg.buckets = 0; fg.log2_buckets = 0; fg.force_fallback = force_scan_fallback ? 1 : 0;
         if (want_cdf && guide_buckets_wanted > 0 && !force_separate_guide) { fg.table = d_guide.p; fg.buckets = guide_buckets_wanted; fg.log2_buckets = __builtin_ctz((unsigned)guide_buckets_wanted); guide_in_cdf = true; }      // (d_guide sized by the caller)
+        // One tile (the reference's own few thousand particles) inside mcl_step: total + adaptive-injection state + normalised
+        // CDF in one launch; ref_resample_front then finds the CDF done.
+        cdf_by_total = false;
+        if (!want_cdf && fuse_cdf_into_total && !force_two_scan_launches && ema && ntf == 1 && n < 4096 && !xs_trace_on && d_total_out == d_scalars.p) {
+            xs_epoch += 2;
+            LAUNCH_PDL(K_XS_BOTH, xs::k_xs_both, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback);
+            CK(cudaGetLastError());
+            cdf_by_total = true;
+            return MCL_OK;
+        }
         ++xs_epoch;
         if (want_cdf)      // divisor: the total (normalise) or the constant 1.0 parked in d_scalars[7]
             LAUNCH_PDL(K_XS_CDF, xs::k_xs_fused<true>, ntf, xs::XS_THREADS, 0, w, n, ntf, xs_epoch, fw, (const double*)(normalise ? d_scalars.p : d_scalars.p + 7), cdf.p,
@@ -919,6 +929,8 @@ int Engine::ref_resample_front() {
         while ((int64_t)buckets * 8 < n && buckets < (1 << 24)) buckets <<= 1;          // ~8 CDF entries per bucket: 3 probes
         CK(d_guide.ensure((size_t)buckets + 2));
     }
+    if (cdf_by_total && buckets == 0) { cdf_by_total = false; return MCL_OK; }      // (k_xs_both: the total's launch wrote the CDF as well)
+    cdf_by_total = false;
     int rc = exact_accumulate(true, nullptr, nullptr, buckets);          // the one-kernel form scatters the guide table as it writes the CDF
     if (rc) return rc;
     if (buckets) {
@@ -1137,8 +1149,10 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     EmaArgs ema;
     ema.a_slow = jitter_state ? cfg.inject_alpha_slow_lost : cfg.inject_alpha_slow_conf;
     ema.a_fast = jitter_state ? cfg.inject_alpha_fast_lost : cfg.inject_alpha_fast_conf;
+    fuse_cdf_into_total = true;              // (the resampling that needs the CDF follows in this very call)
     if (host_scan) rc = ref_run_update(nullptr, step_used.data(), n_used, beams_all, nullptr, true, &ema);
     else rc = ref_run_update(staged[slot].d_used.p, nullptr, staged[slot].n_used, staged[slot].all, nullptr, true, &ema);
+    fuse_cdf_into_total = false;
     if (rc) { flush_pending_motion(); return rc; }        // (a tick that failed before its computeWeight kernel still moves the particles)
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
     if (rc) return rc;

@@ -103,7 +103,7 @@ public:
     int debug_exact_scan_trace(unsigned long long* out, int64_t cap_tiles, int* n_tiles);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_XS_TOTAL, K_XS_CDF, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_NS_POSE_REDUCE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_XS_TOTAL, K_XS_CDF, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_NS_POSE_REDUCE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_XS_BOTH, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
@@ -120,6 +120,9 @@ public:
     int xs_resident_tiles = -1;          // blocks of the one-kernel exact scan the device holds at once (queried on first use)
     bool force_scan_tickets = false;     // tests: ticket order even when the grid is co-resident
     bool force_separate_guide = false;   // tests / A-B: the guide table by its own launch (k_ref_guide) behind the one-kernel CDF
+    bool fuse_cdf_into_total = false;    // mcl_step: the accumulation of the total may also write the normalised CDF (one tile: k_xs_both)
+    bool cdf_by_total = false;           // ... and did
+    bool force_two_scan_launches = false; // tests / A-B: never k_xs_both
     bool force_scan_fallback = false;    // tests: the one-kernel exact scan takes its in-kernel single-chain fallback every time
     bool guide_in_cdf = false;           // the last CDF accumulation also scattered the guide table
     bool force_multilaunch_scan = false; // tests / A-B: the multi-launch exact scan (exact_scan.cuh) instead of the one-kernel form

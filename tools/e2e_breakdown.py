@@ -83,3 +83,12 @@ print("particles %d  steps %d" % (n, K))
 print("a  host scan, result back : median %.1f us  min %.1f" % (np.median(wa), wa.min()))
 print("b  staged scan, result back: median %.1f us  min %.1f" % (np.median(wb), wb.min()))
 print("c  staged, queued (device) : %.1f us per tick" % dev)
+fresh()
+for s in range(W):
+    cq(s)
+pf.profileEnable(True)
+for s in range(W, K + W):
+    cq(s)
+prof = pf.profileRead()
+pf.profileEnable(False)
+print("d  per kernel (events around every launch, serialised, ~4 us high each): " + "  ".join("%s %.1f" % (k.replace("k_ref_", "").replace("k_", ""), 1e3 * v[0] / v[1]) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])))
