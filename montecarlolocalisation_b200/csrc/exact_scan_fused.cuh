@@ -406,13 +406,15 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
                 d->idx0 = (uint32_t)base; d->n_items = n_mine; d->pre = pre.v; d->first_in_tile = pre.reset ? 0 : 1; d->E_prev = q0.E;
 #pragma unroll
                 for (int j = 0; j < XSF_ITEMS / 4; j++) reinterpret_cast<float4*>(d->w)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-                int4* g = reinterpret_cast<int4*>(ws.blocks + (size_t)t * XSF_BSTRIDE + pre.cnt);
-                const int4* sb4 = reinterpret_cast<const int4*>(d);
+                if (!single) {                                     // (a lone tile's blocks are read by nobody else)
+                    int4* g = reinterpret_cast<int4*>(ws.blocks + (size_t)t * XSF_BSTRIDE + pre.cnt);
+                    const int4* sb4 = reinterpret_cast<const int4*>(d);
 #pragma unroll
-                for (int k = 0; k < XSF_BPIECES; k++) g[k] = sb4[k];
-                if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 12] = xsf_now();
-                __threadfence();                               // the block before the summary words
-                if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 13] = xsf_now();
+                    for (int k = 0; k < XSF_BPIECES; k++) g[k] = sb4[k];
+                    if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 12] = xsf_now();
+                    __threadfence();                               // the block before the summary words
+                    if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 13] = xsf_now();
+                }
             } else sm_fail = 1;
         }
         __syncthreads();
@@ -493,7 +495,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         // carried into its tile
         const int n_below = sm_fail ? 0 : min(sm_carry_in.cnt, XSF_WALK);
         XSF_STAMP(8);
-        __threadfence();
+        if (!single) __threadfence();
         XSF_STAMP(9);
         for (int q = tid; q < n_below * XSF_BPIECES; q += XS_THREADS) {
             const int f = q / XSF_BPIECES, piece = q - f * XSF_BPIECES;
@@ -536,12 +538,30 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
             }
             sm_start = sv; sm_start_valid = carry.cnt > 0;
             const int own = min(tstate.cnt, XSF_BLOCKS);
-            for (int q = 0; q < own; q++) {
+            if (own > 0) {
+#pragma unroll
+                for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_own[0].w)[k];
+            }
+            for (int q = 0; q < own; q++) {                          // (items past a block's count are +0, as above)
                 const SeqBlock* b = sm_own + q;
+                float4 cur[XSF_ITEMS / 4];
+#pragma unroll
+                for (int k = 0; k < XSF_ITEMS / 4; k++) cur[k] = nx[k];
+                if (q + 1 < own) {
+#pragma unroll
+                    for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_own[q + 1].w)[k];
+                }
                 const Par comp = b->first_in_tile ? par_compose(carry.v, b->pre) : b->pre;
                 sv = par_apply(sv, comp, b->E_prev, ok);
                 sm_own_pre[q] = sv;
-                for (int k = 0; k < XSF_ITEMS; k++) { sv = dadd(sv, k < b->n_items ? (double)b->w[k] : 0.0); sm_own_s[q * XSF_ITEMS + k] = sv; }
+                double* const so = sm_own_s + q * XSF_ITEMS;
+#pragma unroll
+                for (int k = 0; k < XSF_ITEMS / 4; k++) {
+                    sv = dadd(sv, (double)cur[k].x); so[4 * k] = sv;
+                    sv = dadd(sv, (double)cur[k].y); so[4 * k + 1] = sv;
+                    sv = dadd(sv, (double)cur[k].z); so[4 * k + 2] = sv;
+                    sv = dadd(sv, (double)cur[k].w); so[4 * k + 3] = sv;
+                }
             }
         }
         if (!ok) sm_fail = 1;
