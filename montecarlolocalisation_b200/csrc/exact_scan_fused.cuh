@@ -702,23 +702,5 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     xsf_run<CDF>(sm_raw, false, w, n, nt, epoch, ws, divisor, cdf_out, total_out, ema, guide);
 }
 
-// Up to one tile of weights (the reference's own few thousand particles), where a tick is bound by the number of dependent
-// launches: the total (+ adaptive-injection state) and then the normalised CDF by the same block in ONE launch. Uses epochs
-// `epoch` and `epoch + 1`. (No guide table: below 4096 particles the CDF search is the plain lower_bound.)
-__global__ void __launch_bounds__(XS_THREADS, 3) k_xs_both(const float* __restrict__ w, int64_t n, unsigned epoch, FusedWs ws, double* __restrict__ cdf_out,
-                                                           double* __restrict__ total_out, FusedEma ema, int force_fallback) {
-    pdl_enter();
-    if (ws.abort != nullptr && *ws.abort != 0) return;
-    __shared__ __align__(16) unsigned char sm_raw[XSF_RAW_BYTES];
-    FusedGuide no_guide;
-    no_guide.table = nullptr; no_guide.buckets = 0; no_guide.log2_buckets = 0; no_guide.force_fallback = force_fallback;
-    FusedEma no_ema;
-    no_ema.inj = nullptr; no_ema.counters = nullptr; no_ema.n = 0; no_ema.a_slow = 0; no_ema.a_fast = 0;
-    xsf_run<false>(sm_raw, true, w, n, 1, epoch, ws, nullptr, nullptr, total_out, ema, no_guide);
-    __threadfence();
-    __syncthreads();
-    xsf_run<true>(sm_raw, true, w, n, 1, epoch + 1u, ws, total_out, cdf_out, nullptr, no_ema, no_guide);
-}
-
 }  // namespace xs
 }  // namespace mcl

@@ -769,6 +769,50 @@ __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restri
     if (threadIdx.x == 0) { *total = carry; *ticket = 0u; }
 }
 
+// Up to one tile of weights (the reference's own few thousand particles), where a tick is bound by the number of dependent
+// launches: the weight total (+ adaptive-injection state), the injection counts of k_ref_inject_count and the normalised CDF
+// by ONE block in one launch (the exact-scan body of exact_scan_fused.cuh run twice; epochs `epoch` and `epoch + 1`). No guide
+// table: below 4096 particles the CDF search is the plain lower_bound. Production draws only (mcl_step).
+__global__ void __launch_bounds__(xs::XS_THREADS, 3) k_ref_scans_one_tile(const float* __restrict__ w, int64_t n, unsigned epoch, xs::FusedWs ws,
+                                                                         double* __restrict__ cdf_out, double* __restrict__ total_out, xs::FusedEma ema,
+                                                                         int force_fallback, RefDrawGen G, int* __restrict__ block_counts,
+                                                                         int* __restrict__ flagged_total) {
+    pdl_enter();
+    if (ws.abort != nullptr && *ws.abort != 0) return;
+    __shared__ __align__(16) unsigned char sm_raw[xs::XSF_RAW_BYTES];
+    __shared__ int seg_counts[xs::XSF_TILE / 256];
+    xs::FusedGuide no_guide;
+    no_guide.table = nullptr; no_guide.buckets = 0; no_guide.log2_buckets = 0; no_guide.force_fallback = force_fallback;
+    xs::FusedEma no_ema;
+    no_ema.inj = nullptr; no_ema.counters = nullptr; no_ema.n = 0; no_ema.a_slow = 0; no_ema.a_fast = 0;
+    xs::xsf_run<false>(sm_raw, true, w, n, 1, epoch, ws, nullptr, nullptr, total_out, ema, no_guide);
+    __threadfence();
+    __syncthreads();
+    // slots flagged for injection (u_r < p_inject, MC:518) per 256-slot segment, then their exclusive offsets: what
+    // k_ref_inject_count leaves for k_ref_resample. Thread t draws for slots 16 t .. 16 t + 15, sixteen threads make a segment.
+    const double p_inject = __ldcg(ema.inj + 2);
+    if (block_counts != nullptr && p_inject > 0.0) {
+        int c = 0;
+#pragma unroll 2
+        for (int j = 0; j < xs::XSF_ITEMS; j++) {
+            const int64_t i = (int64_t)threadIdx.x * xs::XSF_ITEMS + j;
+            if (i < n) { uint32_t a[4]; ref_philox_draws(2 * (uint64_t)i, G, a); c += canonical53(a[0], a[1]) < p_inject ? 1 : 0; }
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 15) == 0) seg_counts[threadIdx.x >> 4] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int n_counts = (int)((n + 255) / 256);
+            int acc = 0;
+            for (int k = 0; k < n_counts; k++) { const int v = seg_counts[k]; block_counts[k] = acc; acc += v; }
+            *flagged_total = acc;
+        }
+    }
+    __syncthreads();
+    xs::xsf_run<true>(sm_raw, true, w, n, 1, epoch + 1u, ws, total_out, cdf_out, nullptr, no_ema, no_guide);
+}
+
 // (float)atan2(sin(t), cos(t)) (MC:550). For |t| < 3 pi the mathematical value is t, t - 2 pi or t + 2 pi; libm's composed
 // result differs from it by a few 1e-16, so the float rounding agrees unless the value sits within 1e-14 of a float
 // rounding boundary: only then (or near +-pi, or for larger |t|) is the libm chain evaluated.

@@ -39,7 +39,7 @@ Engine::~Engine() {
 const char* Engine::kernel_name(int id) {
     static const char* names[K_COUNT] = {"k_ref_init", "k_ref_predict", "k_ref_first_touch", "k_ref_touch_theta", "k_ref_update", "k_ref_update_v2",
                                          "k_ref_seq_total", "k_fill_resample_draws", "k_ref_inject_count", "k_ref_ema",
-                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_ns_pose_reduce", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials", "k_xs_both"};
+                                         "k_ref_seq_cdf", "k_ref_guide", "k_ref_resample", "k_xs_tilesum", "k_xs_offsets", "k_xs_scan", "k_xs_chain", "k_xs_apply", "k_xs_total", "k_xs_cdf", "k_ns_edt_cols", "k_ns_edt_rows", "k_ns_init", "k_ns_predict", "k_ns_update", "k_ns_weights_sum", "k_ns_weights_scan", "k_ns_plan", "k_ns_resample_bounds", "k_ns_resample", "k_ns_pose_partials", "k_ns_pose_reduce", "k_km_assign", "k_km_update", "k_km_stats", "k_pose_array", "k_pose_wsum", "k_pose_sums", "k_reduce_partials", "k_ref_scans_one_tile"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 void Engine::profile_enable(bool on) {
@@ -326,11 +326,15 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
         // One tile (the reference's own few thousand particles) inside mcl_step: total + adaptive-injection state + normalised
         // CDF in one launch; ref_resample_front then finds the CDF done.
         cdf_by_total = false;
+        if (!want_cdf) inject_by_scans = false;
         if (!want_cdf && fuse_cdf_into_total && !force_two_scan_launches && ema && ntf == 1 && n < 4096 && !xs_trace_on && d_total_out == d_scalars.p) {
             xs_epoch += 2;
-            LAUNCH_PDL(K_XS_BOTH, xs::k_xs_both, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback);
+            CK(d_block_counts.ensure(xs::XSF_TILE / 256));
+            const RefDrawGen G{(uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)};       // (ref_resample's, which follows in this call)
+            LAUNCH_PDL(K_XS_BOTH, k_ref_scans_one_tile, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
+                       d_block_counts.p, d_counters.p + 2);
             CK(cudaGetLastError());
-            cdf_by_total = true;
+            cdf_by_total = true; inject_by_scans = true;
             return MCL_OK;
         }
         ++xs_epoch;
@@ -929,7 +933,7 @@ int Engine::ref_resample_front() {
         while ((int64_t)buckets * 8 < n && buckets < (1 << 24)) buckets <<= 1;          // ~8 CDF entries per bucket: 3 probes
         CK(d_guide.ensure((size_t)buckets + 2));
     }
-    if (cdf_by_total && buckets == 0) { cdf_by_total = false; return MCL_OK; }      // (k_xs_both: the total's launch wrote the CDF as well)
+    if (cdf_by_total && buckets == 0) { cdf_by_total = false; return MCL_OK; }      // (k_ref_scans_one_tile: the total's launch wrote the CDF as well)
     cdf_by_total = false;
     int rc = exact_accumulate(true, nullptr, nullptr, buckets);          // the one-kernel form scatters the guide table as it writes the CDF
     if (rc) return rc;
@@ -1018,13 +1022,16 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const unsigned blocks = grid_for(n, 256);
     // NaN p_inject compares false (MC:492, std::max(0.0, NaN) = 0.0); dev_ema: the kernels decide from inj_dev[2]
     const bool inject_possible = max_inj > 0 && (dev_ema || p_inject > 0.0);
-    if (inject_possible) {
+    if (inject_possible && inject_by_scans && dev_ema && !d) {
+        // (k_ref_scans_one_tile counted the flagged slots behind the total)
+    } else if (inject_possible) {
         CK(d_block_counts.ensure(blocks));
         // (counts per block, then - by the last block to finish - their exclusive offsets and total: [5] = that kernel's ticket)
         if (d) LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<false>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, d_u_r.p, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5), tick_abort);
         else LAUNCH_PDL(K_INJECT_COUNT, k_ref_inject_count<true>, (blocks + RIC_SEGS - 1) / RIC_SEGS, 256, 0, (const double*)nullptr, n, p_inject, d_block_counts.p, (int)blocks, G, inj_dev, d_counters.p + 2, (unsigned*)(d_counters.p + 5), tick_abort);
         CK(cudaGetLastError());
     }
+    inject_by_scans = false;
     if (!front_done) { rc = ref_resample_front(); if (rc) return rc; }
     // the guide table is used whenever the CDF is known to be non-decreasing: finite positive total weight (dev_ema: inj_dev[3])
     const bool use_guide = guide_built && (dev_ema || (std::isfinite(last_total) && last_total > 0.0));
