@@ -663,6 +663,73 @@ __global__ void __launch_bounds__(256) k_ref_seq_cdf(const float* __restrict__ w
     flush((n_tiles - 1) & 1, n_tiles - 1, threadIdx.x, blockDim.x);
 }
 
+// ---- estimateWeightedPose (MC:782-800): the pieces k_pose_sums and (for small filters) k_ref_resample share --------------
+// Sums of w, w x, w y, w sin(theta), w cos(theta) with w = weight / weight_sum: fp32 element math as the reference,
+// f64 accumulation in a fixed order: thread -> warp tree -> the block's warps in order -> partials[block][4]; the last block
+// to finish adds the per-block partials (lane-strided, then a warp tree) and leaves the four sums in out4. In a whole-tick call
+// it also stores the tick's scalar results straight into the caller's pinned host block (zero-copy): the four pose sums,
+// the adaptive-injection state and the resampling counters, the tick's sequence number last. (struct RefStepReport: mcl_engine.hpp)
+struct PoseTail {
+    double* partials;            // [grid][4]; null: no pose sums asked of this kernel
+    unsigned* ticket;
+    double* out4;
+    RefStepReport* report;       // null: none
+    const double* inj5;
+    const int* counters4;
+    unsigned long long seq;
+};
+__device__ __forceinline__ void pose_add(const float4& p, float weight_sum, double (&a)[4]) {
+    float w = __fdiv_rn(p.w, weight_sum);
+    a[0] += (double)__fmul_rn(w, p.x);
+    a[1] += (double)__fmul_rn(w, p.y);
+    // fp32 sin/cos within 2 ulp (the reference's are Eigen's fp32 psin/pcos, MC:790-791; the estimate is graded to 1e-5
+    // and feeds nothing downstream, so the f64-evaluated correctly rounded form predict needs would be wasted here)
+    float sn, cs;
+    sincosf(p.z, &sn, &cs);
+    a[2] += (double)__fmul_rn(w, sn);
+    a[3] += (double)__fmul_rn(w, cs);
+}
+__device__ __forceinline__ void pose_report_aborted(const PoseTail& T) {          // optimistic tick that did not run: tell the watching host
+    if (blockIdx.x == 0 && threadIdx.x == 0 && T.report) {
+        T.report->aborted = 1;
+        __threadfence_system();
+        *(volatile unsigned long long*)&T.report->seq = T.seq;
+    }
+}
+__device__ __forceinline__ void pose_block_finish(double (&a)[4], const PoseTail& T) {          // whole block, 256 threads
+    __shared__ double ws[8][4];
+    __shared__ bool last;
+#pragma unroll
+    for (int k = 0; k < 4; k++) a[k] = warp_sum(a[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 4; k++) ws[threadIdx.x >> 5][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < 4) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w][threadIdx.x]; T.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = s; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(T.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (o < 4) {
+            double s = 0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(T.partials + (size_t)b * 4 + o);
+            s = warp_sum(s);
+            if (lane == 0) { T.out4[o] = s; if (T.report) T.report->pose[o] = s; }
+        } else if (T.report) {
+            const int k = threadIdx.x - 128;
+            if (k < 5) T.report->inj[k] = __ldcg(T.inj5 + k);
+            else if (k < 9) T.report->counters[k - 5] = __ldcg(T.counters4 + (k - 5));
+        }
+        if (threadIdx.x == 0) *T.ticket = 0;
+        if (T.report) {                             // the report is complete: the host may be spinning on its sequence number
+            __syncthreads();
+            if (threadIdx.x == 0) { T.report->aborted = 0; __threadfence_system(); *(volatile unsigned long long*)&T.report->seq = T.seq; }
+        }
+    }
+}
+
 // ---- resample (MC:508-555) ---------------------------------------------------------------------------------
 struct RefResampleParams {
     double p_inject;       // MC:492
@@ -886,9 +953,11 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       int* __restrict__ counters /* [0]=injected, [1]=clamped */, RefDrawGen G,
                                                       const int* __restrict__ guide /* null: full-range search */, int buckets,
                                                       const double* __restrict__ inj_dev /* mcl_step: {.., p_inject, cdf_is_monotone} on the device */,
-                                                      const int* __restrict__ abort /* optimistic tick: see RefParams */) {
+                                                      const int* __restrict__ abort /* optimistic tick: see RefParams */,
+                                                      PoseTail T /* small filters inside mcl_step: the pose sums of the new particles too */,
+                                                      float pose_weight_sum) {
     pdl_enter();
-    if (abort != nullptr && *abort != 0) return;
+    if (abort != nullptr && *abort != 0) { if (T.partials != nullptr) pose_report_aborted(T); return; }
     __shared__ int warp_counts[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
@@ -915,8 +984,9 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
         for (int w = 0; w < warp; w++) before += warp_counts[w];
         rank = before + __popc(ballot & ((1u << lane) - 1u));
     }
-    if (!live) return;
-    float4 o;
+    if (!live && T.partials == nullptr) return;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
     if (flag && rank < R.max_inject) {
         // sampleParticles(1) with named draws (MC:434-446). Production draws (GEN): injection slot `rank` takes Philox
         // counters 2*rank, 2*rank+1 of stream 0x31: u_yaw = c53(A.0,A.1), u_dx = c53(A.2,A.3), u_dy = c53(B.0,B.1),
@@ -981,6 +1051,12 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
         ancestors[i] = (int)lo;
     }
     dst[i] = o;
+    }   // live
+    if (T.partials != nullptr) {                    // same thread -> particle mapping and summation order as k_pose_sums: the same bits
+        double a[4] = {0, 0, 0, 0};
+        if (live) pose_add(o, pose_weight_sum, a);
+        pose_block_finish(a, T);
+    }
 }
 
 // ---- the production draw streams materialised (for checkers) ---------------------------------------------------------------
@@ -1068,64 +1144,13 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n_par
 // the four pose sums, the adaptive-injection state k_ref_ema left and the resampling counters.
 // (struct RefStepReport: mcl_engine.hpp)
 __global__ void __launch_bounds__(256) k_pose_sums(const float4* __restrict__ part, int64_t n, const double* __restrict__ wsum_dev, double wsum_host,
-                                                   double* __restrict__ partials /* [grid][4] */, unsigned* __restrict__ ticket,
-                                                   double* __restrict__ out4, RefStepReport* __restrict__ report /* null: none */,
-                                                   const double* __restrict__ inj5, const int* __restrict__ counters4, unsigned long long seq,
-                                                   const int* __restrict__ abort /* optimistic tick: see RefParams */) {
+                                                   PoseTail T, const int* __restrict__ abort /* optimistic tick: see RefParams */) {
     pdl_enter();
-    if (abort != nullptr && *abort != 0) {         // nothing ran: tell the host, which is watching the report
-        if (blockIdx.x == 0 && threadIdx.x == 0 && report) {
-            report->aborted = 1;
-            __threadfence_system();
-            *(volatile unsigned long long*)&report->seq = seq;
-        }
-        return;
-    }
-    __shared__ double ws[8][4];
-    __shared__ bool last;
+    if (abort != nullptr && *abort != 0) { pose_report_aborted(T); return; }
     const float weight_sum = __double2float_rn(wsum_dev ? *wsum_dev : wsum_host);
     double a[4] = {0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 p = part[i];
-        float w = __fdiv_rn(p.w, weight_sum);
-        a[0] += (double)__fmul_rn(w, p.x);
-        a[1] += (double)__fmul_rn(w, p.y);
-        // fp32 sin/cos within 2 ulp (the reference's are Eigen's fp32 psin/pcos, MC:790-791; the estimate is graded to 1e-5
-        // and feeds nothing downstream, so the f64-evaluated correctly rounded form predict needs would be wasted here)
-        float sn, cs;
-        sincosf(p.z, &sn, &cs);
-        a[2] += (double)__fmul_rn(w, sn);
-        a[3] += (double)__fmul_rn(w, cs);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) a[k] = warp_sum(a[k]);
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < 4; k++) ws[threadIdx.x >> 5][k] = a[k];
-    __syncthreads();
-    if (threadIdx.x < 4) { double s = 0; for (int w = 0; w < 8; w++) s += ws[w][threadIdx.x]; partials[(size_t)blockIdx.x * 4 + threadIdx.x] = s; }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last) {
-        __threadfence();
-        const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (o < 4) {
-            double s = 0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * 4 + o);
-            s = warp_sum(s);
-            if (lane == 0) { out4[o] = s; if (report) report->pose[o] = s; }
-        } else if (report) {
-            const int k = threadIdx.x - 128;
-            if (k < 5) report->inj[k] = inj5[k];
-            else if (k < 9) report->counters[k - 5] = counters4[k - 5];
-        }
-        if (threadIdx.x == 0) *ticket = 0;
-        if (report) {                             // the report is complete: the host may be spinning on its sequence number
-            __syncthreads();
-            if (threadIdx.x == 0) { report->aborted = 0; __threadfence_system(); *(volatile unsigned long long*)&report->seq = seq; }
-        }
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) pose_add(part[i], weight_sum, a);
+    pose_block_finish(a, T);
 }
 
 }  // namespace mcl

@@ -1037,14 +1037,27 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
     const bool use_guide = guide_built && (dev_ema || (std::isfinite(last_total) && last_total > 0.0));
     const int* guide = use_guide ? d_guide.p : nullptr;
     const int buckets = use_guide ? guide_buckets : 0;
+    // Small filters inside mcl_step: the resampling kernel also sums the pose of the particles it writes and its last block
+    // stores the tick's report (k_pose_sums' work: same thread -> particle mapping, same summation order, same bits), so the
+    // tick ends one dependent launch earlier. (Not at large N: a fence and a ticket per 256-particle block cost more than the
+    // launch they save.)
+    PoseTail PT;
+    PT.partials = nullptr; PT.ticket = nullptr; PT.out4 = nullptr; PT.report = nullptr; PT.inj5 = nullptr; PT.counters4 = nullptr; PT.seq = 0;
+    pose_by_resample = false;
+    if (dev_ema && fuse_pose_into_resample && !force_two_scan_launches && blocks <= 64) {
+        CK(d_partials.ensure(4 * 1024));
+        PT.partials = d_partials.p; PT.ticket = (unsigned*)(d_counters.p + 4); PT.out4 = d_scalars.p + 2; PT.report = h_step;
+        PT.inj5 = d_inj.p; PT.counters4 = d_counters.p; PT.seq = ++step_seq;
+        pose_by_resample = true;
+    }
     if (d)
         LAUNCH_PDL(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
                d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort, PT, (float)((double)n * (double)R.new_weight));
     else
         LAUNCH_PDL(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
                d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort);
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort, PT, (float)((double)n * (double)R.new_weight));
     CK(cudaGetLastError());
     int counters[4] = {0, 0, 0, 0};
     if (!dev_ema) {
@@ -1086,6 +1099,8 @@ int Engine::inj_sync_to_device() {
 // h_sums4: where the four sums are copied to; step_report (mcl_step, pinned host block): the sums, the injection state and
 // the resampling counters are written there by the kernel itself instead (no copy command).
 int Engine::estimate_enqueue(double* h_sums4, RefStepReport* step_report) {
+    if (pose_by_resample && step_report && !h_sums4) { pose_by_resample = false; return MCL_OK; }       // (k_ref_resample did it)
+    pose_by_resample = false;
     { int rc = ns_materialise_weights(); if (rc) return rc; }
     const int blocks = (int)std::min<int64_t>(1024, grid_for(n, 256));
     CK(d_partials.ensure(4 * 1024));
@@ -1095,8 +1110,10 @@ int Engine::estimate_enqueue(double* h_sums4, RefStepReport* step_report) {
         LAUNCH(K_REDUCE, k_reduce_partials, 1, 32, 0, d_partials.p, blocks, 1, 1, d_scalars.p + 1);
         wsum_dev = d_scalars.p + 1;
     }
-    LAUNCH_PDL(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, d_partials.p, (unsigned*)(d_counters.p + 4), d_scalars.p + 2,
-           step_report, (const double*)d_inj.p, (const int*)d_counters.p, step_report ? ++step_seq : 0ull, step_report ? tick_abort : (const int*)nullptr);
+    PoseTail PT;
+    PT.partials = d_partials.p; PT.ticket = (unsigned*)(d_counters.p + 4); PT.out4 = d_scalars.p + 2; PT.report = step_report;
+    PT.inj5 = d_inj.p; PT.counters4 = d_counters.p; PT.seq = step_report ? ++step_seq : 0ull;
+    LAUNCH_PDL(K_POSE_SUMS, k_pose_sums, blocks, 256, 0, part[cur].p, n, wsum_dev, known_wsum, PT, step_report ? tick_abort : (const int*)nullptr);
     CK(cudaGetLastError());
     if (h_sums4) CK(cudaMemcpyAsync(h_sums4, d_scalars.p + 2, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return MCL_OK;
@@ -1161,7 +1178,9 @@ int Engine::ref_step(double enc_l, double enc_r, int slot, const float* ranges, 
     else rc = ref_run_update(staged[slot].d_used.p, nullptr, staged[slot].n_used, staged[slot].all, nullptr, true, &ema);
     fuse_cdf_into_total = false;
     if (rc) { flush_pending_motion(); return rc; }        // (a tick that failed before its computeWeight kernel still moves the particles)
+    fuse_pose_into_resample = true;
     rc = ref_resample(jitter_state, nullptr, nullptr, false, true);
+    fuse_pose_into_resample = false;
     if (rc) return rc;
     // the estimate is part of every tick; its last block writes the tick's scalars straight into the pinned block
     rc = estimate_enqueue(nullptr, h_step);

@@ -122,6 +122,8 @@ public:
     bool force_separate_guide = false;   // tests / A-B: the guide table by its own launch (k_ref_guide) behind the one-kernel CDF
     bool fuse_cdf_into_total = false;    // mcl_step: the accumulation of the total may also write the normalised CDF (one tile: k_xs_both)
     bool cdf_by_total = false;           // ... and did
+    bool fuse_pose_into_resample = false; // mcl_step: the resampling kernel of a small filter may also produce the pose sums and the report
+    bool pose_by_resample = false;       // ... and did
     bool inject_by_scans = false;        // ... and counted the slots flagged for injection (k_ref_inject_count's work) too
     bool force_two_scan_launches = false; // tests / A-B: never k_xs_both
     bool force_scan_fallback = false;    // tests: the one-kernel exact scan takes its in-kernel single-chain fallback every time

@@ -435,7 +435,7 @@ def test_optimistic_tick_equals_separate_calls_on_the_robot_scan():
     mcl_step enqueues the tick behind the pre-pass without waiting for it and runs it again only when the pre-pass found a
     new key (DESIGN.md section 3 "Tick plumbing"): same particles, ancestors, pose, injection state and ray table as the
     separate calls (which wait for the pre-pass every tick) over 40 ticks; some ticks ran twice, most ran once behind an
-    unwaited pre-pass (6 launches: pre-pass 2 + tick 4)."""
+    unwaited pre-pass (5 launches: pre-pass 2 + tick 3)."""
     from montecarlolocalisation_b200 import synth
     n, ticks = 300, 40
     sc = Scenario(ticks, n_beams=360, seed=9)
@@ -461,7 +461,7 @@ def test_optimistic_tick_equals_separate_calls_on_the_robot_scan():
             pose_a, st_a = a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, slot=step)
         else:
             pose_a, st_a = a.executeParticleFilter(sc.enc_left[step], sc.enc_right[step], lost, scan=scan)
-        if a.optimisticRedos() == r0 and a.kernelLaunches() - l0 == 6:          # pre-pass 2 + tick 4 (one tile: total, injection counts and CDF in one launch)
+        if a.optimisticRedos() == r0 and a.kernelLaunches() - l0 == 5:          # pre-pass 2 + tick 3 (computeWeight; total, injection counts and CDF; resampling with the pose sums)
             unwaited += 1
         b.diffDriveModel(sc.enc_left[step], sc.enc_right[step])
         total = b.computeWeight(scan["ranges"], scan["angle_min"], scan["angle_inc"], scan["range_min"], scan["range_max"])
@@ -481,7 +481,8 @@ def test_optimistic_tick_equals_separate_calls_on_the_robot_scan():
 
 def test_one_launch_total_and_cdf_below_one_tile():
     """Below 4096 particles mcl_step accumulates the weight total (+ adaptive-injection state) and the normalised CDF in one
-    launch (k_ref_scans_one_tile), the injection counts included. Same particles, ancestors, CDF, injection state and pose as with the two launches (force bit 10) and
+    launch (k_ref_scans_one_tile), the injection counts included, and the resampling kernel also sums the pose and writes the
+    tick's report: three launches per tick. Same particles, ancestors, CDF, injection state and pose as with the two launches (force bit 10) and
     with the in-kernel single-chain fallback forced in both passes (bit 7), over ticks that include a weight collapse."""
     n, ticks = 1500, 8
     sc = Scenario(ticks, n_beams=360, seed=4)
@@ -503,7 +504,7 @@ def test_one_launch_total_and_cdf_below_one_tile():
             assert np.array_equal(pf.downloadParticles(), P0) and np.array_equal(pf.ancestors(), A0), step
             assert np.array_equal(pf.cdf(), C0, equal_nan=True), step
     names = pfs[0].profileRead()
-    assert "k_ref_scans_one_tile" in names and not {"k_xs_cdf", "k_xs_total", "k_ref_inject_count"} & set(names), sorted(names)
+    assert "k_ref_scans_one_tile" in names and not {"k_xs_cdf", "k_xs_total", "k_ref_inject_count", "k_pose_sums"} & set(names), sorted(names)
     assert np.array_equal(pfs[0].injectionState(), pfs[1].injectionState()) and np.array_equal(pfs[0].injectionState(), pfs[2].injectionState())
 
 def test_whole_step_calls_queued_without_waiting():
