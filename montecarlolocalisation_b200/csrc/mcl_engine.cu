@@ -331,7 +331,7 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
             xs_epoch += 2;
             CK(d_block_counts.ensure(xs::XSF_TILE / 256));
             const RefDrawGen G{(uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)};       // (ref_resample's, which follows in this call)
-            LAUNCH_PDL(K_XS_BOTH, k_ref_scans_one_tile, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
+            LAUNCH_PDL(K_SCANS_ONE_TILE, k_ref_scans_one_tile, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
                        d_block_counts.p, d_counters.p + 2);
             CK(cudaGetLastError());
             cdf_by_total = true; inject_by_scans = true;

@@ -103,7 +103,7 @@ public:
     int debug_exact_scan_trace(unsigned long long* out, int64_t cap_tiles, int* n_tiles);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
-                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_XS_TOTAL, K_XS_CDF, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_NS_POSE_REDUCE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_XS_BOTH, K_COUNT };
+                    K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_XS_TOTAL, K_XS_CDF, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_NS_POSE_REDUCE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_SCANS_ONE_TILE, K_COUNT };
     static const char* kernel_name(int id);
     void profile_enable(bool on);
     int profile_read(int id, double* total_ms, int64_t* count);
