@@ -134,6 +134,7 @@ SYMBOLS = [
     ("mcl_synchronize", _i32, [_vp]),
     ("mcl_kernel_launches", _i64, [_vp]),
     ("mcl_debug_optimistic_redos", _i64, [_vp]),
+    ("mcl_debug_last_scan_fell_back", _i32, [_vp, _ip]),
 ]
 
 _lib = None

@@ -95,14 +95,15 @@ __device__ __forceinline__ unsigned long long xsf_now() {
 }
 #define XSF_STAMP(k) do { if (ws.trace != nullptr && tid == 0) ws.trace[(size_t)t * 16 + (k)] = xsf_now(); } while (0)
 
-__device__ __forceinline__ void load_items12(const float* __restrict__ w, int64_t base, int64_t n, float (&x)[XSF_ITEMS]) {
-    if (base + XSF_ITEMS <= n) {
-        const float4* p = reinterpret_cast<const float4*>(w + base);          // base is a multiple of 16 floats
+template <int ITEMS>
+__device__ __forceinline__ void load_items12(const float* __restrict__ w, int64_t base, int64_t n, float (&x)[ITEMS]) {
+    if (base + ITEMS <= n) {
+        const float4* p = reinterpret_cast<const float4*>(w + base);          // base is a multiple of ITEMS (4, 8 or 16) floats
 #pragma unroll
-        for (int q = 0; q < XSF_ITEMS / 4; q++) { const float4 a = __ldg(p + q); x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w; }
+        for (int q = 0; q < ITEMS / 4; q++) { const float4 a = __ldg(p + q); x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w; }
     } else {
 #pragma unroll
-        for (int j = 0; j < XSF_ITEMS; j++) x[j] = (base + j < n) ? w[base + j] : 0.f;
+        for (int j = 0; j < ITEMS; j++) x[j] = (base + j < n) ? w[base + j] : 0.f;
     }
 }
 
@@ -160,15 +161,18 @@ __device__ __forceinline__ void fused_sequential(const float* __restrict__ w, in
 
 // A thread's 16 weights that go through the hardware adder in order, with the composite of the PAR items between the previous
 // SEQ block of the tile (or the tile's start) and the block, and the predicted binade of the value that composite applies to.
-struct SeqBlock {
+template <int ITEMS>
+struct SeqBlockT {
     uint32_t idx0;
     int n_items;
     Par pre;
     int first_in_tile, E_prev;
-    float w[XSF_ITEMS];
+    float w[ITEMS];
 };
+struct SeqBlock : SeqBlockT<XSF_ITEMS> {};          // the form that travels through global memory between tiles
 constexpr int XSF_BPIECES = (int)sizeof(SeqBlock) / 16;
 static_assert(sizeof(SeqBlock) == 32 + 4 * XSF_ITEMS && sizeof(SeqBlock) % 16 == 0, "published as 16-byte words");
+static_assert(sizeof(SeqBlockT<4>) % 16 == 0 && sizeof(SeqBlockT<8>) % 16 == 0, "read back as 16-byte words");
 
 // published words, one 128-byte line per tile: pub[16 t] = the bits of tile t's f64 sum (never the EMPTY NaN pattern);
 // pub[16 t + 2], pub[16 t + 3] = the tile summary, word = composite component (clamped to 2^58: anything that large means a
@@ -203,10 +207,15 @@ constexpr int XSF_RAW_BYTES = XSF_WALK_BYTES + XSF_OWN_BYTES + XSF_OWNS_BYTES > 
 
 // The body of the kernels below. single: the accumulation is ONE tile handled by this block alone (no ticket, nobody to wait
 // for, the block is its own "last block to finish"), which lets k_xs_both run the total and the CDF back to back in one launch.
-template <bool CDF>
+template <bool CDF, int ITEMS>
 __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, const bool single, const float* __restrict__ w, const int64_t n, const int nt,
                                         const unsigned epoch, const FusedWs& ws, const double* __restrict__ divisor, double* __restrict__ cdf_out,
                                         double* __restrict__ total_out, const FusedEma& ema, const FusedGuide& guide) {
+    // ITEMS weights per thread: 16 in general; 4 or 8 when a lone tile is small (single), so that its few thousand weights spread
+    // over more threads and every per-thread chain (increments, SEQ blocks, apply) is that much shorter
+    using SB = SeqBlockT<ITEMS>;
+    constexpr int TILE = XS_THREADS * ITEMS;
+    constexpr int BPIECES = (int)sizeof(SB) / 16;
     __shared__ double sm_d[8];
     __shared__ double sm_last[8];
     __shared__ unsigned long long sm_u[8];
@@ -218,8 +227,8 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
     __shared__ double sm_own_pre[XSF_BLOCKS];                           // exact value entering every SEQ block of this tile
     __shared__ double sm_start;                                        // exact value after the last SEQ block below this tile
     __shared__ int sm_start_valid;                                     // 0: no SEQ block below this tile (the sum so far is exactly 0)
-    SeqBlock* const sm_walk = reinterpret_cast<SeqBlock*>(sm_raw);
-    SeqBlock* const sm_own = reinterpret_cast<SeqBlock*>(sm_raw + XSF_WALK_BYTES);
+    SB* const sm_walk = reinterpret_cast<SB*>(sm_raw);
+    SB* const sm_own = reinterpret_cast<SB*>(sm_raw + XSF_WALK_BYTES);
     double* const sm_own_s = reinterpret_cast<double*>(sm_raw + XSF_WALK_BYTES + XSF_OWN_BYTES);      // [block][item]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool by_index = single || ws.by_index != 0;
@@ -244,8 +253,8 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         guide_emit(pf + 1, hi, (int)i);
         pf = hi;
     };
-    const int64_t base = (int64_t)t * XSF_TILE + (int64_t)tid * XSF_ITEMS;
-    float x[XSF_ITEMS];
+    const int64_t base = (int64_t)t * TILE + (int64_t)tid * ITEMS;
+    float x[ITEMS];
     load_items12(w, base, n, x);
     if (CDF) {
         // x = (float)((double)w / total) (MC:497,503) without a division per element: r = w * (1 / total) is within 1.5 ulp of
@@ -254,7 +263,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         const double tot = single ? __ldcg(divisor) : *divisor;      // (single: written a moment ago by this very block)
         const double inv = ddiv(1.0, tot);
 #pragma unroll
-        for (int j = 0; j < XSF_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const double r = dmul((double)x[j], inv);
             const float lo = __double2float_rn(dmul(r, 1.0 - 0x1p-50)), hi = __double2float_rn(dmul(r, 1.0 + 0x1p-50));
             x[j] = (base + j < n) ? (lo == hi ? lo : __double2float_rn(ddiv((double)x[j], tot))) : 0.f;
@@ -263,7 +272,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
     // ---- stage 1: tile sum, then P~ at the tile's edges from the lower tiles' sums --------------------------------------------
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < XSF_ITEMS; j++) s = dadd(s, (double)x[j]);
+    for (int j = 0; j < ITEMS; j++) s = dadd(s, (double)x[j]);
     const double incl = block_scan_incl(s, sm_d);
     double excl_thr = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 31) sm_last[warp] = incl;
@@ -291,10 +300,10 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
     if (tid == (t % XS_THREADS)) part = dadd(part, tile_sum);
     const double toff_next = block_sum_fixed(part, sm_d);                                   // F(t + 1): the same value tile t + 1 computes as its F
     XSF_STAMP(2);
-    const int64_t tile_end = min(n, (int64_t)(t + 1) * XSF_TILE);       // one past the last valid element of this tile
+    const int64_t tile_end = min(n, (int64_t)(t + 1) * TILE);       // one past the last valid element of this tile
     // P~ after this thread's last item, and after the previous thread's (tile edges are shared values)
     double my_last = dadd(toff, dadd(excl_thr, s));
-    if (base + XSF_ITEMS - 1 >= tile_end - 1 && base <= tile_end - 1) my_last = toff_next;
+    if (base + ITEMS - 1 >= tile_end - 1 && base <= tile_end - 1) my_last = toff_next;
     double prev_last = __shfl_up_sync(0xffffffffu, my_last, 1);
     __syncthreads();
     if (lane == 31) sm_last[warp] = my_last;
@@ -302,15 +311,15 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
     if (lane == 0) prev_last = warp ? sm_last[warp - 1] : toff;
     const uint64_t depth = 2ull * (uint64_t)((nt + 31) / 32) + 64;
     // ---- stage 2: thread kinds, increments, segmented parity-monoid scan ---------------------------------------------------------
-    const int n_mine = (int)max((int64_t)0, min((int64_t)XSF_ITEMS, n - base));              // valid items of this thread
-    const uint64_t thr_margin = margin_for((uint64_t)min(n, base + XSF_ITEMS), depth);
+    const int n_mine = (int)max((int64_t)0, min((int64_t)ITEMS, n - base));              // valid items of this thread
+    const uint64_t thr_margin = margin_for((uint64_t)min(n, base + ITEMS), depth);
     const Pred q0 = predict(prev_last, thr_margin), q1 = predict(my_last, thr_margin);
     // P~ exactly zero after the thread and its own weights all (+-)0: every weight so far is zero, so are the sums. (Earlier
     // weights that cancel, +1 then -1, sit in a SEQ block - a negative weight is never PAR - and the apply stage checks
     // that no block precedes a zero thread.)
     bool own_zero = true;
 #pragma unroll
-    for (int j = 0; j < XSF_ITEMS; j++) own_zero &= (x[j] == 0.f);
+    for (int j = 0; j < ITEMS; j++) own_zero &= (x[j] == 0.f);
     const bool zero = n_mine == 0 || (my_last == 0.0 && own_zero);
     const int thr_E = q0.E;
     bool easy = !zero && q0.ok && q1.ok && q0.E == q1.E && thr_E >= -900 && thr_E <= 900;
@@ -332,7 +341,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
     if (easy) {
         bool any_invalid = false;
 #pragma unroll
-        for (int j = 0; j < XSF_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             unsigned long long o; bool inv;
             const unsigned long long e = increment(x[j], o, inv);              // (items past n are +0: nothing)
             any_invalid |= inv; has_tie |= (o != e);
@@ -343,11 +352,11 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
             // (rare, but a tile with a tie anywhere publishes its summary only after this and every higher tile waits for it: the
             // weights go through a local array, touched in this branch only, instead of a register select per item. Folding the
             // ties into the pass above was measured: the extra branch there slows every tile by more than this costs one)
-            float xl[XSF_ITEMS];
+            float xl[ITEMS];
 #pragma unroll
-            for (int j = 0; j < XSF_ITEMS; j++) xl[j] = x[j];
+            for (int j = 0; j < ITEMS; j++) xl[j] = x[j];
 #pragma unroll 1
-            for (int j = 0; j < XSF_ITEMS; j++) {
+            for (int j = 0; j < ITEMS; j++) {
                 unsigned long long o; bool inv;
                 Par f;
                 f.e = increment(xl[j], o, inv); f.o = o;
@@ -402,15 +411,15 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         XSF_STAMP(11);
         if (is_block) {
             if (pre.cnt < XSF_BLOCKS) {
-                SeqBlock* const d = sm_own + pre.cnt;              // built in shared memory, copied out by the same thread as 16-byte words
+                SB* const d = sm_own + pre.cnt;              // built in shared memory, copied out by the same thread as 16-byte words
                 d->idx0 = (uint32_t)base; d->n_items = n_mine; d->pre = pre.v; d->first_in_tile = pre.reset ? 0 : 1; d->E_prev = q0.E;
 #pragma unroll
-                for (int j = 0; j < XSF_ITEMS / 4; j++) reinterpret_cast<float4*>(d->w)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                for (int j = 0; j < ITEMS / 4; j++) reinterpret_cast<float4*>(d->w)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
                 if (!single) {                                     // (a lone tile's blocks are read by nobody else)
-                    int4* g = reinterpret_cast<int4*>(ws.blocks + (size_t)t * XSF_BSTRIDE + pre.cnt);
+                    int4* g = reinterpret_cast<int4*>(reinterpret_cast<SB*>(ws.blocks) + (size_t)t * XSF_BSTRIDE + pre.cnt);
                     const int4* sb4 = reinterpret_cast<const int4*>(d);
 #pragma unroll
-                    for (int k = 0; k < XSF_BPIECES; k++) g[k] = sb4[k];
+                    for (int k = 0; k < BPIECES; k++) g[k] = sb4[k];
                     if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 12] = xsf_now();
                     __threadfence();                               // the block before the summary words
                     if (ws.trace != nullptr) ws.trace[(size_t)t * 16 + 13] = xsf_now();
@@ -497,9 +506,9 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         XSF_STAMP(8);
         if (!single) __threadfence();
         XSF_STAMP(9);
-        for (int q = tid; q < n_below * XSF_BPIECES; q += XS_THREADS) {
-            const int f = q / XSF_BPIECES, piece = q - f * XSF_BPIECES;
-            reinterpret_cast<int4*>(sm_walk + f)[piece] = __ldcg(reinterpret_cast<const int4*>(ws.blocks + sm_src[f]) + piece);
+        for (int q = tid; q < n_below * BPIECES; q += XS_THREADS) {
+            const int f = q / BPIECES, piece = q - f * BPIECES;
+            reinterpret_cast<int4*>(sm_walk + f)[piece] = __ldcg(reinterpret_cast<const int4*>(reinterpret_cast<const SB*>(ws.blocks) + sm_src[f]) + piece);
         }
         __syncthreads();
         for (int f = tid; f < n_below; f += XS_THREADS)
@@ -516,23 +525,23 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
             const int n_below = min(carry.cnt, XSF_WALK);
             // one dependent chain of hardware additions (exactly the reference's roundings); the next block's weights are fetched
             // while the current block's sixteen additions run. Items past a block's count are +0: adding them changes nothing.
-            float4 nx[XSF_ITEMS / 4];
+            float4 nx[ITEMS / 4];
             if (n_below > 0) {
 #pragma unroll
-                for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_walk[0].w)[k];
+                for (int k = 0; k < ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_walk[0].w)[k];
             }
             for (int q = 0; q < n_below; q++) {
-                const SeqBlock* b = sm_walk + q;
-                float4 cur[XSF_ITEMS / 4];
+                const SB* b = sm_walk + q;
+                float4 cur[ITEMS / 4];
 #pragma unroll
-                for (int k = 0; k < XSF_ITEMS / 4; k++) cur[k] = nx[k];
+                for (int k = 0; k < ITEMS / 4; k++) cur[k] = nx[k];
                 if (q + 1 < n_below) {
 #pragma unroll
-                    for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_walk[q + 1].w)[k];
+                    for (int k = 0; k < ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_walk[q + 1].w)[k];
                 }
                 sv = par_apply(sv, b->pre, b->E_prev, ok);
 #pragma unroll
-                for (int k = 0; k < XSF_ITEMS / 4; k++) {
+                for (int k = 0; k < ITEMS / 4; k++) {
                     sv = dadd(sv, (double)cur[k].x); sv = dadd(sv, (double)cur[k].y); sv = dadd(sv, (double)cur[k].z); sv = dadd(sv, (double)cur[k].w);
                 }
             }
@@ -540,23 +549,23 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
             const int own = min(tstate.cnt, XSF_BLOCKS);
             if (own > 0) {
 #pragma unroll
-                for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_own[0].w)[k];
+                for (int k = 0; k < ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_own[0].w)[k];
             }
             for (int q = 0; q < own; q++) {                          // (items past a block's count are +0, as above)
-                const SeqBlock* b = sm_own + q;
-                float4 cur[XSF_ITEMS / 4];
+                const SB* b = sm_own + q;
+                float4 cur[ITEMS / 4];
 #pragma unroll
-                for (int k = 0; k < XSF_ITEMS / 4; k++) cur[k] = nx[k];
+                for (int k = 0; k < ITEMS / 4; k++) cur[k] = nx[k];
                 if (q + 1 < own) {
 #pragma unroll
-                    for (int k = 0; k < XSF_ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_own[q + 1].w)[k];
+                    for (int k = 0; k < ITEMS / 4; k++) nx[k] = reinterpret_cast<const float4*>(sm_own[q + 1].w)[k];
                 }
                 const Par comp = b->first_in_tile ? par_compose(carry.v, b->pre) : b->pre;
                 sv = par_apply(sv, comp, b->E_prev, ok);
                 sm_own_pre[q] = sv;
-                double* const so = sm_own_s + q * XSF_ITEMS;
+                double* const so = sm_own_s + q * ITEMS;
 #pragma unroll
-                for (int k = 0; k < XSF_ITEMS / 4; k++) {
+                for (int k = 0; k < ITEMS / 4; k++) {
                     sv = dadd(sv, (double)cur[k].x); so[4 * k] = sv;
                     sv = dadd(sv, (double)cur[k].y); so[4 * k + 1] = sv;
                     sv = dadd(sv, (double)cur[k].z); so[4 * k + 2] = sv;
@@ -577,7 +586,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         Par thr_comp = carry.v;
         bool have_start = sm_start_valid != 0;
         if (!fast) {
-            if (pre.reset) { thr_start = sm_own_s[min(pre.cnt - 1, XSF_BLOCKS - 1) * XSF_ITEMS + XSF_ITEMS - 1]; thr_comp = pre.v; have_start = true; }
+            if (pre.reset) { thr_start = sm_own_s[min(pre.cnt - 1, XSF_BLOCKS - 1) * ITEMS + ITEMS - 1]; thr_comp = pre.v; have_start = true; }
             else thr_comp = par_compose(carry.v, pre.v);
         }
         // integer significand entering the thread; every item adds its increment
@@ -593,7 +602,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         int pf = -1;
         if (want_guide && base > 0) pf = (int)min(A >> gsh, (unsigned long long)guide.buckets);
 #pragma unroll
-        for (int j = 0; j < XSF_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const int64_t i = base + j;
             if (i >= n) break;
             unsigned long long o; bool inv;
@@ -613,10 +622,10 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         int pf = -1;
         if (want_guide && base > 0) pf = xsf_guide_floor(sm_own_pre[min(pre.cnt, XSF_BLOCKS - 1)], GB, guide.buckets);
 #pragma unroll
-        for (int j = 0; j < XSF_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const int64_t i = base + j;
             if (i >= n) break;
-            const double v = sm_own_s[min(pre.cnt, XSF_BLOCKS - 1) * XSF_ITEMS + j];
+            const double v = sm_own_s[min(pre.cnt, XSF_BLOCKS - 1) * ITEMS + j];
             if (CDF) cdf_out[i] = v;
             if (want_guide) guide_item(i, v, pf);
             if (i == n - 1 && total_out) *total_out = v;
@@ -627,7 +636,7 @@ __device__ __forceinline__ void xsf_run(unsigned char* __restrict__ sm_raw, cons
         if (n_mine > 0 && (carry.cnt != 0 || pre.cnt != 0)) okflag = false;       // (cannot happen: a SEQ block means a non-zero P~ before here)
         int pf = base > 0 ? 0 : -1;
 #pragma unroll
-        for (int j = 0; j < XSF_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const int64_t i = base + j;
             if (i >= n) break;
             if (CDF) cdf_out[i] = 0.0;
@@ -699,7 +708,7 @@ __global__ void __launch_bounds__(XS_THREADS, 3) k_xs_fused(const float* __restr
     pdl_enter();
     if (ws.abort != nullptr && *ws.abort != 0) return;
     __shared__ __align__(16) unsigned char sm_raw[XSF_RAW_BYTES];
-    xsf_run<CDF>(sm_raw, false, w, n, nt, epoch, ws, divisor, cdf_out, total_out, ema, guide);
+    xsf_run<CDF, XSF_ITEMS>(sm_raw, false, w, n, nt, epoch, ws, divisor, cdf_out, total_out, ema, guide);
 }
 
 }  // namespace xs

@@ -840,6 +840,7 @@ __global__ void __launch_bounds__(256) k_ref_inject_count(const double* __restri
 // launches: the weight total (+ adaptive-injection state), the injection counts of k_ref_inject_count and the normalised CDF
 // by ONE block in one launch (the exact-scan body of exact_scan_fused.cuh run twice; epochs `epoch` and `epoch + 1`). No guide
 // table: below 4096 particles the CDF search is the plain lower_bound. Production draws only (mcl_step).
+template <int ITEMS>          // weights per thread of the exact-scan passes: 4 up to 1024 particles, 8 up to 2048, else 16
 __global__ void __launch_bounds__(xs::XS_THREADS, 3) k_ref_scans_one_tile(const float* __restrict__ w, int64_t n, unsigned epoch, xs::FusedWs ws,
                                                                          double* __restrict__ cdf_out, double* __restrict__ total_out, xs::FusedEma ema,
                                                                          int force_fallback, RefDrawGen G, int* __restrict__ block_counts,
@@ -852,7 +853,7 @@ __global__ void __launch_bounds__(xs::XS_THREADS, 3) k_ref_scans_one_tile(const 
     no_guide.table = nullptr; no_guide.buckets = 0; no_guide.log2_buckets = 0; no_guide.force_fallback = force_fallback;
     xs::FusedEma no_ema;
     no_ema.inj = nullptr; no_ema.counters = nullptr; no_ema.n = 0; no_ema.a_slow = 0; no_ema.a_fast = 0;
-    xs::xsf_run<false>(sm_raw, true, w, n, 1, epoch, ws, nullptr, nullptr, total_out, ema, no_guide);
+    xs::xsf_run<false, ITEMS>(sm_raw, true, w, n, 1, epoch, ws, nullptr, nullptr, total_out, ema, no_guide);
     __threadfence();
     __syncthreads();
     // slots flagged for injection (u_r < p_inject, MC:518) per 256-slot segment, then their exclusive offsets: what
@@ -877,7 +878,7 @@ __global__ void __launch_bounds__(xs::XS_THREADS, 3) k_ref_scans_one_tile(const 
         }
     }
     __syncthreads();
-    xs::xsf_run<true>(sm_raw, true, w, n, 1, epoch + 1u, ws, total_out, cdf_out, nullptr, no_ema, no_guide);
+    xs::xsf_run<true, ITEMS>(sm_raw, true, w, n, 1, epoch + 1u, ws, total_out, cdf_out, nullptr, no_ema, no_guide);
 }
 
 // (float)atan2(sin(t), cos(t)) (MC:550). For |t| < 3 pi the mathematical value is t, t - 2 pi or t + 2 pi; libm's composed

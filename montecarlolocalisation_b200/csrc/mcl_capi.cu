@@ -125,7 +125,7 @@ int mcl_get_ray_lut(mcl_handle* h, int32_t* keys, double* dx, double* dy, int32_
 int mcl_debug_download_resample_draws(mcl_handle* h, double* u_r, double* u_jitter) { GUARD(h); TRY(h->engine.download_resample_draws(u_r, u_jitter)) }
 int mcl_debug_exact_scan(mcl_handle* h, const float* w, int64_t n, double* cdf, double* total, int32_t* fell_back) { GUARD(h); TRY(h->engine.debug_exact_scan(w, n, cdf, total, fell_back)) }
 int mcl_debug_force_sequential(mcl_handle* h, int32_t on) { GUARD(h); h->engine.force_sequential = (on & 1) != 0; h->engine.force_v1_update = (on & 2) != 0; h->engine.force_f64_probe = (on & 4) != 0;
-    h->engine.ns_force_field = (on & 8) ? 2 : (on & 16) ? 1 : -1; h->engine.ns_force_scalar = (on & 32) != 0; h->engine.force_multilaunch_scan = (on & 64) != 0; h->engine.force_scan_fallback = (on & 128) != 0; h->engine.force_scan_tickets = (on & 256) != 0; h->engine.force_separate_guide = (on & 512) != 0; h->engine.force_two_scan_launches = (on & 1024) != 0; return MCL_OK; }
+    h->engine.ns_force_field = (on & 8) ? 2 : (on & 16) ? 1 : -1; h->engine.ns_force_scalar = (on & 32) != 0; h->engine.force_multilaunch_scan = (on & 64) != 0; h->engine.force_scan_fallback = (on & 128) != 0; h->engine.force_scan_tickets = (on & 256) != 0; h->engine.force_separate_guide = (on & 512) != 0; h->engine.force_two_scan_launches = (on & 1024) != 0; h->engine.force_scan_items16 = (on & 2048) != 0; return MCL_OK; }
 int mcl_debug_exact_scan_trace(mcl_handle* h, unsigned long long* out, int64_t cap_tiles, int32_t* n_tiles) { GUARD(h); TRY(h->engine.debug_exact_scan_trace(out, cap_tiles, n_tiles)) }
 int mcl_debug_ns_last_plan(mcl_handle* h, int64_t* k_lo, int64_t* k_hi, int64_t* own_begin, int64_t* own_count) { GUARD(h); TRY(h->engine.ns_last_plan(k_lo, k_hi, own_begin, own_count)) }
 int mcl_debug_trigf(mcl_handle* h, const float* x, int64_t n, float* s, float* c, int32_t* kind) { GUARD(h); TRY(h->engine.debug_trigf(x, n, s, c, kind)) }
@@ -213,5 +213,6 @@ void* mcl_stream(mcl_handle* h) { return h ? (void*)h->engine.stream : nullptr; 
 int mcl_synchronize(mcl_handle* h) { GUARD(h); TRY(h->engine.synchronize()) }
 int64_t mcl_kernel_launches(mcl_handle* h) { return h ? h->engine.launches : 0; }
 int64_t mcl_debug_optimistic_redos(mcl_handle* h) { return h ? h->engine.optimistic_redos : 0; }
+int mcl_debug_last_scan_fell_back(mcl_handle* h, int32_t* fell_back) { GUARD(h); TRY(h->engine.debug_last_scan_fell_back(fell_back)) }
 
 }  // extern "C"

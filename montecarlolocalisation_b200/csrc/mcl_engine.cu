@@ -331,8 +331,16 @@ int Engine::exact_accumulate_on(const float* w, bool normalise, bool want_cdf, d
             xs_epoch += 2;
             CK(d_block_counts.ensure(xs::XSF_TILE / 256));
             const RefDrawGen G{(uint32_t)step_counter, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)};       // (ref_resample's, which follows in this call)
-            LAUNCH_PDL(K_SCANS_ONE_TILE, k_ref_scans_one_tile, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
-                       d_block_counts.p, d_counters.p + 2);
+            // (the fewer weights, the fewer per thread: the passes are chains of per-thread latencies)
+            if (n <= 1024 && !force_scan_items16)
+                LAUNCH_PDL(K_SCANS_ONE_TILE, k_ref_scans_one_tile<4>, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
+                           d_block_counts.p, d_counters.p + 2);
+            else if (n <= 2048 && !force_scan_items16)
+                LAUNCH_PDL(K_SCANS_ONE_TILE, k_ref_scans_one_tile<8>, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
+                           d_block_counts.p, d_counters.p + 2);
+            else
+                LAUNCH_PDL(K_SCANS_ONE_TILE, k_ref_scans_one_tile<16>, 1, xs::XS_THREADS, 0, w, n, xs_epoch - 1, fw, cdf.p, d_total_out, fe, fg.force_fallback, G,
+                           d_block_counts.p, d_counters.p + 2);
             CK(cudaGetLastError());
             cdf_by_total = true; inject_by_scans = true;
             return MCL_OK;
@@ -411,6 +419,19 @@ int Engine::debug_exact_scan_trace(unsigned long long* out, int64_t cap_tiles, i
         CK(cudaMemcpyAsync(out, xs_trace.p, (size_t)cnt * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
     }
+    return MCL_OK;
+}
+
+int Engine::debug_last_scan_fell_back(int* fell_back) {
+    CK(cudaSetDevice(cfg.device));
+    if (!fell_back) return fail(MCL_ERR_ARG, "debug_last_scan_fell_back: null pointer");
+    unsigned flag = 0;
+    *fell_back = 0;
+    if (!xs_counters.p || xs_epoch == 0) return MCL_OK;
+    CK(cudaMemcpyAsync(&flag, xs_counters.p + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    // a tick uses two consecutive epochs (total, CDF): either of them flagged counts
+    *fell_back = (flag == xs_epoch || flag == xs_epoch - 1) ? 1 : 0;
     return MCL_OK;
 }
 

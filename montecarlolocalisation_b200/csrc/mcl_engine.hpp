@@ -101,6 +101,7 @@ public:
     int debug_exact_scan(const float* w, int64_t count, double* cdf_out, double* total_out, int* fell_back);
     int debug_trigf(const float* x, int64_t count, float* s_out, float* c_out, int* kind_out);
     int debug_exact_scan_trace(unsigned long long* out, int64_t cap_tiles, int* n_tiles);
+    int debug_last_scan_fell_back(int* fell_back);
     // per-kernel CUDA-event timing (off by default; bench.py turns it on for its roofline pass)
     enum KernelId { K_INIT = 0, K_PREDICT, K_FIRST_TOUCH, K_TOUCH_THETA, K_UPDATE, K_UPDATE_V2, K_SEQ_TOTAL, K_FILL_DRAWS, K_INJECT_COUNT,
                     K_INJECT_SCAN, K_SEQ_CDF, K_GUIDE, K_RESAMPLE, K_XS_TILESUM, K_XS_OFFSETS, K_XS_SCAN, K_XS_CHAIN, K_XS_APPLY, K_XS_TOTAL, K_XS_CDF, K_NS_EDT_COLS, K_NS_EDT_ROWS, K_NS_INIT, K_NS_PREDICT, K_NS_UPDATE, K_NS_WSUM, K_NS_WSCAN, K_NS_PLAN, K_NS_BOUNDS, K_NS_RESAMPLE, K_NS_POSE, K_NS_POSE_REDUCE, K_KM_ASSIGN, K_KM_UPDATE, K_KM_STATS, K_POSE_ARRAY, K_POSE_WSUM, K_POSE_SUMS, K_REDUCE, K_SCANS_ONE_TILE, K_COUNT };
@@ -125,6 +126,7 @@ public:
     bool fuse_pose_into_resample = false; // mcl_step: the resampling kernel of a small filter may also produce the pose sums and the report
     bool pose_by_resample = false;       // ... and did
     bool inject_by_scans = false;        // ... and counted the slots flagged for injection (k_ref_inject_count's work) too
+    bool force_scan_items16 = false;      // tests / A-B: k_ref_scans_one_tile with 16 weights per thread whatever the size
     bool force_two_scan_launches = false; // tests / A-B: never k_xs_both
     bool force_scan_fallback = false;    // tests: the one-kernel exact scan takes its in-kernel single-chain fallback every time
     bool guide_in_cdf = false;           // the last CDF accumulation also scattered the guide table

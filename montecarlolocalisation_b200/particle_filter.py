@@ -321,6 +321,12 @@ class ParticleFilter:
     def kernelLaunches(self):
         return self.L.mcl_kernel_launches(self.h)
 
+    def lastScanFellBack(self):
+        """True if the last tick's exact accumulations took the single-chain fallback (mcl_debug_last_scan_fell_back)."""
+        f = C.c_int32()
+        self._ck(self.L.mcl_debug_last_scan_fell_back(self.h, C.byref(f)))
+        return bool(f.value)
+
     def optimisticRedos(self):
         """Whole-tick calls that ran twice because their first-touch pre-pass found new ray directions (mcl_debug_optimistic_redos)."""
         return self.L.mcl_debug_optimistic_redos(self.h)

@@ -479,17 +479,20 @@ def test_optimistic_tick_equals_separate_calls_on_the_robot_scan():
     assert b.optimisticRedos() == 0
 
 
-def test_one_launch_total_and_cdf_below_one_tile():
+@pytest.mark.parametrize("n", [700, 1024, 1500, 2048, 3000])
+def test_one_launch_total_and_cdf_below_one_tile(n):
     """Below 4096 particles mcl_step accumulates the weight total (+ adaptive-injection state) and the normalised CDF in one
     launch (k_ref_scans_one_tile), the injection counts included, and the resampling kernel also sums the pose and writes the
-    tick's report: three launches per tick. Same particles, ancestors, CDF, injection state and pose as with the two launches (force bit 10) and
-    with the in-kernel single-chain fallback forced in both passes (bit 7), over ticks that include a weight collapse."""
-    n, ticks = 1500, 8
+    tick's report: three launches per tick. The exact-scan passes take 4 weights per thread up to 1024 particles, 8 up to
+    2048, else 16. Same particles, ancestors, CDF, injection state and pose as with a large filter's launches (force bit 10),
+    with 16 weights per thread (bit 11) and with the in-kernel single-chain fallback forced in both passes (bit 7), over
+    ticks that include a weight collapse; and the unforced filters never need the fallback."""
+    ticks = 8
     sc = Scenario(ticks, n_beams=360, seed=4)
     scans = [dict(s_) for s_ in sc.scans]
     scans[3]["ranges"] = np.full_like(scans[3]["ranges"], 0.05)          # nothing fits: the total collapses, injections follow
     pfs = []
-    for bits in (0, 1024, 128):
+    for bits in (0, 1024, 2048, 128):
         pf = m.ParticleFilter(max_particles=n, seed=55)
         pf.setMap(sc.occ, RES)
         pf.sampleParticles(n)
@@ -503,9 +506,14 @@ def test_one_launch_total_and_cdf_below_one_tile():
             assert o[1] == out[0][1] and np.array_equal(o[0], out[0][0]), step
             assert np.array_equal(pf.downloadParticles(), P0) and np.array_equal(pf.ancestors(), A0), step
             assert np.array_equal(pf.cdf(), C0, equal_nan=True), step
+        if np.isfinite(out[0][1]["total_weight"]) and out[0][1]["total_weight"] > 0:
+            assert not pfs[0].lastScanFellBack() and not pfs[1].lastScanFellBack() and not pfs[2].lastScanFellBack(), step
+        assert pfs[3].lastScanFellBack()
     names = pfs[0].profileRead()
     assert "k_ref_scans_one_tile" in names and not {"k_xs_cdf", "k_xs_total", "k_ref_inject_count", "k_pose_sums"} & set(names), sorted(names)
-    assert np.array_equal(pfs[0].injectionState(), pfs[1].injectionState()) and np.array_equal(pfs[0].injectionState(), pfs[2].injectionState())
+    for pf in pfs[1:]:
+        assert np.array_equal(pfs[0].injectionState(), pf.injectionState())
+
 
 def test_whole_step_calls_queued_without_waiting():
     """mcl_step with no outputs asked for returns as soon as the tick is queued (the adaptive-injection state advances on
