@@ -350,7 +350,9 @@ __host__ __device__ inline size_t ru_smem_bytes(int n_keys, int n_beams, int n_r
 // addresses (IMAD + IADD + LDS.U8) instead of through a generic 64-bit pointer.
 template <bool ZERO_ORIGIN, bool FAST32, int NR, bool MAP_SMEM>
 __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ part, float* __restrict__ w_dense, int64_t n, RefParams P,
-                                                           uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32) {
+                                                           uint32_t div_magic /* ceil(2^32 / n_beams) */, float tol32,
+                                                           int ppb /* particles a block takes per pass, <= RU_TILE: fewer for small filters,
+                                                                      so that their rays spread over more SMs */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[RU_TILE / 32];
     RuSmem S;
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     const int W = P.width, H = P.height;
     const int nb = P.n_beams, nr = P.n_radii, stride = nb + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n_tiles = (n + RU_TILE - 1) / RU_TILE;
+    const int64_t n_tiles = (n + ppb - 1) / ppb;
     // Everything above read only tables that no kernel of a tick writes (map, ray directions, beams, Gaussian table: set by
     // host copies, which serialise the stream), so under a programmatic launch it overlaps the predecessor's tail; the
     // particles are the predecessor's output.
@@ -418,11 +420,12 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
     if (P.abort != nullptr && *P.abort != 0) return;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- phase A -------------------------------------------------------------------------------------------------
-        const int64_t j = tile * RU_TILE + threadIdx.x;
+        const int64_t j = tile * ppb + threadIdx.x;
+        const bool mine = (int)threadIdx.x < ppb && j < n;                                // this thread holds a particle of the tile
         bool valid = false, yaw_exact = false;
         double posx = 0, posy = 0, yawd = 0;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < n) {
+        if (mine) {
             p = part[j];
             if (P.do_predict) {                                                          // updateParticlePos, MC:746-753 (fp32 element math)
                 const float h = __fadd_rn(p.z, P.rot1);
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
                     double a = dadd(S.yawd[v], off);
                     const double fr = fabs(dsub(a, trunc(a)));
                     if (!(S.vlist[v] & 0x10000) && !(fabs(fr - 0.5) > 1e-9)) {
-                        const float th = part[tile * RU_TILE + (S.vlist[v] & 0xffff)].z;
+                        const float th = part[tile * ppb + (S.vlist[v] & 0xffff)].z;
                         a = dadd(ddiv(dmul(ref_yaw(th), 180.0), 3.14159265358979323846), off);
                     }
                     const int kk = trunc_x86(round(a)) - P.key_min;
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(RU_TILE) k_ref_update_v2(float4* __restrict__ 
             S.wout[S.vlist[threadIdx.x] & 0xffff] = __double2float_rn(prob);             // MC:673
         }
         __syncthreads();
-        if (j < n) {                                                                     // the particle's own thread writes it back whole
+        if (mine) {                                                                      // the particle's own thread writes it back whole
             p.w = valid ? S.wout[threadIdx.x] : 0.f;
             part[j] = p;
             w_dense[j] = p.w;

@@ -835,7 +835,11 @@ int Engine::ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_u
         // the bounded fast path needs every probe quotient below 2^31: particle inside the map, ray at most max_range long
         const bool zero_origin = origin_x == 0.0 && origin_y == 0.0;
         const int nr_ct = (fast32 && P.n_radii == 11) ? 11 : 0;
-        const int64_t tiles = (n + RU_TILE - 1) / RU_TILE;
+        // particles per block and pass: a whole tile normally; a small filter is cut finer so that its rays reach more SMs
+        // (1500 particles: 47 blocks of 32 instead of 6 of 256)
+        int ppb = RU_TILE;
+        while (ppb > 32 && (n + ppb - 1) / ppb < (int64_t)sms) ppb >>= 1;
+        const int64_t tiles = (n + ppb - 1) / ppb;
         // ceil(2^32 / n_used); n_used == 1 would need 2^32 itself: the kernel divides by one without it
         const uint32_t div_magic = n_used == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)n_used - 1) / (uint64_t)n_used);
         bool launched = false;
@@ -843,7 +847,7 @@ int Engine::ref_run_update(const RefBeam* d_used, const RefBeam* h_used, int n_u
         if (!launched && zero_origin == Z && fast32 == F && nr_ct == N && ms == M) {                                                     \
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, (k_ref_update_v2<Z, F, N, M>), RU_TILE, smem2));               \
             const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * std::max(1, occ_blocks));                                      \
-            LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<Z, F, N, M>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32); \
+            LAUNCH_PDL(K_UPDATE_V2, (k_ref_update_v2<Z, F, N, M>), grid, RU_TILE, smem2, part[cur].p, d_wraw.p, n, P, div_magic, tol32, ppb); \
             launched = true;                                                                                                             \
         }
         RU_FOR_ALL(X)
