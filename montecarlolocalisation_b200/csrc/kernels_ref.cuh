@@ -959,10 +959,20 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       const double* __restrict__ inj_dev /* mcl_step: {.., p_inject, cdf_is_monotone} on the device */,
                                                       const int* __restrict__ abort /* optimistic tick: see RefParams */,
                                                       PoseTail T /* small filters inside mcl_step: the pose sums of the new particles too */,
-                                                      float pose_weight_sum) {
+                                                      float pose_weight_sum,
+                                                      int cdf_in_smem /* a whole small CDF (n doubles of dynamic shared memory) is staged first:
+                                                                         the search's dependent loads then cost a shared-memory round trip each */) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
     pdl_enter();
     if (abort != nullptr && *abort != 0) { if (T.partials != nullptr) pose_report_aborted(T); return; }
     __shared__ int warp_counts[8];
+    const double* cs = cdf;                      // where the search reads the CDF (a generic pointer: global or shared)
+    if (cdf_in_smem) {
+        double* sc = reinterpret_cast<double*>(rs_smem);
+        for (int64_t k = threadIdx.x; k < n; k += blockDim.x) sc[k] = cdf[k];
+        __syncthreads();
+        cs = sc;
+    }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
     uint32_t A[4] = {0, 0, 0, 0};
@@ -1026,7 +1036,7 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
         }
         while (len > 0) {
             int64_t half = len >> 1;
-            if (cdf[lo + half] < r) { lo += half + 1; len -= half + 1; } else { len = half; }
+            if (cs[lo + half] < r) { lo += half + 1; len -= half + 1; } else { len = half; }
         }
         if (lo >= n) { lo = n - 1; atomicAdd(&counters[1], 1); }
         float4 a = src[lo];

@@ -1075,14 +1075,15 @@ int Engine::ref_resample(int jitter_state, const mcl_resample_draws* d, mcl_resa
         PT.inj5 = d_inj.p; PT.counters4 = d_counters.p; PT.seq = ++step_seq;
         pose_by_resample = true;
     }
+    const size_t cdf_smem = (!guide && n <= 4096) ? (size_t)n * sizeof(double) : 0;      // (32 KB at most: no opt-in needed)
     if (d)
-        LAUNCH_PDL(K_RESAMPLE, k_ref_resample<false>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
+        LAUNCH_PDL(K_RESAMPLE, k_ref_resample<false>, blocks, 256, cdf_smem, part[cur].p, part[cur ^ 1].p, n, cdf.p, d_u_r.p, d_u_jit.p, d_inj_f64.p, d_inj_i32.p,
                d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort, PT, (float)((double)n * (double)R.new_weight));
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort, PT, (float)((double)n * (double)R.new_weight), cdf_smem ? 1 : 0);
     else
-        LAUNCH_PDL(K_RESAMPLE, k_ref_resample<true>, blocks, 256, 0, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
+        LAUNCH_PDL(K_RESAMPLE, k_ref_resample<true>, blocks, 256, cdf_smem, part[cur].p, part[cur ^ 1].p, n, cdf.p, (const double*)nullptr, (const double*)nullptr,
                d_inj_f64.p, d_inj_i32.p, d_inj_i32.p + max_inj, d_inj_f64.p + max_inj, d_inj_f64.p + 2 * max_inj,
-               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort, PT, (float)((double)n * (double)R.new_weight));
+               inject_possible ? (const int*)d_block_counts.p : (const int*)nullptr, R, ancestors.p, d_counters.p, G, guide, buckets, inj_dev, tick_abort, PT, (float)((double)n * (double)R.new_weight), cdf_smem ? 1 : 0);
     CK(cudaGetLastError());
     int counters[4] = {0, 0, 0, 0};
     if (!dev_ema) {
