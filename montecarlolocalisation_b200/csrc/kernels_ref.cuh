@@ -962,8 +962,8 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
                                                       float pose_weight_sum,
                                                       int cdf_in_smem /* a whole small CDF (n doubles of dynamic shared memory) is staged first:
                                                                          the search's dependent loads then cost a shared-memory round trip each */) {
-    extern __shared__ __align__(16) unsigned char rs_smem[];
     pdl_enter();
+    extern __shared__ __align__(16) unsigned char rs_smem[];
     if (abort != nullptr && *abort != 0) { if (T.partials != nullptr) pose_report_aborted(T); return; }
     __shared__ int warp_counts[8];
     const double* cs = cdf;                      // where the search reads the CDF (a generic pointer: global or shared)
