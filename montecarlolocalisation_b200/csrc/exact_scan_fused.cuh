@@ -31,6 +31,10 @@
 // be trusted, so correctness never rests on the margin analysis, and (optionally) advances the adaptive-injection state from
 // the total (what k_ref_ema did as a launch of its own).
 //
+// The body is the device function xsf_run<CDF, ITEMS>; the kernels around it: k_xs_fused<CDF> below (ITEMS = 16, any number of
+// tiles) and kernels_ref.cuh's k_ref_scans_one_tile<ITEMS>, which runs the total and then the CDF of a filter of one tile in a
+// single launch by calling the body twice (ITEMS = 4 / 8 / 16 by size: the fewer weights, the fewer per thread).
+//
 // Where the time goes (profiles/r2_xs_trace.txt, 1M weights, 245 tiles, ~22 us): every stage is a latency, not a throughput:
 // load + tile sum 2.8 us, first exchange 1.2, classification 1.5 (3 for the handful of tiles that hold a SEQ block or a tie,
 // and every higher tile waits for those), second exchange + scan of 244 summaries ~4, block fetch 1.4, walk 3.7, apply 3.
