@@ -395,7 +395,7 @@ def test_nonzero_map_origin():
     assert total_g == total_o and np.array_equal(pf.downloadParticles()[:, 3], Po[:, 3])
 
 
-@pytest.mark.parametrize("n", [1000, 30011])
+@pytest.mark.parametrize("n", [1000, 8000, 30011])          # one tile; several tiles with the pose summed by the resampling kernel; neither
 def test_whole_step_call_equals_separate_calls(n):
     """mcl_step / mcl_step_staged (one tick enqueued as one piece, the host waiting once) against the four separate calls
     on a twin filter with the same seed: same particles, ancestors, injection state, stats and pose, over steps that
