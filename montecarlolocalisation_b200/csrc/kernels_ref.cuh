@@ -717,7 +717,13 @@ __device__ __forceinline__ void pose_block_finish(double (&a)[4], const PoseTail
         const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (o < 4) {
             double s = 0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(T.partials + (size_t)b * 4 + o);
+            for (int b0 = lane; b0 < (int)gridDim.x; b0 += 32 * 8) {          // eight loads in flight, added in the same order as one by one
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int b = b0 + 32 * k; v[k] = b < (int)gridDim.x ? __ldcg(T.partials + (size_t)b * 4 + o) : 0.0; }
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (b0 + 32 * k < (int)gridDim.x) s += v[k];
+            }
             s = warp_sum(s);
             if (lane == 0) { T.out4[o] = s; if (T.report) T.report->pose[o] = s; }
         } else if (T.report) {
