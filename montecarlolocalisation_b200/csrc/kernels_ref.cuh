@@ -1007,70 +1007,70 @@ __global__ void __launch_bounds__(256) k_ref_resample(const float4* __restrict__
     if (!live && T.partials == nullptr) return;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
-    if (flag && rank < R.max_inject) {
-        // sampleParticles(1) with named draws (MC:434-446). Production draws (GEN): injection slot `rank` takes Philox
-        // counters 2*rank, 2*rank+1 of stream 0x31: u_yaw = c53(A.0,A.1), u_dx = c53(A.2,A.3), u_dy = c53(B.0,B.1),
-        // row = B.2 mod rows, col = B.3 mod cols.
-        double u_yaw, u_dx, u_dy;
-        int row, col;
-        if (GEN) {
-            uint32_t a[4], b[4];
-            ref_philox_inject_draws(2 * (uint64_t)rank, G, a); ref_philox_inject_draws(2 * (uint64_t)rank + 1, G, b);
-            u_yaw = canonical53(a[0], a[1]); u_dx = canonical53(a[2], a[3]); u_dy = canonical53(b[0], b[1]);
-            row = (int)(b[2] % R.inj_rows); col = (int)(b[3] % R.inj_cols);
+        if (flag && rank < R.max_inject) {
+            // sampleParticles(1) with named draws (MC:434-446). Production draws (GEN): injection slot `rank` takes Philox
+            // counters 2*rank, 2*rank+1 of stream 0x31: u_yaw = c53(A.0,A.1), u_dx = c53(A.2,A.3), u_dy = c53(B.0,B.1),
+            // row = B.2 mod rows, col = B.3 mod cols.
+            double u_yaw, u_dx, u_dy;
+            int row, col;
+            if (GEN) {
+                uint32_t a[4], b[4];
+                ref_philox_inject_draws(2 * (uint64_t)rank, G, a); ref_philox_inject_draws(2 * (uint64_t)rank + 1, G, b);
+                u_yaw = canonical53(a[0], a[1]); u_dx = canonical53(a[2], a[3]); u_dy = canonical53(b[0], b[1]);
+                row = (int)(b[2] % R.inj_rows); col = (int)(b[3] % R.inj_cols);
+            } else {
+                u_yaw = inj_u_yaw[rank]; u_dx = inj_u_dx[rank]; u_dy = inj_u_dy[rank];
+                row = inj_row[rank]; col = inj_col[rank];
+            }
+            double orientation = dadd(dmul(u_yaw, R.yaw_w), R.yaw_a);
+            double x_move = dadd(dmul(u_dx, R.init_w), R.init_a);
+            double y_move = dadd(dmul(u_dy, R.init_w), R.init_a);
+            double base_x = dadd(dmul((double)col, R.cell_meters), R.half_cell);
+            double base_y = dadd(dmul((double)row, R.cell_meters), R.half_cell);
+            o.x = __double2float_rn(dadd(dadd(base_x, x_move), R.init_shift));
+            o.y = __double2float_rn(dadd(dadd(base_y, y_move), R.init_shift));
+            o.z = __double2float_rn(orientation);
+            o.w = R.new_weight;
+            ancestors[i] = -1;
+            atomicAdd(&counters[0], 1);
         } else {
-            u_yaw = inj_u_yaw[rank]; u_dx = inj_u_dx[rank]; u_dy = inj_u_dy[rank];
-            row = inj_row[rank]; col = inj_col[rank];
+            // std::lower_bound(cdf, r): first idx with !(cdf[idx] < r) (MC:530); NaN entries compare false.
+            int64_t lo = 0, len = n;
+            if (guide && r >= 0.0 && r < 1.0) {                           // (injected draws outside [0, 1): full-range search)
+                const int b = (int)(r * (double)buckets);                // exact: power-of-two scaling, r in [0, 1)
+                lo = guide[b]; len = (int64_t)guide[b + 1] - lo;         // answer in [guide[b], guide[b+1]]
+            }
+            while (len > 0) {
+                int64_t half = len >> 1;
+                if (cs[lo + half] < r) { lo += half + 1; len -= half + 1; } else { len = half; }
+            }
+            if (lo >= n) { lo = n - 1; atomicAdd(&counters[1], 1); }
+            float4 a = src[lo];
+            int64_t inj_before = rank < R.max_inject ? rank : R.max_inject;
+            // jitter draws are consumed in slot order by non-injected slots only: this slot takes stream entry i - inj_before
+            double ux, uy, ut = 0.0;
+            if (GEN) {
+                const uint64_t j = (uint64_t)(i - inj_before);
+                uint32_t B[4];
+                if (inj_before != 0) ref_philox_draws(2 * j, G, A);
+                ref_philox_draws(2 * j + 1, G, B);
+                ux = canonical53(A[2], A[3]); uy = canonical53(B[0], B[1]); ut = canonical53(B[2], B[3]);
+            } else {
+                const int64_t jpos = (i - inj_before) * (R.jitter_state ? 3 : 2);
+                ux = u_jit[jpos]; uy = u_jit[jpos + 1];
+                if (R.jitter_state) ut = u_jit[jpos + 2];
+            }
+            double jx = dadd(dmul(ux, R.jit_xy_w), R.jit_xy_a);
+            double jy = dadd(dmul(uy, R.jit_xy_w), R.jit_xy_a);
+            double jt = (double)a.z;
+            if (R.jitter_state) jt = dadd(jt, dadd(dmul(ut, R.jit_th_w), R.jit_th_a));
+            o.x = __double2float_rn(dadd((double)a.x, jx));          // MC:548
+            o.y = __double2float_rn(dadd((double)a.y, jy));          // MC:549
+            o.z = ref_wrap_theta(jt);                                // MC:550
+            o.w = R.new_weight;                                      // MC:551
+            ancestors[i] = (int)lo;
         }
-        double orientation = dadd(dmul(u_yaw, R.yaw_w), R.yaw_a);
-        double x_move = dadd(dmul(u_dx, R.init_w), R.init_a);
-        double y_move = dadd(dmul(u_dy, R.init_w), R.init_a);
-        double base_x = dadd(dmul((double)col, R.cell_meters), R.half_cell);
-        double base_y = dadd(dmul((double)row, R.cell_meters), R.half_cell);
-        o.x = __double2float_rn(dadd(dadd(base_x, x_move), R.init_shift));
-        o.y = __double2float_rn(dadd(dadd(base_y, y_move), R.init_shift));
-        o.z = __double2float_rn(orientation);
-        o.w = R.new_weight;
-        ancestors[i] = -1;
-        atomicAdd(&counters[0], 1);
-    } else {
-        // std::lower_bound(cdf, r): first idx with !(cdf[idx] < r) (MC:530); NaN entries compare false.
-        int64_t lo = 0, len = n;
-        if (guide && r >= 0.0 && r < 1.0) {                           // (injected draws outside [0, 1): full-range search)
-            const int b = (int)(r * (double)buckets);                // exact: power-of-two scaling, r in [0, 1)
-            lo = guide[b]; len = (int64_t)guide[b + 1] - lo;         // answer in [guide[b], guide[b+1]]
-        }
-        while (len > 0) {
-            int64_t half = len >> 1;
-            if (cs[lo + half] < r) { lo += half + 1; len -= half + 1; } else { len = half; }
-        }
-        if (lo >= n) { lo = n - 1; atomicAdd(&counters[1], 1); }
-        float4 a = src[lo];
-        int64_t inj_before = rank < R.max_inject ? rank : R.max_inject;
-        // jitter draws are consumed in slot order by non-injected slots only: this slot takes stream entry i - inj_before
-        double ux, uy, ut = 0.0;
-        if (GEN) {
-            const uint64_t j = (uint64_t)(i - inj_before);
-            uint32_t B[4];
-            if (inj_before != 0) ref_philox_draws(2 * j, G, A);
-            ref_philox_draws(2 * j + 1, G, B);
-            ux = canonical53(A[2], A[3]); uy = canonical53(B[0], B[1]); ut = canonical53(B[2], B[3]);
-        } else {
-            const int64_t jpos = (i - inj_before) * (R.jitter_state ? 3 : 2);
-            ux = u_jit[jpos]; uy = u_jit[jpos + 1];
-            if (R.jitter_state) ut = u_jit[jpos + 2];
-        }
-        double jx = dadd(dmul(ux, R.jit_xy_w), R.jit_xy_a);
-        double jy = dadd(dmul(uy, R.jit_xy_w), R.jit_xy_a);
-        double jt = (double)a.z;
-        if (R.jitter_state) jt = dadd(jt, dadd(dmul(ut, R.jit_th_w), R.jit_th_a));
-        o.x = __double2float_rn(dadd((double)a.x, jx));          // MC:548
-        o.y = __double2float_rn(dadd((double)a.y, jy));          // MC:549
-        o.z = ref_wrap_theta(jt);                                // MC:550
-        o.w = R.new_weight;                                      // MC:551
-        ancestors[i] = (int)lo;
-    }
-    dst[i] = o;
+        dst[i] = o;
     }   // live
     if (T.partials != nullptr) {                    // same thread -> particle mapping and summation order as k_pose_sums: the same bits
         double a[4] = {0, 0, 0, 0};
